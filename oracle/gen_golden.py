@@ -1,0 +1,197 @@
+"""Generate tests/golden/*.npz by running THE REFERENCE'S OWN CODE (imported from /root/reference,
+read-only) and the un-vendored third-party code it relies on (HF transformers ViTPose processor)
+on seeded synthetic inputs.  Run in the build container only:
+
+    python oracle/gen_golden.py
+
+The GPU box has no /root/reference; tests read only the committed fixtures.  TEST INFRASTRUCTURE.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+OUT = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+synth = importlib.import_module("person-recognition-for-pose-estimation_b200.synth")
+
+
+def _stub_modules():
+    """pytorch_lightning / pycocotools / albumentations are not installed: stub just
+    enough for the reference's Lightning modules to import."""
+    class LightningModule(torch.nn.Module):
+        def save_hyperparameters(self, *a, **k):
+            self.hparams = types.SimpleNamespace()
+
+        def log(self, *a, **k):
+            pass
+
+    pl = types.ModuleType("pytorch_lightning")
+    pl.LightningModule = LightningModule
+    pl.LightningDataModule = object
+    sys.modules["pytorch_lightning"] = pl
+    class _Permissive(types.ModuleType):
+        """any attribute resolves to a dummy class (only used in type annotations / unused imports)"""
+        def __getattr__(self, item):
+            if item.startswith("__"):
+                raise AttributeError(item)
+            return type(item, (), {})
+
+    for name in ["pycocotools", "pycocotools.coco", "pycocotools.cocoeval", "albumentations",
+                 "albumentations.pytorch"]:
+        if name not in sys.modules:
+            sys.modules[name] = _Permissive(name)
+
+
+class _Slice(torch.nn.Module):
+    def __init__(self, a, b):
+        super().__init__()
+        self.a, self.b = a, b
+
+    def forward(self, x):
+        return x[:, self.a:self.b]
+
+
+def gen_det():
+    sys.path.insert(0, os.path.join(REF, "training"))
+    from yolopt.nets.nn import Head
+    import yolopt.util as yutil
+
+    yutil.time = lambda: 0.0          # neutralise the wall-clock bail-out (util.py:133-134,166-167)
+    for tag, nc, seed in (("nc1", 1, 11), ("nc3", 3, 12)):
+        hm = synth.make_head_maps(2, 256, 320, n_obj=4, nc=nc, seed=seed, min_size=24, max_size=160)
+        head = Head(nc=nc, filters=(64, 64, 64))
+        head.stride = torch.tensor([8.0, 16.0, 32.0])
+        head.box = torch.nn.ModuleList([_Slice(0, 64) for _ in range(3)])      # raw maps already hold
+        head.cls = torch.nn.ModuleList([_Slice(64, 64 + nc) for _ in range(3)])  # cat(box(x), cls(x))
+        head.eval()
+        with torch.no_grad():
+            decoded = head([l.clone() for l in hm.levels])                     # nn.py:255-270
+        conf = 0.001 if nc == 1 else 0.25
+        dets = yutil.non_max_suppression(decoded, conf, 0.65)                   # util.py:123-169
+        np.savez_compressed(
+            os.path.join(OUT, f"det_{tag}.npz"),
+            l0=hm.levels[0].numpy(), l1=hm.levels[1].numpy(), l2=hm.levels[2].numpy(),
+            decoded=decoded.numpy(), conf=np.float32(conf), iou=np.float32(0.65),
+            n=np.array([d.shape[0] for d in dets]),
+            dets=np.concatenate([d.numpy() for d in dets], 0),
+            anchors=head.anchors.numpy(), strides=head.strides.numpy())
+        print("det", tag, [d.shape[0] for d in dets])
+
+
+def gen_match():
+    sys.path.insert(0, os.path.join(REF, "libs"))
+    import net_adaface
+    import head_adaface
+
+    torch.manual_seed(3)
+    net = net_adaface.build_model("ir_18").eval()
+    feats = {}
+    net.output_layer.register_forward_hook(lambda m, i, o: feats.__setitem__("pre", o.detach().clone()))
+    with torch.no_grad():
+        emb, norm = net(torch.randn(6, 3, 112, 112))                            # net_adaface.py:324-337
+    ms = synth.make_match_set(48, 300, seed=5)
+    kernel = (ms.gallery * torch.empty(300, 1).uniform_(0.5, 2.0)).t().contiguous()   # [512, N] un-normalised
+    kn = head_adaface.l2_norm(kernel, axis=0)                                   # head_adaface.py:39-42,79
+
+    # the live match, training/lightning/face_recognition/module.py:119-145, via the real module
+    _stub_modules()
+    sys.path.insert(0, os.path.join(REF, "training"))
+    from lightning.face_recognition.module import FaceRecognitionModule
+    import torch.nn.functional as F
+
+    def run(labels, k):
+        fake = types.SimpleNamespace()
+        fake.model = lambda images: (images, None)                              # embeddings pass-through
+        fake.model.ada_face = types.SimpleNamespace(head=types.SimpleNamespace(kernel=k))
+        fake.hparams = types.SimpleNamespace(s=64.0)
+        fake.validation_step_outputs = []
+        fake.log = lambda *a, **kw: None
+        return float(FaceRecognitionModule.validation_step(fake, (ms.embeddings, labels), 0)["val_acc"])
+
+    # Recover the module's predictions probe by probe: acc==1 iff label == its argmax.
+    cos_q3 = F.linear(F.normalize(ms.embeddings), F.normalize(kernel).t())     # what :137-138 computes (quirk Q3)
+    pred_q3 = (cos_q3 * 64.0).max(1)[1]
+    assert run(pred_q3, kernel) == 1.0 and run((pred_q3 + 1) % 300, kernel) == 0.0
+    # with a kernel that is already column-normalised the quirk is (almost) a no-op on the ranking
+    cos = F.linear(F.normalize(ms.embeddings), kn.t())
+    pred = (cos * 64.0).max(1)[1]
+    np.savez_compressed(
+        os.path.join(OUT, "match.npz"),
+        pre=feats["pre"].numpy(), emb=emb.numpy(), norm=norm.numpy(),
+        probes=ms.embeddings.numpy(), kernel=kernel.numpy(), kernel_l2=kn.numpy(),
+        pred_q3=pred_q3.numpy(), sim_q3=cos_q3.gather(1, pred_q3[:, None]).squeeze(1).numpy(),
+        pred=pred.numpy(), sim=cos.gather(1, pred[:, None]).squeeze(1).numpy(), true_ids=ms.true_ids.numpy())
+    print("match ok; acc vs planted:", float((pred == ms.true_ids).float().mean()))
+
+
+def gen_pose_live():
+    _stub_modules()
+    sys.path.insert(0, os.path.join(REF, "training"))
+    from lightning.pose_estimation.module import PoseEstimationModule
+    from lightning.pose_estimation.datamodule import COCO_FLIP_PAIRS
+
+    class M(torch.nn.Module):
+        def set_task(self, t):
+            pass
+
+    mod = PoseEstimationModule(M())
+    hs = synth.make_heatmaps(4, 17, seed=21)
+    boxes = torch.tensor([[10., 20., 110., 320.], [0., 0., 30., 40.], [5., 5., 400., 700.], [50., 60., 146., 156.]])
+    # correct flip-back + average (module copy.py:465-472 semantics) computed with plain torch
+    fb = hs.flipped.clone()
+    for a, b in COCO_FLIP_PAIRS:
+        fb[:, [a, b]] = fb[:, [b, a]]
+    avg = (hs.heatmaps + fb.flip(-1)) * 0.5
+    # the live module's own (buggy, Q1) flip-back, module.py:479-484
+    q1 = torch.flip(hs.flipped.clone(), dims=[-1])
+    for pair in COCO_FLIP_PAIRS:
+        q1[:, pair] = q1[:, pair].flip(0)
+    avg_q1 = (hs.heatmaps + q1) * 0.5
+    c0, s0 = mod._get_keypoints_from_heatmaps(hs.heatmaps)                      # module.py:237-296
+    c1, s1 = mod._get_keypoints_from_heatmaps(avg, boxes=boxes)
+    np.savez_compressed(
+        os.path.join(OUT, "pose_live.npz"),
+        hm=hs.heatmaps.numpy(), flipped=hs.flipped.numpy(), perm=hs.perm.numpy(), boxes_xyxy=boxes.numpy(),
+        avg=avg.numpy(), avg_q1=avg_q1.numpy(),
+        coords_plain=c0.numpy(), scores_plain=s0.numpy(), coords_avg_box=c1.numpy(), scores_avg_box=s1.numpy())
+    print("pose_live ok")
+
+
+def gen_pose_hf():
+    """Third-party HF code (the DARK/UDP oracle, a9/a14).  Same package on both boxes; the fixtures
+    guard against silent behaviour changes and give the GPU tests a reference-independent target."""
+    from transformers import VitPoseImageProcessor
+    from transformers.models.vitpose.modeling_vitpose import VitPoseEstimatorOutput
+
+    proc = VitPoseImageProcessor()
+    hs = synth.make_heatmaps(5, 17, seed=22)
+    perm = hs.perm.long()
+    avg = (hs.heatmaps + hs.flipped[:, perm].flip(-1)) * 0.5
+    cs = synth.make_crop_set(1, 240, 320, per_frame=5, seed=23)
+    boxes = [[[float(v) for v in b] for b in cs.boxes]]
+    res = proc.post_process_pose_estimation(VitPoseEstimatorOutput(heatmaps=avg), boxes=boxes, kernel_size=11)
+    kp = torch.stack([r["keypoints"] for r in res[0]]).numpy()
+    sc = torch.stack([r["scores"] for r in res[0]]).numpy()
+    pix = proc.preprocess([cs.frames[0]], boxes=boxes, do_rescale=False, return_tensors="pt")["pixel_values"].numpy()
+    np.savez_compressed(
+        os.path.join(OUT, "pose_hf.npz"),
+        hm=hs.heatmaps.numpy(), flipped=hs.flipped.numpy(), perm=hs.perm.numpy(), boxes=cs.boxes.numpy(),
+        keypoints=kp, scores=sc, frame=cs.frames[0].numpy(), crop_sub=pix[:, :, ::4, ::4].copy(),
+        crop_sum=pix.astype(np.float64).sum(axis=(2, 3)))
+    print("pose_hf ok", kp.shape, pix.shape)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    gen_det()
+    gen_match()
+    gen_pose_live()
+    gen_pose_hf()

@@ -1,0 +1,133 @@
+"""The oracle against (a) fixtures produced by the reference's own code (oracle/gen_golden.py) and
+(b) the installed third-party code the reference relies on (torchvision nms, HF ViTPose processor)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import crop as ocrop
+from oracle import det as odet
+from oracle import match as omatch
+from oracle import pose as opose
+
+
+@pytest.mark.parametrize("tag", ["nc1", "nc3"])
+def test_head_decode_and_nms_match_reference(golden, tag):
+    g = golden(f"det_{tag}.npz")
+    levels = [torch.from_numpy(g[k]) for k in ("l0", "l1", "l2")]
+    dec = odet.head_decode(levels)
+    ref = torch.from_numpy(g["decoded"])
+    assert dec.shape == ref.shape
+    np.testing.assert_array_equal(dec.numpy(), ref.numpy())        # same torch calls -> bit-exact
+    a, s = odet.make_anchors([tuple(l.shape[2:]) for l in levels], (8, 16, 32))
+    np.testing.assert_array_equal(a.t().numpy(), g["anchors"])
+    np.testing.assert_array_equal(s.t().numpy(), g["strides"])
+    # NMS on the reference's own decoded tensor: bit-exact rows
+    for fn in (odet.nms_greedy, odet.nms_greedy_np):
+        dets = odet.non_max_suppression(ref, float(g["conf"]), float(g["iou"]), nms_fn=fn)
+        assert [d.shape[0] for d in dets] == list(g["n"])
+        np.testing.assert_array_equal(torch.cat(dets).numpy(), g["dets"])
+
+
+def test_nms_restatement_matches_torchvision():
+    import torchvision
+    gen = torch.Generator().manual_seed(0)
+    for trial in range(20):
+        n = 200
+        xy = torch.rand(n, 2, generator=gen) * 100
+        wh = torch.rand(n, 2, generator=gen) * 40 + 1
+        boxes = torch.cat([xy, xy + wh], 1)
+        scores = torch.rand(n, generator=gen)
+        if trial % 4 == 0:
+            scores = (scores * 8).round() / 8          # many exact ties -> stable order matters
+        keep_tv = torchvision.ops.nms(boxes, scores, 0.5).numpy()
+        for fn in (odet.nms_greedy, odet.nms_greedy_np):
+            np.testing.assert_array_equal(fn(boxes.numpy(), scores.numpy(), 0.5), keep_tv)
+
+
+def test_match_oracle(golden):
+    g = golden("match.npz")
+    emb, norm = omatch.backbone_tail(torch.from_numpy(g["pre"]))
+    np.testing.assert_array_equal(emb.numpy(), g["emb"])
+    np.testing.assert_array_equal(norm.numpy(), g["norm"])
+    kernel = torch.from_numpy(g["kernel"])
+    np.testing.assert_array_equal(omatch.l2_norm(kernel, 0).numpy(), g["kernel_l2"])
+    probes = torch.from_numpy(g["probes"])
+    pred, sim = omatch.match_top1(probes, omatch.enrol_gallery(kernel, quirk_q3=True))
+    np.testing.assert_array_equal(pred.numpy(), g["pred_q3"])       # confirmed by the real validation_step
+    np.testing.assert_allclose(sim.numpy(), g["sim_q3"], rtol=1e-6, atol=1e-7)
+    pred, sim = omatch.match_top1(probes, omatch.enrol_gallery(kernel))
+    np.testing.assert_array_equal(pred.numpy(), g["pred"])
+    np.testing.assert_allclose(sim.numpy(), g["sim"], rtol=1e-6, atol=1e-7)
+    gated, _ = omatch.match_top1(probes, omatch.enrol_gallery(kernel), threshold=0.4)
+    known = g["true_ids"] >= 0
+    np.testing.assert_array_equal(gated.numpy()[known], g["true_ids"][known])
+    assert (gated.numpy()[~known] == -1).all()
+
+
+def test_pose_live_oracle(golden):
+    g = golden("pose_live.npz")
+    hm, fl, perm = (torch.from_numpy(g[k]) for k in ("hm", "flipped", "perm"))
+    avg = opose.flip_average(hm, fl, perm)
+    np.testing.assert_array_equal(avg.numpy(), g["avg"])
+    from importlib import import_module
+    pairs = import_module("person-recognition-for-pose-estimation_b200.synth").COCO_FLIP_PAIRS
+    np.testing.assert_array_equal(((hm + opose.flip_back_quirk_q1(fl, pairs)) * 0.5).numpy(), g["avg_q1"])
+    c, s = opose.soft_argmax_decode(hm)
+    np.testing.assert_array_equal(c.numpy(), g["coords_plain"])
+    np.testing.assert_array_equal(s.numpy(), g["scores_plain"])
+    c, s = opose.soft_argmax_decode(avg, torch.from_numpy(g["boxes_xyxy"]))
+    np.testing.assert_array_equal(c.numpy(), g["coords_avg_box"])
+    np.testing.assert_array_equal(s.numpy(), g["scores_avg_box"])
+
+
+def test_pose_hf_oracle_fixture(golden):
+    g = golden("pose_hf.npz")
+    hm, fl, perm = (torch.from_numpy(g[k]) for k in ("hm", "flipped", "perm"))
+    avg = opose.flip_average(hm, fl, perm).numpy()
+    boxes = [[float(v) for v in b] for b in g["boxes"]]
+    kp, sc, idx = opose.hf_dark_decode(avg, boxes)
+    np.testing.assert_allclose(kp, g["keypoints"], rtol=1e-6, atol=1e-4)
+    np.testing.assert_array_equal(sc, g["scores"])
+    kp2, sc2, idx2 = opose.dark_decode_local(avg, boxes)
+    np.testing.assert_array_equal(idx2, idx)
+    np.testing.assert_allclose(kp2, kp, rtol=1e-5, atol=2e-3)
+    pix = ocrop.crop_affine_hf(g["frame"][None], boxes, [0] * len(boxes))
+    np.testing.assert_allclose(pix[:, :, ::4, ::4], g["crop_sub"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(pix.astype(np.float64).sum(axis=(2, 3)), g["crop_sum"], rtol=1e-6)
+
+
+def test_oracle_against_installed_hf(synth):
+    """Live comparison with the third-party code itself (same package on the GPU box)."""
+    from transformers import VitPoseImageProcessor
+    from transformers.models.vitpose.modeling_vitpose import VitPoseEstimatorOutput
+    proc = VitPoseImageProcessor()
+    hs = synth.make_heatmaps(3, 17, seed=31, negative_frac=0.1)
+    avg = opose.flip_average(hs.heatmaps, hs.flipped, hs.perm)
+    cs = synth.make_crop_set(1, 200, 260, per_frame=3, seed=32)
+    boxes = [[float(v) for v in b] for b in cs.boxes]
+    res = proc.post_process_pose_estimation(VitPoseEstimatorOutput(heatmaps=avg), boxes=[boxes])
+    kp_hf = torch.stack([r["keypoints"] for r in res[0]]).numpy()
+    sc_hf = torch.stack([r["scores"] for r in res[0]]).numpy()
+    kp, sc, _ = opose.hf_dark_decode(avg.numpy(), boxes)
+    np.testing.assert_allclose(kp, kp_hf, rtol=1e-6, atol=1e-4)
+    np.testing.assert_array_equal(sc, sc_hf)
+    pix_hf = proc.preprocess([cs.frames[0]], boxes=[boxes], do_rescale=False, return_tensors="pt")["pixel_values"]
+    pix = ocrop.crop_affine_hf(cs.frames.numpy(), boxes, [0, 0, 0])
+    np.testing.assert_allclose(pix, pix_hf.numpy(), rtol=1e-5, atol=2e-6)
+    # default HF path (rescale 1/255 folded into mean/std)
+    fr255 = (cs.frames * 255.0)
+    pix_hf = proc.preprocess([fr255[0]], boxes=[boxes], return_tensors="pt")["pixel_values"]
+    pix = ocrop.crop_affine_hf(fr255.numpy(), boxes, [0, 0, 0], rescale_factor=1 / 255)
+    np.testing.assert_allclose(pix, pix_hf.numpy(), rtol=1e-5, atol=2e-5)
+
+
+def test_quarter_offset_hand_made():
+    hm = np.zeros((1, 2, 8, 6), np.float32)
+    hm[0, 0, 3, 2] = 1.0; hm[0, 0, 3, 3] = 0.5; hm[0, 0, 2, 2] = 0.25     # peak (2,3): right>left, up>down
+    hm[0, 1] = -1.0                                                        # all negative -> zeroed coords
+    centers = np.array([[100.0, 200.0]]); scales = np.array([[60.0, 80.0]])
+    preds, maxv, idx = opose.quarter_offset_decode(hm, centers, scales)
+    assert idx[0, 0] == 3 * 6 + 2 and maxv[0, 0] == 1.0
+    r = 60.0 / 6
+    np.testing.assert_allclose(preds[0, 0], [(2 + 0.25) * r + 100 - 30, (3 - 0.25) * r + 200 - r * 4], rtol=1e-6)
+    np.testing.assert_allclose(preds[0, 1], [100 - 30, 200 - r * 4], rtol=1e-6)
