@@ -1,0 +1,169 @@
+/* spp.h — C ABI of the B200-native selective-pose glue path (libspp.so).
+ *
+ * The reference (Person-Recognition-for-Pose-Estimation) has no plugin / FFI interface: its hot path
+ * is a set of Python functions.  Each entry point below replaces one of them and says
+ * which (paths relative to the reference root; HF = transformers/models/vitpose, the un-vendored
+ * third-party processor the reference imports at training/modify_models.py:335).
+ *
+ * Conventions
+ *   - every pointer marked DEVICE is a CUDA device pointer on the current device; HOST pointers are
+ *     small parameter arrays read before the launch.  The caller owns all buffers; nothing is
+ *     allocated here except through the caller-provided workspace.
+ *   - all work is enqueued on `stream` (a cudaStream_t); no entry point synchronises, all of them
+ *     are CUDA-graph capturable.
+ *   - return value 0 = success, negative = error; spp_last_error() returns the thread-local message.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef SPP_H_
+#define SPP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *spp_stream_t; /* cudaStream_t */
+
+#define SPP_OK 0
+#define SPP_ERR_INVALID (-1)   /* bad argument / unsupported shape */
+#define SPP_ERR_CUDA (-2)      /* a CUDA runtime call failed */
+#define SPP_ERR_WORKSPACE (-3) /* workspace too small */
+
+#define SPP_MAX_LEVELS 4
+
+/* ABI version (bumped when a signature changes). */
+int spp_abi_version(void);
+const char *spp_last_error(void);
+/* Number of SMs of the current device (grid sizing is a multiple of it); <0 on error. */
+int spp_device_sm_count(void);
+
+/* ------------------------------------------------------------------ detection head + NMS ----- */
+
+/* Replaces Head.forward, eval branch — training/yolopt/nets/nn.py:255-270 (after the per-level conv
+ * stacks) incl. make_anchors (training/yolopt/util.py:85-96) and DFL (nn.py:222-225).
+ *   levels[l]  DEVICE  raw map [batch, 64+nc, level_h[l], level_w[l]] fp32, NCHW contiguous
+ *   out        DEVICE  [batch, 4+nc, A] fp32: (cx, cy, w, h) in pixels, sigmoid class scores
+ */
+int spp_head_decode(const float *const *levels, const int *level_h, const int *level_w, const float *strides,
+                    int num_levels, int batch, int nc, float *out, spp_stream_t stream);
+
+/* Workspace for the two NMS entry points below (bytes).  max_candidates bounds the per-image
+ * candidate list: min(num_anchors * nc, max_candidates) candidates are kept per image (pass <= 0 for
+ * "all of them").  Results are exact whenever the number of candidates of every image fits; beyond
+ * that the surplus (arbitrary) candidates are dropped and out_count[b] is returned negated.  With
+ * nc == 1 and max_candidates <= 0 this cannot happen. */
+size_t spp_nms_workspace_bytes(int batch, int num_anchors, int nc, int max_candidates);
+
+/* Replaces non_max_suppression(outputs, conf, iou) — training/yolopt/util.py:123-169, without its
+ * wall-clock bail-out (:133-134,:166-167).
+ *   pred       DEVICE  [batch, 4+nc, A] fp32 (the tensor spp_head_decode produces)
+ *   out_dets   DEVICE  [batch, max_det, 6] fp32 rows (x1, y1, x2, y2, conf, cls), conf-descending;
+ *                      rows >= out_count[b] are zero
+ *   out_count  DEVICE  [batch] int32
+ *   out_keys   DEVICE  [batch, max_det] int32 candidate key anchor*nc + cls of each kept row (may be NULL)
+ * nc == 1: best class only; nc > 1: multi-label, one candidate per (anchor, class) above conf.
+ * Suppression: class-aware through the reference's +cls*max_wh box offset; IoU > iou (strict), fp32,
+ * no FMA contraction; equal scores: lower candidate key first.
+ */
+int spp_nms_decoded(const float *pred, int batch, int nc, int num_anchors, float conf_thres, float iou_thres,
+                    int max_det, int max_nms, float max_wh, int max_candidates, float *out_dets, int *out_count,
+                    int *out_keys, void *workspace, size_t workspace_bytes, spp_stream_t stream);
+
+/* Fused Head.forward(eval) + non_max_suppression straight from the raw per-level maps: the decoded
+ * [batch, 4+nc, A] tensor is never materialised and box channels are only read for candidates.
+ * Same outputs as spp_nms_decoded. */
+int spp_decode_nms(const float *const *levels, const int *level_h, const int *level_w, const float *strides,
+                   int num_levels, int batch, int nc, float conf_thres, float iou_thres, int max_det, int max_nms,
+                   float max_wh, int max_candidates, float *out_dets, int *out_count, int *out_keys,
+                   void *workspace, size_t workspace_bytes, spp_stream_t stream);
+
+/* ------------------------------------------------------------------ embedding + gallery match - */
+
+/* Replaces the tail of Backbone.forward — libs/net_adaface.py:334-337 (mode 0: x / ||x||, no eps)
+ * and F.normalize — training/lightning/face_recognition/module.py:138 (mode 1: x / max(||x||, eps)).
+ *   x DEVICE [m, dim] fp32; out DEVICE [m, dim] fp32 (may be NULL); norm DEVICE [m] fp32 (may be NULL);
+ *   out_bf16 DEVICE [m, dim] bf16 bits (may be NULL) — the GEMM operand. */
+int spp_l2_normalize(const float *x, int m, int dim, int mode, float eps, float *out, float *norm,
+                     uint16_t *out_bf16, spp_stream_t stream);
+
+/* fp32 [n, dim] -> bf16 [n, dim] (gallery enrolment; off the hot path). */
+int spp_f32_to_bf16(const float *x, size_t count, uint16_t *out, spp_stream_t stream);
+
+size_t spp_match_workspace_bytes(int m, int n, int dim);
+
+/* Replaces the cosine match + top-1 — training/lightning/face_recognition/module.py:136-145
+ * (F.linear(F.normalize(emb), gallery) ; max(1)) and libs/head_adaface.py:79-81, plus the north-star's
+ * threshold gate (not in the reference).
+ *   emb        DEVICE  [m, dim] fp32 raw embeddings (normalised here, F.normalize semantics)
+ *   gallery    DEVICE  [n, dim] bf16 bits, rows unit-norm (enrolment-time normalisation), dim == 512
+ *   threshold  gate: id = -1 where sim < threshold; pass NaN for "no gate"
+ *   id_offset  added to every returned id (gallery shard base on a multi-GPU run)
+ *   out_id     DEVICE  [m] int32;  out_sim DEVICE [m] fp32 (cosine of the winner, fp32 re-scored)
+ *   out_key    DEVICE  [m] uint64 (may be NULL): (orderable(sim) << 32) | (0xFFFFFFFF - global id),
+ *              so that an integer MAX all-reduce over gallery shards yields the global top-1 with the
+ *              lowest index winning ties (what torch.max does).
+ * The dense contraction runs as a tcgen05/TMEM bf16 GEMM with a fused per-row top-2 epilogue; the
+ * surviving candidates are re-scored in fp32 so the returned id is the fp32 arg-max.
+ */
+int spp_match_top1(const float *emb, const uint16_t *gallery, int m, int n, int dim, float threshold,
+                   int id_offset, int *out_id, float *out_sim, unsigned long long *out_key, void *workspace,
+                   size_t workspace_bytes, spp_stream_t stream);
+
+/* Unpack all-reduced keys: id = -1 where sim < threshold (NaN: no gate). */
+int spp_match_unpack_keys(const unsigned long long *keys, int m, float threshold, int *out_id, float *out_sim,
+                          spp_stream_t stream);
+
+/* ------------------------------------------------------------------ crop --------------------- */
+
+#define SPP_CROP_HF_UDP 0   /* HF VitPoseImageProcessor (box_to_center_and_scale + get_warp_matrix) */
+#define SPP_CROP_GLUONCV 1  /* training/lightning/pose_estimation/datamodule_v2.py:119-129,213-226 */
+
+/* Replaces VitPoseImageProcessor.preprocess(images, boxes) — HF image_processing_vitpose.py:68-172,
+ * 386-448 (variant 0), or the dataset crop of datamodule_v2.py (variant 1; exact bilinear, no cv2
+ * fixed-point quantisation).
+ *   frames     DEVICE  [num_frames, 3, frame_h, frame_w] fp32
+ *   boxes      DEVICE  [p, 4] fp32 COCO (x, y, w, h) in frame pixels
+ *   frame_idx  DEVICE  [p] int32
+ *   mean, std  HOST    [3] fp32: out = (sample - mean[c]) / std[c]
+ *   out        DEVICE  [p, 3, out_h, out_w] fp32
+ * Sample = exact bilinear at the UDP source coordinate, 0 when it falls outside
+ * [0, frame_w-1] x [0, frame_h-1] (scipy order=1, mode='constant').
+ */
+int spp_crop_affine(const float *frames, int num_frames, int frame_h, int frame_w, const float *boxes,
+                    const int *frame_idx, int p, int out_h, int out_w, const float *mean, const float *std,
+                    int variant, float *out, spp_stream_t stream);
+
+/* ------------------------------------------------------------------ heatmap decode ----------- */
+
+#define SPP_DECODE_DARK 0        /* HF post_process_pose_estimation: argmax + DARK + UDP back-projection */
+#define SPP_DECODE_SOFTARGMAX 1  /* live module: training/lightning/pose_estimation/module.py:237-296,534-546 */
+#define SPP_DECODE_QUARTER 2     /* gluoncv get_final_preds as called at pose_estimation/module_v2.py:214-222 */
+
+#define SPP_DECODE_FLAG_SCALE_SCORE 1 /* softargmax: score *= clamp(sqrt(box area)/96, .5, 2) (module.py:287-294) */
+#define SPP_DECODE_FLAG_BACKPROJECT 2 /* softargmax: x = kx*(x2-x1)+x1 ... (module.py:543-544); else normalised */
+#define SPP_DECODE_FLAG_CENTER_SCALE 4 /* DARK / QUARTER: `boxes` rows are (center_x, center_y, scale_x, scale_y) as in
+                                          HF keypoints_from_heatmaps(heatmaps, center, scale) (scale = size/200*1.25) and
+                                          gluoncv get_final_preds(heatmaps, center, scale) (scale in pixels) */
+
+/* Replaces flip-test averaging (module.py:473-484 with the correct channel swap of
+ * "module copy.py":465-472 / HF modeling_vitpose.py:80-117) + the three decode variants, in one pass
+ * over the heatmaps.
+ *   hm          DEVICE  [p, k, h, w] fp32 heatmaps of the crop
+ *   hm_flipped  DEVICE  [p, k, h, w] fp32 heatmaps of the MIRRORED crop, not flipped back (NULL: no flip test)
+ *   perm        DEVICE  [k] int32 left/right channel permutation (NULL: identity — module_v2.py:201)
+ *   boxes       DEVICE  [p, 4] fp32: COCO (x, y, w, h) for DARK / QUARTER, (x1, y1, x2, y2) for SOFTARGMAX;
+ *                       NULL: coordinates stay in heatmap space (DARK/QUARTER) or normalised (SOFTARGMAX)
+ *   kernel      DARK Gaussian modulation kernel size (HF default 11); odd, 3..17
+ *   crop_h/w    model input size the boxes were cropped to (256 x 192): fixes the aspect ratio
+ *   keypoints   DEVICE  [p, k, 2] fp32; scores DEVICE [p, k] fp32; argmax DEVICE [p, k] int32 (flat y*w+x)
+ */
+int spp_heatmap_decode(const float *hm, const float *hm_flipped, const int *perm, int p, int k, int h, int w,
+                       const float *boxes, int mode, int flags, int kernel, int crop_h, int crop_w,
+                       float *keypoints, float *scores, int *argmax, spp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPP_H_ */

@@ -1,0 +1,82 @@
+"""ctypes binding of libspp.so (the C ABI declared in include/spp.h).
+
+The library is built in-tree by ``csrc/Makefile`` (``build()`` below, also called from
+``__graft_entry__.build``).  There is deliberately no fallback: if the shared object is missing or
+there is no CUDA device, every op raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import POINTER, c_char_p, c_float, c_int, c_size_t, c_uint16, c_ulonglong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libspp.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+# name -> (restype, argtypes); mirrors include/spp.h and include/spp_internal.h
+_P = c_void_p
+SIGNATURES = {
+    "spp_abi_version": (c_int, []),
+    "spp_last_error": (c_char_p, []),
+    "spp_device_sm_count": (c_int, []),
+    "spp_head_decode": (c_int, [POINTER(_P), POINTER(c_int), POINTER(c_int), POINTER(c_float), c_int, c_int, c_int, _P, _P]),
+    "spp_nms_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "spp_nms_decoded": (c_int, [_P, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_float, c_int, _P, _P, _P, _P,
+                                c_size_t, _P]),
+    "spp_decode_nms": (c_int, [POINTER(_P), POINTER(c_int), POINTER(c_int), POINTER(c_float), c_int, c_int, c_int, c_float,
+                               c_float, c_int, c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "spp_l2_normalize": (c_int, [_P, c_int, c_int, c_int, c_float, _P, _P, _P, _P]),
+    "spp_f32_to_bf16": (c_int, [_P, c_size_t, _P, _P]),
+    "spp_match_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "spp_match_top1": (c_int, [_P, _P, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "spp_match_unpack_keys": (c_int, [_P, c_int, c_float, _P, _P, _P]),
+    "spp_crop_affine": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float),
+                                c_int, _P, _P]),
+    "spp_heatmap_decode": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P,
+                                   _P, _P]),
+    # test hook (include/spp_internal.h)
+    "spp_debug_match_top1_simt": (c_int, [_P, _P, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
+}
+
+_lib = None
+
+
+class SppError(RuntimeError):
+    """Raised when a libspp entry point returns an error code (message from spp_last_error)."""
+
+
+def build(verbose: bool = False, force: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into libspp.so (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", CSRC, "-j8"]
+    if force:
+        subprocess.run(["make", "-C", CSRC, "clean"], check=True, capture_output=not verbose)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+        print(res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("building libspp.so failed (see output above)")
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SppError(f"{LIB_PATH} is missing: run `make -C {CSRC}` (or __graft_entry__.build()); "
+                           "there is no CPU / PyTorch fallback for the spp ops")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().spp_last_error().decode("utf-8", "replace")
+        raise SppError(f"{what} failed (code {rc}): {msg}")

@@ -1,0 +1,479 @@
+// Detection-head decode + class-aware NMS.
+//
+// Replaces:
+//   make_anchors          training/yolopt/util.py:85-96
+//   DFL / Head.forward    training/yolopt/nets/nn.py:222-225, 255-270 (eval branch)
+//   non_max_suppression   training/yolopt/util.py:123-169 (+ wh2xy :76-82; torchvision.ops.nms :162)
+//
+// Kernels
+//   head_decode_kernel     full decode to [B, 4+nc, A] (drop-in for Head.forward); one thread per
+//                          anchor, every channel plane read as coalesced 128 B lines.
+//   cand_raw_kernel        fused path: reads ONLY the class planes for all anchors; the 64 DFL planes are
+//                          touched just for anchors that pass the confidence threshold, whose decoded
+//                          boxes are parked in a per-image [A] float4 table.  Candidates are appended with
+//                          warp-aggregated atomics as 64-bit sort keys (~score | anchor*nc+cls).
+//   cand_decoded_kernel    same candidate pass over an already decoded [B, 4+nc, A] tensor.
+//   nms_kernel             one CTA per image: bitonic sort of the keys (score descending, candidate key
+//                          ascending — a stable order), then greedy suppression in that order against
+//                          the list of boxes kept so far.  A box survives iff no earlier KEPT box has
+//                          IoU > thr, so only n * kept (<= n * max_det) IoUs are needed instead of the
+//                          n^2/2 of a full bitmask; inside each 32-box chunk the survivors are resolved
+//                          with warp ballots (each kept lane broadcasts its box, the ballot of "IoU > thr"
+//                          clears the alive mask).  The loop stops after max_det kept boxes.
+// IoU arithmetic is fp32 with round-to-nearest intrinsics (never contracted to FMA): it must agree bit
+// for bit with torchvision's CPU loop, which is what the reference's keep indices come from.
+#include "spp_common.cuh"
+
+#include <cmath>
+
+namespace spp {
+
+namespace {
+
+constexpr int kDfl = 16;
+constexpr int kNmsThreads = 256;
+constexpr int kSortSmemMax = 8192;  // keys sorted in shared memory up to this (padded) count
+
+struct Levels {
+    const float *ptr[SPP_MAX_LEVELS];
+    int h[SPP_MAX_LEVELS], w[SPP_MAX_LEVELS], off[SPP_MAX_LEVELS + 1];
+    float stride[SPP_MAX_LEVELS];
+    int n, A;
+};
+
+__device__ __forceinline__ int find_level(const Levels &lv, int a) {
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < SPP_MAX_LEVELS; ++i)
+        if (i < lv.n && a >= lv.off[i]) l = i;
+    return l;
+}
+
+__device__ __forceinline__ float sigmoidf_ref(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+// DFL expectation for the four sides + dist2bbox; returns (cx, cy, w, h) in pixels.  `base` points at
+// channel 0 of this (image, level) for anchor i; `hw` is the plane stride.
+__device__ __forceinline__ float4 decode_box(const float *base, int hw, float ax, float ay, float stride) {
+    float d[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        float v[kDfl];
+#pragma unroll
+        for (int j = 0; j < kDfl; ++j) v[j] = __ldg(base + (size_t)(s * kDfl + j) * hw);
+        float m = v[0];
+#pragma unroll
+        for (int j = 1; j < kDfl; ++j) m = fmaxf(m, v[j]);
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < kDfl; ++j) {
+            v[j] = expf(__fsub_rn(v[j], m));
+            sum = __fadd_rn(sum, v[j]);
+        }
+        float e = 0.f;
+#pragma unroll
+        for (int j = 0; j < kDfl; ++j) e = __fadd_rn(e, __fmul_rn((float)j, __fdiv_rn(v[j], sum)));
+        d[s] = e;
+    }
+    const float x1 = __fsub_rn(ax, d[0]), y1 = __fsub_rn(ay, d[1]);
+    const float x2 = __fadd_rn(ax, d[2]), y2 = __fadd_rn(ay, d[3]);
+    float4 r;
+    r.x = __fmul_rn(__fmul_rn(__fadd_rn(x1, x2), 0.5f), stride);
+    r.y = __fmul_rn(__fmul_rn(__fadd_rn(y1, y2), 0.5f), stride);
+    r.z = __fmul_rn(__fsub_rn(x2, x1), stride);
+    r.w = __fmul_rn(__fsub_rn(y2, y1), stride);
+    return r;
+}
+
+// wh2xy, util.py:76-82
+__device__ __forceinline__ float4 wh2xy(float4 c) {
+    float4 r;
+    const float hw = __fmul_rn(c.z, 0.5f), hh = __fmul_rn(c.w, 0.5f);
+    r.x = __fsub_rn(c.x, hw);
+    r.y = __fsub_rn(c.y, hh);
+    r.z = __fadd_rn(c.x, hw);
+    r.w = __fadd_rn(c.y, hh);
+    return r;
+}
+
+__global__ void __launch_bounds__(256) head_decode_kernel(const Levels lv, int nc, float *__restrict__ out) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (a >= lv.A) return;
+    const int l = find_level(lv, a);
+    const int i = a - lv.off[l];
+    const int w = lv.w[l], hw = lv.h[l] * w;
+    const int y = i / w, x = i - y * w;
+    const int no = 4 * kDfl + nc;
+    const float *base = lv.ptr[l] + (size_t)b * no * hw + i;
+    const float4 box = decode_box(base, hw, (float)x + 0.5f, (float)y + 0.5f, lv.stride[l]);
+    float *o = out + (size_t)b * (4 + nc) * lv.A + a;
+    o[0] = box.x;
+    o[(size_t)lv.A] = box.y;
+    o[(size_t)2 * lv.A] = box.z;
+    o[(size_t)3 * lv.A] = box.w;
+    for (int j = 0; j < nc; ++j) o[(size_t)(4 + j) * lv.A] = sigmoidf_ref(__ldg(base + (size_t)(4 * kDfl + j) * hw));
+}
+
+__device__ __forceinline__ unsigned long long make_sort_key(float score, unsigned cand) {
+    // ascending sort on this key == score descending, candidate key ascending (scores are > 0)
+    return ((unsigned long long)(~__float_as_uint(score)) << 32) | cand;
+}
+
+// warp-aggregated append of one candidate per participating lane
+__device__ __forceinline__ void append_candidate(bool is_cand, unsigned long long key, int *count, unsigned long long *keys,
+                                                 int cap) {
+    const unsigned m = __ballot_sync(FULL, is_cand);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(FULL, base, leader);
+    const int slot = base + __popc(m & ((1u << lane) - 1u));
+    if (is_cand && slot < cap) keys[slot] = key;
+}
+
+__global__ void __launch_bounds__(256) cand_decoded_kernel(const float *__restrict__ pred, int nc, int A, float conf, int cap,
+                                                           int cap_pad, int *counts, unsigned long long *keys) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    const float *cls = pred + ((size_t)b * (4 + nc) + 4) * A;
+    unsigned long long *k = keys + (size_t)b * cap_pad;
+    for (int j = 0; j < nc; ++j) {
+        float s = 0.f;
+        bool c = false;
+        if (a < A) {
+            s = __ldg(cls + (size_t)j * A + a);
+            c = s > conf;
+        }
+        append_candidate(c, make_sort_key(s, (unsigned)(a * nc + j)), counts + b, k, cap);
+    }
+}
+
+__global__ void __launch_bounds__(256) cand_raw_kernel(const Levels lv, int nc, float conf, int cap, int cap_pad, int *counts,
+                                                       unsigned long long *keys, float4 *__restrict__ boxes) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    const bool in = a < lv.A;
+    const int l = find_level(lv, in ? a : 0);
+    const int i = (in ? a : 0) - lv.off[l];
+    const int w = lv.w[l], hw = lv.h[l] * w;
+    const int no = 4 * kDfl + nc;
+    const float *base = lv.ptr[l] + (size_t)b * no * hw + i;
+    unsigned long long *k = keys + (size_t)b * cap_pad;
+    bool any = false;
+    for (int j = 0; j < nc; ++j) {
+        float s = 0.f;
+        bool c = false;
+        if (in) {
+            s = sigmoidf_ref(__ldg(base + (size_t)(4 * kDfl + j) * hw));
+            c = s > conf;
+        }
+        any |= c;
+        append_candidate(c, make_sort_key(s, (unsigned)(a * nc + j)), counts + b, k, cap);
+    }
+    if (any) {
+        const int y = i / w, x = i - y * w;
+        boxes[(size_t)b * lv.A + a] = wh2xy(decode_box(base, hw, (float)x + 0.5f, (float)y + 0.5f, lv.stride[l]));
+    }
+}
+
+struct NmsParams {
+    const float *pred;          // decoded path
+    const float4 *boxes;        // raw path: [B, A] xyxy
+    const int *counts;
+    unsigned long long *keys;   // [B, cap_pad]
+    int nc, A, cap, cap_pad;
+    float iou, max_wh;
+    int max_det, max_nms;
+    float *out_dets;
+    int *out_count, *out_keys;
+};
+
+__device__ __forceinline__ bool iou_gt(const float4 &a, float area_a, const float4 &b, float area_b, float thr) {
+    const float w = fmaxf(0.0f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
+    const float h = fmaxf(0.0f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
+    const float inter = __fmul_rn(w, h);
+    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+    return ovr > thr;
+}
+
+__device__ void bitonic_sort(unsigned long long *d, int npad) {
+    for (int k = 2; k <= npad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (npad >> 1); t += blockDim.x) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int p = i | j;
+                const bool up = (i & k) == 0;
+                const unsigned long long x = d[i], y = d[p];
+                if ((x > y) == up) {
+                    d[i] = y;
+                    d[p] = x;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <bool RAW>
+__global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams prm) {
+    extern __shared__ __align__(16) unsigned char nms_smem[];
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kNmsThreads / 32;
+
+    float4 *kbox = reinterpret_cast<float4 *>(nms_smem);                    // [max_det] kept boxes (class-offset)
+    float *karea = reinterpret_cast<float *>(kbox + prm.max_det);           // [max_det]
+    unsigned long long *skeys = reinterpret_cast<unsigned long long *>(
+        nms_smem + align_up((size_t)prm.max_det * 20, 16));                 // [<= kSortSmemMax]
+    __shared__ int s_nk;
+
+    const int raw_count = prm.counts[b];
+    int n = raw_count < prm.cap ? raw_count : prm.cap;
+    int npad = 1;
+    while (npad < n) npad <<= 1;
+    unsigned long long *gkeys = prm.keys + (size_t)b * prm.cap_pad;
+    const bool in_smem = npad <= kSortSmemMax;
+    unsigned long long *keys = in_smem ? skeys : gkeys;
+    if (in_smem) {
+        for (int i = tid; i < npad; i += kNmsThreads) skeys[i] = i < n ? gkeys[i] : ~0ull;
+    } else {
+        for (int i = n + tid; i < npad; i += kNmsThreads) gkeys[i] = ~0ull;
+    }
+    if (tid == 0) s_nk = 0;
+    __syncthreads();
+    bitonic_sort(keys, npad);
+    if (n > prm.max_nms) n = prm.max_nms;                                   // util.py:157 [:max_nms]
+
+    float *dets = prm.out_dets + (size_t)b * prm.max_det * 6;
+    int *okeys = prm.out_keys ? prm.out_keys + (size_t)b * prm.max_det : nullptr;
+    const float thr = prm.iou;
+    const int max_det = prm.max_det;
+
+    int nk = 0;
+    for (int base = 0; base < n && nk < max_det; base += kNmsThreads) {
+        const int j = base + tid;
+        bool alive = j < n;
+        float4 box = make_float4(0.f, 0.f, 0.f, 0.f), obox = box;
+        float area = 0.f, score = 0.f, clsf = 0.f;
+        unsigned cand = 0;
+        if (alive) {
+            const unsigned long long key = keys[j];
+            cand = (unsigned)(key & 0xffffffffu);
+            score = __uint_as_float(~(unsigned)(key >> 32));
+            const int anchor = cand / prm.nc, cls = cand - anchor * prm.nc;
+            clsf = (float)cls;
+            if (RAW) {
+                box = prm.boxes[(size_t)b * prm.A + anchor];
+            } else {
+                const float *pb = prm.pred + (size_t)b * (4 + prm.nc) * prm.A + anchor;
+                box = wh2xy(make_float4(__ldg(pb), __ldg(pb + prm.A), __ldg(pb + 2 * (size_t)prm.A), __ldg(pb + 3 * (size_t)prm.A)));
+            }
+            const float off = __fmul_rn(clsf, prm.max_wh);                   // util.py:160
+            obox = make_float4(__fadd_rn(box.x, off), __fadd_rn(box.y, off), __fadd_rn(box.z, off), __fadd_rn(box.w, off));
+            area = __fmul_rn(__fsub_rn(obox.z, obox.x), __fsub_rn(obox.w, obox.y));
+        }
+        // phase A: against everything kept before this super-chunk
+        int checked = 0;
+        for (; checked < nk && alive; ++checked)
+            if (iou_gt(kbox[checked], karea[checked], obox, area, thr)) alive = false;
+        // phase B: warps take turns in score order; each first catches up with boxes kept by the
+        // warps before it, then resolves its own 32 boxes with ballots.
+        for (int w = 0; w < NW; ++w) {
+            __syncthreads();
+            if (warp == w) {
+                const int nkc = s_nk;
+                if (alive) {
+                    for (int i = (checked < nk ? nk : checked); i < nkc && i < max_det && alive; ++i)
+                        if (iou_gt(kbox[i], karea[i], obox, area, thr)) alive = false;
+                }
+                if (nkc >= max_det) alive = false;
+                unsigned am = __ballot_sync(FULL, alive);
+                unsigned keepm = 0;
+                while (am) {
+                    const int i = __ffs(am) - 1;
+                    am &= am - 1;
+                    keepm |= 1u << i;
+                    float4 bi;
+                    bi.x = __shfl_sync(FULL, obox.x, i);
+                    bi.y = __shfl_sync(FULL, obox.y, i);
+                    bi.z = __shfl_sync(FULL, obox.z, i);
+                    bi.w = __shfl_sync(FULL, obox.w, i);
+                    const float ai = __shfl_sync(FULL, area, i);
+                    const bool sup = alive && lane > i && iou_gt(bi, ai, obox, area, thr);
+                    const unsigned sm = __ballot_sync(FULL, sup);
+                    if (sup) alive = false;
+                    am &= ~sm;
+                }
+                const bool kept = (keepm >> lane) & 1u;
+                const int pos = nkc + __popc(keepm & ((1u << lane) - 1u));
+                if (kept && pos < max_det) {
+                    kbox[pos] = obox;
+                    karea[pos] = area;
+                    float *r = dets + (size_t)pos * 6;
+                    r[0] = box.x; r[1] = box.y; r[2] = box.z; r[3] = box.w; r[4] = score; r[5] = clsf;
+                    if (okeys) okeys[pos] = (int)cand;
+                }
+                if (lane == 0) {
+                    const int t = nkc + __popc(keepm);
+                    s_nk = t < max_det ? t : max_det;
+                }
+            }
+        }
+        __syncthreads();
+        nk = s_nk;
+    }
+    __syncthreads();
+    nk = s_nk;
+    if (tid == 0) prm.out_count[b] = raw_count > prm.cap ? -nk : nk;
+    for (int i = nk * 6 + tid; i < max_det * 6; i += kNmsThreads) dets[i] = 0.f;
+    if (okeys)
+        for (int i = nk + tid; i < max_det; i += kNmsThreads) okeys[i] = -1;
+}
+
+int fill_levels(Levels &lv, const float *const *levels, const int *level_h, const int *level_w, const float *strides,
+                int num_levels) {
+    SPP_CHECK_ARG(levels && level_h && level_w && strides, "detection: null level description");
+    SPP_CHECK_ARG(num_levels >= 1 && num_levels <= SPP_MAX_LEVELS, "detection: num_levels must be 1..%d", SPP_MAX_LEVELS);
+    lv.n = num_levels;
+    lv.off[0] = 0;
+    for (int l = 0; l < num_levels; ++l) {
+        SPP_CHECK_ARG(levels[l] && level_h[l] > 0 && level_w[l] > 0, "detection: bad level %d", l);
+        lv.ptr[l] = levels[l];
+        lv.h[l] = level_h[l];
+        lv.w[l] = level_w[l];
+        lv.stride[l] = strides[l];
+        lv.off[l + 1] = lv.off[l] + level_h[l] * level_w[l];
+    }
+    lv.A = lv.off[num_levels];
+    return SPP_OK;
+}
+
+struct Workspace {
+    int *counts;
+    unsigned long long *keys;
+    float4 *boxes;
+    int cap, cap_pad;
+    size_t bytes;
+};
+
+Workspace carve(void *ws, int batch, int num_anchors, int nc, int max_candidates) {
+    Workspace w{};
+    long long cap = (long long)num_anchors * nc;
+    if (max_candidates > 0 && cap > max_candidates) cap = max_candidates;
+    if (cap < 1) cap = 1;
+    long long pad = 1;
+    while (pad < cap) pad <<= 1;
+    w.cap = (int)cap;
+    w.cap_pad = (int)pad;
+    size_t off = 0;
+    unsigned char *p = static_cast<unsigned char *>(ws);
+    w.counts = reinterpret_cast<int *>(p + off);
+    off += align_up((size_t)batch * sizeof(int), 256);
+    w.keys = reinterpret_cast<unsigned long long *>(p + off);
+    off += align_up((size_t)batch * pad * sizeof(unsigned long long), 256);
+    w.boxes = reinterpret_cast<float4 *>(p + off);
+    off += align_up((size_t)batch * num_anchors * sizeof(float4), 256);
+    w.bytes = off;
+    return w;
+}
+
+template <bool RAW>
+int launch_nms(const NmsParams &prm, int batch, cudaStream_t st) {
+    const size_t smem = align_up((size_t)prm.max_det * 20, 16) + (size_t)kSortSmemMax * 8;
+    static bool configured = false;
+    if (!configured) {
+        SPP_CHECK_CUDA(cudaFuncSetAttribute(nms_kernel<RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        configured = true;
+    }
+    SPP_CHECK_ARG(smem <= 160 * 1024, "nms: max_det %d too large", prm.max_det);
+    nms_kernel<RAW><<<batch, kNmsThreads, smem, st>>>(prm);
+    SPP_CHECK_LAUNCH();
+    return SPP_OK;
+}
+
+int check_nms_args(int batch, int nc, float iou, int max_det, int max_nms, const float *out_dets, const int *out_count,
+                   const void *ws) {
+    SPP_CHECK_ARG(batch >= 0 && nc >= 1, "nms: bad batch %d / nc %d", batch, nc);
+    SPP_CHECK_ARG(max_det >= 1 && max_det <= 4096 && max_nms >= 1, "nms: bad max_det %d / max_nms %d", max_det, max_nms);
+    SPP_CHECK_ARG(out_dets && out_count && ws, "nms: null output / workspace");
+    (void)iou;
+    return SPP_OK;
+}
+
+}  // namespace
+}  // namespace spp
+
+using namespace spp;
+
+extern "C" int spp_head_decode(const float *const *levels, const int *level_h, const int *level_w, const float *strides,
+                               int num_levels, int batch, int nc, float *out, spp_stream_t stream) {
+    Levels lv{};
+    int rc = fill_levels(lv, levels, level_h, level_w, strides, num_levels);
+    if (rc) return rc;
+    SPP_CHECK_ARG(out && batch >= 0 && nc >= 1, "head_decode: bad arguments");
+    if (batch == 0) return SPP_OK;
+    dim3 grid((lv.A + 255) / 256, batch);
+    head_decode_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(lv, nc, out);
+    SPP_CHECK_LAUNCH();
+    return SPP_OK;
+}
+
+extern "C" size_t spp_nms_workspace_bytes(int batch, int num_anchors, int nc, int max_candidates) {
+    if (batch < 0 || num_anchors < 1 || nc < 1) return 0;
+    return carve(nullptr, batch, num_anchors, nc, max_candidates).bytes;
+}
+
+extern "C" int spp_nms_decoded(const float *pred, int batch, int nc, int num_anchors, float conf_thres, float iou_thres,
+                               int max_det, int max_nms, float max_wh, int max_candidates, float *out_dets, int *out_count,
+                               int *out_keys, void *workspace, size_t workspace_bytes, spp_stream_t stream) {
+    int rc = check_nms_args(batch, nc, iou_thres, max_det, max_nms, out_dets, out_count, workspace);
+    if (rc) return rc;
+    SPP_CHECK_ARG(pred && num_anchors >= 1, "nms_decoded: bad pred / num_anchors");
+    if (batch == 0) return SPP_OK;
+    Workspace w = carve(workspace, batch, num_anchors, nc, max_candidates);
+    if (workspace_bytes < w.bytes) {
+        set_error("nms_decoded: workspace %zu < required %zu bytes", workspace_bytes, w.bytes);
+        return SPP_ERR_WORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SPP_CHECK_CUDA(cudaMemsetAsync(w.counts, 0, (size_t)batch * sizeof(int), st));
+    dim3 grid((num_anchors + 255) / 256, batch);
+    cand_decoded_kernel<<<grid, 256, 0, st>>>(pred, nc, num_anchors, conf_thres, w.cap, w.cap_pad, w.counts, w.keys);
+    SPP_CHECK_LAUNCH();
+    NmsParams prm{};
+    prm.pred = pred; prm.boxes = nullptr; prm.counts = w.counts; prm.keys = w.keys;
+    prm.nc = nc; prm.A = num_anchors; prm.cap = w.cap; prm.cap_pad = w.cap_pad;
+    prm.iou = iou_thres; prm.max_wh = max_wh; prm.max_det = max_det; prm.max_nms = max_nms;
+    prm.out_dets = out_dets; prm.out_count = out_count; prm.out_keys = out_keys;
+    return launch_nms<false>(prm, batch, st);
+}
+
+extern "C" int spp_decode_nms(const float *const *levels, const int *level_h, const int *level_w, const float *strides,
+                              int num_levels, int batch, int nc, float conf_thres, float iou_thres, int max_det,
+                              int max_nms, float max_wh, int max_candidates, float *out_dets, int *out_count,
+                              int *out_keys, void *workspace, size_t workspace_bytes, spp_stream_t stream) {
+    Levels lv{};
+    int rc = fill_levels(lv, levels, level_h, level_w, strides, num_levels);
+    if (rc) return rc;
+    rc = check_nms_args(batch, nc, iou_thres, max_det, max_nms, out_dets, out_count, workspace);
+    if (rc) return rc;
+    if (batch == 0) return SPP_OK;
+    Workspace w = carve(workspace, batch, lv.A, nc, max_candidates);
+    if (workspace_bytes < w.bytes) {
+        set_error("decode_nms: workspace %zu < required %zu bytes", workspace_bytes, w.bytes);
+        return SPP_ERR_WORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SPP_CHECK_CUDA(cudaMemsetAsync(w.counts, 0, (size_t)batch * sizeof(int), st));
+    dim3 grid((lv.A + 255) / 256, batch);
+    cand_raw_kernel<<<grid, 256, 0, st>>>(lv, nc, conf_thres, w.cap, w.cap_pad, w.counts, w.keys, w.boxes);
+    SPP_CHECK_LAUNCH();
+    NmsParams prm{};
+    prm.pred = nullptr; prm.boxes = w.boxes; prm.counts = w.counts; prm.keys = w.keys;
+    prm.nc = nc; prm.A = lv.A; prm.cap = w.cap; prm.cap_pad = w.cap_pad;
+    prm.iou = iou_thres; prm.max_wh = max_wh; prm.max_det = max_det; prm.max_nms = max_nms;
+    prm.out_dets = out_dets; prm.out_count = out_count; prm.out_keys = out_keys;
+    return launch_nms<true>(prm, batch, st);
+}

@@ -1,0 +1,425 @@
+// Heatmap decode: flip-test averaging + per-joint arg-max + {DARK/UDP | soft-argmax | quarter-offset}
+// refinement + back-projection, ONE pass over the heatmaps.
+//
+// Replaces:
+//   flip-back + average   training/lightning/pose_estimation/module.py:473-484 (channel swap as in
+//                         "module copy.py":465-472 / HF modeling_vitpose.py:80-117)
+//   DARK + UDP            HF image_processing_vitpose.py:175-313, 450-463
+//   soft-argmax           training/lightning/pose_estimation/module.py:237-296, 534-546
+//   quarter offset        gluoncv get_final_preds as called at pose_estimation/module_v2.py:214-222
+//
+// Design (HBM-bound: K*H*W*4 bytes per crop, x2 with the flip test, 16 B out per joint):
+//   * persistent grid, one CTA per SM; every warp owns a private ring of smem stages and is its own
+//     producer: lane 0 issues 1-D bulk-TMA copies (cp.async.bulk, one 12 KB joint map per copy, two
+//     with the flip test) that complete on a per-stage mbarrier; no block-wide barrier anywhere.
+//     ~190 KB of loads are in flight per SM, far above the ~45 KB Little's-law requirement.
+//   * the warp scans the map from shared memory with 128-bit conflict-free reads, forming the
+//     flip-average on the fly (mirrored column, pair-swapped channel) and keeping a running
+//     (max, first index) per lane, then a shuffle arg-max with lowest-index tie-break.
+//   * DARK touches only the (2r+3)^2 window around the arg-max: the separable Gaussian is evaluated
+//     for the 3x3 tap block exactly as scipy does it (axis 0 first, fp64 accumulation in scipy's
+//     summation order, fp32 intermediate, 'reflect' borders), then clip/log in fp32 and the 2x2
+//     Newton step in fp64.  All of it lives in registers + 64 floats of per-warp scratch.
+#include "spp_common.cuh"
+
+#include <cfloat>
+#include <climits>
+#include <cmath>
+
+namespace spp {
+
+namespace {
+
+constexpr int kMaxRadius = 8;
+constexpr int kScratch = 64;  // floats per warp: 3 * (2*kMaxRadius + 3) = 57
+
+struct DecodeParams {
+    const float *hm;
+    const float *hmf;
+    const int *perm;
+    const float *boxes;
+    float *kpts;
+    float *scores;
+    int *amax;
+    int P, K, H, W;
+    int mode, flags, radius, crop_h, crop_w;
+    int warps, stages;
+    double gw[kMaxRadius + 1];  // Gaussian weights, gw[0] = centre (scipy _gaussian_kernel1d, normalised)
+};
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+    // scipy 'reflect': (d c b a | a b c d | d c b a)
+    if (n == 1) return 0;
+    const int period = 2 * n;
+    i %= period;
+    if (i < 0) i += period;
+    return i < n ? i : period - 1 - i;
+}
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// One (possibly flip-averaged) heatmap; A/B may point to shared or global memory.
+template <bool FLIP>
+struct MapView {
+    const float *A;
+    const float *B;  // raw map of the mirrored crop, channel already pair-swapped
+    int W;
+    __device__ __forceinline__ float at(int r, int c) const {
+        float a = A[r * W + c];
+        if (FLIP) a = (a + B[r * W + (W - 1 - c)]) * 0.5f;
+        return a;
+    }
+};
+
+// scipy.ndimage.correlate1d, symmetric-kernel branch: centre first, then pairs from the far end in.
+template <typename F>
+__device__ __forceinline__ double sym_filter(F sample, const double *gw, int radius) {
+    double acc = __dmul_rn((double)sample(0), gw[0]);
+    for (int jj = radius; jj >= 1; --jj) {
+        double pair = __dadd_rn((double)sample(-jj), (double)sample(jj));
+        acc = __dadd_rn(acc, __dmul_rn(pair, gw[jj]));
+    }
+    return acc;
+}
+
+__device__ __forceinline__ float clip_log(float v) {
+    v = fminf(fmaxf(v, 0.001f), 50.0f);
+    return logf(v);
+}
+
+// log(clip(blur(map)))[y, x] for ONE position, whole warp cooperating (rare path: score <= 0 quirk).
+template <bool FLIP>
+__device__ float warp_blurred_log_single(const MapView<FLIP> &mv, int H, int y, int x, const double *gw, int radius,
+                                         float *scratch, int lane) {
+    const int n = 2 * radius + 1;
+    __syncwarp();
+    if (lane < n) {
+        const int xx = reflect_idx(x - radius + lane, mv.W);
+        double acc = sym_filter([&](int d) { return mv.at(reflect_idx(y + d, H), xx); }, gw, radius);
+        scratch[lane] = (float)acc;
+    }
+    __syncwarp();
+    double acc = sym_filter([&](int d) { return scratch[radius + d]; }, gw, radius);
+    return clip_log((float)acc);
+}
+
+template <bool FLIP>
+__global__ void __launch_bounds__(256, 1) heatmap_decode_kernel(const DecodeParams prm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int H = prm.H, W = prm.W, K = prm.K;
+    const int map_elems = H * W;
+    const uint32_t map_bytes = (uint32_t)map_elems * 4u;
+    constexpr int NB = FLIP ? 2 : 1;
+    const int stages = prm.stages, warps = prm.warps;
+
+    float *wbase = reinterpret_cast<float *>(smem_raw) + (size_t)warp * stages * NB * map_elems;
+    unsigned char *after = smem_raw + (size_t)warps * stages * NB * map_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(after) + warp * stages;
+    float *scratch = reinterpret_cast<float *>(after + (size_t)warps * stages * 8) + warp * kScratch;
+
+    const long long total = (long long)prm.P * K;
+    const long long gwarp = (long long)blockIdx.x * warps + warp;
+    const long long nwarps = (long long)gridDim.x * warps;
+
+    if (lane == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+        fence_proxy_async();
+    }
+    __syncwarp();
+
+    auto issue = [&](long long q, int s) {  // lane 0 only
+        mbar_arrive_expect_tx(&bars[s], NB * map_bytes);
+        float *dst = wbase + (size_t)s * NB * map_elems;
+        bulk_g2s(dst, prm.hm + q * map_elems, map_bytes, &bars[s]);
+        if (FLIP) {
+            const long long p = q / K;
+            const int k = (int)(q - p * K);
+            const int kk = prm.perm ? __ldg(prm.perm + k) : k;
+            bulk_g2s(dst + map_elems, prm.hmf + (p * K + kk) * map_elems, map_bytes, &bars[s]);
+        }
+    };
+
+    if (lane == 0) {
+        for (int s = 0; s < stages; ++s) {
+            const long long q = gwarp + (long long)s * nwarps;
+            if (q < total) issue(q, s);
+        }
+    }
+
+    const int W4 = W >> 2;
+    const int n4 = map_elems >> 2;
+    const int radius = prm.radius;
+    const double *gw = prm.gw;
+
+    int it = 0;
+    for (long long q = gwarp; q < total; q += nwarps, ++it) {
+        const int s = it % stages;
+        const uint32_t parity = (uint32_t)((it / stages) & 1);
+        mbar_wait(&bars[s], parity);
+
+        const float *A = wbase + (size_t)s * NB * map_elems;
+        const float *B = A + map_elems;
+        const float4 *A4 = reinterpret_cast<const float4 *>(A);
+        const float4 *B4 = reinterpret_cast<const float4 *>(B);
+
+        // ---- pass 1: arg-max of the (flip-averaged) map ------------------------------------
+        float best = -INFINITY;
+        int bidx = 4 * lane;
+        {
+            int r = lane / W4, c4 = lane - r * W4;
+            for (int q4 = lane; q4 < n4; q4 += 32) {
+                float4 v = A4[q4];
+                if (FLIP) {
+                    const float4 m = B4[r * W4 + (W4 - 1 - c4)];
+                    v.x = (v.x + m.w) * 0.5f;
+                    v.y = (v.y + m.z) * 0.5f;
+                    v.z = (v.z + m.y) * 0.5f;
+                    v.w = (v.w + m.x) * 0.5f;
+                }
+                const int base = q4 << 2;
+                if (v.x > best) { best = v.x; bidx = base; }
+                if (v.y > best) { best = v.y; bidx = base + 1; }
+                if (v.z > best) { best = v.z; bidx = base + 2; }
+                if (v.w > best) { best = v.w; bidx = base + 3; }
+                c4 += 32;
+                while (c4 >= W4) { c4 -= W4; ++r; }
+            }
+        }
+        warp_argmax(best, bidx);
+        const int ax = bidx % W, ay = bidx / W;
+        const long long p = q / K;
+        MapView<FLIP> mv{A, B, W};
+
+        float out_x = 0.f, out_y = 0.f, out_s = best;
+
+        if (prm.mode == SPP_DECODE_DARK) {
+            // HF get_keypoint_predictions: coordinates -1 where score <= 0
+            const bool valid = best > 0.0f;
+            const float cx = valid ? (float)ax : -1.0f, cy = valid ? (float)ay : -1.0f;
+            float L00, L01, L10, L11, L12, L21, L22;
+            if (valid) {
+                const int ncols = 2 * radius + 3;
+                __syncwarp();
+                for (int tt = lane; tt < 3 * ncols; tt += 32) {
+                    const int r3 = tt / ncols, j = tt - r3 * ncols;
+                    const int yy = clampi(ay + r3 - 1, 0, H - 1);           // np.pad(mode="edge") on the taps
+                    const int xx = reflect_idx(ax - (radius + 1) + j, W);   // scipy 'reflect' inside the blur
+                    double acc = sym_filter([&](int d) { return mv.at(reflect_idx(yy + d, H), xx); }, gw, radius);
+                    scratch[tt] = (float)acc;                               // fp32 intermediate between the axes
+                }
+                __syncwarp();
+                float Lv = 0.f;
+                if (lane < 9) {
+                    const int r3 = lane / 3, c3 = lane - r3 * 3;
+                    const int xc = clampi(ax + c3 - 1, 0, W - 1);
+                    const float *row = scratch + r3 * ncols + (xc - ax) + radius + 1;
+                    double acc = sym_filter([&](int d) { return row[d]; }, gw, radius);
+                    Lv = clip_log((float)acc);
+                }
+                L00 = __shfl_sync(FULL, Lv, 0);
+                L01 = __shfl_sync(FULL, Lv, 1);
+                L10 = __shfl_sync(FULL, Lv, 3);
+                L11 = __shfl_sync(FULL, Lv, 4);
+                L12 = __shfl_sync(FULL, Lv, 5);
+                L21 = __shfl_sync(FULL, Lv, 7);
+                L22 = __shfl_sync(FULL, Lv, 8);
+            } else {
+                // HF indexes the flattened, edge-padded batch with coordinate -1: the centre taps land on
+                // padded[0,0] of this map, the "minus" taps on the tail of the PREVIOUS map (numpy
+                // negative indices wrap to the last map for q == 0).  Reproduced for parity.
+                const long long qp = (q + total - 1) % total;
+                const long long pp = qp / K;
+                const int kp = (int)(qp - pp * K);
+                MapView<FLIP> prev{prm.hm + qp * map_elems, nullptr, W};
+                if (FLIP) prev.B = prm.hmf + (pp * K + (prm.perm ? __ldg(prm.perm + kp) : kp)) * map_elems;
+                const float c = warp_blurred_log_single(mv, H, 0, 0, gw, radius, scratch, lane);
+                const float br = warp_blurred_log_single(prev, H, H - 1, W - 1, gw, radius, scratch, lane);
+                const float bl = warp_blurred_log_single(prev, H, H - 1, 0, gw, radius, scratch, lane);
+                L11 = L12 = L21 = L22 = c;
+                L10 = br;  // padded[index - 1]
+                L01 = bl;  // padded[index - (W + 2)]
+                L00 = br;  // padded[index - (W + 3)]
+            }
+            const float i_ = L11, ix1 = L12, iy1 = L21, ix1y1 = L22, ix1_y1_ = L00, ix1_ = L10, iy1_ = L01;
+            const float dx = 0.5f * (ix1 - ix1_);
+            const float dy = 0.5f * (iy1 - iy1_);
+            const float dxx = (ix1 - 2.0f * i_) + ix1_;
+            const float dyy = (iy1 - 2.0f * i_) + iy1_;
+            const float dxy = 0.5f * (((((((ix1y1 - ix1) - iy1) + i_) + i_) - ix1_) - iy1_) + ix1_y1_);
+            const double eps = (double)FLT_EPSILON;
+            const double ha = (double)dxx + eps, hb = (double)dxy, hd = (double)dyy + eps;
+            const double det = ha * hd - hb * hb;
+            const double sx = (hd * (double)dx - hb * (double)dy) / det;
+            const double sy = (ha * (double)dy - hb * (double)dx) / det;
+            out_x = (float)((double)cx - sx);
+            out_y = (float)((double)cy - sy);
+            if (prm.boxes) {
+                // box_to_center_and_scale (HF:68-109) in double, as for Python-float boxes; then
+                // transform_preds (HF:268-313) in fp32, left to right.
+                const float4 bx = __ldg(reinterpret_cast<const float4 *>(prm.boxes) + p);
+                float cxf, cyf, s0, s1;
+                if (prm.flags & SPP_DECODE_FLAG_CENTER_SCALE) {
+                    // HF keypoints_from_heatmaps(heatmaps, center, scale): (cx, cy, scale_x, scale_y) given
+                    cxf = bx.x; cyf = bx.y;
+                    s0 = __fmul_rn(bx.z, 200.0f);
+                    s1 = __fmul_rn(bx.w, 200.0f);
+                } else {
+                    double bw = bx.z, bh = bx.w;
+                    const double aspect = (double)prm.crop_w / (double)prm.crop_h;
+                    cxf = (float)((double)bx.x + bw * 0.5);
+                    cyf = (float)((double)bx.y + bh * 0.5);
+                    if (bw > aspect * bh) bh = bw * 1.0 / aspect;
+                    else if (bw < aspect * bh) bw = bh * aspect;
+                    s0 = __fmul_rn(__fmul_rn((float)(bw / 200.0), 1.25f), 200.0f);
+                    s1 = __fmul_rn(__fmul_rn((float)(bh / 200.0), 1.25f), 200.0f);
+                }
+                const float scale_x = __fdiv_rn(s0, (float)(W - 1));
+                const float scale_y = __fdiv_rn(s1, (float)(H - 1));
+                out_x = __fsub_rn(__fadd_rn(__fmul_rn(out_x, scale_x), cxf), __fmul_rn(s0, 0.5f));
+                out_y = __fsub_rn(__fadd_rn(__fmul_rn(out_y, scale_y), cyf), __fmul_rn(s1, 0.5f));
+            }
+        } else if (prm.mode == SPP_DECODE_SOFTARGMAX) {
+            // softmax over the flattened map (max-subtracted), expected column / row, max probability
+            float se = 0.f, sxe = 0.f, sye = 0.f;
+            int r = lane / W4, c4 = lane - r * W4;
+            for (int q4 = lane; q4 < n4; q4 += 32) {
+                float4 v = A4[q4];
+                if (FLIP) {
+                    const float4 m = B4[r * W4 + (W4 - 1 - c4)];
+                    v.x = (v.x + m.w) * 0.5f;
+                    v.y = (v.y + m.z) * 0.5f;
+                    v.z = (v.z + m.y) * 0.5f;
+                    v.w = (v.w + m.x) * 0.5f;
+                }
+                const float e0 = expf(v.x - best), e1 = expf(v.y - best), e2 = expf(v.z - best), e3 = expf(v.w - best);
+                const float c0 = (float)(c4 << 2);
+                const float es = (e0 + e1) + (e2 + e3);
+                se += es;
+                sxe += e0 * c0 + e1 * (c0 + 1.f) + e2 * (c0 + 2.f) + e3 * (c0 + 3.f);
+                sye += es * (float)r;
+                c4 += 32;
+                while (c4 >= W4) { c4 -= W4; ++r; }
+            }
+            se = warp_sum(se);
+            sxe = warp_sum(sxe);
+            sye = warp_sum(sye);
+            const float inv = 1.0f / se;
+            out_s = inv;  // exp(max - max) / sum
+            out_x = (sxe * inv + 0.5f) / (float)W;
+            out_y = (sye * inv + 0.5f) / (float)H;
+            if (prm.boxes) {
+                const float4 bx = __ldg(reinterpret_cast<const float4 *>(prm.boxes) + p);  // x1 y1 x2 y2
+                const float bw = bx.z - bx.x, bh = bx.w - bx.y;
+                if (prm.flags & SPP_DECODE_FLAG_SCALE_SCORE) {
+                    const float wgt = fminf(fmaxf(sqrtf(bw * bh) / 96.0f, 0.5f), 2.0f);
+                    out_s = out_s * wgt;
+                }
+                if (prm.flags & SPP_DECODE_FLAG_BACKPROJECT) {
+                    out_x = __fadd_rn(__fmul_rn(out_x, bw), bx.x);
+                    out_y = __fadd_rn(__fmul_rn(out_y, bh), bx.y);
+                }
+            }
+        } else {  // SPP_DECODE_QUARTER
+            const bool valid = best > 0.0f;
+            float cx = valid ? (float)ax : 0.f, cy = valid ? (float)ay : 0.f;
+            const int px = valid ? ax : 0, py = valid ? ay : 0;
+            if (px > 1 && px < W - 1 && py > 1 && py < H - 1) {
+                const float ddx = mv.at(py, px + 1) - mv.at(py, px - 1);
+                const float ddy = mv.at(py + 1, px) - mv.at(py - 1, px);
+                cx += 0.25f * (float)((ddx > 0.f) - (ddx < 0.f));
+                cy += 0.25f * (float)((ddy > 0.f) - (ddy < 0.f));
+            }
+            out_x = cx;
+            out_y = cy;
+            if (prm.boxes) {
+                // centre/scale of datamodule_v2.py:119-129 (double), inverse similarity in fp32
+                const float4 bx = __ldg(reinterpret_cast<const float4 *>(prm.boxes) + p);  // x y w h
+                const double aspect = (double)prm.crop_w / (double)prm.crop_h;
+                double ccx = (double)bx.x + (double)bx.z * 0.5, ccy = (double)bx.y + (double)bx.w * 0.5;
+                if (prm.flags & SPP_DECODE_FLAG_CENTER_SCALE) {   // get_final_preds(heatmaps, center, scale)
+                    ccx = bx.x; ccy = bx.y;
+                } else if (aspect > 1.0) ccx += (double)bx.z * 0.5 * (aspect - 1.0);
+                else ccy += (double)bx.w * 0.5 * (1.0 / aspect - 1.0);
+                const float sw = bx.z;
+                const float rr = __fdiv_rn(sw, (float)W);
+                out_x = __fsub_rn(__fadd_rn(__fmul_rn(cx, rr), (float)ccx), __fmul_rn(sw, 0.5f));
+                out_y = __fsub_rn(__fadd_rn(__fmul_rn(cy, rr), (float)ccy), __fmul_rn(__fmul_rn(rr, (float)H), 0.5f));
+            }
+        }
+
+        if (lane == 0) {
+            reinterpret_cast<float2 *>(prm.kpts)[q] = make_float2(out_x, out_y);
+            prm.scores[q] = out_s;
+            if (prm.amax) prm.amax[q] = bidx;
+        }
+
+        __syncwarp();  // every lane is done with this stage before it is refilled
+        const long long qn = q + (long long)stages * nwarps;
+        if (lane == 0 && qn < total) issue(qn, s);
+    }
+}
+
+}  // namespace
+
+}  // namespace spp
+
+extern "C" int spp_heatmap_decode(const float *hm, const float *hm_flipped, const int *perm, int p, int k, int h, int w,
+                                  const float *boxes, int mode, int flags, int kernel, int crop_h, int crop_w,
+                                  float *keypoints, float *scores, int *argmax, spp_stream_t stream) {
+    using namespace spp;
+    SPP_CHECK_ARG(hm && keypoints && scores, "heatmap_decode: hm, keypoints and scores must be non-null");
+    SPP_CHECK_ARG(p >= 0 && k > 0 && h > 0 && w > 0, "heatmap_decode: bad shape p=%d k=%d h=%d w=%d", p, k, h, w);
+    SPP_CHECK_ARG(w % 4 == 0, "heatmap_decode: heatmap width must be a multiple of 4 (got %d)", w);
+    SPP_CHECK_ARG(mode >= SPP_DECODE_DARK && mode <= SPP_DECODE_QUARTER, "heatmap_decode: unknown mode %d", mode);
+    SPP_CHECK_ARG(kernel >= 3 && kernel <= 2 * kMaxRadius + 1 && (kernel & 1), "heatmap_decode: kernel must be odd in 3..%d (got %d)",
+                  2 * kMaxRadius + 1, kernel);
+    SPP_CHECK_ARG(crop_h > 0 && crop_w > 0, "heatmap_decode: bad crop size");
+    SPP_CHECK_ARG((reinterpret_cast<uintptr_t>(hm) & 15) == 0 && (reinterpret_cast<uintptr_t>(hm_flipped) & 15) == 0,
+                  "heatmap_decode: heatmaps must be 16-byte aligned");
+    SPP_CHECK_ARG(!boxes || (reinterpret_cast<uintptr_t>(boxes) & 15) == 0, "heatmap_decode: boxes must be 16-byte aligned");
+    SPP_CHECK_ARG((reinterpret_cast<uintptr_t>(keypoints) & 7) == 0, "heatmap_decode: keypoints must be 8-byte aligned");
+    if (p == 0) return SPP_OK;
+
+    DecodeParams prm{};
+    prm.hm = hm; prm.hmf = hm_flipped; prm.perm = perm; prm.boxes = boxes;
+    prm.kpts = keypoints; prm.scores = scores; prm.amax = argmax;
+    prm.P = p; prm.K = k; prm.H = h; prm.W = w;
+    prm.mode = mode; prm.flags = flags; prm.radius = (kernel - 1) / 2; prm.crop_h = crop_h; prm.crop_w = crop_w;
+    {   // scipy.ndimage._filters._gaussian_kernel1d(sigma=0.8, order=0, radius)
+        const double sigma = 0.8;
+        double phi[kMaxRadius + 1], sum = 0.0;
+        for (int x = 0; x <= prm.radius; ++x) phi[x] = std::exp(-0.5 / (sigma * sigma) * (double)(x * x));
+        for (int x = -prm.radius; x <= prm.radius; ++x) sum += phi[x < 0 ? -x : x];
+        for (int x = 0; x <= prm.radius; ++x) prm.gw[x] = phi[x] / sum;
+    }
+
+    const bool flip = hm_flipped != nullptr;
+    const size_t stage_bytes = (size_t)(flip ? 2 : 1) * h * w * 4;
+    const size_t budget = 200 * 1024;
+    const int slots = (int)(budget / stage_bytes);
+    SPP_CHECK_ARG(slots >= 2, "heatmap_decode: a %dx%d map does not fit the shared-memory pipeline", h, w);
+    int warps = slots / 2;
+    if (warps > 8) warps = 8;
+    int stages = slots / warps;
+    if (stages > 4) stages = 4;
+    prm.warps = warps; prm.stages = stages;
+    const size_t smem = (size_t)warps * stages * stage_bytes + (size_t)warps * stages * 8 + (size_t)warps * kScratch * 4;
+
+    const long long total = (long long)p * k;
+    int sms = sm_count();
+    if (sms <= 0) return SPP_ERR_CUDA;
+    long long grid = (total + warps - 1) / warps;
+    if (grid > sms) grid = sms;
+
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (flip) {
+        SPP_CHECK_CUDA(cudaFuncSetAttribute(heatmap_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        heatmap_decode_kernel<true><<<(unsigned)grid, warps * 32, smem, st>>>(prm);
+    } else {
+        SPP_CHECK_CUDA(cudaFuncSetAttribute(heatmap_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        heatmap_decode_kernel<false><<<(unsigned)grid, warps * 32, smem, st>>>(prm);
+    }
+    SPP_CHECK_LAUNCH();
+    return SPP_OK;
+}

@@ -1,0 +1,296 @@
+"""Low-level ops: torch CUDA tensors in, torch CUDA tensors out, work done by libspp.so.
+
+PyTorch is only plumbing here (device memory, the current stream).  Every function validates its
+arguments the way the reference surfaces errors — plain exceptions — and raises if the tensors are
+not on a CUDA device: there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+MAX_WH = 7680.0     # training/yolopt/util.py:124
+MAX_DET = 300       # util.py:125
+MAX_NMS = 30000     # util.py:126
+
+DECODE_MODES = {"dark": 0, "softargmax": 1, "quarter": 2}
+CROP_VARIANTS = {"hf": 0, "udp": 0, "gluoncv": 1}
+
+
+def _stream(t: torch.Tensor) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _need_cuda(name: str, *tensors: Optional[torch.Tensor]) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"{name}: expected torch.Tensor, got {type(t).__name__}")
+        if not t.is_cuda:
+            raise RuntimeError(f"{name}: tensors must live on a CUDA device (no CPU fallback); got {t.device}")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"{name}: tensors on different devices ({dev} vs {t.device})")
+    return dev
+
+
+def _f32c(name: str, t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name}: expected float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# detection
+# ------------------------------------------------------------------------------------------------
+
+def _levels_args(levels: Sequence[torch.Tensor], strides: Sequence[float]):
+    if len(levels) < 1 or len(levels) > 4 or len(levels) != len(strides):
+        raise ValueError("detection: need 1..4 levels and one stride per level")
+    lv = [_f32c("detection level", l) for l in levels]
+    b, no = lv[0].shape[0], lv[0].shape[1]
+    for l in lv:
+        if l.dim() != 4 or l.shape[0] != b or l.shape[1] != no:
+            raise ValueError("detection: every level must be [B, 64+nc, H, W] with the same B and channel count")
+    nc = no - 64
+    if nc < 1:
+        raise ValueError(f"detection: levels have {no} channels, need 64 + nc")
+    n = len(lv)
+    ptrs = (ctypes.c_void_p * n)(*[l.data_ptr() for l in lv])
+    hs = (ctypes.c_int * n)(*[l.shape[2] for l in lv])
+    ws = (ctypes.c_int * n)(*[l.shape[3] for l in lv])
+    st = (ctypes.c_float * n)(*[float(s) for s in strides])
+    a = sum(l.shape[2] * l.shape[3] for l in lv)
+    return lv, ptrs, hs, ws, st, n, b, nc, a
+
+
+def head_decode(levels: Sequence[torch.Tensor], strides: Sequence[float] = (8, 16, 32)) -> torch.Tensor:
+    """``Head.forward`` eval branch (training/yolopt/nets/nn.py:255-270): raw per-level maps
+    ``[B, 64+nc, H_l, W_l]`` -> ``[B, 4+nc, A]`` (cx, cy, w, h in pixels; sigmoid scores)."""
+    _need_cuda("head_decode", *levels)
+    lv, ptrs, hs, ws, st, n, b, nc, a = _levels_args(levels, strides)
+    out = torch.empty((b, 4 + nc, a), dtype=torch.float32, device=lv[0].device)
+    _lib.check(_lib.lib().spp_head_decode(ptrs, hs, ws, st, n, b, nc, _ptr(out), _stream(out)), "spp_head_decode")
+    return out
+
+
+class NmsResult:
+    """Padded, device-resident NMS output: ``dets [B, max_det, 6]``, ``count [B]`` (negative = candidate
+    list overflowed), ``keys [B, max_det]`` (anchor*nc + cls of every kept row, -1 padding)."""
+
+    def __init__(self, dets, count, keys):
+        self.dets, self.count, self.keys = dets, count, keys
+
+    def to_list(self) -> List[torch.Tensor]:
+        """The reference's return type: a list of ``[n_i, 6]`` tensors (one D2H of the counts)."""
+        counts = self.count.abs().tolist()
+        return [self.dets[i, :c] for i, c in enumerate(counts)]
+
+    def keys_list(self) -> List[torch.Tensor]:
+        counts = self.count.abs().tolist()
+        return [self.keys[i, :c] for i, c in enumerate(counts)]
+
+
+_ws_cache = {}
+
+
+def _workspace(dev: torch.device, nbytes: int, tag: str) -> torch.Tensor:
+    """Grow-only per-(device, stream, tag) scratch buffer, 1 KB aligned (caching allocator gives 512 B)."""
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream, tag)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes + 1024:
+        buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        _ws_cache[key] = buf
+    off = (-buf.data_ptr()) % 1024
+    return buf[off:off + nbytes]
+
+
+def nms_decoded(pred: torch.Tensor, conf_thres: float = 0.001, iou_thres: float = 0.65, max_det: int = MAX_DET,
+                max_nms: int = MAX_NMS, max_wh: float = MAX_WH, max_candidates: int = 0) -> NmsResult:
+    """``non_max_suppression`` (training/yolopt/util.py:123-169) on a decoded ``[B, 4+nc, A]`` tensor."""
+    _need_cuda("nms_decoded", pred)
+    pred = _f32c("nms_decoded", pred)
+    if pred.dim() != 3 or pred.shape[1] < 5:
+        raise ValueError(f"nms_decoded: expected [B, 4+nc, A], got {tuple(pred.shape)}")
+    b, nc, a = pred.shape[0], pred.shape[1] - 4, pred.shape[2]
+    L = _lib.lib()
+    dets = torch.empty((b, max_det, 6), dtype=torch.float32, device=pred.device)
+    count = torch.empty((b,), dtype=torch.int32, device=pred.device)
+    keys = torch.empty((b, max_det), dtype=torch.int32, device=pred.device)
+    nbytes = L.spp_nms_workspace_bytes(b, a, nc, max_candidates)
+    ws = _workspace(pred.device, nbytes, "nms")
+    _lib.check(L.spp_nms_decoded(_ptr(pred), b, nc, a, conf_thres, iou_thres, max_det, max_nms, max_wh, max_candidates,
+                                 _ptr(dets), _ptr(count), _ptr(keys), _ptr(ws), nbytes, _stream(pred)), "spp_nms_decoded")
+    return NmsResult(dets, count, keys)
+
+
+def decode_nms(levels: Sequence[torch.Tensor], strides: Sequence[float] = (8, 16, 32), conf_thres: float = 0.001,
+               iou_thres: float = 0.65, max_det: int = MAX_DET, max_nms: int = MAX_NMS, max_wh: float = MAX_WH,
+               max_candidates: int = 0, out: Optional[NmsResult] = None) -> NmsResult:
+    """Fused ``Head.forward`` (eval) + ``non_max_suppression`` from the raw per-level maps."""
+    _need_cuda("decode_nms", *levels)
+    lv, ptrs, hs, ws_, st, n, b, nc, a = _levels_args(levels, strides)
+    dev = lv[0].device
+    L = _lib.lib()
+    if out is None:
+        out = NmsResult(torch.empty((b, max_det, 6), dtype=torch.float32, device=dev),
+                        torch.empty((b,), dtype=torch.int32, device=dev),
+                        torch.empty((b, max_det), dtype=torch.int32, device=dev))
+    nbytes = L.spp_nms_workspace_bytes(b, a, nc, max_candidates)
+    ws = _workspace(dev, nbytes, "nms")
+    _lib.check(L.spp_decode_nms(ptrs, hs, ws_, st, n, b, nc, conf_thres, iou_thres, max_det, max_nms, max_wh,
+                                max_candidates, _ptr(out.dets), _ptr(out.count), _ptr(out.keys), _ptr(ws), nbytes,
+                                _stream(out.dets)), "spp_decode_nms")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# embeddings / gallery match
+# ------------------------------------------------------------------------------------------------
+
+def l2_normalize(x: torch.Tensor, mode: str = "backbone", eps: float = 1e-12, want_bf16: bool = False):
+    """``mode='backbone'``: libs/net_adaface.py:334-337 -> (x/||x||, ||x|| [M,1]);
+    ``mode='normalize'``: ``F.normalize`` (x / max(||x||, eps))."""
+    _need_cuda("l2_normalize", x)
+    x = _f32c("l2_normalize", x)
+    if x.dim() != 2:
+        raise ValueError("l2_normalize: expected [M, D]")
+    m, d = x.shape
+    out = torch.empty_like(x)
+    norm = torch.empty((m, 1), dtype=torch.float32, device=x.device)
+    ob = torch.empty((m, d), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    _lib.check(_lib.lib().spp_l2_normalize(_ptr(x), m, d, 0 if mode == "backbone" else 1, eps, _ptr(out), _ptr(norm),
+                                           _ptr(ob), _stream(x)), "spp_l2_normalize")
+    return (out, norm, ob) if want_bf16 else (out, norm)
+
+
+def to_bf16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 -> bf16 (round to nearest even) — gallery enrolment."""
+    _need_cuda("to_bf16", x)
+    x = _f32c("to_bf16", x)
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.lib().spp_f32_to_bf16(_ptr(x), x.numel(), _ptr(out), _stream(x)), "spp_f32_to_bf16")
+    return out
+
+
+def match_top1(emb: torch.Tensor, gallery_bf16: torch.Tensor, threshold: Optional[float] = None, id_offset: int = 0,
+               want_keys: bool = False, _simt: bool = False):
+    """Cosine top-1 of every probe against a bf16, row-normalised gallery ``[N, 512]``.
+    Returns ``(ids int32 [M], sims fp32 [M])`` (+ packed int64 keys for a cross-shard MAX reduce)."""
+    _need_cuda("match_top1", emb, gallery_bf16)
+    emb = _f32c("match_top1", emb)
+    if gallery_bf16.dtype != torch.bfloat16 or not gallery_bf16.is_contiguous():
+        raise TypeError("match_top1: gallery must be a contiguous bfloat16 [N, 512] tensor (see enrol_gallery)")
+    if emb.dim() != 2 or gallery_bf16.dim() != 2 or emb.shape[1] != gallery_bf16.shape[1]:
+        raise ValueError(f"match_top1: shape mismatch {tuple(emb.shape)} vs {tuple(gallery_bf16.shape)}")
+    m, d = emb.shape
+    n = gallery_bf16.shape[0]
+    L = _lib.lib()
+    ids = torch.empty((m,), dtype=torch.int32, device=emb.device)
+    sims = torch.empty((m,), dtype=torch.float32, device=emb.device)
+    keys = torch.empty((m,), dtype=torch.int64, device=emb.device) if want_keys else None
+    nbytes = L.spp_match_workspace_bytes(m, n, d)
+    if nbytes == 0:
+        raise ValueError(f"match_top1: unsupported shape M={m} N={n} D={d} (D must be 512, N >= 1)")
+    ws = _workspace(emb.device, nbytes, "match")
+    fn = L.spp_debug_match_top1_simt if _simt else L.spp_match_top1
+    thr = float("nan") if threshold is None else float(threshold)
+    _lib.check(fn(_ptr(emb), _ptr(gallery_bf16), m, n, d, thr, id_offset, _ptr(ids), _ptr(sims), _ptr(keys), _ptr(ws),
+                  nbytes, _stream(emb)), "spp_match_top1")
+    return (ids, sims, keys) if want_keys else (ids, sims)
+
+
+def match_unpack_keys(keys: torch.Tensor, threshold: Optional[float] = None):
+    _need_cuda("match_unpack_keys", keys)
+    m = keys.numel()
+    ids = torch.empty((m,), dtype=torch.int32, device=keys.device)
+    sims = torch.empty((m,), dtype=torch.float32, device=keys.device)
+    thr = float("nan") if threshold is None else float(threshold)
+    _lib.check(_lib.lib().spp_match_unpack_keys(_ptr(keys), m, thr, _ptr(ids), _ptr(sims), _stream(keys)),
+               "spp_match_unpack_keys")
+    return ids, sims
+
+
+# ------------------------------------------------------------------------------------------------
+# crop
+# ------------------------------------------------------------------------------------------------
+
+def crop_affine(frames: torch.Tensor, boxes: torch.Tensor, frame_idx: torch.Tensor, out_hw: Tuple[int, int] = (256, 192),
+                mean: Sequence[float] = (0.485, 0.456, 0.406), std: Sequence[float] = (0.229, 0.224, 0.225),
+                variant: str = "hf", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Bilinear affine crop of every box to ``out_hw`` with ``(x - mean) / std`` fused.
+    ``frames [B,3,H,W]`` fp32, ``boxes [P,4]`` COCO (x,y,w,h), ``frame_idx [P]`` int32."""
+    _need_cuda("crop_affine", frames, boxes, frame_idx)
+    frames = _f32c("crop_affine frames", frames)
+    boxes = _f32c("crop_affine boxes", boxes)
+    if frames.dim() != 4 or frames.shape[1] != 3:
+        raise ValueError(f"crop_affine: frames must be [B, 3, H, W], got {tuple(frames.shape)}")
+    if boxes.dim() != 2 or boxes.shape[1] != 4 or frame_idx.shape[0] != boxes.shape[0]:
+        raise ValueError("crop_affine: boxes must be [P, 4] with one frame index per box")
+    if frame_idx.dtype != torch.int32:
+        frame_idx = frame_idx.to(torch.int32)
+    p = boxes.shape[0]
+    oh, ow = out_hw
+    if out is None:
+        out = torch.empty((p, 3, oh, ow), dtype=torch.float32, device=frames.device)
+    m3 = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    s3 = (ctypes.c_float * 3)(*[float(v) for v in std])
+    _lib.check(_lib.lib().spp_crop_affine(_ptr(frames), frames.shape[0], frames.shape[2], frames.shape[3], _ptr(boxes),
+                                          _ptr(frame_idx.contiguous()), p, oh, ow, m3, s3, CROP_VARIANTS[variant], _ptr(out),
+                                          _stream(out)), "spp_crop_affine")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# heatmap decode
+# ------------------------------------------------------------------------------------------------
+
+FLAG_SCALE_SCORE = 1
+FLAG_BACKPROJECT = 2
+
+
+def heatmap_decode(hm: torch.Tensor, hm_flipped: Optional[torch.Tensor] = None, perm: Optional[torch.Tensor] = None,
+                   boxes: Optional[torch.Tensor] = None, mode: str = "dark", kernel: int = 11, flags: int = 0,
+                   crop_hw: Tuple[int, int] = (256, 192), out=None):
+    """One pass over the heatmaps: flip-average (optional), arg-max, refinement, back-projection.
+    Returns ``(keypoints [P,K,2] fp32, scores [P,K] fp32, argmax [P,K] int32)``."""
+    _need_cuda("heatmap_decode", hm, hm_flipped, perm, boxes)
+    hm = _f32c("heatmap_decode", hm)
+    if hm.dim() != 4:
+        raise ValueError(f"heatmap_decode: expected [P, K, H, W], got {tuple(hm.shape)}")
+    if hm_flipped is not None:
+        hm_flipped = _f32c("heatmap_decode flipped", hm_flipped)
+        if hm_flipped.shape != hm.shape:
+            raise ValueError("heatmap_decode: flipped heatmaps must have the same shape")
+    p, k, h, w = hm.shape
+    if perm is not None:
+        if perm.dtype != torch.int32 or perm.numel() != k:
+            raise ValueError("heatmap_decode: perm must be int32 [K]")
+    if boxes is not None:
+        boxes = _f32c("heatmap_decode boxes", boxes)
+        if boxes.shape != (p, 4):
+            raise ValueError("heatmap_decode: boxes must be [P, 4]")
+    if mode not in DECODE_MODES:
+        raise ValueError(f"heatmap_decode: unknown mode {mode!r}")
+    if out is None:
+        kp = torch.empty((p, k, 2), dtype=torch.float32, device=hm.device)
+        sc = torch.empty((p, k), dtype=torch.float32, device=hm.device)
+        am = torch.empty((p, k), dtype=torch.int32, device=hm.device)
+    else:
+        kp, sc, am = out
+    _lib.check(_lib.lib().spp_heatmap_decode(_ptr(hm), _ptr(hm_flipped), _ptr(perm), p, k, h, w, _ptr(boxes),
+                                             DECODE_MODES[mode], flags, kernel, crop_hw[0], crop_hw[1], _ptr(kp), _ptr(sc),
+                                             _ptr(am), _stream(hm)), "spp_heatmap_decode")
+    return kp, sc, am

@@ -1,0 +1,195 @@
+"""Drop-in replacements that keep the reference's call signatures.
+
+Every function here has the name, argument order, defaults and return types of the reference
+function it replaces, and forwards to the sm_100a kernels in ``ops``.  Inputs must be CUDA tensors
+(host tensors raise: there is no CPU fallback); variable-length results are produced on the device as
+padded tensors + counts and only converted to the reference's Python ``list`` forms here.
+"""
+from __future__ import annotations
+
+import itertools
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from .synth import COCO_FLIP_PAIRS, flip_perm
+
+IMAGENET_DEFAULT_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_DEFAULT_STD = (0.229, 0.224, 0.225)
+
+
+# ---- training/yolopt/util.py:123 -----------------------------------------------------------------
+def non_max_suppression(outputs: torch.Tensor, confidence_threshold: float = 0.001, iou_threshold: float = 0.65
+                        ) -> List[torch.Tensor]:
+    """``non_max_suppression(outputs, confidence_threshold=0.001, iou_threshold=0.65)`` —
+    training/yolopt/util.py:123-169.  ``outputs``: ``[B, 4+nc, A]`` as returned by ``Head.forward`` in
+    eval mode; returns a list of ``[n_i, 6]`` tensors (x1, y1, x2, y2, conf, cls), n_i <= 300.
+    Unlike the reference there is no wall-clock bail-out (util.py:166-167)."""
+    return ops.nms_decoded(outputs, confidence_threshold, iou_threshold).to_list()
+
+
+# ---- training/yolopt/nets/nn.py:255 (eval branch, after the conv stacks) ---------------------------
+def head_forward(levels: Sequence[torch.Tensor], strides: Sequence[float] = (8, 16, 32)) -> torch.Tensor:
+    """Eval-mode ``Head.forward`` on the per-level ``cat(box(x), cls(x))`` maps -> ``[B, 4+nc, A]``."""
+    return ops.head_decode(levels, strides)
+
+
+def detect(levels: Sequence[torch.Tensor], confidence_threshold: float = 0.001, iou_threshold: float = 0.65,
+           strides: Sequence[float] = (8, 16, 32)) -> List[torch.Tensor]:
+    """Fused fast path: ``non_max_suppression(Head.forward(levels))`` without materialising the decoded tensor."""
+    return ops.decode_nms(levels, strides, confidence_threshold, iou_threshold).to_list()
+
+
+# ---- libs/head_adaface.py:39 / libs/net_adaface.py:334 ---------------------------------------------
+def l2_norm(input: torch.Tensor, axis: int = 1) -> torch.Tensor:  # noqa: A002 (reference's argument name)
+    """``l2_norm(input, axis=1)`` — libs/head_adaface.py:39-42."""
+    if axis in (1, -1) and input.dim() == 2:
+        return ops.l2_normalize(input, mode="backbone")[0]
+    if axis == 0 and input.dim() == 2:
+        return ops.l2_normalize(input.t().contiguous(), mode="backbone")[0].t()
+    raise ValueError("l2_norm: only 2-D inputs with axis 0 or 1 are supported")
+
+
+def backbone_tail(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``Backbone.forward`` lines libs/net_adaface.py:334-337: returns ``(x / ||x||, ||x||)``."""
+    return ops.l2_normalize(x, mode="backbone")
+
+
+class Gallery:
+    """Enrolled identities: a row-normalised bf16 ``[N, 512]`` matrix resident in HBM.
+
+    ``Gallery.from_kernel`` takes the AdaFace classifier kernel ``[512, N]`` whose columns are
+    identities (libs/head_adaface.py:79 normalises it along axis 0); ``quirk_q3=True`` reproduces
+    ``F.normalize(kernel)`` of training/lightning/face_recognition/module.py:137 (wrong axis).
+    Enrolment is off the hot path."""
+
+    def __init__(self, rows_bf16: torch.Tensor, id_offset: int = 0):
+        if rows_bf16.dtype != torch.bfloat16 or rows_bf16.dim() != 2:
+            raise TypeError("Gallery: expected a bfloat16 [N, 512] tensor")
+        self.rows = rows_bf16.contiguous()
+        self.id_offset = int(id_offset)
+
+    @classmethod
+    def from_kernel(cls, kernel: torch.Tensor, quirk_q3: bool = False) -> "Gallery":
+        kn = torch.nn.functional.normalize(kernel) if quirk_q3 else kernel / torch.norm(kernel, 2, 0, True)
+        return cls(ops.to_bf16(kn.t().contiguous()))
+
+    @classmethod
+    def from_rows(cls, rows: torch.Tensor, normalize: bool = True, id_offset: int = 0) -> "Gallery":
+        if normalize:
+            rows = ops.l2_normalize(rows, mode="normalize")[0]
+        return cls(ops.to_bf16(rows), id_offset)
+
+    def __len__(self) -> int:
+        return self.rows.shape[0]
+
+    def match(self, embeddings: torch.Tensor, threshold: Optional[float] = None):
+        """``pred = (F.linear(F.normalize(emb), G) * s).max(1)[1]`` (face_recognition/module.py:136-145) plus the
+        optional similarity gate; returns ``(ids int64 [M], sims fp32 [M])``, ``ids == -1`` where gated."""
+        ids, sims = ops.match_top1(embeddings, self.rows, threshold, self.id_offset)
+        return ids.long(), sims
+
+
+# ---- HF VitPoseImageProcessor (transformers/models/vitpose/image_processing_vitpose.py) -------------
+def _flatten_boxes(boxes, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``list[list[list[float]]]`` (per image, per box, COCO x,y,w,h) or a ready ``[P,4]`` tensor."""
+    if isinstance(boxes, torch.Tensor):
+        raise TypeError("pass (boxes[P,4], frame_idx[P]) tensors through ops.crop_affine directly")
+    flat, idx = [], []
+    for i, per_image in enumerate(boxes):
+        for b in per_image:
+            flat.append([float(v) for v in b[:4]])
+            idx.append(i)
+    return (torch.tensor(flat, dtype=torch.float32, device=device).reshape(-1, 4),
+            torch.tensor(idx, dtype=torch.int32, device=device))
+
+
+class VitPoseImageProcessor:
+    """Signature-compatible subset of HF ``VitPoseImageProcessor`` (preprocess + post-process)."""
+
+    def __init__(self, size=None, do_rescale: bool = True, rescale_factor: float = 1 / 255, do_normalize: bool = True,
+                 image_mean=IMAGENET_DEFAULT_MEAN, image_std=IMAGENET_DEFAULT_STD):
+        self.size = size or {"height": 256, "width": 192}
+        self.do_rescale, self.rescale_factor, self.do_normalize = do_rescale, rescale_factor, do_normalize
+        self.image_mean, self.image_std = tuple(image_mean), tuple(image_std)
+
+    def _mean_std(self, do_rescale, do_normalize):
+        mean = torch.tensor(self.image_mean if do_normalize else (0.0, 0.0, 0.0), dtype=torch.float32)
+        std = torch.tensor(self.image_std if do_normalize else (1.0, 1.0, 1.0), dtype=torch.float32)
+        if do_rescale:   # image_processing_backends.py:301-305 — rescale folded into mean/std in fp32
+            mean = mean * (1.0 / self.rescale_factor)
+            std = std * (1.0 / self.rescale_factor)
+        return mean.tolist(), std.tolist()
+
+    def preprocess(self, images, boxes, do_rescale: Optional[bool] = None, do_normalize: Optional[bool] = None, **_):
+        """HF:355-448.  ``images``: ``[B,3,H,W]`` float tensor or list of ``[3,H,W]`` tensors of equal size."""
+        frames = images if isinstance(images, torch.Tensor) else torch.stack(list(images))
+        b, idx = _flatten_boxes(boxes, frames.device)
+        mean, std = self._mean_std(self.do_rescale if do_rescale is None else do_rescale,
+                                   self.do_normalize if do_normalize is None else do_normalize)
+        pix = ops.crop_affine(frames.float(), b, idx, (self.size["height"], self.size["width"]), mean, std, "hf")
+        return {"pixel_values": pix}
+
+    def post_process_pose_estimation(self, outputs, boxes, kernel_size: int = 11, threshold: Optional[float] = None,
+                                     flipped_heatmaps: Optional[torch.Tensor] = None,
+                                     flip_pairs: Optional[Sequence[Tuple[int, int]]] = COCO_FLIP_PAIRS):
+        """HF:465-535.  ``outputs`` has ``.heatmaps [P,K,H,W]`` (or is that tensor).  Extension: pass the raw
+        heatmaps of the mirrored crops as ``flipped_heatmaps`` and the flip test is fused into the decode."""
+        hm = outputs.heatmaps if hasattr(outputs, "heatmaps") else outputs
+        b, _ = _flatten_boxes(boxes, hm.device)
+        perm = None
+        if flipped_heatmaps is not None:
+            perm = flip_perm(hm.shape[1], flip_pairs).to(hm.device)
+        kp, sc, _ = ops.heatmap_decode(hm, flipped_heatmaps, perm, b, "dark", kernel_size,
+                                       crop_hw=(self.size["height"], self.size["width"]))
+        kp, sc = kp.cpu(), sc.cpu()
+        labels = torch.arange(0, hm.shape[1])
+        # bbox field exactly as HF builds it: (cx, cy, scale_x, scale_y) pushed through coco_to_pascal_voc
+        from .hostmath import hf_center_scale
+        cs = hf_center_scale(b.cpu(), self.size["width"], self.size["height"])
+        bbox = cs.clone()
+        bbox[:, 2] = cs[:, 2] + cs[:, 0] - 1
+        bbox[:, 3] = cs[:, 3] + cs[:, 1] - 1
+        results, it = [], iter(range(hm.shape[0]))
+        for per_image in boxes:
+            image_results = []
+            for _ in per_image:
+                i = next(it)
+                pose, score, lab = kp[i], sc[i], labels
+                if threshold is not None:
+                    keep = score > threshold
+                    pose, score, lab = pose[keep], score[keep], lab[keep]
+                image_results.append({"keypoints": pose, "scores": score, "labels": lab, "bbox": bbox[i]})
+            results.append(image_results)
+        return results
+
+
+# ---- training/lightning/pose_estimation/module.py:237 ----------------------------------------------
+def get_keypoints_from_heatmaps(heatmaps: torch.Tensor, boxes: Optional[torch.Tensor] = None
+                                ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``PoseEstimationModule._get_keypoints_from_heatmaps(heatmaps, boxes=None)`` — soft-argmax decode,
+    returns ``(coords [B,K,2] in [0,1], scores [B,K])``; ``boxes`` ``[B,4]`` xyxy scale the scores."""
+    kp, sc, _ = ops.heatmap_decode(heatmaps, None, None, boxes, "softargmax",
+                                   flags=ops.FLAG_SCALE_SCORE if boxes is not None else 0)
+    return kp, sc
+
+
+def flip_test_keypoints(heatmaps: torch.Tensor, flipped_heatmaps: torch.Tensor, boxes: torch.Tensor,
+                        keypoint_thresh: float = 0.3, flip_pairs=COCO_FLIP_PAIRS) -> torch.Tensor:
+    """module.py:473-484 (with the correct channel swap) + :499 + :534-546 in one pass: returns COCO-style
+    ``[B, K, 3]`` (x, y, v) in image pixels, v = 2 where score > thresh else 1."""
+    perm = flip_perm(heatmaps.shape[1], flip_pairs).to(heatmaps.device)
+    kp, sc, _ = ops.heatmap_decode(heatmaps, flipped_heatmaps, perm, boxes, "softargmax",
+                                   flags=ops.FLAG_SCALE_SCORE | ops.FLAG_BACKPROJECT)
+    v = torch.where(sc > keypoint_thresh, 2.0, 1.0)
+    return torch.cat([kp, v[..., None]], -1)
+
+
+# ---- gluoncv get_final_preds as called at pose_estimation/module_v2.py:216 --------------------------
+def get_final_preds(batch_heatmaps: torch.Tensor, center: torch.Tensor, scale: torch.Tensor):
+    """``get_final_preds(heatmaps, center, scale)`` -> ``(preds [N,K,2], maxvals [N,K,1])`` (arg-max +
+    quarter offset + inverse affine; scale in pixels as produced by datamodule_v2.py:122)."""
+    cs = torch.cat([center.float(), scale.float()], 1).to(batch_heatmaps.device).contiguous()
+    kp, sc, _ = ops.heatmap_decode(batch_heatmaps, None, None, cs, "quarter", flags=4)
+    return kp, sc[..., None]

@@ -1,0 +1,277 @@
+"""Parity of the sm_100a kernels (through the C ABI) against the CPU oracle.  Needs a B200.
+
+Bars (BASELINE.json north_star): bit-exact NMS keep indices, arg-max joint indices and matched
+identity ids; keypoint / score / embedding floats within 1e-3 relative tolerance.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import crop as ocrop
+from oracle import det as odet
+from oracle import match as omatch
+from oracle import pose as opose
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-3
+
+
+def _close(a, b, rtol=RTOL, atol=0.0, what=""):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    err = np.abs(a - b)
+    tol = atol + rtol * np.abs(b)
+    bad = err > tol
+    assert not bad.any(), f"{what}: {bad.sum()} / {bad.size} beyond tolerance, max err {err.max():.3e} at {np.argmax(err - tol)}"
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+# ------------------------------------------------------------------------------------------------
+# heatmap decode
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("flip", [False, True])
+@pytest.mark.parametrize("k", [17, 5])
+def test_heatmap_dark_vs_oracle(spp, synth, dev, flip, k):
+    hs = synth.make_heatmaps(9, k, seed=100 + k, negative_frac=0.1)
+    cs = synth.make_crop_set(1, 480, 640, per_frame=9, seed=7)
+    boxes = [[float(v) for v in b] for b in cs.boxes]
+    avg = opose.flip_average(hs.heatmaps, hs.flipped, hs.perm) if flip else hs.heatmaps
+    kp_o, sc_o, idx_o = opose.hf_dark_decode(avg.numpy(), boxes)
+    kp, sc, am = spp.heatmap_decode(hs.heatmaps.to(dev), hs.flipped.to(dev) if flip else None,
+                                    hs.perm.to(dev) if flip else None, cs.boxes.to(dev), "dark", 11)
+    np.testing.assert_array_equal(am.cpu().numpy(), idx_o)                 # arg-max indices: bit-exact
+    np.testing.assert_array_equal(sc.cpu().numpy(), sc_o)                   # max of the averaged map: bit-exact
+    valid = sc_o > 0
+    _close(kp.cpu().numpy()[valid], kp_o[valid], what="DARK keypoints (valid joints)")
+    # joints with score <= 0 follow HF's flat-index behaviour (reads the previous map's tail)
+    _close(kp.cpu().numpy()[~valid], kp_o[~valid], atol=1e-2, what="DARK keypoints (score<=0 joints)")
+
+
+def test_heatmap_dark_golden(spp, golden, dev):
+    g = golden("pose_hf.npz")
+    kp, sc, _ = spp.heatmap_decode(torch.from_numpy(g["hm"]).to(dev), torch.from_numpy(g["flipped"]).to(dev),
+                                   torch.from_numpy(g["perm"]).to(dev), torch.from_numpy(g["boxes"]).to(dev), "dark", 11)
+    np.testing.assert_array_equal(sc.cpu().numpy(), g["scores"])
+    valid = g["scores"] > 0
+    _close(kp.cpu().numpy()[valid], g["keypoints"][valid], what="DARK vs HF fixture")
+
+
+def test_heatmap_dark_heatmap_space_and_kernel_sizes(spp, synth, dev):
+    hs = synth.make_heatmaps(4, 17, seed=5, negative_frac=0.0)
+    for kernel in (3, 7, 11, 17):
+        coords, scores, idx = opose.argmax_predictions(hs.heatmaps.numpy())
+        ref = opose.dark_refine_full(coords, hs.heatmaps.numpy(), kernel=kernel)
+        kp, sc, am = spp.heatmap_decode(hs.heatmaps.to(dev), mode="dark", kernel=kernel)
+        np.testing.assert_array_equal(am.cpu().numpy(), idx)
+        _close(kp.cpu().numpy(), ref, atol=1e-3, what=f"DARK heatmap-space kernel={kernel}")
+
+
+def test_heatmap_softargmax_vs_oracle_and_golden(spp, golden, dev):
+    g = golden("pose_live.npz")
+    hm, fl, perm = (torch.from_numpy(g[k]) for k in ("hm", "flipped", "perm"))
+    boxes = torch.from_numpy(g["boxes_xyxy"])
+    c, s = spp.get_keypoints_from_heatmaps(hm.to(dev))
+    _close(c.cpu().numpy(), g["coords_plain"], what="softargmax coords (reference fixture)")
+    _close(s.cpu().numpy(), g["scores_plain"], what="softargmax scores (reference fixture)")
+    kp, sc, am = spp.heatmap_decode(hm.to(dev), fl.to(dev), perm.to(dev), boxes.to(dev), "softargmax", flags=1)
+    _close(kp.cpu().numpy(), g["coords_avg_box"], what="softargmax+flip coords")
+    _close(sc.cpu().numpy(), g["scores_avg_box"], what="softargmax+flip scores")
+    np.testing.assert_array_equal(am.cpu().numpy(), torch.from_numpy(g["avg"]).flatten(2).argmax(2).numpy())
+    out = spp.flip_test_keypoints(hm.to(dev), fl.to(dev), boxes.to(dev))
+    ref = opose.backproject_live(torch.from_numpy(g["coords_avg_box"]), torch.from_numpy(g["scores_avg_box"]), boxes)
+    _close(out.cpu().numpy(), ref.numpy(), what="flip_test_keypoints")
+
+
+def test_heatmap_quarter_vs_oracle(spp, synth, dev):
+    hs = synth.make_heatmaps(6, 17, seed=9, negative_frac=0.1)
+    cs = synth.make_crop_set(1, 480, 640, per_frame=6, seed=3)
+    cen, scl = zip(*[ocrop.center_scale_v2(b.tolist()) for b in cs.boxes])
+    cen, scl = np.asarray(cen, np.float32), np.asarray(scl, np.float32)
+    ref, mv, idx = opose.quarter_offset_decode(hs.heatmaps.numpy(), cen, scl)
+    kp, sc, am = spp.heatmap_decode(hs.heatmaps.to(dev), None, None, cs.boxes.to(dev), "quarter")
+    np.testing.assert_array_equal(am.cpu().numpy(), idx)
+    _close(kp.cpu().numpy(), ref, atol=1e-3, what="quarter-offset keypoints")
+    kp2, mv2 = spp.get_final_preds(hs.heatmaps.to(dev), torch.from_numpy(cen), torch.from_numpy(scl))
+    _close(kp2.cpu().numpy(), ref, atol=1e-3, what="get_final_preds shim")
+    np.testing.assert_array_equal(mv2.cpu().numpy()[..., 0], mv)
+
+
+def test_heatmap_full_size_properties(spp, synth, dev):
+    """cfg2 size (640 crops x 17 joints, flip test): arg-max indices against torch on the device-side
+    average, and the planted sub-pixel centres are recovered."""
+    hs = synth.make_heatmaps(640, 17, seed=0)
+    hm, fl, perm = hs.heatmaps.to(dev), hs.flipped.to(dev), hs.perm.to(dev)
+    kp, sc, am = spp.heatmap_decode(hm, fl, perm, None, "dark", 11)
+    avg = (hm + fl[:, perm.long()].flip(-1)) * 0.5
+    ref_max, ref_idx = avg.flatten(2).max(2)
+    assert torch.equal(am.long(), ref_idx) and torch.equal(sc, ref_max)
+    good = (~hs.negative).to(dev)
+    err = (kp - hs.centres.to(dev)).norm(dim=-1)[good]
+    assert float(err.median()) < 0.15 and float(err.quantile(0.99)) < 1.0
+
+
+# ------------------------------------------------------------------------------------------------
+# detection decode + NMS
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("tag", ["nc1", "nc3"])
+def test_det_golden(spp, golden, dev, tag):
+    g = golden(f"det_{tag}.npz")
+    levels = [torch.from_numpy(g[k]).to(dev) for k in ("l0", "l1", "l2")]
+    conf, iou = float(g["conf"]), float(g["iou"])
+    dec = spp.head_forward(levels)
+    _close(dec.cpu().numpy(), g["decoded"], atol=1e-3, what="head decode")
+    # (1) the reference's signature on the reference's own decoded tensor: bit-exact rows
+    dets = spp.non_max_suppression(torch.from_numpy(g["decoded"]).to(dev), conf, iou)
+    assert [d.shape[0] for d in dets] == list(g["n"])
+    np.testing.assert_array_equal(torch.cat(dets).cpu().numpy(), g["dets"])
+    # (2) fused raw path: same keep set (bit-exact class / anchor keys), floats within tolerance
+    ref_rows, ref_keys = odet.non_max_suppression(torch.from_numpy(g["decoded"]), conf, iou, return_index=True)
+    res = spp.decode_nms(levels, conf_thres=conf, iou_thres=iou)
+    assert res.count.tolist() == [r.shape[0] for r in ref_rows]
+    for rows, keys, rr, rk in zip(res.to_list(), res.keys_list(), ref_rows, ref_keys):
+        np.testing.assert_array_equal(keys.cpu().numpy(), rk.numpy())
+        _close(rows.cpu().numpy(), rr.numpy(), atol=1e-3, what="fused decode+NMS rows")
+
+
+@pytest.mark.parametrize("dense", [False, True])
+def test_det_vs_oracle_bigger(spp, synth, dev, dense):
+    hm = synth.make_head_maps(3, 384, 640, n_obj=12, nc=1, seed=4, dense=dense)
+    dec_o = odet.head_decode(hm.levels)
+    conf = 0.001 if not dense else 0.3
+    rows_o, keys_o = odet.non_max_suppression(dec_o, conf, 0.65, return_index=True)
+    near = sum(odet.near_threshold_pairs(r, 0.65) for r in rows_o)
+    # NMS on the oracle's decoded tensor must be bit-exact regardless of borderline pairs
+    res = spp.nms_decoded(dec_o.to(dev), conf, 0.65)
+    for rows, keys, rr, rk in zip(res.to_list(), res.keys_list(), rows_o, keys_o):
+        np.testing.assert_array_equal(keys.cpu().numpy(), rk.numpy())
+        np.testing.assert_array_equal(rows.cpu().numpy(), rr.numpy())
+    if near == 0 and not dense:
+        res = spp.decode_nms([l.to(dev) for l in hm.levels], conf_thres=conf, iou_thres=0.65)
+        for keys, rk in zip(res.keys_list(), keys_o):
+            np.testing.assert_array_equal(keys.cpu().numpy(), rk.numpy())
+
+
+def test_det_edge_cases(spp, synth, dev):
+    # no candidates at all
+    hm = synth.make_head_maps(2, 64, 64, n_obj=0, nc=1, seed=1)
+    res = spp.decode_nms([l.to(dev) for l in hm.levels])
+    assert res.count.tolist() == [0, 0] and all(r.shape == (0, 6) for r in res.to_list())
+    # more than max_det survivors: distinct far-apart boxes, every anchor a candidate
+    pred = torch.zeros(1, 5, 1000)
+    pred[0, 0] = torch.arange(1000) * 50.0
+    pred[0, 1] = 10.0
+    pred[0, 2:4] = 20.0
+    pred[0, 4] = torch.linspace(0.9, 0.1, 1000)
+    out = spp.non_max_suppression(pred.to(dev))
+    ref = odet.non_max_suppression(pred)
+    assert out[0].shape == (300, 6)
+    np.testing.assert_array_equal(out[0].cpu().numpy(), ref[0].numpy())
+    # exact score ties resolve to the lower anchor first (stable order)
+    pred[0, 4] = 0.5
+    pred[0, 0] = (torch.arange(1000) // 2) * 50.0          # pairs of identical boxes
+    out = spp.nms_decoded(pred.to(dev))
+    ref_rows, ref_keys = odet.non_max_suppression(pred, return_index=True)
+    np.testing.assert_array_equal(out.keys_list()[0].cpu().numpy(), ref_keys[0].numpy())
+
+
+# ------------------------------------------------------------------------------------------------
+# crop
+# ------------------------------------------------------------------------------------------------
+
+def test_crop_vs_oracle(spp, synth, dev):
+    cs = synth.make_crop_set(2, 360, 480, per_frame=6, seed=11)
+    ref = ocrop.crop_affine_hf(cs.frames.numpy(), cs.boxes.tolist(), cs.frame_idx.tolist())
+    out = spp.crop_affine(cs.frames.to(dev), cs.boxes.to(dev), cs.frame_idx.to(dev))
+    _close(out.cpu().numpy(), ref, atol=1e-3, what="HF/UDP crop")
+    assert float(np.abs(out.cpu().numpy() - ref).max()) < 2e-5
+    ref = ocrop.crop_affine_v2(cs.frames.numpy(), cs.boxes.tolist(), cs.frame_idx.tolist())
+    out = spp.crop_affine(cs.frames.to(dev), cs.boxes.to(dev), cs.frame_idx.to(dev), variant="gluoncv")
+    assert float(np.abs(out.cpu().numpy() - ref).max()) < 2e-5
+
+
+def test_crop_golden_and_processor_shim(spp, golden, dev):
+    g = golden("pose_hf.npz")
+    proc = spp.VitPoseImageProcessor()
+    boxes = [[[float(v) for v in b] for b in g["boxes"]]]
+    pix = proc.preprocess([torch.from_numpy(g["frame"]).to(dev)], boxes, do_rescale=False)["pixel_values"].cpu().numpy()
+    assert float(np.abs(pix[:, :, ::4, ::4] - g["crop_sub"]).max()) < 2e-5
+    np.testing.assert_allclose(pix.astype(np.float64).sum(axis=(2, 3)), g["crop_sum"], rtol=1e-5)
+
+
+def test_crop_then_decode_round_trip(spp, synth, dev):
+    """Back-projection is the exact inverse of the crop warp (UDP): a keypoint at heatmap position
+    (x, y) maps to the frame position that the crop sampled for input pixel (x*191/47, y*255/63)."""
+    cs = synth.make_crop_set(1, 480, 640, per_frame=4, seed=2)
+    hs = synth.make_heatmaps(4, 17, seed=8, negative_frac=0.0)
+    kp_hm, _, _ = spp.heatmap_decode(hs.heatmaps.to(dev), mode="dark")
+    kp_img, _, _ = spp.heatmap_decode(hs.heatmaps.to(dev), None, None, cs.boxes.to(dev), "dark")
+    for i, b in enumerate(cs.boxes.tolist()):
+        c, s = ocrop.box_to_center_and_scale(b)
+        xs, ys = ocrop.source_coords(ocrop.warp_matrix(c, s), 192, 256)
+        x_in = kp_hm[i, :, 0].cpu().numpy().astype(np.float64) * 191 / 47
+        y_in = kp_hm[i, :, 1].cpu().numpy().astype(np.float64) * 255 / 63
+        ex = xs[0] + x_in * (xs[1] - xs[0])
+        ey = ys[0] + y_in * (ys[1] - ys[0])
+        _close(kp_img[i, :, 0].cpu().numpy(), ex, rtol=1e-4, atol=1e-3, what="round trip x")
+        _close(kp_img[i, :, 1].cpu().numpy(), ey, rtol=1e-4, atol=1e-3, what="round trip y")
+
+
+# ------------------------------------------------------------------------------------------------
+# gallery match
+# ------------------------------------------------------------------------------------------------
+
+def _bf16_gallery(ms):
+    return ms.gallery.to(torch.bfloat16)
+
+
+def test_l2_normalize_matches_reference_fixture(spp, golden, dev):
+    g = golden("match.npz")
+    emb, norm = spp.backbone_tail(torch.from_numpy(g["pre"]).to(dev))
+    _close(emb.cpu().numpy(), g["emb"], rtol=1e-5, atol=1e-7, what="embedding")
+    _close(norm.cpu().numpy(), g["norm"], rtol=1e-5, what="norm")
+    kn = spp.l2_norm(torch.from_numpy(g["kernel"]).to(dev), axis=0)
+    _close(kn.cpu().numpy(), g["kernel_l2"], rtol=1e-5, atol=1e-8, what="l2_norm axis 0")
+
+
+@pytest.mark.parametrize("m,n", [(5, 100), (48, 300), (640, 10000), (130, 777)])
+@pytest.mark.parametrize("simt", [True, False])
+def test_match_vs_oracle(spp, synth, dev, m, n, simt):
+    ms = synth.make_match_set(m, n, seed=m + n)
+    gal = _bf16_gallery(ms)
+    pred_o, sim_o = omatch.match_top1(ms.embeddings, gal.float(), threshold=0.4)
+    gap = omatch.top2_gap(ms.embeddings, gal.float())
+    ids, sims = spp.match_top1(ms.embeddings.to(dev), gal.to(dev), 0.4, _simt=simt)
+    _close(sims.cpu().numpy(), sim_o.numpy(), rtol=RTOL, atol=1e-5, what="match similarity")
+    decided = (gap > 1e-5) & ((sim_o - 0.4).abs() > 1e-5)
+    np.testing.assert_array_equal(ids.cpu().numpy()[decided], pred_o.numpy()[decided])
+    known = ms.true_ids >= 0
+    np.testing.assert_array_equal(ids.cpu().numpy()[known], ms.true_ids.numpy()[known])
+    # un-gated: fp32 arg-max ids
+    pred_o, _ = omatch.match_top1(ms.embeddings, gal.float())
+    ids, _ = spp.match_top1(ms.embeddings.to(dev), gal.to(dev), None, _simt=simt)
+    np.testing.assert_array_equal(ids.cpu().numpy()[gap > 1e-5], pred_o.numpy()[gap > 1e-5])
+
+
+def test_match_reference_fixture_and_keys(spp, golden, dev):
+    g = golden("match.npz")
+    kernel = torch.from_numpy(g["kernel"])
+    gal = spp.Gallery.from_kernel(kernel.to(dev))
+    ids, sims = gal.match(torch.from_numpy(g["probes"]).to(dev), threshold=0.4)
+    known = g["true_ids"] >= 0
+    np.testing.assert_array_equal(ids.cpu().numpy()[known], g["pred"][known])
+    assert (ids.cpu().numpy()[~known] == -1).all()
+    _close(sims.cpu().numpy()[known], g["sim"][known], rtol=5e-3, what="similarity vs fp32-gallery fixture")
+    # sharded gallery: per-shard keys + integer MAX == single-shard result
+    rows = gal.rows
+    full_ids, full_sims = spp.match_top1(torch.from_numpy(g["probes"]).to(dev), rows)
+    k0 = spp.match_top1(torch.from_numpy(g["probes"]).to(dev), rows[:128].contiguous(), None, 0, want_keys=True)[2]
+    k1 = spp.match_top1(torch.from_numpy(g["probes"]).to(dev), rows[128:].contiguous(), None, 128, want_keys=True)[2]
+    ids2, sims2 = spp.match_unpack_keys(torch.maximum(k0, k1))
+    assert torch.equal(ids2, full_ids) and torch.equal(sims2, full_sims)
