@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""Benchmark of the post-backbone selective-pose glue path (BASELINE.json metric: frames/s at batch 64).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's sm_100a path
+    python bench.py --impl reference [--gpus N] ...                # the reference's CPU path (oracle port)
+
+One "step" = one pass of decode+NMS (face head, person head), gallery match, crop and heatmap decode
+over one batch of synthetic backbone outputs (config 2 of BASELINE.json: 64 frames of 1280x720,
+10 faces + 10 persons per frame, 10k-identity gallery, ViTPose-B heatmaps with flip test).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+PKG = "person-recognition-for-pose-estimation_b200"
+
+WORKLOADS = {
+    # name: frames per GPU, frame H, W, persons(=faces) per frame, joints, gallery ids
+    "cfg2": dict(batch=64, height=720, width=1280, per_frame=10, joints=17, gallery=10000,
+                 desc="batch 64 synthetic 1280x720 frames, 10 faces and persons per frame, 10k-ID gallery, "
+                      "ViTPose-B 17-joint 64x48 heatmaps with flip test"),
+    "cfg1": dict(batch=1, height=640, width=640, per_frame=5, joints=17, gallery=100,
+                 desc="one synthetic 640x640 frame, 5 faces, 100-ID gallery, 17-joint heatmaps"),
+    "cfg4": dict(batch=64, height=720, width=1280, per_frame=100, joints=133, gallery=10000,
+                 desc="crowd: 64 frames, 100 persons/frame, 133-joint heatmaps with flip test"),
+}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], bf16=p["bf16_tflops"], bf16_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """Polls SM clock and throttle reasons through NVML while the timed regions run."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+                 "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                mask = get(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._stop.clear()
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join()
+            self._thread = None
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------
+# the reference's CPU path (oracle port) — used only as the timed baseline / checker
+# ----------------------------------------------------------------------------------------------
+
+def cpu_reference_step(inp, gallery_f32, n_frames: int, per_frame: int, threshold: float = 0.4):
+    """The reference functions of SURVEY.md §8c on the first ``n_frames`` frames of the batch: torch CPU
+    Head decode + non_max_suppression (torchvision nms) for both heads, F.normalize/F.linear/max match,
+    HF VitPoseImageProcessor.preprocess crop, flip-average + HF post_process_pose_estimation."""
+    import torchvision
+    from transformers import VitPoseImageProcessor
+    from transformers.models.vitpose.modeling_vitpose import VitPoseEstimatorOutput
+    from oracle import det as odet, match as omatch, pose as opose
+
+    def tv_nms(boxes, scores, thr):
+        return torchvision.ops.nms(torch.from_numpy(boxes), torch.from_numpy(scores), thr).numpy()
+
+    p = n_frames * per_frame
+    out = {}
+    for name, levels in (("face", inp.face_levels), ("person", inp.person_levels)):
+        dec = odet.head_decode([l[:n_frames] for l in levels])
+        out[name] = odet.non_max_suppression(dec, 0.001, 0.65, nms_fn=tv_nms)
+    out["ids"], out["sims"] = omatch.match_top1(inp.embeddings[:p], gallery_f32, threshold)
+    boxes = [[[float(v) for v in inp.boxes[f * per_frame + j]] for j in range(per_frame)] for f in range(n_frames)]
+    proc = cpu_reference_step.proc = getattr(cpu_reference_step, "proc", None) or VitPoseImageProcessor()
+    out["pixel_values"] = proc.preprocess([inp.frames[f] for f in range(n_frames)], boxes=boxes, do_rescale=False,
+                                          return_tensors="pt")["pixel_values"]
+    hm = inp.heatmaps[:p]
+    if inp.flipped is not None:
+        hm = opose.flip_average(hm, inp.flipped[:p], inp.perm)
+    out["poses"] = proc.post_process_pose_estimation(VitPoseEstimatorOutput(heatmaps=hm), boxes=boxes, kernel_size=11)
+    return out
+
+
+def time_cpu_reference(inp, gallery_f32, batch, per_frame, budget_s: float, reps: int = 1, warm: int = 0):
+    """Time the CPU path on a bounded sample: a probe on 2 frames sizes the sample to ~budget_s."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    cpu_reference_step(inp, gallery_f32, min(2, batch), per_frame)
+    per_frame_s = (time.perf_counter() - t0) / min(2, batch)
+    total = max(1, reps + warm)
+    n = int(max(1, min(batch, budget_s / (per_frame_s * total))))
+    times = []
+    for i in range(total):
+        t0 = time.perf_counter()
+        cpu_reference_step(inp, gallery_f32, n, per_frame)
+        if i >= warm:
+            times.append(time.perf_counter() - t0)
+    return n, times
+
+
+# ----------------------------------------------------------------------------------------------
+
+def roi_bytes(boxes, frame_h, frame_w, out_h=256, out_w=192):
+    """Unique source bytes a crop has to read: the padded, aspect-fixed box clipped to the frame, 3 x fp32."""
+    spp = importlib.import_module(PKG)
+    cs = spp.hostmath.hf_center_scale(boxes, out_w, out_h)
+    w, h = cs[:, 2] * 200.0, cs[:, 3] * 200.0
+    x0 = (cs[:, 0] - w / 2).clamp(0, frame_w - 1)
+    x1 = (cs[:, 0] + w / 2).clamp(0, frame_w - 1)
+    y0 = (cs[:, 1] - h / 2).clamp(0, frame_h - 1)
+    y1 = (cs[:, 1] + h / 2).clamp(0, frame_h - 1)
+    return float(((x1 - x0 + 1) * (y1 - y0 + 1)).sum()) * 3 * 4
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="spp", choices=["spp", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--decode-mode", default="dark", choices=["dark", "softargmax", "quarter"])
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "spp" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    wl = WORKLOADS[args.workload]
+    spp = importlib.import_module(PKG)
+    pipeline = importlib.import_module(PKG + ".pipeline")
+
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world, pipeline)
+        return
+
+    assert torch.cuda.is_available(), "bench.py (impl spp) needs a CUDA device: there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+
+    # ---- inputs (per-rank shard: every rank owns `batch` frames; weak scaling) ------------------
+    inp = pipeline.synthetic_inputs(wl["batch"], wl["height"], wl["width"], wl["per_frame"], wl["joints"], seed=rank)
+    ms = spp.synth.make_match_set(wl["batch"] * wl["per_frame"], wl["gallery"], seed=1000 + rank)
+    inp.embeddings = ms.embeddings
+    gallery_bf16 = ms.gallery.to(torch.bfloat16)
+    pipe = pipeline.SelectivePosePipeline(inp, gallery_bf16, dev, decode_mode=args.decode_mode, use_graph=not args.no_graph)
+    pipe.bind_host(inp)
+    B, P, K, M = wl["batch"], wl["batch"] * wl["per_frame"], wl["joints"], wl["batch"] * wl["per_frame"]
+    A = sum(l.shape[2] * l.shape[3] for l in inp.face_levels)
+    nc = inp.face_levels[0].shape[1] - 64
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms_val: float) -> float:
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms_val], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms_val
+
+    sampler = ClockSampler(local_rank)
+    st = pipe.stream
+
+    # ---- (1) device-resident timed region --------------------------------------------------------
+    for _ in range(args.warmup):
+        pipe.step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with sampler:
+        e0.record(st)
+        for _ in range(args.steps):
+            pipe.step()
+        e1.record(st)
+        barrier()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    ms_per_step = dev_ms / args.steps
+    frames_per_s = world * B * args.steps / (dev_ms / 1e3)
+
+    # ---- (2) end to end from pinned host buffers ---------------------------------------------------
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(2):
+        pipe.run_host()
+    barrier()
+    with sampler:
+        e0.record(st)
+        for _ in range(e2e_steps):
+            pipe.run_host()
+        e1.record(st)
+        barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_fps = world * B * e2e_steps / (e2e_ms / 1e3)
+
+    # ---- (3) per-kernel durations (eager launches, CUDA events around each op on its stream) ------
+    ops = spp.ops
+    i = pipe.inp
+    stages = {
+        "decode_nms_face": lambda: ops.decode_nms(i.face_levels, out=pipe.out["_face"]),
+        "decode_nms_person": lambda: ops.decode_nms(i.person_levels, out=pipe.out["_person"]),
+        "match_top1": lambda: ops.match_top1(i.embeddings, pipe.gallery, 0.4),
+        "crop_affine": lambda: ops.crop_affine(i.frames, i.boxes, i.frame_idx, out=pipe.out["pixel_values"]),
+        "heatmap_decode": lambda: ops.heatmap_decode(i.heatmaps, i.flipped, i.perm, i.boxes, args.decode_mode, 11,
+                                                     out=(pipe.out["keypoints"], pipe.out["scores"], pipe.out["argmax"])),
+    }
+    n_rep = max(10, min(args.steps, 50))
+    evs = {k: [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_rep)] for k in stages}
+    filler = torch.empty(64 << 20, dtype=torch.float32, device=dev)
+    with torch.cuda.stream(st), sampler:
+        for fn in stages.values():
+            fn()
+        filler.fill_(1.0)                       # lets the host run ahead of the device
+        filler.fill_(2.0)
+        for r in range(n_rep):
+            for k, fn in stages.items():
+                a, b = evs[k][r]
+                a.record(st)
+                fn()
+                b.record(st)
+    st.synchronize()
+    kern_us = {k: 1e3 * statistics.median(a.elapsed_time(b) for a, b in v) for k, v in evs.items()}
+
+    hm_bytes = P * (K * 64 * 48 * 4 * (2 if i.flipped is not None else 1) + K * 16)
+    n_cand = float(pipe.out["_face"].count.abs().sum())   # kept rows; candidates are a small multiple
+    det_full_bytes = B * ((64 + nc) * A * 4 + 300 * 6 * 4 + 4)
+    crop_bytes = P * 3 * 256 * 192 * 4 + roi_bytes(inp.boxes, wl["height"], wl["width"])
+    match_flops = 2.0 * M * wl["gallery"] * 512
+    kernels = {
+        "heatmap_decode": dict(bound="hbm", us=kern_us["heatmap_decode"], bytes=hm_bytes),
+        "crop_affine": dict(bound="hbm", us=kern_us["crop_affine"], bytes=crop_bytes),
+        "decode_nms_face": dict(bound="hbm", us=kern_us["decode_nms_face"], bytes=det_full_bytes,
+                                note="bytes = SURVEY 8(d) figure (all 64+nc planes); the fused kernel only reads the class "
+                                     "planes plus the DFL planes of candidate anchors, so achieved can exceed peak"),
+        "decode_nms_person": dict(bound="hbm", us=kern_us["decode_nms_person"], bytes=det_full_bytes),
+        "match_top1": dict(bound="tensor", us=kern_us["match_top1"], flops=match_flops),
+    }
+    for k, d in kernels.items():
+        if d["bound"] == "hbm":
+            d["achieved"] = d["bytes"] / (d["us"] * 1e-6) / 1e9
+            d["peak"], d["unit"] = peaks["hbm"], "GB/s"
+        else:
+            d["achieved"] = d["flops"] / (d["us"] * 1e-6) / 1e12
+            d["peak"], d["unit"] = peaks["bf16"], "TFLOP/s"
+        d["frac"] = d["achieved"] / d["peak"]
+    dominant = max(kernels, key=lambda k: kernels[k]["us"])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(args.workload, {}).get(dominant)
+    dk = kernels[dominant]
+    roofline = dict(kernel=dominant, bound=dk["bound"], achieved=round(dk["achieved"], 1), peak=dk["peak"], unit=dk["unit"],
+                    frac=round(dk["frac"], 4), traffic=traffic, peak_source=peaks["source"],
+                    launch_us=round(dk["us"], 2), algorithmic=dk.get("bytes", dk.get("flops")),
+                    step_share=round(dk["us"] / sum(v["us"] for v in kernels.values()), 3))
+
+    # ---- (4) CPU baseline on this host (rank 0, N=1 only) ------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n, times = time_cpu_reference(inp, ms.gallery, B, wl["per_frame"], args.cpu_budget)
+        cpu = dict(value=round(n / statistics.median(times), 3), unit="frames/s", cores=os.cpu_count(), kind="port",
+                   sample=f"{n} of {B} frames of {args.workload} ({n * wl['per_frame']} crops), 1 timed pass: torch CPU head decode + "
+                          "torchvision nms x2 heads, F.normalize/F.linear/max, HF VitPoseImageProcessor.preprocess, "
+                          "flip-average + HF post_process_pose_estimation",
+                   seconds=round(statistics.median(times), 3))
+
+    if rank == 0:
+        line = {
+            "metric": "frames/sec post-backbone selective-pose pipeline (batch 64, 1/2/4/8 B200)",
+            "value": round(frames_per_s, 1), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (bf16 tensor-core candidates + fp32 re-score in the match)", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {wl['desc']}", "frames_per_gpu": B, "crops_per_gpu": P,
+                       "decode_mode": args.decode_mode, "parallelism": f"dp{world} (frames sharded, no data-path collective)",
+                       "l2": "inputs (1.6 GB per step) are larger than the 126 MB L2; no flush",
+                       "cuda_graph": not args.no_graph},
+            "crops_per_s": round(world * P * args.steps / (dev_ms / 1e3), 1),
+            "e2e": {"value": round(e2e_fps, 1), "unit": "frames/s", "h2d_bytes_per_step": pipe.h2d_bytes,
+                    "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": round(e2e_ms / e2e_steps, 3), "steps": e2e_steps},
+            "gpu_launches": pipe.launches_per_step * args.steps,
+            "roofline": roofline,
+            "kernels": {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in d.items()} for k, d in kernels.items()},
+            "cpu_baseline": cpu,
+            "clocks": sampler.summary(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def run_reference(args, wl, rank, world, pipeline):
+    """--impl reference: the reference's CPU implementation of the path (oracle port: the same torch /
+    torchvision / HF calls the reference makes) on this box's host cores.  Rank 0 only."""
+    if rank != 0:
+        return
+    spp = importlib.import_module(PKG)
+    inp = pipeline.synthetic_inputs(wl["batch"], wl["height"], wl["width"], wl["per_frame"], wl["joints"], seed=0)
+    ms = spp.synth.make_match_set(wl["batch"] * wl["per_frame"], wl["gallery"], seed=1000)
+    inp.embeddings = ms.embeddings
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    n, times = time_cpu_reference(inp, ms.gallery, wl["batch"], wl["per_frame"], budget_s=150.0, reps=steps, warm=warm)
+    total = sum(times)
+    fps = n * len(times) / total
+    line = {
+        "impl": "reference",
+        "metric": "frames/sec post-backbone selective-pose pipeline (batch 64, 1/2/4/8 B200)",
+        "value": round(fps, 3), "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": round(1e3 * total / len(times), 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {wl['desc']}", "frames_per_step": n, "crops_per_step": n * wl["per_frame"],
+                   "decode_mode": "dark"},
+        "cpu_baseline": {"value": round(fps, 3), "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"each step = the first {n} of {wl['batch']} frames of {args.workload} "
+                                   f"({n * wl['per_frame']} crops) through the reference's CPU calls"},
+        "e2e": {"value": round(fps, 3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -80,68 +80,129 @@ __device__ __forceinline__ void axis_entry(double s, int n, int &i0, int &i1, fl
     t = (float)(s - f);
 }
 
-__global__ void __launch_bounds__(256) crop_affine_kernel(const CropParams prm) {
-    extern __shared__ __align__(16) unsigned char crop_smem[];
+constexpr int kCropThreads = 256;
+constexpr int kStageBytes = 40 * 1024;   // source band buffer per CTA -> 4 CTAs (1024 threads) per SM
+
+// One CTA per (crop, channel).
+//   * coordinate tables (fp64 -> index + fp32 weight) for the out_w columns and out_h rows in smem;
+//   * the valid output rows are processed in bands; for each band the needed source rows, restricted to
+//     the needed (16 B aligned) column range, are copied into shared memory by bulk-TMA row copies
+//     (cp.async.bulk, issued by warp 0, all completing on one mbarrier) — coalesced full-line HBM reads
+//     instead of four scattered 4-byte gathers per output pixel;
+//   * thread = output column: 4 shared-memory reads, 3 FMA (bilinear) + 1 FMA ((v - mean)/std) and one
+//     coalesced 4-byte streaming store per pixel.
+// `staged == 0` (frame width not a multiple of 4, unaligned base, or a band that cannot fit): the same
+// loop gathers straight from global memory.
+__global__ void __launch_bounds__(kCropThreads) crop_affine_kernel(const CropParams prm, int staged) {
+    extern __shared__ __align__(128) unsigned char crop_smem[];
     const int ow = prm.ow, oh = prm.oh;
-    int *x0 = reinterpret_cast<int *>(crop_smem);
+    float *buf = reinterpret_cast<float *>(crop_smem);                       // [kStageBytes]
+    int *x0 = reinterpret_cast<int *>(crop_smem + kStageBytes);
     int *x1 = x0 + ow;
     float *tx = reinterpret_cast<float *>(x1 + ow);
     int *y0 = reinterpret_cast<int *>(tx + ow);
     int *y1 = y0 + oh;
     float *ty = reinterpret_cast<float *>(y1 + oh);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(reinterpret_cast<uintptr_t>(ty + oh + 1) & ~(uintptr_t)7);
+    __shared__ int s_v[4];   // first/last valid column, first/last valid row
 
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int p = blockIdx.x, c = blockIdx.y;
     const float4 box = __ldg(reinterpret_cast<const float4 *>(prm.boxes) + p);
     const AxisMap m = crop_axis_map(box, ow, oh, prm.variant);
-    for (int i = threadIdx.x; i < ow + oh; i += blockDim.x) {
-        if (i < ow) axis_entry(m.ax * (double)i + m.bx, prm.fw, x0[i], x1[i], tx[i]);
-        else axis_entry(m.ay * (double)(i - ow) + m.by, prm.fh, y0[i - ow], y1[i - ow], ty[i - ow]);
+    if (tid == 0) {
+        s_v[0] = ow; s_v[1] = -1; s_v[2] = oh; s_v[3] = -1;
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        fence_proxy_async();
     }
     __syncthreads();
+    for (int i = tid; i < ow + oh; i += kCropThreads) {
+        if (i < ow) {
+            axis_entry(m.ax * (double)i + m.bx, prm.fw, x0[i], x1[i], tx[i]);
+            if (x0[i] >= 0) { atomicMin(&s_v[0], i); atomicMax(&s_v[1], i); }
+        } else {
+            const int y = i - ow;
+            axis_entry(m.ay * (double)y + m.by, prm.fh, y0[y], y1[y], ty[y]);
+            if (y0[y] >= 0) { atomicMin(&s_v[2], y); atomicMax(&s_v[3], y); }
+        }
+    }
+    __syncthreads();
+    const int vx0 = s_v[0], vx1 = s_v[1], vy0 = s_v[2], vy1 = s_v[3];
 
     int f = __ldg(prm.frame_idx + p);
     f = f < 0 ? 0 : (f >= prm.num_frames ? prm.num_frames - 1 : f);
     const float *src = prm.frames + ((size_t)f * 3 + c) * prm.fh * prm.fw;
     float *dst = prm.out + ((size_t)p * 3 + c) * oh * ow;
-    const float mean = prm.mean[c], sd = prm.stdv[c];
-    const float zero_out = __fdiv_rn(__fsub_rn(0.f, mean), sd);
+    const float mean = c == 0 ? prm.mean[0] : (c == 1 ? prm.mean[1] : prm.mean[2]);     // constant-bank selects
+    const float inv_sd = 1.0f / (c == 0 ? prm.stdv[0] : (c == 1 ? prm.stdv[1] : prm.stdv[2]));
+    const float nmean = -mean * inv_sd;              // out = v * inv_sd + nmean
+    const float zero_out = nmean;
 
-    const int ow4 = ow >> 2;
-    const int rows_per_pass = blockDim.x / ow4;
-    const int xq = threadIdx.x % ow4, yr = threadIdx.x / ow4;
-    if (yr >= rows_per_pass) return;
-    int ix0[4], ix1[4];
-    float wx[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        ix0[k] = x0[xq * 4 + k];
-        ix1[k] = x1[xq * 4 + k];
-        wx[k] = tx[xq * 4 + k];
+    const bool any = vx1 >= vx0 && vy1 >= vy0;
+    // rows with no valid source: constant
+    for (int y = warp; y < oh; y += kCropThreads / 32) {
+        if (any && y >= vy0 && y <= vy1) continue;
+        for (int x = lane; x < ow; x += 32) __stcs(dst + (size_t)y * ow + x, zero_out);
     }
-    for (int y = yr; y < oh; y += rows_per_pass) {
-        const int iy0 = y0[y], iy1 = y1[y];
-        const float wy = ty[y];
-        float o[4];
-        if (iy0 < 0) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) o[k] = zero_out;
-        } else {
-            const float *r0 = src + (size_t)iy0 * prm.fw, *r1 = src + (size_t)iy1 * prm.fw;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (ix0[k] < 0) {
-                    o[k] = zero_out;
+    if (!any) return;
+
+    // source column window, 16-byte aligned
+    const int cx0 = x0[vx0] & ~3;
+    int cx1 = (x1[vx1] + 4) & ~3;                    // exclusive
+    if (cx1 > prm.fw) cx1 = prm.fw;
+    const int row_elems = cx1 - cx0;
+    const int rows_cap = kStageBytes / (row_elems * 4);
+    const bool use_stage = staged && rows_cap >= 3;
+    int band = oh;
+    if (use_stage) {
+        const double per = m.ay > 0.0 ? m.ay : 1.0;
+        double br = floor((double)(rows_cap - 3) / per) + 1.0;
+        band = br > (double)oh ? oh : (int)br;
+        if (band < 1) band = 1;
+    }
+
+    uint32_t parity = 0;
+    for (int r0 = vy0; r0 <= vy1; r0 += band) {
+        const int r1 = (r0 + band - 1) < vy1 ? (r0 + band - 1) : vy1;
+        const int sy_lo = y0[r0], sy_hi = y1[r1];
+        if (use_stage) {
+            const int nrows = sy_hi - sy_lo + 1;
+            if (warp == 0) {
+                if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(nrows * row_elems * 4));
+                for (int r = lane; r < nrows; r += 32)
+                    bulk_g2s(buf + (size_t)r * row_elems, src + (size_t)(sy_lo + r) * prm.fw + cx0, (uint32_t)(row_elems * 4), bar);
+            }
+            mbar_wait(bar, parity);
+            parity ^= 1;
+        }
+        for (int x = tid; x < ow; x += kCropThreads) {
+            const int ix0 = x0[x], ix1 = x1[x];
+            const float wx = tx[x];
+            if (ix0 < 0) {
+                for (int y = r0; y <= r1; ++y) __stcs(dst + (size_t)y * ow + x, zero_out);
+                continue;
+            }
+#pragma unroll 4
+            for (int y = r0; y <= r1; ++y) {
+                const int iy0 = y0[y], iy1 = y1[y];
+                const float wy = ty[y];
+                float p00, p01, p10, p11;
+                if (use_stage) {
+                    const float *ra = buf + (size_t)(iy0 - sy_lo) * row_elems - cx0;
+                    const float *rb = buf + (size_t)(iy1 - sy_lo) * row_elems - cx0;
+                    p00 = ra[ix0]; p01 = ra[ix1]; p10 = rb[ix0]; p11 = rb[ix1];
                 } else {
-                    const float p00 = __ldg(r0 + ix0[k]), p01 = __ldg(r0 + ix1[k]);
-                    const float p10 = __ldg(r1 + ix0[k]), p11 = __ldg(r1 + ix1[k]);
-                    const float top = fmaf(p01 - p00, wx[k], p00);
-                    const float bot = fmaf(p11 - p10, wx[k], p10);
-                    const float v = fmaf(bot - top, wy, top);
-                    o[k] = __fdiv_rn(__fsub_rn(v, mean), sd);
+                    const float *ra = src + (size_t)iy0 * prm.fw, *rb = src + (size_t)iy1 * prm.fw;
+                    p00 = __ldg(ra + ix0); p01 = __ldg(ra + ix1); p10 = __ldg(rb + ix0); p11 = __ldg(rb + ix1);
                 }
+                const float top = fmaf(p01 - p00, wx, p00);
+                const float bot = fmaf(p11 - p10, wx, p10);
+                const float v = fmaf(bot - top, wy, top);
+                __stcs(dst + (size_t)y * ow + x, fmaf(v, inv_sd, nmean));
             }
         }
-        __stcs(reinterpret_cast<float4 *>(dst + (size_t)y * ow) + xq, make_float4(o[0], o[1], o[2], o[3]));
+        if (use_stage) __syncthreads();              // the band buffer is refilled next
     }
 }
 
@@ -154,23 +215,25 @@ extern "C" int spp_crop_affine(const float *frames, int num_frames, int frame_h,
     using namespace spp;
     SPP_CHECK_ARG(frames && boxes && frame_idx && out && mean && std, "crop_affine: null pointer");
     SPP_CHECK_ARG(num_frames > 0 && frame_h > 0 && frame_w > 0 && p >= 0, "crop_affine: bad frame shape");
-    SPP_CHECK_ARG(out_h > 0 && out_w > 0 && out_w % 4 == 0 && out_w <= 1024, "crop_affine: out_w must be a multiple of 4, <= 1024");
+    SPP_CHECK_ARG(out_h > 0 && out_w > 0 && out_w <= 2048 && out_h <= 2048, "crop_affine: output size must be within 2048 x 2048");
     SPP_CHECK_ARG(variant == SPP_CROP_HF_UDP || variant == SPP_CROP_GLUONCV, "crop_affine: unknown variant %d", variant);
-    SPP_CHECK_ARG((reinterpret_cast<uintptr_t>(boxes) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
-                  "crop_affine: boxes and out must be 16-byte aligned");
-    SPP_CHECK_ARG(p <= 2147483647 / 1 && 3 <= 65535, "crop_affine: too many crops");
+    SPP_CHECK_ARG((reinterpret_cast<uintptr_t>(boxes) & 15) == 0, "crop_affine: boxes must be 16-byte aligned");
     if (p == 0) return SPP_OK;
     CropParams prm{};
     prm.frames = frames; prm.boxes = boxes; prm.frame_idx = frame_idx; prm.out = out;
     prm.num_frames = num_frames; prm.fh = frame_h; prm.fw = frame_w; prm.P = p; prm.oh = out_h; prm.ow = out_w;
     prm.variant = variant;
     for (int c = 0; c < 3; ++c) { prm.mean[c] = mean[c]; prm.stdv[c] = std[c]; }
-    const int ow4 = out_w / 4;
-    int threads = ow4 * (256 / ow4 > 0 ? 256 / ow4 : 1);
-    if (threads < 32) threads = 32;
-    const size_t smem = (size_t)(out_w + out_h) * 12;
+    const int staged = (frame_w % 4 == 0) && ((reinterpret_cast<uintptr_t>(frames) & 15) == 0);
+    const size_t smem = (size_t)kStageBytes + (size_t)(out_w + out_h) * 12 + 32;
+    static bool configured = false;
+    if (!configured) {
+        SPP_CHECK_CUDA(cudaFuncSetAttribute(crop_affine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        configured = true;
+    }
+    SPP_CHECK_ARG(smem <= 100 * 1024, "crop_affine: output size too large");
     dim3 grid(p, 3);
-    crop_affine_kernel<<<grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(prm);
+    crop_affine_kernel<<<grid, kCropThreads, smem, static_cast<cudaStream_t>(stream)>>>(prm, staged);
     SPP_CHECK_LAUNCH();
     return SPP_OK;
 }

@@ -31,8 +31,10 @@ namespace spp {
 namespace {
 
 constexpr int kDfl = 16;
-constexpr int kNmsThreads = 256;
+constexpr int kNmsThreads = 512;
 constexpr int kSortSmemMax = 8192;  // keys sorted in shared memory up to this (padded) count
+constexpr int kBoxSmemMax = 2048;   // sorted boxes kept in shared memory (the rest is re-gathered)
+constexpr int kAliveWords = 1024;   // one alive bit per candidate: max_nms <= 32768
 
 struct Levels {
     const float *ptr[SPP_MAX_LEVELS];
@@ -41,12 +43,19 @@ struct Levels {
     int n, A;
 };
 
-__device__ __forceinline__ int find_level(const Levels &lv, int a) {
-    int l = 0;
+// Resolved pyramid level of one anchor.  Selected with compile-time indices only, so the by-value
+// kernel parameter stays in the constant bank (dynamic indexing would copy it to local memory per thread).
+struct LevelRef {
+    const float *ptr;
+    int w, hw, i;
+    float stride;
+};
+__device__ __forceinline__ LevelRef find_level(const Levels &lv, int a) {
+    LevelRef r{lv.ptr[0], lv.w[0], lv.h[0] * lv.w[0], a, lv.stride[0]};
 #pragma unroll
     for (int i = 1; i < SPP_MAX_LEVELS; ++i)
-        if (i < lv.n && a >= lv.off[i]) l = i;
-    return l;
+        if (i < lv.n && a >= lv.off[i]) r = LevelRef{lv.ptr[i], lv.w[i], lv.h[i] * lv.w[i], a - lv.off[i], lv.stride[i]};
+    return r;
 }
 
 __device__ __forceinline__ float sigmoidf_ref(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
@@ -99,13 +108,12 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const Levels lv, int n
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     if (a >= lv.A) return;
-    const int l = find_level(lv, a);
-    const int i = a - lv.off[l];
-    const int w = lv.w[l], hw = lv.h[l] * w;
+    const LevelRef lr = find_level(lv, a);
+    const int i = lr.i, w = lr.w, hw = lr.hw;
     const int y = i / w, x = i - y * w;
     const int no = 4 * kDfl + nc;
-    const float *base = lv.ptr[l] + (size_t)b * no * hw + i;
-    const float4 box = decode_box(base, hw, (float)x + 0.5f, (float)y + 0.5f, lv.stride[l]);
+    const float *base = lr.ptr + (size_t)b * no * hw + i;
+    const float4 box = decode_box(base, hw, (float)x + 0.5f, (float)y + 0.5f, lr.stride);
     float *o = out + (size_t)b * (4 + nc) * lv.A + a;
     o[0] = box.x;
     o[(size_t)lv.A] = box.y;
@@ -155,11 +163,10 @@ __global__ void __launch_bounds__(256) cand_raw_kernel(const Levels lv, int nc, 
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     const bool in = a < lv.A;
-    const int l = find_level(lv, in ? a : 0);
-    const int i = (in ? a : 0) - lv.off[l];
-    const int w = lv.w[l], hw = lv.h[l] * w;
+    const LevelRef lr = find_level(lv, in ? a : 0);
+    const int i = lr.i, w = lr.w, hw = lr.hw;
     const int no = 4 * kDfl + nc;
-    const float *base = lv.ptr[l] + (size_t)b * no * hw + i;
+    const float *base = lr.ptr + (size_t)b * no * hw + i;
     unsigned long long *k = keys + (size_t)b * cap_pad;
     bool any = false;
     for (int j = 0; j < nc; ++j) {
@@ -174,7 +181,7 @@ __global__ void __launch_bounds__(256) cand_raw_kernel(const Levels lv, int nc, 
     }
     if (any) {
         const int y = i / w, x = i - y * w;
-        boxes[(size_t)b * lv.A + a] = wh2xy(decode_box(base, hw, (float)x + 0.5f, (float)y + 0.5f, lv.stride[l]));
+        boxes[(size_t)b * lv.A + a] = wh2xy(decode_box(base, hw, (float)x + 0.5f, (float)y + 0.5f, lr.stride));
     }
 }
 
@@ -216,6 +223,14 @@ __device__ void bitonic_sort(unsigned long long *d, int npad) {
     }
 }
 
+// One CTA per image.
+//   1. bitonic sort of the 64-bit keys (shared memory up to kSortSmemMax keys, else in the workspace);
+//   2. sorted, class-offset boxes + areas are staged in shared memory (first kBoxSmemMax; beyond that they
+//      are re-gathered on the fly), one "alive" bit per candidate;
+//   3. greedy loop, serial over KEPT boxes only: warp 0 finds the first alive candidate at or after the
+//      cursor; every warp then clears, with one ballot per 32-candidate word it owns, the later
+//      candidates whose IoU with that box exceeds the threshold.  Two block barriers per kept box,
+//      n/32/16 ballots per warp per kept box; stops after max_det.
 template <bool RAW>
 __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams prm) {
     extern __shared__ __align__(16) unsigned char nms_smem[];
@@ -223,11 +238,12 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams prm) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kNmsThreads / 32;
 
-    float4 *kbox = reinterpret_cast<float4 *>(nms_smem);                    // [max_det] kept boxes (class-offset)
-    float *karea = reinterpret_cast<float *>(kbox + prm.max_det);           // [max_det]
-    unsigned long long *skeys = reinterpret_cast<unsigned long long *>(
-        nms_smem + align_up((size_t)prm.max_det * 20, 16));                 // [<= kSortSmemMax]
-    __shared__ int s_nk;
+    unsigned long long *skeys = reinterpret_cast<unsigned long long *>(nms_smem);             // [kSortSmemMax]
+    float4 *sbox = reinterpret_cast<float4 *>(skeys + kSortSmemMax);                           // [kBoxSmemMax]
+    float *sarea = reinterpret_cast<float *>(sbox + kBoxSmemMax);                              // [kBoxSmemMax]
+    unsigned *alive = reinterpret_cast<unsigned *>(sarea + kBoxSmemMax);                       // [kAliveWords]
+    int *kept_idx = reinterpret_cast<int *>(alive + kAliveWords);                              // [max_det]
+    __shared__ int s_next;
 
     const int raw_count = prm.counts[b];
     int n = raw_count < prm.cap ? raw_count : prm.cap;
@@ -241,95 +257,118 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams prm) {
     } else {
         for (int i = n + tid; i < npad; i += kNmsThreads) gkeys[i] = ~0ull;
     }
-    if (tid == 0) s_nk = 0;
     __syncthreads();
     bitonic_sort(keys, npad);
     if (n > prm.max_nms) n = prm.max_nms;                                   // util.py:157 [:max_nms]
 
-    float *dets = prm.out_dets + (size_t)b * prm.max_det * 6;
-    int *okeys = prm.out_keys ? prm.out_keys + (size_t)b * prm.max_det : nullptr;
+    // class-offset box (util.py:160-161) and its area for sorted candidate j
+    auto load_box = [&](int j, float4 &obox, float &area) {
+        const unsigned cand = (unsigned)(keys[j] & 0xffffffffu);
+        const int anchor = cand / prm.nc, cls = cand - anchor * prm.nc;
+        float4 box;
+        if (RAW) {
+            box = prm.boxes[(size_t)b * prm.A + anchor];
+        } else {
+            const float *pb = prm.pred + (size_t)b * (4 + prm.nc) * prm.A + anchor;
+            box = wh2xy(make_float4(__ldg(pb), __ldg(pb + prm.A), __ldg(pb + 2 * (size_t)prm.A), __ldg(pb + 3 * (size_t)prm.A)));
+        }
+        const float off = __fmul_rn((float)cls, prm.max_wh);
+        obox = make_float4(__fadd_rn(box.x, off), __fadd_rn(box.y, off), __fadd_rn(box.z, off), __fadd_rn(box.w, off));
+        area = __fmul_rn(__fsub_rn(obox.z, obox.x), __fsub_rn(obox.w, obox.y));
+    };
+    auto get_box = [&](int j, float4 &obox, float &area) {
+        if (j < kBoxSmemMax) {
+            obox = sbox[j];
+            area = sarea[j];
+        } else {
+            load_box(j, obox, area);
+        }
+    };
+
+    const int nwords = (n + 31) >> 5;
+    for (int j = tid; j < n && j < kBoxSmemMax; j += kNmsThreads) {
+        float4 ob;
+        float ar;
+        load_box(j, ob, ar);
+        sbox[j] = ob;
+        sarea[j] = ar;
+    }
+    for (int w = tid; w < nwords; w += kNmsThreads) alive[w] = (w * 32 + 32 <= n) ? 0xffffffffu : ((1u << (n - w * 32)) - 1u);
+    __syncthreads();
+
     const float thr = prm.iou;
     const int max_det = prm.max_det;
+    int nk = 0, cursor = 0;
+    while (nk < max_det) {
+        if (warp == 0) {
+            int found = -1;
+            for (int w0 = cursor >> 5; w0 < nwords && found < 0; w0 += 32) {
+                const int wi = w0 + lane;
+                unsigned word = wi < nwords ? alive[wi] : 0u;
+                if (wi == (cursor >> 5)) word &= ~((1u << (cursor & 31)) - 1u);
+                const unsigned bal = __ballot_sync(FULL, word != 0u);
+                if (bal) {
+                    const int src = __ffs(bal) - 1;
+                    const unsigned wsel = __shfl_sync(FULL, word, src);
+                    found = (w0 + src) * 32 + __ffs(wsel) - 1;
+                }
+            }
+            if (lane == 0) {
+                s_next = found;
+                if (found >= 0) kept_idx[nk] = found;
+            }
+        }
+        __syncthreads();
+        const int i = s_next;
+        if (i < 0) break;
+        ++nk;
+        if (nk >= max_det) break;
+        float4 bi;
+        float ai;
+        get_box(i, bi, ai);
+        for (int wi = (i >> 5) + warp; wi < nwords; wi += NW) {
+            const unsigned word = alive[wi];
+            const int j = wi * 32 + lane;
+            bool sup = false;
+            if (((word >> lane) & 1u) && j > i) {
+                float4 bj;
+                float aj;
+                get_box(j, bj, aj);
+                sup = iou_gt(bi, ai, bj, aj, thr);
+            }
+            const unsigned sm = __ballot_sync(FULL, sup);
+            if (lane == 0 && sm) alive[wi] = word & ~sm;
+        }
+        cursor = i + 1;
+        __syncthreads();
+    }
+    __syncthreads();
 
-    int nk = 0;
-    for (int base = 0; base < n && nk < max_det; base += kNmsThreads) {
-        const int j = base + tid;
-        bool alive = j < n;
-        float4 box = make_float4(0.f, 0.f, 0.f, 0.f), obox = box;
-        float area = 0.f, score = 0.f, clsf = 0.f;
-        unsigned cand = 0;
-        if (alive) {
-            const unsigned long long key = keys[j];
-            cand = (unsigned)(key & 0xffffffffu);
-            score = __uint_as_float(~(unsigned)(key >> 32));
+    // emit the kept rows (un-offset box, score, class) in parallel
+    float *dets = prm.out_dets + (size_t)b * max_det * 6;
+    int *okeys = prm.out_keys ? prm.out_keys + (size_t)b * max_det : nullptr;
+    for (int r = tid; r < max_det; r += kNmsThreads) {
+        float *row = dets + (size_t)r * 6;
+        if (r < nk) {
+            const unsigned long long key = keys[kept_idx[r]];
+            const unsigned cand = (unsigned)(key & 0xffffffffu);
+            const float score = __uint_as_float(~(unsigned)(key >> 32));
             const int anchor = cand / prm.nc, cls = cand - anchor * prm.nc;
-            clsf = (float)cls;
+            float4 box;
             if (RAW) {
                 box = prm.boxes[(size_t)b * prm.A + anchor];
             } else {
                 const float *pb = prm.pred + (size_t)b * (4 + prm.nc) * prm.A + anchor;
                 box = wh2xy(make_float4(__ldg(pb), __ldg(pb + prm.A), __ldg(pb + 2 * (size_t)prm.A), __ldg(pb + 3 * (size_t)prm.A)));
             }
-            const float off = __fmul_rn(clsf, prm.max_wh);                   // util.py:160
-            obox = make_float4(__fadd_rn(box.x, off), __fadd_rn(box.y, off), __fadd_rn(box.z, off), __fadd_rn(box.w, off));
-            area = __fmul_rn(__fsub_rn(obox.z, obox.x), __fsub_rn(obox.w, obox.y));
+            row[0] = box.x; row[1] = box.y; row[2] = box.z; row[3] = box.w; row[4] = score; row[5] = (float)cls;
+            if (okeys) okeys[r] = (int)cand;
+        } else {
+            row[0] = row[1] = row[2] = row[3] = row[4] = row[5] = 0.f;
+            if (okeys) okeys[r] = -1;
         }
-        // phase A: against everything kept before this super-chunk
-        int checked = 0;
-        for (; checked < nk && alive; ++checked)
-            if (iou_gt(kbox[checked], karea[checked], obox, area, thr)) alive = false;
-        // phase B: warps take turns in score order; each first catches up with boxes kept by the
-        // warps before it, then resolves its own 32 boxes with ballots.
-        for (int w = 0; w < NW; ++w) {
-            __syncthreads();
-            if (warp == w) {
-                const int nkc = s_nk;
-                if (alive) {
-                    for (int i = (checked < nk ? nk : checked); i < nkc && i < max_det && alive; ++i)
-                        if (iou_gt(kbox[i], karea[i], obox, area, thr)) alive = false;
-                }
-                if (nkc >= max_det) alive = false;
-                unsigned am = __ballot_sync(FULL, alive);
-                unsigned keepm = 0;
-                while (am) {
-                    const int i = __ffs(am) - 1;
-                    am &= am - 1;
-                    keepm |= 1u << i;
-                    float4 bi;
-                    bi.x = __shfl_sync(FULL, obox.x, i);
-                    bi.y = __shfl_sync(FULL, obox.y, i);
-                    bi.z = __shfl_sync(FULL, obox.z, i);
-                    bi.w = __shfl_sync(FULL, obox.w, i);
-                    const float ai = __shfl_sync(FULL, area, i);
-                    const bool sup = alive && lane > i && iou_gt(bi, ai, obox, area, thr);
-                    const unsigned sm = __ballot_sync(FULL, sup);
-                    if (sup) alive = false;
-                    am &= ~sm;
-                }
-                const bool kept = (keepm >> lane) & 1u;
-                const int pos = nkc + __popc(keepm & ((1u << lane) - 1u));
-                if (kept && pos < max_det) {
-                    kbox[pos] = obox;
-                    karea[pos] = area;
-                    float *r = dets + (size_t)pos * 6;
-                    r[0] = box.x; r[1] = box.y; r[2] = box.z; r[3] = box.w; r[4] = score; r[5] = clsf;
-                    if (okeys) okeys[pos] = (int)cand;
-                }
-                if (lane == 0) {
-                    const int t = nkc + __popc(keepm);
-                    s_nk = t < max_det ? t : max_det;
-                }
-            }
-        }
-        __syncthreads();
-        nk = s_nk;
     }
-    __syncthreads();
-    nk = s_nk;
     if (tid == 0) prm.out_count[b] = raw_count > prm.cap ? -nk : nk;
-    for (int i = nk * 6 + tid; i < max_det * 6; i += kNmsThreads) dets[i] = 0.f;
-    if (okeys)
-        for (int i = nk + tid; i < max_det; i += kNmsThreads) okeys[i] = -1;
 }
 
 int fill_levels(Levels &lv, const float *const *levels, const int *level_h, const int *level_w, const float *strides,
@@ -381,7 +420,7 @@ Workspace carve(void *ws, int batch, int num_anchors, int nc, int max_candidates
 
 template <bool RAW>
 int launch_nms(const NmsParams &prm, int batch, cudaStream_t st) {
-    const size_t smem = align_up((size_t)prm.max_det * 20, 16) + (size_t)kSortSmemMax * 8;
+    const size_t smem = (size_t)kSortSmemMax * 8 + (size_t)kBoxSmemMax * 20 + (size_t)kAliveWords * 4 + (size_t)prm.max_det * 4;
     static bool configured = false;
     if (!configured) {
         SPP_CHECK_CUDA(cudaFuncSetAttribute(nms_kernel<RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -396,7 +435,8 @@ int launch_nms(const NmsParams &prm, int batch, cudaStream_t st) {
 int check_nms_args(int batch, int nc, float iou, int max_det, int max_nms, const float *out_dets, const int *out_count,
                    const void *ws) {
     SPP_CHECK_ARG(batch >= 0 && nc >= 1, "nms: bad batch %d / nc %d", batch, nc);
-    SPP_CHECK_ARG(max_det >= 1 && max_det <= 4096 && max_nms >= 1, "nms: bad max_det %d / max_nms %d", max_det, max_nms);
+    SPP_CHECK_ARG(max_det >= 1 && max_det <= 4096 && max_nms >= 1 && max_nms <= kAliveWords * 32,
+                  "nms: need 1 <= max_det <= 4096 and 1 <= max_nms <= %d (got %d / %d)", kAliveWords * 32, max_det, max_nms);
     SPP_CHECK_ARG(out_dets && out_count && ws, "nms: null output / workspace");
     (void)iou;
     return SPP_OK;

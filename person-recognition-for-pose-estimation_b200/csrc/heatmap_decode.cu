@@ -44,16 +44,15 @@ struct DecodeParams {
     int P, K, H, W;
     int mode, flags, radius, crop_h, crop_w;
     int warps, stages;
+    unsigned w4_magic;
     double gw[kMaxRadius + 1];  // Gaussian weights, gw[0] = centre (scipy _gaussian_kernel1d, normalised)
 };
 
+// scipy 'reflect' (d c b a | a b c d | d c b a) for -n <= i < 2n (the host checks radius + 1 <= n)
 __device__ __forceinline__ int reflect_idx(int i, int n) {
-    // scipy 'reflect': (d c b a | a b c d | d c b a)
-    if (n == 1) return 0;
-    const int period = 2 * n;
-    i %= period;
-    if (i < 0) i += period;
-    return i < n ? i : period - 1 - i;
+    if (i < 0) i = -i - 1;
+    if (i >= n) i = 2 * n - 1 - i;
+    return i;
 }
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
@@ -70,15 +69,30 @@ struct MapView {
     }
 };
 
-// scipy.ndimage.correlate1d, symmetric-kernel branch: centre first, then pairs from the far end in.
-template <typename F>
+// scipy.ndimage.correlate1d, symmetric-kernel branch: centre tap first, then the pairs from the far
+// end inwards, accumulated in fp64 without contraction.  R > 0: compile-time radius (all taps are
+// loaded before the dependent fp64 chain starts); R == 0: run-time radius.
+template <int R, typename F>
 __device__ __forceinline__ double sym_filter(F sample, const double *gw, int radius) {
-    double acc = __dmul_rn((double)sample(0), gw[0]);
-    for (int jj = radius; jj >= 1; --jj) {
-        double pair = __dadd_rn((double)sample(-jj), (double)sample(jj));
-        acc = __dadd_rn(acc, __dmul_rn(pair, gw[jj]));
+    if constexpr (R > 0) {
+        float lo[R > 0 ? R : 1], hi[R > 0 ? R : 1];
+        const float c = sample(0);
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            lo[j] = sample(-(j + 1));
+            hi[j] = sample(j + 1);
+        }
+        double acc = __dmul_rn((double)c, gw[0]);
+#pragma unroll
+        for (int j = R - 1; j >= 0; --j)
+            acc = __dadd_rn(acc, __dmul_rn(__dadd_rn((double)lo[j], (double)hi[j]), gw[j + 1]));
+        return acc;
+    } else {
+        double acc = __dmul_rn((double)sample(0), gw[0]);
+        for (int jj = radius; jj >= 1; --jj)
+            acc = __dadd_rn(acc, __dmul_rn(__dadd_rn((double)sample(-jj), (double)sample(jj)), gw[jj]));
+        return acc;
     }
-    return acc;
 }
 
 __device__ __forceinline__ float clip_log(float v) {
@@ -94,15 +108,24 @@ __device__ float warp_blurred_log_single(const MapView<FLIP> &mv, int H, int y, 
     __syncwarp();
     if (lane < n) {
         const int xx = reflect_idx(x - radius + lane, mv.W);
-        double acc = sym_filter([&](int d) { return mv.at(reflect_idx(y + d, H), xx); }, gw, radius);
+        double acc = sym_filter<0>([&](int d) { return mv.at(reflect_idx(y + d, H), xx); }, gw, radius);
         scratch[lane] = (float)acc;
     }
     __syncwarp();
-    double acc = sym_filter([&](int d) { return scratch[radius + d]; }, gw, radius);
+    double acc = sym_filter<0>([&](int d) { return scratch[radius + d]; }, gw, radius);
     return clip_log((float)acc);
 }
 
-template <bool FLIP>
+// running "first maximum" of one lane-private chain
+struct Best {
+    float v;
+    int i;
+    __device__ __forceinline__ void take(float x, int idx) {
+        if (x > v) { v = x; i = idx; }
+    }
+};
+
+template <bool FLIP, int RADIUS>
 __global__ void __launch_bounds__(256, 1) heatmap_decode_kernel(const DecodeParams prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -149,7 +172,8 @@ __global__ void __launch_bounds__(256, 1) heatmap_decode_kernel(const DecodePara
 
     const int W4 = W >> 2;
     const int n4 = map_elems >> 2;
-    const int radius = prm.radius;
+    const unsigned magic = prm.w4_magic;  // (q * magic) >> 16 == q / W4 for q < n4 (checked on the host)
+    const int radius = RADIUS > 0 ? RADIUS : prm.radius;
     const double *gw = prm.gw;
 
     int it = 0;
@@ -163,30 +187,53 @@ __global__ void __launch_bounds__(256, 1) heatmap_decode_kernel(const DecodePara
         const float4 *A4 = reinterpret_cast<const float4 *>(A);
         const float4 *B4 = reinterpret_cast<const float4 *>(B);
 
-        // ---- pass 1: arg-max of the (flip-averaged) map ------------------------------------
-        float best = -INFINITY;
-        int bidx = 4 * lane;
-        {
-            int r = lane / W4, c4 = lane - r * W4;
-            for (int q4 = lane; q4 < n4; q4 += 32) {
-                float4 v = A4[q4];
-                if (FLIP) {
-                    const float4 m = B4[r * W4 + (W4 - 1 - c4)];
-                    v.x = (v.x + m.w) * 0.5f;
-                    v.y = (v.y + m.z) * 0.5f;
-                    v.z = (v.z + m.y) * 0.5f;
-                    v.w = (v.w + m.x) * 0.5f;
-                }
-                const int base = q4 << 2;
-                if (v.x > best) { best = v.x; bidx = base; }
-                if (v.y > best) { best = v.y; bidx = base + 1; }
-                if (v.z > best) { best = v.z; bidx = base + 2; }
-                if (v.w > best) { best = v.w; bidx = base + 3; }
-                c4 += 32;
-                while (c4 >= W4) { c4 -= W4; ++r; }
+        // one float4 of the (flip-averaged) map: element e of quad q4 is flat index 4*q4 + e
+        auto quad = [&](int q4) -> float4 {
+            float4 v = A4[q4];
+            if (FLIP) {
+                const int r = (int)(((unsigned)q4 * magic) >> 16);
+                const float4 m = B4[2 * r * W4 + W4 - 1 - q4];     // same row, mirrored quad, reversed lanes
+                v.x = (v.x + m.w) * 0.5f;
+                v.y = (v.y + m.z) * 0.5f;
+                v.z = (v.z + m.y) * 0.5f;
+                v.w = (v.w + m.x) * 0.5f;
+            }
+            return v;
+        };
+
+        // ---- pass 1: arg-max of the (flip-averaged) map; 4 independent chains per lane -------------
+        Best ch[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) ch[c] = Best{-INFINITY, INT_MAX};
+        int q4 = lane;
+        for (; q4 + 96 < n4; q4 += 128) {
+            float4 v[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[c] = quad(q4 + 32 * c);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int base = (q4 + 32 * c) << 2;
+                ch[c].take(v[c].x, base);
+                ch[c].take(v[c].y, base + 1);
+                ch[c].take(v[c].z, base + 2);
+                ch[c].take(v[c].w, base + 3);
             }
         }
+        for (; q4 < n4; q4 += 32) {
+            const float4 v = quad(q4);
+            const int base = q4 << 2;
+            ch[0].take(v.x, base);
+            ch[0].take(v.y, base + 1);
+            ch[0].take(v.z, base + 2);
+            ch[0].take(v.w, base + 3);
+        }
+        float best = ch[0].v;
+        int bidx = ch[0].i;
+#pragma unroll
+        for (int c = 1; c < 4; ++c)
+            if (ch[c].v > best || (ch[c].v == best && ch[c].i < bidx)) { best = ch[c].v; bidx = ch[c].i; }
         warp_argmax(best, bidx);
+        if (bidx == INT_MAX) bidx = 0;                  // nothing compared greater than -inf: np.argmax gives 0
         const int ax = bidx % W, ay = bidx / W;
         const long long p = q / K;
         MapView<FLIP> mv{A, B, W};
@@ -201,20 +248,25 @@ __global__ void __launch_bounds__(256, 1) heatmap_decode_kernel(const DecodePara
             if (valid) {
                 const int ncols = 2 * radius + 3;
                 __syncwarp();
-                for (int tt = lane; tt < 3 * ncols; tt += 32) {
-                    const int r3 = tt / ncols, j = tt - r3 * ncols;
-                    const int yy = clampi(ay + r3 - 1, 0, H - 1);           // np.pad(mode="edge") on the taps
-                    const int xx = reflect_idx(ax - (radius + 1) + j, W);   // scipy 'reflect' inside the blur
-                    double acc = sym_filter([&](int d) { return mv.at(reflect_idx(yy + d, H), xx); }, gw, radius);
-                    scratch[tt] = (float)acc;                               // fp32 intermediate between the axes
-                }
+                // vertical pass (scipy filters axis 0 first): T[r3][j] for the 3 tap rows x (2r+3) columns.
+                // Two outputs per lane, issued together.
+                const int t0 = lane, t1 = lane + 32;
+                const bool has1 = t1 < 3 * ncols;
+                const int r30 = t0 / ncols, j0 = t0 - r30 * ncols;
+                const int r31 = has1 ? t1 / ncols : 0, j1 = has1 ? t1 - r31 * ncols : 0;
+                const int yy0 = clampi(ay + r30 - 1, 0, H - 1), yy1 = clampi(ay + r31 - 1, 0, H - 1);   // np.pad(mode="edge")
+                const int xx0 = reflect_idx(ax - (radius + 1) + j0, W), xx1 = reflect_idx(ax - (radius + 1) + j1, W);
+                const double a0 = sym_filter<RADIUS>([&](int d) { return mv.at(reflect_idx(yy0 + d, H), xx0); }, gw, radius);
+                const double a1 = sym_filter<RADIUS>([&](int d) { return mv.at(reflect_idx(yy1 + d, H), xx1); }, gw, radius);
+                if (t0 < 3 * ncols) scratch[t0] = (float)a0;    // fp32 intermediate between the axes
+                if (has1) scratch[t1] = (float)a1;
                 __syncwarp();
                 float Lv = 0.f;
                 if (lane < 9) {
                     const int r3 = lane / 3, c3 = lane - r3 * 3;
                     const int xc = clampi(ax + c3 - 1, 0, W - 1);
                     const float *row = scratch + r3 * ncols + (xc - ax) + radius + 1;
-                    double acc = sym_filter([&](int d) { return row[d]; }, gw, radius);
+                    const double acc = sym_filter<RADIUS>([&](int d) { return row[d]; }, gw, radius);
                     Lv = clip_log((float)acc);
                 }
                 L00 = __shfl_sync(FULL, Lv, 0);
@@ -282,24 +334,16 @@ __global__ void __launch_bounds__(256, 1) heatmap_decode_kernel(const DecodePara
         } else if (prm.mode == SPP_DECODE_SOFTARGMAX) {
             // softmax over the flattened map (max-subtracted), expected column / row, max probability
             float se = 0.f, sxe = 0.f, sye = 0.f;
-            int r = lane / W4, c4 = lane - r * W4;
             for (int q4 = lane; q4 < n4; q4 += 32) {
-                float4 v = A4[q4];
-                if (FLIP) {
-                    const float4 m = B4[r * W4 + (W4 - 1 - c4)];
-                    v.x = (v.x + m.w) * 0.5f;
-                    v.y = (v.y + m.z) * 0.5f;
-                    v.z = (v.z + m.y) * 0.5f;
-                    v.w = (v.w + m.x) * 0.5f;
-                }
+                const float4 v = quad(q4);
+                const int r = (int)(((unsigned)q4 * magic) >> 16);
+                const int c4 = q4 - r * W4;
                 const float e0 = expf(v.x - best), e1 = expf(v.y - best), e2 = expf(v.z - best), e3 = expf(v.w - best);
                 const float c0 = (float)(c4 << 2);
                 const float es = (e0 + e1) + (e2 + e3);
                 se += es;
                 sxe += e0 * c0 + e1 * (c0 + 1.f) + e2 * (c0 + 2.f) + e3 * (c0 + 3.f);
                 sye += es * (float)r;
-                c4 += 32;
-                while (c4 >= W4) { c4 -= W4; ++r; }
             }
             se = warp_sum(se);
             sxe = warp_sum(sxe);
@@ -360,6 +404,18 @@ __global__ void __launch_bounds__(256, 1) heatmap_decode_kernel(const DecodePara
     }
 }
 
+template <bool FLIP, int RADIUS>
+int launch_decode(const DecodeParams &prm, unsigned grid, size_t smem, cudaStream_t st) {
+    static size_t configured = 0;
+    if (configured < smem) {
+        SPP_CHECK_CUDA(cudaFuncSetAttribute(heatmap_decode_kernel<FLIP, RADIUS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    heatmap_decode_kernel<FLIP, RADIUS><<<grid, prm.warps * 32, smem, st>>>(prm);
+    SPP_CHECK_LAUNCH();
+    return SPP_OK;
+}
+
 }  // namespace
 
 }  // namespace spp
@@ -394,16 +450,26 @@ extern "C" int spp_heatmap_decode(const float *hm, const float *hm_flipped, cons
         for (int x = 0; x <= prm.radius; ++x) prm.gw[x] = phi[x] / sum;
     }
 
+    SPP_CHECK_ARG(h >= prm.radius + 2 && w >= prm.radius + 2, "heatmap_decode: map %dx%d too small for kernel %d", h, w, kernel);
     const bool flip = hm_flipped != nullptr;
     const size_t stage_bytes = (size_t)(flip ? 2 : 1) * h * w * 4;
     const size_t budget = 200 * 1024;
     const int slots = (int)(budget / stage_bytes);
-    SPP_CHECK_ARG(slots >= 2, "heatmap_decode: a %dx%d map does not fit the shared-memory pipeline", h, w);
-    int warps = slots / 2;
-    if (warps > 8) warps = 8;
+    SPP_CHECK_ARG(slots >= 1, "heatmap_decode: a %dx%d map does not fit the shared-memory pipeline", h, w);
+    // 8 warps per SM hide the ALU latency of the scan; whatever shared memory is left deepens each
+    // warp's private ring (flip test, 64x48: 8 warps x 1 stage x 24 KB; no flip: 8 x 2 x 12 KB).
+    int warps = slots < 8 ? slots : 8;
     int stages = slots / warps;
     if (stages > 4) stages = 4;
     prm.warps = warps; prm.stages = stages;
+    {   // q / W4 by multiply-shift, verified for every quad index of a map
+        const unsigned w4 = (unsigned)(w / 4), n4 = (unsigned)(h * w / 4);
+        unsigned magic = (65536u + w4 - 1) / w4;
+        bool ok = n4 < 65536u;
+        for (unsigned q = 0; ok && q < n4; ++q) ok = ((q * magic) >> 16) == q / w4;
+        SPP_CHECK_ARG(ok, "heatmap_decode: unsupported map shape %dx%d", h, w);
+        prm.w4_magic = magic;
+    }
     const size_t smem = (size_t)warps * stages * stage_bytes + (size_t)warps * stages * 8 + (size_t)warps * kScratch * 4;
 
     const long long total = (long long)p * k;
@@ -413,13 +479,7 @@ extern "C" int spp_heatmap_decode(const float *hm, const float *hm_flipped, cons
     if (grid > sms) grid = sms;
 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (flip) {
-        SPP_CHECK_CUDA(cudaFuncSetAttribute(heatmap_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        heatmap_decode_kernel<true><<<(unsigned)grid, warps * 32, smem, st>>>(prm);
-    } else {
-        SPP_CHECK_CUDA(cudaFuncSetAttribute(heatmap_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        heatmap_decode_kernel<false><<<(unsigned)grid, warps * 32, smem, st>>>(prm);
-    }
-    SPP_CHECK_LAUNCH();
-    return SPP_OK;
+    if (flip) return prm.radius == 5 ? launch_decode<true, 5>(prm, (unsigned)grid, smem, st) : launch_decode<true, 0>(prm, (unsigned)grid, smem, st);
+    return prm.radius == 5 ? launch_decode<false, 5>(prm, (unsigned)grid, smem, st) : launch_decode<false, 0>(prm, (unsigned)grid, smem, st);
 }
+

@@ -324,7 +324,12 @@ __global__ void __launch_bounds__(128) match_simt_top2_kernel(const float *__res
     }
 }
 
-// exact fp32 re-score of the surviving candidates, gate, key packing.  One warp per probe.
+// Exact fp32 re-score of the surviving candidates, gate, key packing.  One warp per probe.
+// A candidate whose bf16 score is more than kPrune below the row's best bf16 score cannot be the fp32
+// arg-max: the probe is rounded to bf16 (unit roundoff 2^-8), the gallery values are exact, so
+// |s_bf16 - s_fp32| <= 2^-8 * sum|q_i g_i| <= 2^-8 for unit vectors, and kPrune = 0.01 > 2 * 2^-8.
+constexpr float kPrune = 0.01f;
+
 __global__ void __launch_bounds__(256) match_finalize_kernel(const float *__restrict__ qn, const __nv_bfloat16 *__restrict__ gal,
                                                              const Cand *__restrict__ part, int m, int n, int ncand,
                                                              float threshold, int id_offset, int *out_id, float *out_sim,
@@ -336,17 +341,31 @@ __global__ void __launch_bounds__(256) match_finalize_kernel(const float *__rest
 #pragma unroll
     for (int i = 0; i < kDim / 32; ++i) q[i] = qn[(size_t)row * kDim + i * 32 + lane];
     const Cand *c = part + (size_t)row * ncand;
+    float vmax = -INFINITY;
+    for (int k = lane; k < ncand; k += 32) {
+        const Cand x = c[k];
+        if (x.i >= 0 && x.i < n) vmax = fmaxf(vmax, x.v);
+    }
+    vmax = warp_max(vmax);
     float best = -INFINITY;
     int bidx = 0x7fffffff;
-    for (int k = 0; k < ncand; ++k) {
-        const int g = c[k].i;
-        if (g < 0 || g >= n) continue;       // empty slot
-        const __nv_bfloat16 *gr = gal + (size_t)g * kDim;
-        float s = 0.f;
+    for (int k0 = 0; k0 < ncand; k0 += 32) {
+        const int k = k0 + lane;
+        Cand x{-INFINITY, -1};
+        if (k < ncand) x = c[k];
+        const bool need = x.i >= 0 && x.i < n && x.v >= vmax - kPrune;
+        unsigned todo = __ballot_sync(FULL, need);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int g = __shfl_sync(FULL, x.i, src);
+            const __nv_bfloat16 *gr = gal + (size_t)g * kDim;
+            float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < kDim / 32; ++i) s = fmaf(q[i], __bfloat162float(gr[i * 32 + lane]), s);
-        s = warp_sum(s);
-        if (s > best || (s == best && g < bidx)) { best = s; bidx = g; }
+            for (int i = 0; i < kDim / 32; ++i) s = fmaf(q[i], __bfloat162float(gr[i * 32 + lane]), s);
+            s = warp_sum(s);
+            if (s > best || (s == best && g < bidx)) { best = s; bidx = g; }
+        }
     }
     if (lane == 0) {
         const bool found = bidx != 0x7fffffff;

@@ -1,0 +1,155 @@
+"""The post-backbone selective-pose pass assembled from the four ops.
+
+The reference has no end-to-end inference function (scripts/modify_models.py:71-76 is a TODO); the
+pieces live in the per-task ``validation_step``s.  ``SelectivePosePipeline`` strings their B200
+replacements together for one batch of backbone outputs:
+
+    face head maps   -> decode + NMS                      (yolopt/nets/nn.py:255-270, util.py:123-169)
+    person head maps -> decode + NMS
+    face embeddings  -> L2-norm + gallery top-1 + gate    (face_recognition/module.py:136-145)
+    frames + person boxes -> 256x192 crops                (HF VitPoseImageProcessor.preprocess)
+    heatmaps (+ mirrored) -> keypoints in frame pixels    (HF post_process_pose_estimation / module.py:237-296)
+
+Everything stays on the device; the whole chain is captured once into a CUDA graph and replayed, so a
+step costs one graph launch.  ``run_host`` is the same pass fed from pinned host buffers with the
+result copied back (what ``bench.py`` reports as ``e2e``).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import ops, synth
+
+
+@dataclass
+class StepInputs:
+    """Backbone outputs for one batch (device or pinned-host tensors)."""
+    face_levels: Sequence[torch.Tensor]      # 3 x [B, 64+nc, H_l, W_l]
+    person_levels: Sequence[torch.Tensor]    # 3 x [B, 64+nc, H_l, W_l]
+    embeddings: torch.Tensor                 # [M, 512]
+    frames: torch.Tensor                     # [B, 3, H, W]
+    boxes: torch.Tensor                      # [P, 4] COCO x,y,w,h
+    frame_idx: torch.Tensor                  # [P] int32
+    heatmaps: torch.Tensor                   # [P, K, 64, 48]
+    flipped: Optional[torch.Tensor]          # [P, K, 64, 48] or None
+    perm: Optional[torch.Tensor]             # [K] int32
+
+    def tensors(self) -> Dict[str, torch.Tensor]:
+        d = {f"face_l{i}": t for i, t in enumerate(self.face_levels)}
+        d.update({f"person_l{i}": t for i, t in enumerate(self.person_levels)})
+        d.update(embeddings=self.embeddings, frames=self.frames, boxes=self.boxes, frame_idx=self.frame_idx,
+                 heatmaps=self.heatmaps)
+        if self.flipped is not None:
+            d["flipped"] = self.flipped
+        if self.perm is not None:
+            d["perm"] = self.perm
+        return d
+
+    @classmethod
+    def from_tensors(cls, d: Dict[str, torch.Tensor]) -> "StepInputs":
+        return cls([d[f"face_l{i}"] for i in range(3)], [d[f"person_l{i}"] for i in range(3)], d["embeddings"],
+                   d["frames"], d["boxes"], d["frame_idx"], d["heatmaps"], d.get("flipped"), d.get("perm"))
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.tensors().values())
+
+
+def synthetic_inputs(batch: int, height: int, width: int, per_frame: int, joints: int = 17, seed: int = 0,
+                     flip: bool = True, nc: int = 1) -> StepInputs:
+    """SURVEY.md §8d synthetic workload (CPU tensors): ``height``/``width`` is the frame size; the
+    detection heads see it letterboxed up to a multiple of 32."""
+    lh, lw = (height + 31) // 32 * 32, (width + 31) // 32 * 32
+    face = synth.make_head_maps_fast(batch, lh, lw, n_obj=per_frame, nc=nc, seed=seed)
+    person = synth.make_head_maps_fast(batch, lh, lw, n_obj=per_frame, nc=nc, seed=seed + 1)
+    cs = synth.make_crop_set(batch, height, width, per_frame=per_frame, seed=seed + 2)
+    p = batch * per_frame
+    hs = synth.make_heatmaps(p, joints, seed=seed + 3)
+    ms = synth.make_match_set(p, 16, seed=seed + 4)     # probes only; the gallery is built separately
+    return StepInputs(face.levels, person.levels, ms.embeddings, cs.frames, cs.boxes, cs.frame_idx, hs.heatmaps,
+                      hs.flipped if flip else None, hs.perm if flip else None)
+
+
+class SelectivePosePipeline:
+    """One CUDA-graphed pass of the glue path over fixed-shape inputs resident on ``device``."""
+
+    def __init__(self, inputs: StepInputs, gallery_bf16: torch.Tensor, device: torch.device, threshold: float = 0.4,
+                 conf_thres: float = 0.001, iou_thres: float = 0.65, decode_mode: str = "dark", use_graph: bool = True,
+                 id_offset: int = 0):
+        self.device = device
+        self.threshold, self.conf, self.iou, self.mode = threshold, conf_thres, iou_thres, decode_mode
+        self.id_offset = id_offset
+        self.gallery = gallery_bf16.to(device).contiguous()
+        self.inp = StepInputs.from_tensors({k: v.to(device).contiguous() for k, v in inputs.tensors().items()})
+        self.out: Dict[str, torch.Tensor] = {}
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.launches_per_step = 0
+        self._stream = torch.cuda.Stream(device)
+        with torch.cuda.stream(self._stream):
+            self._enqueue()                       # warm-up: sizes workspaces, sets kernel attributes
+            self._enqueue()
+        self._stream.synchronize()
+        if use_graph:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self._stream):
+                self._enqueue()
+            self.graph = g
+
+    def _enqueue(self) -> None:
+        i = self.inp
+        n = 0
+        face = ops.decode_nms(i.face_levels, conf_thres=self.conf, iou_thres=self.iou, out=self.out.get("_face"))
+        person = ops.decode_nms(i.person_levels, conf_thres=self.conf, iou_thres=self.iou, out=self.out.get("_person"))
+        n += 2 * 3      # memset + candidate kernel + NMS kernel per head
+        ids, sims, keys = ops.match_top1(i.embeddings, self.gallery, self.threshold, self.id_offset, want_keys=True)
+        n += 3          # normalise, tcgen05 GEMM + top-2, fp32 re-score
+        pix = ops.crop_affine(i.frames, i.boxes, i.frame_idx, out=self.out.get("pixel_values"))
+        n += 1
+        flags = (ops.FLAG_SCALE_SCORE | ops.FLAG_BACKPROJECT) if self.mode == "softargmax" else 0
+        kp = ops.heatmap_decode(i.heatmaps, i.flipped, i.perm, i.boxes, self.mode, 11, flags,
+                                out=(self.out["keypoints"], self.out["scores"], self.out["argmax"]) if "keypoints" in self.out else None)
+        n += 1
+        self.launches_per_step = n
+        self.out.update(_face=face, _person=person, face_dets=face.dets, face_count=face.count, person_dets=person.dets,
+                        person_count=person.count, ids=ids, sims=sims, keys=keys, pixel_values=pix, keypoints=kp[0],
+                        scores=kp[1], argmax=kp[2])
+
+    def step(self) -> Dict[str, torch.Tensor]:
+        """Enqueue one pass on the pipeline's stream (graph replay when captured)."""
+        with torch.cuda.stream(self._stream):
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._enqueue()
+        return self.out
+
+    @property
+    def stream(self) -> torch.cuda.Stream:
+        return self._stream
+
+    # ---- host-fed pass --------------------------------------------------------------------------
+    RESULT_KEYS = ("face_dets", "face_count", "person_dets", "person_count", "ids", "sims", "keypoints", "scores")
+
+    def bind_host(self, host_inputs: StepInputs) -> None:
+        """Pin the host-side inputs and allocate pinned result buffers."""
+        self._host_in = {k: (v if v.is_pinned() else v.contiguous().pin_memory()) for k, v in host_inputs.tensors().items()}
+        self._host_out = {k: torch.empty(self.out[k].shape, dtype=self.out[k].dtype).pin_memory() for k in self.RESULT_KEYS}
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self._host_in.values())
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in self._host_out.values())
+
+    def run_host(self) -> Dict[str, torch.Tensor]:
+        """H2D of every input from pinned memory, one pass, D2H of the compact results (async on the
+        pipeline stream; call ``stream.synchronize()`` to wait)."""
+        dst = self.inp.tensors()
+        with torch.cuda.stream(self._stream):
+            for k, src in self._host_in.items():
+                dst[k].copy_(src, non_blocking=True)
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._enqueue()
+            for k, buf in self._host_out.items():
+                buf.copy_(self.out[k], non_blocking=True)
+        return self._host_out
