@@ -68,45 +68,51 @@ __device__ __forceinline__ AxisMap crop_axis_map(const float4 box, int ow, int o
     return m;
 }
 
-// (i0, i1, t): sample = v[i0]*(1-t) + v[i1]*t; i0 < 0 marks "outside the frame -> 0"
-__device__ __forceinline__ void axis_entry(double s, int n, int &i0, int &i1, float &t) {
+// (i0, t): sample = v[i0]*(1-t) + v[i0+1]*t with i0 + 1 always inside the axis (at the far edge the pair
+// (n-2, t=1) stands for (n-1, t=0)); i0 < 0 marks "outside the frame -> 0".  n >= 2.
+struct AxisEntry {
+    int i0;
+    float t;
+};
+__device__ __forceinline__ AxisEntry axis_entry(double s, int n) {
+    AxisEntry e;
     if (!(s >= 0.0 && s <= (double)(n - 1))) {
-        i0 = -1; i1 = 0; t = 0.f;
-        return;
+        e.i0 = -1;
+        e.t = 0.f;
+        return e;
     }
     const double f = floor(s);
-    i0 = (int)f;
-    i1 = i0 + 1 < n ? i0 + 1 : n - 1;
-    t = (float)(s - f);
+    e.i0 = (int)f;
+    e.t = (float)(s - f);
+    if (e.i0 >= n - 1) {
+        e.i0 = n - 2;
+        e.t = 1.0f;
+    }
+    return e;
 }
 
-constexpr int kCropThreads = 256;
-constexpr int kStageBytes = 40 * 1024;   // source band buffer per CTA -> 4 CTAs (1024 threads) per SM
+constexpr int kStageBytes = 40 * 1024;   // source band buffer per CTA -> 4-5 CTAs per SM
 
-// One CTA per (crop, channel).
+// One CTA per (crop, channel), one thread per output column.
 //   * coordinate tables (fp64 -> index + fp32 weight) for the out_w columns and out_h rows in smem;
 //   * the valid output rows are processed in bands; for each band the needed source rows, restricted to
 //     the needed (16 B aligned) column range, are copied into shared memory by bulk-TMA row copies
 //     (cp.async.bulk, issued by warp 0, all completing on one mbarrier) — coalesced full-line HBM reads
 //     instead of four scattered 4-byte gathers per output pixel;
-//   * thread = output column: 4 shared-memory reads, 3 FMA (bilinear) + 1 FMA ((v - mean)/std) and one
-//     coalesced 4-byte streaming store per pixel.
+//   * per pixel: one 8-byte table read, 4 shared-memory reads at fixed offsets from one address, 7 FP
+//     ops (bilinear + (v - mean)/std as one FMA) and one coalesced 4-byte streaming store.
 // `staged == 0` (frame width not a multiple of 4, unaligned base, or a band that cannot fit): the same
 // loop gathers straight from global memory.
-__global__ void __launch_bounds__(kCropThreads) crop_affine_kernel(const CropParams prm, int staged) {
+__global__ void __launch_bounds__(256) crop_affine_kernel(const CropParams prm, int staged) {
     extern __shared__ __align__(128) unsigned char crop_smem[];
     const int ow = prm.ow, oh = prm.oh;
-    float *buf = reinterpret_cast<float *>(crop_smem);                       // [kStageBytes]
-    int *x0 = reinterpret_cast<int *>(crop_smem + kStageBytes);
-    int *x1 = x0 + ow;
-    float *tx = reinterpret_cast<float *>(x1 + ow);
-    int *y0 = reinterpret_cast<int *>(tx + ow);
-    int *y1 = y0 + oh;
-    float *ty = reinterpret_cast<float *>(y1 + oh);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(reinterpret_cast<uintptr_t>(ty + oh + 1) & ~(uintptr_t)7);
+    float *buf = reinterpret_cast<float *>(crop_smem);                                   // [kStageBytes]
+    AxisEntry *xt = reinterpret_cast<AxisEntry *>(crop_smem + kStageBytes);              // [ow]
+    AxisEntry *yt = xt + ow;                                                             // [oh]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(yt + oh);
     __shared__ int s_v[4];   // first/last valid column, first/last valid row
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
     const int p = blockIdx.x, c = blockIdx.y;
     const float4 box = __ldg(reinterpret_cast<const float4 *>(prm.boxes) + p);
     const AxisMap m = crop_axis_map(box, ow, oh, prm.variant);
@@ -117,14 +123,16 @@ __global__ void __launch_bounds__(kCropThreads) crop_affine_kernel(const CropPar
         fence_proxy_async();
     }
     __syncthreads();
-    for (int i = tid; i < ow + oh; i += kCropThreads) {
+    for (int i = tid; i < ow + oh; i += nthreads) {
         if (i < ow) {
-            axis_entry(m.ax * (double)i + m.bx, prm.fw, x0[i], x1[i], tx[i]);
-            if (x0[i] >= 0) { atomicMin(&s_v[0], i); atomicMax(&s_v[1], i); }
+            const AxisEntry e = axis_entry(m.ax * (double)i + m.bx, prm.fw);
+            xt[i] = e;
+            if (e.i0 >= 0) { atomicMin(&s_v[0], i); atomicMax(&s_v[1], i); }
         } else {
             const int y = i - ow;
-            axis_entry(m.ay * (double)y + m.by, prm.fh, y0[y], y1[y], ty[y]);
-            if (y0[y] >= 0) { atomicMin(&s_v[2], y); atomicMax(&s_v[3], y); }
+            const AxisEntry e = axis_entry(m.ay * (double)y + m.by, prm.fh);
+            yt[y] = e;
+            if (e.i0 >= 0) { atomicMin(&s_v[2], y); atomicMax(&s_v[3], y); }
         }
     }
     __syncthreads();
@@ -141,15 +149,15 @@ __global__ void __launch_bounds__(kCropThreads) crop_affine_kernel(const CropPar
 
     const bool any = vx1 >= vx0 && vy1 >= vy0;
     // rows with no valid source: constant
-    for (int y = warp; y < oh; y += kCropThreads / 32) {
+    for (int y = warp; y < oh; y += nthreads / 32) {
         if (any && y >= vy0 && y <= vy1) continue;
         for (int x = lane; x < ow; x += 32) __stcs(dst + (size_t)y * ow + x, zero_out);
     }
     if (!any) return;
 
-    // source column window, 16-byte aligned
-    const int cx0 = x0[vx0] & ~3;
-    int cx1 = (x1[vx1] + 4) & ~3;                    // exclusive
+    // source column window, 16-byte aligned; xt[].i0 + 1 is always a valid column
+    const int cx0 = xt[vx0].i0 & ~3;
+    int cx1 = (xt[vx1].i0 + 2 + 3) & ~3;             // exclusive
     if (cx1 > prm.fw) cx1 = prm.fw;
     const int row_elems = cx1 - cx0;
     const int rows_cap = kStageBytes / (row_elems * 4);
@@ -165,9 +173,9 @@ __global__ void __launch_bounds__(kCropThreads) crop_affine_kernel(const CropPar
     uint32_t parity = 0;
     for (int r0 = vy0; r0 <= vy1; r0 += band) {
         const int r1 = (r0 + band - 1) < vy1 ? (r0 + band - 1) : vy1;
-        const int sy_lo = y0[r0], sy_hi = y1[r1];
+        const int sy_lo = yt[r0].i0;
         if (use_stage) {
-            const int nrows = sy_hi - sy_lo + 1;
+            const int nrows = yt[r1].i0 + 1 - sy_lo + 1;
             if (warp == 0) {
                 if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(nrows * row_elems * 4));
                 for (int r = lane; r < nrows; r += 32)
@@ -176,30 +184,28 @@ __global__ void __launch_bounds__(kCropThreads) crop_affine_kernel(const CropPar
             mbar_wait(bar, parity);
             parity ^= 1;
         }
-        for (int x = tid; x < ow; x += kCropThreads) {
-            const int ix0 = x0[x], ix1 = x1[x];
-            const float wx = tx[x];
-            if (ix0 < 0) {
-                for (int y = r0; y <= r1; ++y) __stcs(dst + (size_t)y * ow + x, zero_out);
+        // staged: tile(iy, ix) = buf[(iy - sy_lo) * row_elems + ix - cx0];  direct: src[iy * fw + ix]
+        const float *tile = use_stage ? buf - (ptrdiff_t)sy_lo * row_elems - cx0 : src;
+        const int pitch = use_stage ? row_elems : prm.fw;
+        for (int x = tid; x < ow; x += nthreads) {
+            const AxisEntry ex = xt[x];
+            float *o = dst + (size_t)r0 * ow + x;
+            if (ex.i0 < 0) {
+                for (int y = r0; y <= r1; ++y, o += ow) __stcs(o, zero_out);
                 continue;
             }
+            const float *col = tile + ex.i0;
+            const float wx = ex.t;
 #pragma unroll 4
-            for (int y = r0; y <= r1; ++y) {
-                const int iy0 = y0[y], iy1 = y1[y];
-                const float wy = ty[y];
-                float p00, p01, p10, p11;
-                if (use_stage) {
-                    const float *ra = buf + (size_t)(iy0 - sy_lo) * row_elems - cx0;
-                    const float *rb = buf + (size_t)(iy1 - sy_lo) * row_elems - cx0;
-                    p00 = ra[ix0]; p01 = ra[ix1]; p10 = rb[ix0]; p11 = rb[ix1];
-                } else {
-                    const float *ra = src + (size_t)iy0 * prm.fw, *rb = src + (size_t)iy1 * prm.fw;
-                    p00 = __ldg(ra + ix0); p01 = __ldg(ra + ix1); p10 = __ldg(rb + ix0); p11 = __ldg(rb + ix1);
-                }
+            for (int y = r0; y <= r1; ++y, o += ow) {
+                const AxisEntry ey = yt[y];
+                const float *ra = col + ey.i0 * pitch;
+                const float *rb = ra + pitch;
+                const float p00 = ra[0], p01 = ra[1], p10 = rb[0], p11 = rb[1];
                 const float top = fmaf(p01 - p00, wx, p00);
                 const float bot = fmaf(p11 - p10, wx, p10);
-                const float v = fmaf(bot - top, wy, top);
-                __stcs(dst + (size_t)y * ow + x, fmaf(v, inv_sd, nmean));
+                const float v = fmaf(bot - top, ey.t, top);
+                __stcs(o, fmaf(v, inv_sd, nmean));
             }
         }
         if (use_stage) __syncthreads();              // the band buffer is refilled next
@@ -214,7 +220,7 @@ extern "C" int spp_crop_affine(const float *frames, int num_frames, int frame_h,
                                int variant, float *out, spp_stream_t stream) {
     using namespace spp;
     SPP_CHECK_ARG(frames && boxes && frame_idx && out && mean && std, "crop_affine: null pointer");
-    SPP_CHECK_ARG(num_frames > 0 && frame_h > 0 && frame_w > 0 && p >= 0, "crop_affine: bad frame shape");
+    SPP_CHECK_ARG(num_frames > 0 && frame_h >= 2 && frame_w >= 2 && p >= 0, "crop_affine: frames must be at least 2x2");
     SPP_CHECK_ARG(out_h > 0 && out_w > 0 && out_w <= 2048 && out_h <= 2048, "crop_affine: output size must be within 2048 x 2048");
     SPP_CHECK_ARG(variant == SPP_CROP_HF_UDP || variant == SPP_CROP_GLUONCV, "crop_affine: unknown variant %d", variant);
     SPP_CHECK_ARG((reinterpret_cast<uintptr_t>(boxes) & 15) == 0, "crop_affine: boxes must be 16-byte aligned");
@@ -225,7 +231,9 @@ extern "C" int spp_crop_affine(const float *frames, int num_frames, int frame_h,
     prm.variant = variant;
     for (int c = 0; c < 3; ++c) { prm.mean[c] = mean[c]; prm.stdv[c] = std[c]; }
     const int staged = (frame_w % 4 == 0) && ((reinterpret_cast<uintptr_t>(frames) & 15) == 0);
-    const size_t smem = (size_t)kStageBytes + (size_t)(out_w + out_h) * 12 + 32;
+    const size_t smem = (size_t)kStageBytes + (size_t)(out_w + out_h) * 8 + 16;
+    int threads = (out_w + 31) / 32 * 32;
+    if (threads > 256) threads = 256;
     static bool configured = false;
     if (!configured) {
         SPP_CHECK_CUDA(cudaFuncSetAttribute(crop_affine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -233,7 +241,7 @@ extern "C" int spp_crop_affine(const float *frames, int num_frames, int frame_h,
     }
     SPP_CHECK_ARG(smem <= 100 * 1024, "crop_affine: output size too large");
     dim3 grid(p, 3);
-    crop_affine_kernel<<<grid, kCropThreads, smem, static_cast<cudaStream_t>(stream)>>>(prm, staged);
+    crop_affine_kernel<<<grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(prm, staged);
     SPP_CHECK_LAUNCH();
     return SPP_OK;
 }

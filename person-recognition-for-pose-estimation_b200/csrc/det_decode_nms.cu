@@ -24,6 +24,7 @@
 // for bit with torchvision's CPU loop, which is what the reference's keep indices come from.
 #include "spp_common.cuh"
 
+#include <climits>
 #include <cmath>
 
 namespace spp {
@@ -35,6 +36,7 @@ constexpr int kNmsThreads = 512;
 constexpr int kSortSmemMax = 8192;  // keys sorted in shared memory up to this (padded) count
 constexpr int kBoxSmemMax = 2048;   // sorted boxes kept in shared memory (the rest is re-gathered)
 constexpr int kAliveWords = 1024;   // one alive bit per candidate: max_nms <= 32768
+constexpr int kRankSortMax = 1024;  // rank sort (no barriers) up to this many candidates
 
 struct Levels {
     const float *ptr[SPP_MAX_LEVELS];
@@ -158,30 +160,90 @@ __global__ void __launch_bounds__(256) cand_decoded_kernel(const float *__restri
     }
 }
 
-__global__ void __launch_bounds__(256) cand_raw_kernel(const Levels lv, int nc, float conf, int cap, int cap_pad, int *counts,
-                                                       unsigned long long *keys, float4 *__restrict__ boxes) {
+// Candidate scan over the raw class planes only.  sigmoid is monotone, so anchors whose logit is below
+// logit(conf) - 0.05 are rejected without evaluating it; the exact fp32 test sigmoid(x) > conf decides
+// the rest.  Candidates are appended as sort keys; their boxes are decoded by cand_decode_kernel.
+__global__ void __launch_bounds__(256) cand_scan_kernel(const Levels lv, int nc, float conf, float logit_lo, int cap, int cap_pad,
+                                                        int *counts, unsigned long long *keys) {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     const bool in = a < lv.A;
     const LevelRef lr = find_level(lv, in ? a : 0);
-    const int i = lr.i, w = lr.w, hw = lr.hw;
     const int no = 4 * kDfl + nc;
-    const float *base = lr.ptr + (size_t)b * no * hw + i;
+    const float *cls = lr.ptr + ((size_t)b * no + 4 * kDfl) * lr.hw + lr.i;
     unsigned long long *k = keys + (size_t)b * cap_pad;
-    bool any = false;
     for (int j = 0; j < nc; ++j) {
         float s = 0.f;
         bool c = false;
         if (in) {
-            s = sigmoidf_ref(__ldg(base + (size_t)(4 * kDfl + j) * hw));
-            c = s > conf;
+            const float x = __ldg(cls + (size_t)j * lr.hw);
+            if (x > logit_lo) {
+                s = sigmoidf_ref(x);
+                c = s > conf;
+            }
         }
-        any |= c;
         append_candidate(c, make_sort_key(s, (unsigned)(a * nc + j)), counts + b, k, cap);
     }
-    if (any) {
-        const int y = i / w, x = i - y * w;
-        boxes[(size_t)b * lv.A + a] = wh2xy(decode_box(base, hw, (float)x + 0.5f, (float)y + 0.5f, lr.stride));
+}
+
+// Box decode for the candidates only: one half-warp per (image, candidate).  Lane j of the half-warp
+// owns DFL bin j of all four sides (4 loads in flight per lane, 64 per candidate); the softmax
+// max / sum and the expectation are 16-lane xor-shuffle reductions, four sides at a time.
+__global__ void __launch_bounds__(256) cand_decode_kernel(const Levels lv, int nc, int batch, int cap, int cap_pad,
+                                                          const int *__restrict__ counts, const unsigned long long *__restrict__ keys,
+                                                          float4 *__restrict__ boxes) {
+    const int lane = threadIdx.x & 31, sub = lane & 15;
+    const int half_id = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 4);
+    const int nhalf = (int)((gridDim.x * blockDim.x) >> 4);
+    int maxn = 0;
+    for (int b = lane; b < batch; b += 32) maxn = max(maxn, min(__ldg(counts + b), cap));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxn = max(maxn, __shfl_xor_sync(FULL, maxn, o));
+    const long long range = (long long)maxn * batch;          // items are (slot, image), image fastest
+    const int no = 4 * kDfl + nc;
+    // both halves of a warp iterate together (full-mask shuffles); an idle half works on a dummy item
+    for (long long base = (half_id & ~1); base < range; base += nhalf) {
+        const long long L = base + (half_id & 1);
+        const int slot = (int)((unsigned long long)L / (unsigned)batch), b = (int)(L - (long long)slot * batch);
+        const bool valid = L < range && slot < min(__ldg(counts + b), cap);
+        const unsigned cand = valid ? (unsigned)(keys[(size_t)b * cap_pad + slot] & 0xffffffffu) : 0u;
+        const int anchor = (int)(cand / (unsigned)nc);
+        const LevelRef lr = find_level(lv, anchor);
+        const float *basep = lr.ptr + (size_t)(valid ? b : 0) * no * lr.hw + lr.i;
+        float v[4];
+#pragma unroll
+        for (int sd = 0; sd < 4; ++sd) v[sd] = __ldg(basep + (size_t)(sd * kDfl + sub) * lr.hw);
+        float m[4], e[4], sum[4], d[4];
+#pragma unroll
+        for (int sd = 0; sd < 4; ++sd) m[sd] = v[sd];
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+            for (int sd = 0; sd < 4; ++sd) m[sd] = fmaxf(m[sd], __shfl_xor_sync(FULL, m[sd], o));
+#pragma unroll
+        for (int sd = 0; sd < 4; ++sd) sum[sd] = e[sd] = expf(__fsub_rn(v[sd], m[sd]));
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+            for (int sd = 0; sd < 4; ++sd) sum[sd] = __fadd_rn(sum[sd], __shfl_xor_sync(FULL, sum[sd], o));
+#pragma unroll
+        for (int sd = 0; sd < 4; ++sd) d[sd] = __fmul_rn((float)sub, __fdiv_rn(e[sd], sum[sd]));
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+            for (int sd = 0; sd < 4; ++sd) d[sd] = __fadd_rn(d[sd], __shfl_xor_sync(FULL, d[sd], o));
+        if (valid && sub == 0) {
+            const int y = lr.i / lr.w, x = lr.i - y * lr.w;
+            const float ax = (float)x + 0.5f, ay = (float)y + 0.5f;
+            const float x1 = __fsub_rn(ax, d[0]), y1 = __fsub_rn(ay, d[1]);
+            const float x2 = __fadd_rn(ax, d[2]), y2 = __fadd_rn(ay, d[3]);
+            float4 r;
+            r.x = __fmul_rn(__fmul_rn(__fadd_rn(x1, x2), 0.5f), lr.stride);
+            r.y = __fmul_rn(__fmul_rn(__fadd_rn(y1, y2), 0.5f), lr.stride);
+            r.z = __fmul_rn(__fsub_rn(x2, x1), lr.stride);
+            r.w = __fmul_rn(__fsub_rn(y2, y1), lr.stride);
+            boxes[(size_t)b * lv.A + anchor] = wh2xy(r);
+        }
     }
 }
 
@@ -223,14 +285,28 @@ __device__ void bitonic_sort(unsigned long long *d, int npad) {
     }
 }
 
+// Rank sort for small candidate lists: keys are unique, so rank = #smaller keys; n^2 broadcast
+// shared-memory reads and no barrier inside.  src -> dst (both shared).
+__device__ void rank_sort(const unsigned long long *src, unsigned long long *dst, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long k = src[i];
+        int r = 0;
+#pragma unroll 8
+        for (int j = 0; j < n; ++j) r += src[j] < k;
+        dst[r] = k;
+    }
+    __syncthreads();
+}
+
 // One CTA per image.
-//   1. bitonic sort of the 64-bit keys (shared memory up to kSortSmemMax keys, else in the workspace);
+//   1. sort of the 64-bit keys: rank sort up to kRankSortMax, bitonic in shared memory up to kSortSmemMax,
+//      bitonic in the workspace beyond;
 //   2. sorted, class-offset boxes + areas are staged in shared memory (first kBoxSmemMax; beyond that they
 //      are re-gathered on the fly), one "alive" bit per candidate;
-//   3. greedy loop, serial over KEPT boxes only: warp 0 finds the first alive candidate at or after the
-//      cursor; every warp then clears, with one ballot per 32-candidate word it owns, the later
-//      candidates whose IoU with that box exceeds the threshold.  Two block barriers per kept box,
-//      n/32/16 ballots per warp per kept box; stops after max_det.
+//   3. greedy loop, serial over KEPT boxes only: every warp clears, with one ballot per 32-candidate word
+//      it owns, the later candidates whose IoU with the current box exceeds the threshold, and proposes
+//      the first survivor it sees (shared-memory atomicMin) as the next box.  One block barrier per kept
+//      box, n/32/16 ballots per warp per kept box; stops after max_det.
 template <bool RAW>
 __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams prm) {
     extern __shared__ __align__(16) unsigned char nms_smem[];
@@ -243,35 +319,46 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams prm) {
     float *sarea = reinterpret_cast<float *>(sbox + kBoxSmemMax);                              // [kBoxSmemMax]
     unsigned *alive = reinterpret_cast<unsigned *>(sarea + kBoxSmemMax);                       // [kAliveWords]
     int *kept_idx = reinterpret_cast<int *>(alive + kAliveWords);                              // [max_det]
-    __shared__ int s_next;
+    __shared__ int s_next[3];
 
     const int raw_count = prm.counts[b];
     int n = raw_count < prm.cap ? raw_count : prm.cap;
-    int npad = 1;
-    while (npad < n) npad <<= 1;
     unsigned long long *gkeys = prm.keys + (size_t)b * prm.cap_pad;
-    const bool in_smem = npad <= kSortSmemMax;
-    unsigned long long *keys = in_smem ? skeys : gkeys;
-    if (in_smem) {
-        for (int i = tid; i < npad; i += kNmsThreads) skeys[i] = i < n ? gkeys[i] : ~0ull;
+    unsigned long long *keys;
+    if (n <= kRankSortMax) {
+        // unsorted keys parked in the (not yet used) box area, sorted into skeys
+        unsigned long long *tmp = reinterpret_cast<unsigned long long *>(sbox);
+        for (int i = tid; i < n; i += kNmsThreads) tmp[i] = gkeys[i];
+        __syncthreads();
+        rank_sort(tmp, skeys, n);
+        keys = skeys;
     } else {
-        for (int i = n + tid; i < npad; i += kNmsThreads) gkeys[i] = ~0ull;
+        int npad = 1;
+        while (npad < n) npad <<= 1;
+        const bool in_smem = npad <= kSortSmemMax;
+        keys = in_smem ? skeys : gkeys;
+        if (in_smem) {
+            for (int i = tid; i < npad; i += kNmsThreads) skeys[i] = i < n ? gkeys[i] : ~0ull;
+        } else {
+            for (int i = n + tid; i < npad; i += kNmsThreads) gkeys[i] = ~0ull;
+        }
+        __syncthreads();
+        bitonic_sort(keys, npad);
     }
-    __syncthreads();
-    bitonic_sort(keys, npad);
     if (n > prm.max_nms) n = prm.max_nms;                                   // util.py:157 [:max_nms]
 
-    // class-offset box (util.py:160-161) and its area for sorted candidate j
+    // un-offset box of sorted candidate j
+    auto raw_box = [&](unsigned cand, int &cls) -> float4 {
+        const int anchor = cand / prm.nc;
+        cls = cand - anchor * prm.nc;
+        if (RAW) return prm.boxes[(size_t)b * prm.A + anchor];
+        const float *pb = prm.pred + (size_t)b * (4 + prm.nc) * prm.A + anchor;
+        return wh2xy(make_float4(__ldg(pb), __ldg(pb + prm.A), __ldg(pb + 2 * (size_t)prm.A), __ldg(pb + 3 * (size_t)prm.A)));
+    };
+    // class-offset box (util.py:160-161) and its area
     auto load_box = [&](int j, float4 &obox, float &area) {
-        const unsigned cand = (unsigned)(keys[j] & 0xffffffffu);
-        const int anchor = cand / prm.nc, cls = cand - anchor * prm.nc;
-        float4 box;
-        if (RAW) {
-            box = prm.boxes[(size_t)b * prm.A + anchor];
-        } else {
-            const float *pb = prm.pred + (size_t)b * (4 + prm.nc) * prm.A + anchor;
-            box = wh2xy(make_float4(__ldg(pb), __ldg(pb + prm.A), __ldg(pb + 2 * (size_t)prm.A), __ldg(pb + 3 * (size_t)prm.A)));
-        }
+        int cls;
+        const float4 box = raw_box((unsigned)(keys[j] & 0xffffffffu), cls);
         const float off = __fmul_rn((float)cls, prm.max_wh);
         obox = make_float4(__fadd_rn(box.x, off), __fadd_rn(box.y, off), __fadd_rn(box.z, off), __fadd_rn(box.w, off));
         area = __fmul_rn(__fsub_rn(obox.z, obox.x), __fsub_rn(obox.w, obox.y));
@@ -294,40 +381,30 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams prm) {
         sarea[j] = ar;
     }
     for (int w = tid; w < nwords; w += kNmsThreads) alive[w] = (w * 32 + 32 <= n) ? 0xffffffffu : ((1u << (n - w * 32)) - 1u);
+    if (tid == 0) {
+        s_next[0] = n > 0 ? 0 : INT_MAX;      // the best-scoring candidate is always kept
+        s_next[1] = INT_MAX;
+        s_next[2] = INT_MAX;
+    }
     __syncthreads();
 
     const float thr = prm.iou;
     const int max_det = prm.max_det;
-    int nk = 0, cursor = 0;
-    while (nk < max_det) {
-        if (warp == 0) {
-            int found = -1;
-            for (int w0 = cursor >> 5; w0 < nwords && found < 0; w0 += 32) {
-                const int wi = w0 + lane;
-                unsigned word = wi < nwords ? alive[wi] : 0u;
-                if (wi == (cursor >> 5)) word &= ~((1u << (cursor & 31)) - 1u);
-                const unsigned bal = __ballot_sync(FULL, word != 0u);
-                if (bal) {
-                    const int src = __ffs(bal) - 1;
-                    const unsigned wsel = __shfl_sync(FULL, word, src);
-                    found = (w0 + src) * 32 + __ffs(wsel) - 1;
-                }
-            }
-            if (lane == 0) {
-                s_next = found;
-                if (found >= 0) kept_idx[nk] = found;
-            }
+    int nk = 0;
+    for (int it = 0;; ++it) {
+        const int i = s_next[it % 3];
+        if (i == INT_MAX || nk >= max_det) break;
+        if (tid == 0) {
+            kept_idx[nk] = i;
+            s_next[(it + 2) % 3] = INT_MAX;   // last read in iteration it - 1, proposals start in it + 1
         }
-        __syncthreads();
-        const int i = s_next;
-        if (i < 0) break;
         ++nk;
-        if (nk >= max_det) break;
         float4 bi;
         float ai;
         get_box(i, bi, ai);
+        int first = INT_MAX;
         for (int wi = (i >> 5) + warp; wi < nwords; wi += NW) {
-            const unsigned word = alive[wi];
+            unsigned word = alive[wi];
             const int j = wi * 32 + lane;
             bool sup = false;
             if (((word >> lane) & 1u) && j > i) {
@@ -337,9 +414,12 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams prm) {
                 sup = iou_gt(bi, ai, bj, aj, thr);
             }
             const unsigned sm = __ballot_sync(FULL, sup);
-            if (lane == 0 && sm) alive[wi] = word & ~sm;
+            word &= ~sm;
+            if (wi == (i >> 5)) word &= ~((2u << (i & 31)) - 1u);        // i and everything before it is resolved
+            if (lane == 0 && (sm || wi == (i >> 5))) alive[wi] = word;
+            if (word && first == INT_MAX) first = wi * 32 + __ffs(word) - 1;
         }
-        cursor = i + 1;
+        if (lane == 0 && first != INT_MAX) atomicMin(&s_next[(it + 1) % 3], first);
         __syncthreads();
     }
     __syncthreads();
@@ -353,14 +433,8 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams prm) {
             const unsigned long long key = keys[kept_idx[r]];
             const unsigned cand = (unsigned)(key & 0xffffffffu);
             const float score = __uint_as_float(~(unsigned)(key >> 32));
-            const int anchor = cand / prm.nc, cls = cand - anchor * prm.nc;
-            float4 box;
-            if (RAW) {
-                box = prm.boxes[(size_t)b * prm.A + anchor];
-            } else {
-                const float *pb = prm.pred + (size_t)b * (4 + prm.nc) * prm.A + anchor;
-                box = wh2xy(make_float4(__ldg(pb), __ldg(pb + prm.A), __ldg(pb + 2 * (size_t)prm.A), __ldg(pb + 3 * (size_t)prm.A)));
-            }
+            int cls;
+            const float4 box = raw_box(cand, cls);
             row[0] = box.x; row[1] = box.y; row[2] = box.z; row[3] = box.w; row[4] = score; row[5] = (float)cls;
             if (okeys) okeys[r] = (int)cand;
         } else {
@@ -508,8 +582,18 @@ extern "C" int spp_decode_nms(const float *const *levels, const int *level_h, co
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     SPP_CHECK_CUDA(cudaMemsetAsync(w.counts, 0, (size_t)batch * sizeof(int), st));
     dim3 grid((lv.A + 255) / 256, batch);
-    cand_raw_kernel<<<grid, 256, 0, st>>>(lv, nc, conf_thres, w.cap, w.cap_pad, w.counts, w.keys, w.boxes);
+    // sigmoid(x) > conf can only hold for x > logit(conf); 0.05 of slack covers fp32 rounding
+    float logit_lo = -INFINITY;
+    if (conf_thres >= 1.0f) logit_lo = INFINITY;
+    else if (conf_thres > 0.0f) logit_lo = (float)(std::log((double)conf_thres / (1.0 - (double)conf_thres)) - 0.05);
+    cand_scan_kernel<<<grid, 256, 0, st>>>(lv, nc, conf_thres, logit_lo, w.cap, w.cap_pad, w.counts, w.keys);
     SPP_CHECK_LAUNCH();
+    {
+        int sms = sm_count();
+        if (sms <= 0) return SPP_ERR_CUDA;
+        cand_decode_kernel<<<sms * 16, 256, 0, st>>>(lv, nc, batch, w.cap, w.cap_pad, w.counts, w.keys, w.boxes);
+        SPP_CHECK_LAUNCH();
+    }
     NmsParams prm{};
     prm.pred = nullptr; prm.boxes = w.boxes; prm.counts = w.counts; prm.keys = w.keys;
     prm.nc = nc; prm.A = lv.A; prm.cap = w.cap; prm.cap_pad = w.cap_pad;

@@ -31,7 +31,7 @@ namespace spp {
 namespace {
 
 constexpr int kMaxRadius = 8;
-constexpr int kScratch = 64;  // floats per warp: 3 * (2*kMaxRadius + 3) = 57
+constexpr int kScratch = 64 + 368;  // floats per warp: 3*(2r+3) <= 57 filter rows, then the (2r+3)^2 <= 361 window
 
 struct DecodeParams {
     const float *hm;
@@ -116,12 +116,13 @@ __device__ float warp_blurred_log_single(const MapView<FLIP> &mv, int H, int y, 
     return clip_log((float)acc);
 }
 
-// running "first maximum" of one lane-private chain
+// running "first maximum" of one lane-private chain, tracked per float4 quad
 struct Best {
     float v;
-    int i;
-    __device__ __forceinline__ void take(float x, int idx) {
-        if (x > v) { v = x; i = idx; }
+    int q;
+    __device__ __forceinline__ void take(const float4 &s, int q4) {
+        const float m = fmaxf(fmaxf(s.x, s.y), fmaxf(s.z, s.w));
+        if (m > v) { v = m; q = q4; }
     }
 };
 
@@ -139,6 +140,7 @@ __global__ void __launch_bounds__(256, 1) heatmap_decode_kernel(const DecodePara
     unsigned char *after = smem_raw + (size_t)warps * stages * NB * map_bytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(after) + warp * stages;
     float *scratch = reinterpret_cast<float *>(after + (size_t)warps * stages * 8) + warp * kScratch;
+    float *win = scratch + 64;       // (2r+3)^2 window of the averaged map around the arg-max
 
     const long long total = (long long)prm.P * K;
     const long long gwarp = (long long)blockIdx.x * warps + warp;
@@ -174,6 +176,7 @@ __global__ void __launch_bounds__(256, 1) heatmap_decode_kernel(const DecodePara
     const int n4 = map_elems >> 2;
     const unsigned magic = prm.w4_magic;  // (q * magic) >> 16 == q / W4 for q < n4 (checked on the host)
     const int radius = RADIUS > 0 ? RADIUS : prm.radius;
+    const int wn = 2 * radius + 3;
     const double *gw = prm.gw;
 
     int it = 0;
@@ -187,21 +190,22 @@ __global__ void __launch_bounds__(256, 1) heatmap_decode_kernel(const DecodePara
         const float4 *A4 = reinterpret_cast<const float4 *>(A);
         const float4 *B4 = reinterpret_cast<const float4 *>(B);
 
-        // one float4 of the (flip-averaged) map: element e of quad q4 is flat index 4*q4 + e
+        // One float4 of 2 x the flip-average (or of the map itself): element e of quad q4 is flat index
+        // 4*q4 + e.  The * 0.5 is an exact power-of-two scaling, so the arg-max can be taken on the sums.
         auto quad = [&](int q4) -> float4 {
             float4 v = A4[q4];
             if (FLIP) {
                 const int r = (int)(((unsigned)q4 * magic) >> 16);
                 const float4 m = B4[2 * r * W4 + W4 - 1 - q4];     // same row, mirrored quad, reversed lanes
-                v.x = (v.x + m.w) * 0.5f;
-                v.y = (v.y + m.z) * 0.5f;
-                v.z = (v.z + m.y) * 0.5f;
-                v.w = (v.w + m.x) * 0.5f;
+                v.x += m.w;
+                v.y += m.z;
+                v.z += m.y;
+                v.w += m.x;
             }
             return v;
         };
 
-        // ---- pass 1: arg-max of the (flip-averaged) map; 4 independent chains per lane -------------
+        // ---- phase 1: arg-max; 4 independent chains per lane, one compare per quad -----------------
         Best ch[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) ch[c] = Best{-INFINITY, INT_MAX};
@@ -211,61 +215,109 @@ __global__ void __launch_bounds__(256, 1) heatmap_decode_kernel(const DecodePara
 #pragma unroll
             for (int c = 0; c < 4; ++c) v[c] = quad(q4 + 32 * c);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int base = (q4 + 32 * c) << 2;
-                ch[c].take(v[c].x, base);
-                ch[c].take(v[c].y, base + 1);
-                ch[c].take(v[c].z, base + 2);
-                ch[c].take(v[c].w, base + 3);
-            }
+            for (int c = 0; c < 4; ++c) ch[c].take(v[c], q4 + 32 * c);
         }
-        for (; q4 < n4; q4 += 32) {
-            const float4 v = quad(q4);
-            const int base = q4 << 2;
-            ch[0].take(v.x, base);
-            ch[0].take(v.y, base + 1);
-            ch[0].take(v.z, base + 2);
-            ch[0].take(v.w, base + 3);
-        }
+        for (; q4 < n4; q4 += 32) ch[0].take(quad(q4), q4);
         float best = ch[0].v;
-        int bidx = ch[0].i;
+        int bq = ch[0].q;
 #pragma unroll
         for (int c = 1; c < 4; ++c)
-            if (ch[c].v > best || (ch[c].v == best && ch[c].i < bidx)) { best = ch[c].v; bidx = ch[c].i; }
-        warp_argmax(best, bidx);
-        if (bidx == INT_MAX) bidx = 0;                  // nothing compared greater than -inf: np.argmax gives 0
+            if (ch[c].v > best || (ch[c].v == best && ch[c].q < bq)) { best = ch[c].v; bq = ch[c].q; }
+        warp_argmax(best, bq);       // lowest quad holding the maximum == quad of the first maximum
+        int bidx = 0;                // nothing compared greater than -inf: np.argmax gives 0
+        if (bq != INT_MAX) {
+            const float4 v = quad(bq);
+            bidx = 4 * bq + (v.x == best ? 0 : (v.y == best ? 1 : (v.z == best ? 2 : 3)));
+        } else {
+            best = quad(0).x;        // all -inf (or NaN): the reference's max is element 0
+        }
+        if (FLIP) best *= 0.5f;
         const int ax = bidx % W, ay = bidx / W;
         const long long p = q / K;
         MapView<FLIP> mv{A, B, W};
 
+        // ---- phase 2: everything that still needs the staged map ---------------------------------------
+        const bool valid = best > 0.0f;
+        float c00 = 0.f, cbr = 0.f, cbl = 0.f;          // DARK, score <= 0 path
+        float se = 0.f, sxe = 0.f, sye = 0.f;           // soft-argmax sums
+        float qdx = 0.f, qdy = 0.f;                     // quarter-offset differences
+        if (prm.mode == SPP_DECODE_DARK) {
+            if (valid) {
+                // (2r+3)^2 window of the averaged map, 'reflect'-indexed like scipy's line extension
+                for (int t = lane; t < wn * wn; t += 32) {
+                    const int wr = t / wn, wc = t - wr * wn;
+                    win[t] = mv.at(reflect_idx(ay - (radius + 1) + wr, H), reflect_idx(ax - (radius + 1) + wc, W));
+                }
+            } else {
+                // HF indexes the flattened, edge-padded batch with coordinate -1: the centre taps land on
+                // padded[0,0] of this map, the "minus" taps on the tail of the PREVIOUS map (numpy
+                // negative indices wrap to the last map for q == 0).  Reproduced for parity.
+                const long long qp = (q + total - 1) % total;
+                const long long pp = qp / K;
+                const int kp = (int)(qp - pp * K);
+                MapView<FLIP> prev{prm.hm + qp * map_elems, nullptr, W};
+                if (FLIP) prev.B = prm.hmf + (pp * K + (prm.perm ? __ldg(prm.perm + kp) : kp)) * map_elems;
+                c00 = warp_blurred_log_single(mv, H, 0, 0, gw, radius, scratch, lane);
+                cbr = warp_blurred_log_single(prev, H, H - 1, W - 1, gw, radius, scratch, lane);
+                cbl = warp_blurred_log_single(prev, H, H - 1, 0, gw, radius, scratch, lane);
+            }
+        } else if (prm.mode == SPP_DECODE_SOFTARGMAX) {
+            // softmax over the flattened map (max-subtracted), expected column / row, max probability
+            const float half = FLIP ? 0.5f : 1.0f;
+            for (int q4 = lane; q4 < n4; q4 += 32) {
+                const float4 v = quad(q4);
+                const int r = (int)(((unsigned)q4 * magic) >> 16);
+                const int c4 = q4 - r * W4;
+                const float e0 = expf(v.x * half - best), e1 = expf(v.y * half - best), e2 = expf(v.z * half - best),
+                            e3 = expf(v.w * half - best);
+                const float c0 = (float)(c4 << 2);
+                const float es = (e0 + e1) + (e2 + e3);
+                se += es;
+                sxe += e0 * c0 + e1 * (c0 + 1.f) + e2 * (c0 + 2.f) + e3 * (c0 + 3.f);
+                sye += es * (float)r;
+            }
+        } else {
+            const int px = valid ? ax : 0, py = valid ? ay : 0;
+            if (px > 1 && px < W - 1 && py > 1 && py < H - 1) {
+                qdx = mv.at(py, px + 1) - mv.at(py, px - 1);
+                qdy = mv.at(py + 1, px) - mv.at(py - 1, px);
+            }
+        }
+
+        // ---- release the stage: the next map streams in while this one is refined ------------------------
+        __syncwarp();
+        {
+            const long long qn = q + (long long)stages * nwarps;
+            if (lane == 0 && qn < total) issue(qn, s);
+        }
+
+        // ---- phase 3: refinement + back-projection (registers and per-warp scratch only) ------------------
         float out_x = 0.f, out_y = 0.f, out_s = best;
 
         if (prm.mode == SPP_DECODE_DARK) {
             // HF get_keypoint_predictions: coordinates -1 where score <= 0
-            const bool valid = best > 0.0f;
             const float cx = valid ? (float)ax : -1.0f, cy = valid ? (float)ay : -1.0f;
             float L00, L01, L10, L11, L12, L21, L22;
             if (valid) {
-                const int ncols = 2 * radius + 3;
-                __syncwarp();
-                // vertical pass (scipy filters axis 0 first): T[r3][j] for the 3 tap rows x (2r+3) columns.
-                // Two outputs per lane, issued together.
+                // vertical pass (scipy filters axis 0 first): T[r3][j] for the 3 tap rows x (2r+3) columns,
+                // two outputs per lane issued together; window row of map row u is u - (ay - r - 1)
                 const int t0 = lane, t1 = lane + 32;
-                const bool has1 = t1 < 3 * ncols;
-                const int r30 = t0 / ncols, j0 = t0 - r30 * ncols;
-                const int r31 = has1 ? t1 / ncols : 0, j1 = has1 ? t1 - r31 * ncols : 0;
-                const int yy0 = clampi(ay + r30 - 1, 0, H - 1), yy1 = clampi(ay + r31 - 1, 0, H - 1);   // np.pad(mode="edge")
-                const int xx0 = reflect_idx(ax - (radius + 1) + j0, W), xx1 = reflect_idx(ax - (radius + 1) + j1, W);
-                const double a0 = sym_filter<RADIUS>([&](int d) { return mv.at(reflect_idx(yy0 + d, H), xx0); }, gw, radius);
-                const double a1 = sym_filter<RADIUS>([&](int d) { return mv.at(reflect_idx(yy1 + d, H), xx1); }, gw, radius);
-                if (t0 < 3 * ncols) scratch[t0] = (float)a0;    // fp32 intermediate between the axes
+                const bool has1 = t1 < 3 * wn;
+                const int r30 = t0 / wn, j0 = t0 - r30 * wn;
+                const int r31 = has1 ? t1 / wn : 0, j1 = has1 ? t1 - r31 * wn : 0;
+                // np.pad(mode="edge") on the tap rows
+                const int wy0 = clampi(ay + r30 - 1, 0, H - 1) - (ay - (radius + 1));
+                const int wy1 = clampi(ay + r31 - 1, 0, H - 1) - (ay - (radius + 1));
+                const double a0 = sym_filter<RADIUS>([&](int d) { return win[(wy0 + d) * wn + j0]; }, gw, radius);
+                const double a1 = sym_filter<RADIUS>([&](int d) { return win[(wy1 + d) * wn + j1]; }, gw, radius);
+                if (t0 < 3 * wn) scratch[t0] = (float)a0;    // fp32 intermediate between the axes
                 if (has1) scratch[t1] = (float)a1;
                 __syncwarp();
                 float Lv = 0.f;
                 if (lane < 9) {
                     const int r3 = lane / 3, c3 = lane - r3 * 3;
                     const int xc = clampi(ax + c3 - 1, 0, W - 1);
-                    const float *row = scratch + r3 * ncols + (xc - ax) + radius + 1;
+                    const float *row = scratch + r3 * wn + (xc - ax) + radius + 1;
                     const double acc = sym_filter<RADIUS>([&](int d) { return row[d]; }, gw, radius);
                     Lv = clip_log((float)acc);
                 }
@@ -276,22 +328,12 @@ __global__ void __launch_bounds__(256, 1) heatmap_decode_kernel(const DecodePara
                 L12 = __shfl_sync(FULL, Lv, 5);
                 L21 = __shfl_sync(FULL, Lv, 7);
                 L22 = __shfl_sync(FULL, Lv, 8);
+                __syncwarp();                                // scratch / win are rewritten for the next map
             } else {
-                // HF indexes the flattened, edge-padded batch with coordinate -1: the centre taps land on
-                // padded[0,0] of this map, the "minus" taps on the tail of the PREVIOUS map (numpy
-                // negative indices wrap to the last map for q == 0).  Reproduced for parity.
-                const long long qp = (q + total - 1) % total;
-                const long long pp = qp / K;
-                const int kp = (int)(qp - pp * K);
-                MapView<FLIP> prev{prm.hm + qp * map_elems, nullptr, W};
-                if (FLIP) prev.B = prm.hmf + (pp * K + (prm.perm ? __ldg(prm.perm + kp) : kp)) * map_elems;
-                const float c = warp_blurred_log_single(mv, H, 0, 0, gw, radius, scratch, lane);
-                const float br = warp_blurred_log_single(prev, H, H - 1, W - 1, gw, radius, scratch, lane);
-                const float bl = warp_blurred_log_single(prev, H, H - 1, 0, gw, radius, scratch, lane);
-                L11 = L12 = L21 = L22 = c;
-                L10 = br;  // padded[index - 1]
-                L01 = bl;  // padded[index - (W + 2)]
-                L00 = br;  // padded[index - (W + 3)]
+                L11 = L12 = L21 = L22 = c00;
+                L10 = cbr;  // padded[index - 1]
+                L01 = cbl;  // padded[index - (W + 2)]
+                L00 = cbr;  // padded[index - (W + 3)]
             }
             const float i_ = L11, ix1 = L12, iy1 = L21, ix1y1 = L22, ix1_y1_ = L00, ix1_ = L10, iy1_ = L01;
             const float dx = 0.5f * (ix1 - ix1_);
@@ -332,19 +374,6 @@ __global__ void __launch_bounds__(256, 1) heatmap_decode_kernel(const DecodePara
                 out_y = __fsub_rn(__fadd_rn(__fmul_rn(out_y, scale_y), cyf), __fmul_rn(s1, 0.5f));
             }
         } else if (prm.mode == SPP_DECODE_SOFTARGMAX) {
-            // softmax over the flattened map (max-subtracted), expected column / row, max probability
-            float se = 0.f, sxe = 0.f, sye = 0.f;
-            for (int q4 = lane; q4 < n4; q4 += 32) {
-                const float4 v = quad(q4);
-                const int r = (int)(((unsigned)q4 * magic) >> 16);
-                const int c4 = q4 - r * W4;
-                const float e0 = expf(v.x - best), e1 = expf(v.y - best), e2 = expf(v.z - best), e3 = expf(v.w - best);
-                const float c0 = (float)(c4 << 2);
-                const float es = (e0 + e1) + (e2 + e3);
-                se += es;
-                sxe += e0 * c0 + e1 * (c0 + 1.f) + e2 * (c0 + 2.f) + e3 * (c0 + 3.f);
-                sye += es * (float)r;
-            }
             se = warp_sum(se);
             sxe = warp_sum(sxe);
             sye = warp_sum(sye);
@@ -365,15 +394,9 @@ __global__ void __launch_bounds__(256, 1) heatmap_decode_kernel(const DecodePara
                 }
             }
         } else {  // SPP_DECODE_QUARTER
-            const bool valid = best > 0.0f;
             float cx = valid ? (float)ax : 0.f, cy = valid ? (float)ay : 0.f;
-            const int px = valid ? ax : 0, py = valid ? ay : 0;
-            if (px > 1 && px < W - 1 && py > 1 && py < H - 1) {
-                const float ddx = mv.at(py, px + 1) - mv.at(py, px - 1);
-                const float ddy = mv.at(py + 1, px) - mv.at(py - 1, px);
-                cx += 0.25f * (float)((ddx > 0.f) - (ddx < 0.f));
-                cy += 0.25f * (float)((ddy > 0.f) - (ddy < 0.f));
-            }
+            cx += 0.25f * (float)((qdx > 0.f) - (qdx < 0.f));
+            cy += 0.25f * (float)((qdy > 0.f) - (qdy < 0.f));
             out_x = cx;
             out_y = cy;
             if (prm.boxes) {
@@ -397,10 +420,6 @@ __global__ void __launch_bounds__(256, 1) heatmap_decode_kernel(const DecodePara
             prm.scores[q] = out_s;
             if (prm.amax) prm.amax[q] = bidx;
         }
-
-        __syncwarp();  // every lane is done with this stage before it is refilled
-        const long long qn = q + (long long)stages * nwarps;
-        if (lane == 0 && qn < total) issue(qn, s);
     }
 }
 

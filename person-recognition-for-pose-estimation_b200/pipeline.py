@@ -100,13 +100,15 @@ class SelectivePosePipeline:
     def _enqueue(self) -> None:
         i = self.inp
         n = 0
-        face = ops.decode_nms(i.face_levels, conf_thres=self.conf, iou_thres=self.iou, out=self.out.get("_face"))
-        person = ops.decode_nms(i.person_levels, conf_thres=self.conf, iou_thres=self.iou, out=self.out.get("_person"))
-        n += 2 * 3      # memset + candidate kernel + NMS kernel per head
-        ids, sims, keys = ops.match_top1(i.embeddings, self.gallery, self.threshold, self.id_offset, want_keys=True)
-        n += 3          # normalise, tcgen05 GEMM + top-2, fp32 re-score
+        # order: the crop writes 377 MB; running the latency-bound detection / match kernels next gives
+        # the L2 time to write that back before the bandwidth-bound heatmap decode starts
         pix = ops.crop_affine(i.frames, i.boxes, i.frame_idx, out=self.out.get("pixel_values"))
         n += 1
+        face = ops.decode_nms(i.face_levels, conf_thres=self.conf, iou_thres=self.iou, out=self.out.get("_face"))
+        person = ops.decode_nms(i.person_levels, conf_thres=self.conf, iou_thres=self.iou, out=self.out.get("_person"))
+        n += 2 * 4      # memset + candidate scan + candidate decode + NMS kernel per head
+        ids, sims, keys = ops.match_top1(i.embeddings, self.gallery, self.threshold, self.id_offset, want_keys=True)
+        n += 3          # normalise, tcgen05 GEMM + top-2, fp32 re-score
         flags = (ops.FLAG_SCALE_SCORE | ops.FLAG_BACKPROJECT) if self.mode == "softargmax" else 0
         kp = ops.heatmap_decode(i.heatmaps, i.flipped, i.perm, i.boxes, self.mode, 11, flags,
                                 out=(self.out["keypoints"], self.out["scores"], self.out["argmax"]) if "keypoints" in self.out else None)

@@ -1,0 +1,112 @@
+"""CPU-side checks: the C-ABI library loads and exports what include/*.h declares, the host logic
+(key packing, shard bounds, shims' argument validation) and the world_size-2 gallery reduction over gloo."""
+import ctypes
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import match as omatch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(spp):
+    spp.build()                                   # nvcc cross-compiles without a GPU
+    lib = ctypes.CDLL(spp._lib.LIB_PATH)
+    declared = set()
+    for header in ("spp.h", "spp_internal.h"):
+        text = open(os.path.join(ROOT, "include", header)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        declared |= set(re.findall(r"\b(spp_[a-z0-9_]+)\s*\(", text))
+    assert len(declared) >= 15
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libspp.so does not export {name}"
+    assert declared == set(spp._lib.SIGNATURES), "ctypes table and headers disagree"
+    assert lib.spp_abi_version() == 1
+
+
+def test_no_cpu_fallback(spp):
+    with pytest.raises(RuntimeError, match="CUDA"):
+        spp.non_max_suppression(torch.zeros(1, 5, 8))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        spp.get_keypoints_from_heatmaps(torch.zeros(1, 17, 64, 48))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        spp.crop_affine(torch.zeros(1, 3, 8, 8), torch.zeros(1, 4), torch.zeros(1, dtype=torch.int32))
+    if not torch.cuda.is_available():
+        L = spp._lib.lib()
+        assert L.spp_device_sm_count() < 0 and b"no CUDA device" in L.spp_last_error()
+    # workspace queries are pure host arithmetic
+    assert spp._lib.lib().spp_nms_workspace_bytes(64, 19320, 1, 0) > 64 * 19320 * 8
+    assert spp._lib.lib().spp_match_workspace_bytes(640, 10000, 512) > 640 * 512 * 6
+    assert spp._lib.lib().spp_match_workspace_bytes(640, 10000, 256) == 0
+
+
+def test_key_packing_round_trip_and_order(spp):
+    d = spp.dist
+    g = torch.Generator().manual_seed(0)
+    sims = torch.cat([torch.randn(1000, generator=g), torch.tensor([0.0, -0.0, 1.0, -1.0, 0.5, 0.5])])
+    ids = torch.randint(0, 2 ** 31 - 2, (sims.numel(),), generator=g)
+    ids[-1], ids[-2] = 7, 9                                  # equal similarity: lower id must win
+    keys = d.pack_keys(sims, ids)
+    rid, rs = d.unpack_keys(keys)
+    assert torch.equal(rid, ids) and torch.equal(rs.abs(), sims.abs())
+    order = torch.argsort(keys, descending=True)
+    assert (sims[order][:-1] >= sims[order][1:]).all()
+    assert keys[-1] > keys[-2]                               # id 7 beats id 9 at equal similarity
+    none = d.pack_keys(torch.tensor([0.3]), torch.tensor([-1]))
+    assert none < keys.min() and d.unpack_keys(none)[0].item() == -1
+    assert d.unpack_keys(d.pack_keys(torch.tensor([0.3]), torch.tensor([5])), threshold=0.4)[0].item() == -1
+    assert [d.shard_bounds(10, 4, r) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, n, m, out):
+    import importlib
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = importlib.import_module("person-recognition-for-pose-estimation_b200.dist")
+    synth = importlib.import_module("person-recognition-for-pose-estimation_b200.synth")
+    ms = synth.make_match_set(world * m, n, seed=3)
+    gal = ms.gallery.to(torch.bfloat16).float()
+    lo, hi = d.shard_bounds(n, world, rank)
+
+    def local(p):      # oracle-based stand-in for the GPU kernel: top-1 of every probe in this shard
+        ids, sims = omatch.match_top1(p, gal[lo:hi])
+        return d.pack_keys(sims, ids + lo)
+
+    matcher = d.ShardedGalleryMatcher(local, threshold=0.4)
+    ids, sims = matcher.match(ms.embeddings[rank * m:(rank + 1) * m])
+    ref_ids, ref_sims = omatch.match_top1(ms.embeddings[rank * m:(rank + 1) * m], gal, threshold=0.4)
+    out[rank] = bool(torch.equal(ids, ref_ids) and torch.allclose(sims, ref_sims, rtol=0, atol=1e-6))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_gallery_top1_gloo_world2():
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, port, 301, 12, out), nprocs=world, join=True)
+        assert dict(out) == {0: True, 1: True}
+
+
+def test_synthetic_inputs_are_deterministic(synth):
+    a = synth.make_heatmaps(3, 17, seed=5)
+    b = synth.make_heatmaps(3, 17, seed=5)
+    assert torch.equal(a.heatmaps, b.heatmaps) and torch.equal(a.flipped, b.flipped)
+    assert synth.num_anchors(736, 1280) == 19320 and synth.num_anchors(640, 640) == 8400
+    hm = synth.make_head_maps(1, 64, 96, n_obj=2, seed=1)
+    assert [tuple(l.shape) for l in hm.levels] == [(1, 65, 8, 12), (1, 65, 4, 6), (1, 65, 2, 3)]
