@@ -179,6 +179,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--serial", action="store_true", help="run the four chains back to back instead of on forked streams")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "spp" else args.warmup
 
@@ -206,7 +207,8 @@ def main():
     ms = spp.synth.make_match_set(wl["batch"] * wl["per_frame"], wl["gallery"], seed=1000 + rank)
     inp.embeddings = ms.embeddings
     gallery_bf16 = ms.gallery.to(torch.bfloat16)
-    pipe = pipeline.SelectivePosePipeline(inp, gallery_bf16, dev, decode_mode=args.decode_mode, use_graph=not args.no_graph)
+    pipe = pipeline.SelectivePosePipeline(inp, gallery_bf16, dev, decode_mode=args.decode_mode, use_graph=not args.no_graph,
+                                          concurrent=not args.serial)
     pipe.bind_host(inp)
     B, P, K, M = wl["batch"], wl["batch"] * wl["per_frame"], wl["joints"], wl["batch"] * wl["per_frame"]
     A = sum(l.shape[2] * l.shape[3] for l in inp.face_levels)
@@ -352,7 +354,8 @@ def main():
                        "decode_mode": args.decode_mode, "parallelism": f"dp{world} (frames sharded, no data-path collective)",
                        "l2": "step region: inputs (1.6 GB per step) are larger than the 126 MB L2, no flush; "
                              "per-kernel region: a 256 MB read between launches evicts L2 (cold, clean)",
-                       "cuda_graph": not args.no_graph},
+                       "cuda_graph": not args.no_graph,
+                       "streams": "serial" if args.serial else "4 forked chains (crop->heatmap | det face | det person | match)"},
             "crops_per_s": round(world * P * args.steps / (dev_ms / 1e3), 1),
             "e2e": {"value": round(e2e_fps, 1), "unit": "frames/s", "h2d_bytes_per_step": pipe.h2d_bytes,
                     "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": round(e2e_ms / e2e_steps, 3), "steps": e2e_steps},

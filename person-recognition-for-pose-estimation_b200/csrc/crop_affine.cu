@@ -184,9 +184,6 @@ __global__ void __launch_bounds__(256) crop_affine_kernel(const CropParams prm, 
             mbar_wait(bar, parity);
             parity ^= 1;
         }
-        // staged: tile(iy, ix) = buf[(iy - sy_lo) * row_elems + ix - cx0];  direct: src[iy * fw + ix]
-        const float *tile = use_stage ? buf - (ptrdiff_t)sy_lo * row_elems - cx0 : src;
-        const int pitch = use_stage ? row_elems : prm.fw;
         for (int x = tid; x < ow; x += nthreads) {
             const AxisEntry ex = xt[x];
             float *o = dst + (size_t)r0 * ow + x;
@@ -194,18 +191,34 @@ __global__ void __launch_bounds__(256) crop_affine_kernel(const CropParams prm, 
                 for (int y = r0; y <= r1; ++y, o += ow) __stcs(o, zero_out);
                 continue;
             }
-            const float *col = tile + ex.i0;
             const float wx = ex.t;
+            if (use_stage) {
+                // shared-memory tile: element (iy, ix) at buf[(iy - sy_lo) * row_elems + (ix - cx0)], 32-bit indices
+                const int colbase = ex.i0 - cx0 - sy_lo * row_elems;
 #pragma unroll 4
-            for (int y = r0; y <= r1; ++y, o += ow) {
-                const AxisEntry ey = yt[y];
-                const float *ra = col + ey.i0 * pitch;
-                const float *rb = ra + pitch;
-                const float p00 = ra[0], p01 = ra[1], p10 = rb[0], p11 = rb[1];
-                const float top = fmaf(p01 - p00, wx, p00);
-                const float bot = fmaf(p11 - p10, wx, p10);
-                const float v = fmaf(bot - top, ey.t, top);
-                __stcs(o, fmaf(v, inv_sd, nmean));
+                for (int y = r0; y <= r1; ++y, o += ow) {
+                    const AxisEntry ey = yt[y];
+                    const int ia = ey.i0 * row_elems + colbase;
+                    const int ib = ia + row_elems;
+                    const float p00 = buf[ia], p01 = buf[ia + 1], p10 = buf[ib], p11 = buf[ib + 1];
+                    const float top = fmaf(p01 - p00, wx, p00);
+                    const float bot = fmaf(p11 - p10, wx, p10);
+                    const float v = fmaf(bot - top, ey.t, top);
+                    __stcs(o, fmaf(v, inv_sd, nmean));
+                }
+            } else {
+                const float *col = src + ex.i0;
+#pragma unroll 4
+                for (int y = r0; y <= r1; ++y, o += ow) {
+                    const AxisEntry ey = yt[y];
+                    const float *ra = col + (size_t)ey.i0 * prm.fw;
+                    const float *rb = ra + prm.fw;
+                    const float p00 = __ldg(ra), p01 = __ldg(ra + 1), p10 = __ldg(rb), p11 = __ldg(rb + 1);
+                    const float top = fmaf(p01 - p00, wx, p00);
+                    const float bot = fmaf(p11 - p10, wx, p10);
+                    const float v = fmaf(bot - top, ey.t, top);
+                    __stcs(o, fmaf(v, inv_sd, nmean));
+                }
             }
         }
         if (use_stage) __syncthreads();              // the band buffer is refilled next

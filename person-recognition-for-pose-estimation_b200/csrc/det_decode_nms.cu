@@ -36,7 +36,6 @@ constexpr int kNmsThreads = 512;
 constexpr int kSortSmemMax = 8192;  // keys sorted in shared memory up to this (padded) count
 constexpr int kBoxSmemMax = 2048;   // sorted boxes kept in shared memory (the rest is re-gathered)
 constexpr int kAliveWords = 1024;   // one alive bit per candidate: max_nms <= 32768
-constexpr int kRankSortMax = 1024;  // rank sort (no barriers) up to this many candidates
 
 struct Levels {
     const float *ptr[SPP_MAX_LEVELS];
@@ -192,20 +191,29 @@ __global__ void __launch_bounds__(256) cand_scan_kernel(const Levels lv, int nc,
 __global__ void __launch_bounds__(256) cand_decode_kernel(const Levels lv, int nc, int batch, int cap, int cap_pad,
                                                           const int *__restrict__ counts, const unsigned long long *__restrict__ keys,
                                                           float4 *__restrict__ boxes) {
+    extern __shared__ int pre[];                                  // [batch + 1] exclusive prefix of the counts
     const int lane = threadIdx.x & 31, sub = lane & 15;
     const int half_id = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 4);
     const int nhalf = (int)((gridDim.x * blockDim.x) >> 4);
-    int maxn = 0;
-    for (int b = lane; b < batch; b += 32) maxn = max(maxn, min(__ldg(counts + b), cap));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) maxn = max(maxn, __shfl_xor_sync(FULL, maxn, o));
-    const long long range = (long long)maxn * batch;          // items are (slot, image), image fastest
+    for (int b = threadIdx.x; b < batch; b += blockDim.x) pre[b + 1] = min(__ldg(counts + b), cap);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        pre[0] = 0;
+        for (int b = 0; b < batch; ++b) pre[b + 1] += pre[b];
+    }
+    __syncthreads();
+    const int total = pre[batch];                                 // items = candidates of all images, back to back
     const int no = 4 * kDfl + nc;
     // both halves of a warp iterate together (full-mask shuffles); an idle half works on a dummy item
-    for (long long base = (half_id & ~1); base < range; base += nhalf) {
-        const long long L = base + (half_id & 1);
-        const int slot = (int)((unsigned long long)L / (unsigned)batch), b = (int)(L - (long long)slot * batch);
-        const bool valid = L < range && slot < min(__ldg(counts + b), cap);
+    for (int base = (half_id & ~1); base < total; base += nhalf) {
+        const int t = base + (half_id & 1);
+        const bool valid = t < total;
+        int lo = 0, hi = batch;                                   // largest b with pre[b] <= t
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (pre[mid] <= (valid ? t : 0)) lo = mid; else hi = mid;
+        }
+        const int b = lo, slot = (valid ? t : 0) - pre[lo];
         const unsigned cand = valid ? (unsigned)(keys[(size_t)b * cap_pad + slot] & 0xffffffffu) : 0u;
         const int anchor = (int)(cand / (unsigned)nc);
         const LevelRef lr = find_level(lv, anchor);
@@ -285,22 +293,34 @@ __device__ void bitonic_sort(unsigned long long *d, int npad) {
     }
 }
 
-// Rank sort for small candidate lists: keys are unique, so rank = #smaller keys; n^2 broadcast
-// shared-memory reads and no barrier inside.  src -> dst (both shared).
-__device__ void rank_sort(const unsigned long long *src, unsigned long long *dst, int n) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const unsigned long long k = src[i];
-        int r = 0;
-#pragma unroll 8
-        for (int j = 0; j < n; ++j) r += src[j] < k;
-        dst[r] = k;
+// Bitonic sort of up to kNmsThreads keys, one per thread: compare-exchange partners closer than 32 are
+// reached with warp shuffles (no barrier, no shared memory), the 10 longer strides go through `xch`.
+__device__ unsigned long long block_bitonic_reg(unsigned long long key, unsigned long long *xch) {
+    const int tid = threadIdx.x;
+    for (int k = 2; k <= kNmsThreads; k <<= 1) {
+        const bool up = (tid & k) == 0;
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            unsigned long long other;
+            if (j >= 32) {
+                xch[tid] = key;
+                __syncthreads();
+                other = xch[tid ^ j];
+                __syncthreads();
+            } else {
+                other = __shfl_xor_sync(FULL, key, j);
+            }
+            const bool lower = (tid & j) == 0;
+            // the lower index of a pair keeps the smaller key in an ascending run, the larger otherwise
+            const bool take_min = lower == up;
+            key = take_min ? (key < other ? key : other) : (key > other ? key : other);
+        }
     }
-    __syncthreads();
+    return key;
 }
 
 // One CTA per image.
-//   1. sort of the 64-bit keys: rank sort up to kRankSortMax, bitonic in shared memory up to kSortSmemMax,
-//      bitonic in the workspace beyond;
+//   1. bitonic sort of the 64-bit keys: in registers + shuffles up to one key per thread, in shared
+//      memory up to kSortSmemMax, in the workspace beyond;
 //   2. sorted, class-offset boxes + areas are staged in shared memory (first kBoxSmemMax; beyond that they
 //      are re-gathered on the fly), one "alive" bit per candidate;
 //   3. greedy loop, serial over KEPT boxes only: every warp clears, with one ballot per 32-candidate word
@@ -325,12 +345,10 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams prm) {
     int n = raw_count < prm.cap ? raw_count : prm.cap;
     unsigned long long *gkeys = prm.keys + (size_t)b * prm.cap_pad;
     unsigned long long *keys;
-    if (n <= kRankSortMax) {
-        // unsorted keys parked in the (not yet used) box area, sorted into skeys
-        unsigned long long *tmp = reinterpret_cast<unsigned long long *>(sbox);
-        for (int i = tid; i < n; i += kNmsThreads) tmp[i] = gkeys[i];
+    if (n <= kNmsThreads) {
+        const unsigned long long mine = block_bitonic_reg(tid < n ? gkeys[tid] : ~0ull, reinterpret_cast<unsigned long long *>(sbox));
+        skeys[tid] = mine;
         __syncthreads();
-        rank_sort(tmp, skeys, n);
         keys = skeys;
     } else {
         int npad = 1;
@@ -399,6 +417,10 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams prm) {
             s_next[(it + 2) % 3] = INT_MAX;   // last read in iteration it - 1, proposals start in it + 1
         }
         ++nk;
+        if ((i >> 5) + warp >= nwords) {          // nothing left for this warp
+            __syncthreads();
+            continue;
+        }
         float4 bi;
         float ai;
         get_box(i, bi, ai);
@@ -508,7 +530,7 @@ int launch_nms(const NmsParams &prm, int batch, cudaStream_t st) {
 
 int check_nms_args(int batch, int nc, float iou, int max_det, int max_nms, const float *out_dets, const int *out_count,
                    const void *ws) {
-    SPP_CHECK_ARG(batch >= 0 && nc >= 1, "nms: bad batch %d / nc %d", batch, nc);
+    SPP_CHECK_ARG(batch >= 0 && batch <= 8192 && nc >= 1, "nms: need 0 <= batch <= 8192 and nc >= 1 (got %d / %d)", batch, nc);
     SPP_CHECK_ARG(max_det >= 1 && max_det <= 4096 && max_nms >= 1 && max_nms <= kAliveWords * 32,
                   "nms: need 1 <= max_det <= 4096 and 1 <= max_nms <= %d (got %d / %d)", kAliveWords * 32, max_det, max_nms);
     SPP_CHECK_ARG(out_dets && out_count && ws, "nms: null output / workspace");
@@ -591,7 +613,7 @@ extern "C" int spp_decode_nms(const float *const *levels, const int *level_h, co
     {
         int sms = sm_count();
         if (sms <= 0) return SPP_ERR_CUDA;
-        cand_decode_kernel<<<sms * 16, 256, 0, st>>>(lv, nc, batch, w.cap, w.cap_pad, w.counts, w.keys, w.boxes);
+        cand_decode_kernel<<<sms * 8, 256, (size_t)(batch + 1) * sizeof(int), st>>>(lv, nc, batch, w.cap, w.cap_pad, w.counts, w.keys, w.boxes);
         SPP_CHECK_LAUNCH();
     }
     NmsParams prm{};

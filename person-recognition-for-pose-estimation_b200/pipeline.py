@@ -77,7 +77,7 @@ class SelectivePosePipeline:
 
     def __init__(self, inputs: StepInputs, gallery_bf16: torch.Tensor, device: torch.device, threshold: float = 0.4,
                  conf_thres: float = 0.001, iou_thres: float = 0.65, decode_mode: str = "dark", use_graph: bool = True,
-                 id_offset: int = 0):
+                 id_offset: int = 0, concurrent: bool = True):
         self.device = device
         self.threshold, self.conf, self.iou, self.mode = threshold, conf_thres, iou_thres, decode_mode
         self.id_offset = id_offset
@@ -87,6 +87,8 @@ class SelectivePosePipeline:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_step = 0
         self._stream = torch.cuda.Stream(device)
+        self.concurrent = concurrent
+        self._side = [torch.cuda.Stream(device) for _ in range(3)]
         with torch.cuda.stream(self._stream):
             self._enqueue()                       # warm-up: sizes workspaces, sets kernel attributes
             self._enqueue()
@@ -98,21 +100,38 @@ class SelectivePosePipeline:
             self.graph = g
 
     def _enqueue(self) -> None:
+        """Enqueue one pass.  Four independent chains run on forked streams and join at the end (inside a
+        capture this becomes a graph with parallel branches): the HBM-bound crop -> heatmap-decode chain on the
+        pipeline stream, the latency-bound detection chains (face / person) and the match chain beside it, so
+        the small kernels fill SM slots and hide behind the two bandwidth-bound ones."""
         i = self.inp
+        main = torch.cuda.current_stream(self.device)
+        if self.concurrent:
+            fork = torch.cuda.Event()
+            fork.record(main)
+            for s in self._side:
+                s.wait_event(fork)
+        sides = self._side if self.concurrent else [main, main, main]
         n = 0
-        # order: the crop writes 377 MB; running the latency-bound detection / match kernels next gives
-        # the L2 time to write that back before the bandwidth-bound heatmap decode starts
+        with torch.cuda.stream(sides[0]):
+            face = ops.decode_nms(i.face_levels, conf_thres=self.conf, iou_thres=self.iou, out=self.out.get("_face"))
+        with torch.cuda.stream(sides[1]):
+            person = ops.decode_nms(i.person_levels, conf_thres=self.conf, iou_thres=self.iou, out=self.out.get("_person"))
+        n += 2 * 4      # memset + candidate scan + candidate decode + NMS kernel per head
+        with torch.cuda.stream(sides[2]):
+            ids, sims, keys = ops.match_top1(i.embeddings, self.gallery, self.threshold, self.id_offset, want_keys=True)
+        n += 3          # normalise, tcgen05 GEMM + top-2, fp32 re-score
         pix = ops.crop_affine(i.frames, i.boxes, i.frame_idx, out=self.out.get("pixel_values"))
         n += 1
-        face = ops.decode_nms(i.face_levels, conf_thres=self.conf, iou_thres=self.iou, out=self.out.get("_face"))
-        person = ops.decode_nms(i.person_levels, conf_thres=self.conf, iou_thres=self.iou, out=self.out.get("_person"))
-        n += 2 * 4      # memset + candidate scan + candidate decode + NMS kernel per head
-        ids, sims, keys = ops.match_top1(i.embeddings, self.gallery, self.threshold, self.id_offset, want_keys=True)
-        n += 3          # normalise, tcgen05 GEMM + top-2, fp32 re-score
         flags = (ops.FLAG_SCALE_SCORE | ops.FLAG_BACKPROJECT) if self.mode == "softargmax" else 0
         kp = ops.heatmap_decode(i.heatmaps, i.flipped, i.perm, i.boxes, self.mode, 11, flags,
                                 out=(self.out["keypoints"], self.out["scores"], self.out["argmax"]) if "keypoints" in self.out else None)
         n += 1
+        if self.concurrent:
+            for s in self._side:
+                join = torch.cuda.Event()
+                join.record(s)
+                main.wait_event(join)
         self.launches_per_step = n
         self.out.update(_face=face, _person=person, face_dets=face.dets, face_count=face.count, person_dets=person.dets,
                         person_count=person.count, ids=ids, sims=sims, keys=keys, pixel_values=pix, keypoints=kp[0],
