@@ -207,8 +207,11 @@ def main():
     ms = spp.synth.make_match_set(wl["batch"] * wl["per_frame"], wl["gallery"], seed=1000 + rank)
     inp.embeddings = ms.embeddings
     gallery_bf16 = ms.gallery.to(torch.bfloat16)
+    matcher = None
+    if world > 1:      # gallery sharded by rows: this rank holds ids [rank*N, (rank+1)*N); NCCL top-1 (value,index) reduce
+        matcher = spp.dist.gpu_matcher(gallery_bf16.to(dev).contiguous(), rank * wl["gallery"], 0.4)
     pipe = pipeline.SelectivePosePipeline(inp, gallery_bf16, dev, decode_mode=args.decode_mode, use_graph=not args.no_graph,
-                                          concurrent=not args.serial)
+                                          concurrent=not args.serial, matcher=matcher)
     pipe.bind_host(inp)
     B, P, K, M = wl["batch"], wl["batch"] * wl["per_frame"], wl["joints"], wl["batch"] * wl["per_frame"]
     A = sum(l.shape[2] * l.shape[3] for l in inp.face_levels)
@@ -351,7 +354,9 @@ def main():
             "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (bf16 tensor-core candidates + fp32 re-score in the match)", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {wl['desc']}", "frames_per_gpu": B, "crops_per_gpu": P,
-                       "decode_mode": args.decode_mode, "parallelism": f"dp{world} (frames sharded, no data-path collective)",
+                       "decode_mode": args.decode_mode, "parallelism": f"dp{world}: frames/crops/heatmaps sharded with no collective" + (
+                           f"; gallery of {world * wl['gallery']} ids sharded by rows, probes all-gathered, NCCL all_reduce(MAX) "
+                           "of packed (sim,id) keys" if world > 1 else ""),
                        "l2": "step region: inputs (1.6 GB per step) are larger than the 126 MB L2, no flush; "
                              "per-kernel region: a 256 MB read between launches evicts L2 (cold, clean)",
                        "cuda_graph": not args.no_graph,

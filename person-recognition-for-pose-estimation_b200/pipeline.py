@@ -77,7 +77,7 @@ class SelectivePosePipeline:
 
     def __init__(self, inputs: StepInputs, gallery_bf16: torch.Tensor, device: torch.device, threshold: float = 0.4,
                  conf_thres: float = 0.001, iou_thres: float = 0.65, decode_mode: str = "dark", use_graph: bool = True,
-                 id_offset: int = 0, concurrent: bool = True):
+                 id_offset: int = 0, concurrent: bool = True, matcher=None):
         self.device = device
         self.threshold, self.conf, self.iou, self.mode = threshold, conf_thres, iou_thres, decode_mode
         self.id_offset = id_offset
@@ -88,8 +88,14 @@ class SelectivePosePipeline:
         self.launches_per_step = 0
         self._stream = torch.cuda.Stream(device)
         self.concurrent = concurrent
+        # multi-GPU: a dist.ShardedGalleryMatcher replaces the local match chain; its NCCL collectives run
+        # eagerly on a side stream next to the graph (they are not captured)
+        self.matcher = matcher
+        self._match_stream = torch.cuda.Stream(device) if matcher is not None else None
         self._side = [torch.cuda.Stream(device) for _ in range(3)]
         with torch.cuda.stream(self._stream):
+            if matcher is not None:
+                self.out["ids"], self.out["sims"] = matcher.match(self.inp.embeddings)
             self._enqueue()                       # warm-up: sizes workspaces, sets kernel attributes
             self._enqueue()
         self._stream.synchronize()
@@ -118,9 +124,13 @@ class SelectivePosePipeline:
         with torch.cuda.stream(sides[1]):
             person = ops.decode_nms(i.person_levels, conf_thres=self.conf, iou_thres=self.iou, out=self.out.get("_person"))
         n += 2 * 4      # memset + candidate scan + candidate decode + NMS kernel per head
-        with torch.cuda.stream(sides[2]):
-            ids, sims, keys = ops.match_top1(i.embeddings, self.gallery, self.threshold, self.id_offset, want_keys=True)
-        n += 3          # normalise, tcgen05 GEMM + top-2, fp32 re-score
+        if self.matcher is None:
+            with torch.cuda.stream(sides[2]):
+                ids, sims, keys = ops.match_top1(i.embeddings, self.gallery, self.threshold, self.id_offset, want_keys=True)
+            n += 3          # normalise, tcgen05 GEMM + top-2, fp32 re-score
+        else:
+            ids, sims, keys = self.out.get("ids"), self.out.get("sims"), None
+            n += 4          # (eager, in step()) normalise, GEMM + top-2, re-score, key unpack
         pix = ops.crop_affine(i.frames, i.boxes, i.frame_idx, out=self.out.get("pixel_values"))
         n += 1
         flags = (ops.FLAG_SCALE_SCORE | ops.FLAG_BACKPROJECT) if self.mode == "softargmax" else 0
@@ -140,11 +150,26 @@ class SelectivePosePipeline:
     def step(self) -> Dict[str, torch.Tensor]:
         """Enqueue one pass on the pipeline's stream (graph replay when captured)."""
         with torch.cuda.stream(self._stream):
-            if self.graph is not None:
-                self.graph.replay()
-            else:
-                self._enqueue()
+            self._launch()
         return self.out
+
+    def _launch(self) -> None:
+        main = torch.cuda.current_stream(self.device)
+        if self.matcher is not None:            # gallery-sharded match: all_gather -> local top-1 -> all_reduce(MAX)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            self._match_stream.wait_event(fork)
+            with torch.cuda.stream(self._match_stream):
+                ids, sims = self.matcher.match(self.inp.embeddings)
+                self.out["ids"], self.out["sims"] = ids, sims
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._enqueue()
+        if self.matcher is not None:
+            join = torch.cuda.Event()
+            join.record(self._match_stream)
+            main.wait_event(join)
 
     @property
     def stream(self) -> torch.cuda.Stream:
@@ -167,10 +192,7 @@ class SelectivePosePipeline:
         with torch.cuda.stream(self._stream):
             for k, src in self._host_in.items():
                 dst[k].copy_(src, non_blocking=True)
-            if self.graph is not None:
-                self.graph.replay()
-            else:
-                self._enqueue()
+            self._launch()
             for k, buf in self._host_out.items():
                 buf.copy_(self.out[k], non_blocking=True)
         return self._host_out

@@ -275,3 +275,42 @@ def test_match_reference_fixture_and_keys(spp, golden, dev):
     k1 = spp.match_top1(torch.from_numpy(g["probes"]).to(dev), rows[128:].contiguous(), None, 128, want_keys=True)[2]
     ids2, sims2 = spp.match_unpack_keys(torch.maximum(k0, k1))
     assert torch.equal(ids2, full_ids) and torch.equal(sims2, full_sims)
+
+
+# ------------------------------------------------------------------------------------------------
+# multi-GPU: gallery sharded by rows, NCCL top-1 (value, index) reduction  (needs >= 2 GPUs)
+# ------------------------------------------------------------------------------------------------
+
+def _nccl_worker(rank, world, port, n, m, out):
+    import importlib
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    spp = importlib.import_module("person-recognition-for-pose-estimation_b200")
+    ms = spp.synth.make_match_set(world * m, n, seed=17)
+    gal = ms.gallery.to(torch.bfloat16)
+    lo, hi = spp.dist.shard_bounds(n, world, rank)
+    matcher = spp.dist.gpu_matcher(gal[lo:hi].contiguous().to(dev), lo, threshold=0.4)
+    ids, sims = matcher.match(ms.embeddings[rank * m:(rank + 1) * m].to(dev))
+    ref_ids, ref_sims = omatch.match_top1(ms.embeddings[rank * m:(rank + 1) * m], gal.float(), threshold=0.4)
+    gap = omatch.top2_gap(ms.embeddings[rank * m:(rank + 1) * m], gal.float())
+    ok = (gap > 1e-5) & ((ref_sims - 0.4).abs() > 1e-5)
+    out[rank] = bool(torch.equal(ids.cpu()[ok], ref_ids[ok]) and torch.allclose(sims.cpu(), ref_sims, rtol=1e-3, atol=1e-5))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_gallery_match_nccl(dev):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_nccl_worker, args=(world, port, 5000, 96, out), nprocs=world, join=True)
+        assert dict(out) == {0: True, 1: True}
