@@ -31,6 +31,7 @@ namespace spp {
 namespace {
 
 constexpr int kMaxRadius = 8;
+constexpr int kModeCopyOnly = 99;   // undocumented: stream the maps through the pipeline and do nothing
 constexpr int kScratch = 64 + 368;  // floats per warp: 3*(2r+3) <= 57 filter rows, then the (2r+3)^2 <= 361 window
 
 struct DecodeParams {
@@ -127,7 +128,7 @@ struct Best {
 };
 
 template <bool FLIP, int RADIUS>
-__global__ void __launch_bounds__(256, 1) heatmap_decode_kernel(const DecodeParams prm) {
+__global__ void __launch_bounds__(FLIP ? 256 : 512, 1) heatmap_decode_kernel(const DecodeParams prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int H = prm.H, W = prm.W, K = prm.K;
@@ -185,6 +186,13 @@ __global__ void __launch_bounds__(256, 1) heatmap_decode_kernel(const DecodePara
         const uint32_t parity = (uint32_t)((it / stages) & 1);
         mbar_wait(&bars[s], parity);
 
+        if (prm.mode == kModeCopyOnly) {     // profiling aid: the bare bulk-TMA pipeline, no arithmetic
+            __syncwarp();
+            const long long qn = q + (long long)stages * nwarps;
+            if (lane == 0 && qn < total) issue(qn, s);
+            if (lane == 0) prm.scores[q] = wbase[(size_t)s * NB * map_elems];
+            continue;
+        }
         const float *A = wbase + (size_t)s * NB * map_elems;
         const float *B = A + map_elems;
         const float4 *A4 = reinterpret_cast<const float4 *>(A);
@@ -268,8 +276,9 @@ __global__ void __launch_bounds__(256, 1) heatmap_decode_kernel(const DecodePara
                 const float4 v = quad(q4);
                 const int r = (int)(((unsigned)q4 * magic) >> 16);
                 const int c4 = q4 - r * W4;
-                const float e0 = expf(v.x * half - best), e1 = expf(v.y * half - best), e2 = expf(v.z * half - best),
-                            e3 = expf(v.w * half - best);
+                // arguments are in [-range, 0]: the fast exponential (ex2.approx) is accurate to ~1e-6 relative here
+                const float e0 = __expf(v.x * half - best), e1 = __expf(v.y * half - best), e2 = __expf(v.z * half - best),
+                            e3 = __expf(v.w * half - best);
                 const float c0 = (float)(c4 << 2);
                 const float es = (e0 + e1) + (e2 + e3);
                 se += es;
@@ -343,9 +352,9 @@ __global__ void __launch_bounds__(256, 1) heatmap_decode_kernel(const DecodePara
             const float dxy = 0.5f * (((((((ix1y1 - ix1) - iy1) + i_) + i_) - ix1_) - iy1_) + ix1_y1_);
             const double eps = (double)FLT_EPSILON;
             const double ha = (double)dxx + eps, hb = (double)dxy, hd = (double)dyy + eps;
-            const double det = ha * hd - hb * hb;
-            const double sx = (hd * (double)dx - hb * (double)dy) / det;
-            const double sy = (ha * (double)dy - hb * (double)dx) / det;
+            const double inv_det = 1.0 / (ha * hd - hb * hb);
+            const double sx = (hd * (double)dx - hb * (double)dy) * inv_det;
+            const double sy = (ha * (double)dy - hb * (double)dx) * inv_det;
             out_x = (float)((double)cx - sx);
             out_y = (float)((double)cy - sy);
             if (prm.boxes) {
@@ -446,7 +455,7 @@ extern "C" int spp_heatmap_decode(const float *hm, const float *hm_flipped, cons
     SPP_CHECK_ARG(hm && keypoints && scores, "heatmap_decode: hm, keypoints and scores must be non-null");
     SPP_CHECK_ARG(p >= 0 && k > 0 && h > 0 && w > 0, "heatmap_decode: bad shape p=%d k=%d h=%d w=%d", p, k, h, w);
     SPP_CHECK_ARG(w % 4 == 0, "heatmap_decode: heatmap width must be a multiple of 4 (got %d)", w);
-    SPP_CHECK_ARG(mode >= SPP_DECODE_DARK && mode <= SPP_DECODE_QUARTER, "heatmap_decode: unknown mode %d", mode);
+    SPP_CHECK_ARG((mode >= SPP_DECODE_DARK && mode <= SPP_DECODE_QUARTER) || mode == kModeCopyOnly, "heatmap_decode: unknown mode %d", mode);
     SPP_CHECK_ARG(kernel >= 3 && kernel <= 2 * kMaxRadius + 1 && (kernel & 1), "heatmap_decode: kernel must be odd in 3..%d (got %d)",
                   2 * kMaxRadius + 1, kernel);
     SPP_CHECK_ARG(crop_h > 0 && crop_w > 0, "heatmap_decode: bad crop size");
@@ -476,8 +485,10 @@ extern "C" int spp_heatmap_decode(const float *hm, const float *hm_flipped, cons
     const int slots = (int)(budget / stage_bytes);
     SPP_CHECK_ARG(slots >= 1, "heatmap_decode: a %dx%d map does not fit the shared-memory pipeline", h, w);
     // 8 warps per SM hide the ALU latency of the scan; whatever shared memory is left deepens each
-    // warp's private ring (flip test, 64x48: 8 warps x 1 stage x 24 KB; no flip: 8 x 2 x 12 KB).
-    int warps = slots < 8 ? slots : 8;
+    // warp's private ring (flip test, 64x48: 8 warps x 1 stage x 24 KB).
+    // (without the flip test a map is half the bytes for the same refinement work: 16 warps x 1 stage)
+    const int max_warps = flip ? 8 : 16;
+    int warps = slots < max_warps ? slots : max_warps;
     int stages = slots / warps;
     if (stages > 4) stages = 4;
     prm.warps = warps; prm.stages = stages;

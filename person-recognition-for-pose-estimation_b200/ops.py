@@ -18,7 +18,7 @@ MAX_WH = 7680.0     # training/yolopt/util.py:124
 MAX_DET = 300       # util.py:125
 MAX_NMS = 30000     # util.py:126
 
-DECODE_MODES = {"dark": 0, "softargmax": 1, "quarter": 2}
+DECODE_MODES = {"dark": 0, "softargmax": 1, "quarter": 2, "_copy_only": 99}
 CROP_VARIANTS = {"hf": 0, "udp": 0, "gluoncv": 1}
 
 

@@ -155,18 +155,21 @@ class SelectivePosePipeline:
 
     def _launch(self) -> None:
         main = torch.cuda.current_stream(self.device)
-        if self.matcher is not None:            # gallery-sharded match: all_gather -> local top-1 -> all_reduce(MAX)
+        if self.matcher is not None:
             fork = torch.cuda.Event()
             fork.record(main)
-            self._match_stream.wait_event(fork)
-            with torch.cuda.stream(self._match_stream):
-                ids, sims = self.matcher.match(self.inp.embeddings)
-                self.out["ids"], self.out["sims"] = ids, sims
         if self.graph is not None:
             self.graph.replay()
         else:
             self._enqueue()
         if self.matcher is not None:
+            # gallery-sharded match: all_gather -> local top-1 -> all_reduce(MAX).  Enqueued AFTER the graph
+            # launch so the host issues these eager calls while the device is busy with the graph; on the
+            # device the chain runs beside the graph on its own stream.
+            self._match_stream.wait_event(fork)
+            with torch.cuda.stream(self._match_stream):
+                ids, sims = self.matcher.match(self.inp.embeddings)
+                self.out["ids"], self.out["sims"] = ids, sims
             join = torch.cuda.Event()
             join.record(self._match_stream)
             main.wait_event(join)
