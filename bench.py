@@ -128,8 +128,8 @@ def cpu_reference_step(inp, gallery_f32, n_frames: int, per_frame: int, threshol
     out["ids"], out["sims"] = omatch.match_top1(inp.embeddings[:p], gallery_f32, threshold)
     boxes = [[[float(v) for v in inp.boxes[f * per_frame + j]] for j in range(per_frame)] for f in range(n_frames)]
     proc = cpu_reference_step.proc = getattr(cpu_reference_step, "proc", None) or VitPoseImageProcessor()
-    out["pixel_values"] = proc.preprocess([inp.frames[f] for f in range(n_frames)], boxes=boxes, do_rescale=False,
-                                          return_tensors="pt")["pixel_values"]
+    out["pixel_values"] = proc.preprocess([inp.frames[f] for f in range(n_frames)], boxes=boxes,
+                                          do_rescale=inp.frames.dtype == torch.uint8, return_tensors="pt")["pixel_values"]
     hm = inp.heatmaps[:p]
     if inp.flipped is not None:
         hm = opose.flip_average(hm, inp.flipped[:p], inp.perm)
@@ -180,6 +180,9 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--frames", default="f32", choices=["f32", "u8"],
+                    help="frame dtype: f32 in [0,1] (SURVEY 8d, default) or uint8 as a video decoder delivers them")
+    ap.add_argument("--capture-collectives", action="store_true", help="N>1: capture the NCCL calls into the CUDA graph (hung in testing)")
     ap.add_argument("--serial", action="store_true", help="run the four chains back to back instead of on forked streams")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "spp" else args.warmup
@@ -212,19 +215,23 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)    # NCCL kernels must not queue behind the crop
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     peaks = load_peaks()
 
     # ---- inputs (per-rank shard: every rank owns `batch` frames; weak scaling) ------------------
     inp = pipeline.synthetic_inputs(wl["batch"], wl["height"], wl["width"], wl["per_frame"], wl["joints"], seed=rank)
     ms = spp.synth.make_match_set(wl["batch"] * wl["per_frame"], wl["gallery"], seed=1000 + rank)
     inp.embeddings = ms.embeddings
+    if args.frames == "u8":
+        inp.frames = (inp.frames * 255.0).round().clamp(0, 255).to(torch.uint8)
     gallery_bf16 = ms.gallery.to(torch.bfloat16)
     matcher = None
     if world > 1:      # gallery sharded by rows: this rank holds ids [rank*N, (rank+1)*N); NCCL top-1 (value,index) reduce
         matcher = spp.dist.gpu_matcher(gallery_bf16.to(dev).contiguous(), rank * wl["gallery"], 0.4)
     pipe = pipeline.SelectivePosePipeline(inp, gallery_bf16, dev, decode_mode=args.decode_mode, use_graph=not args.no_graph,
-                                          concurrent=not args.serial, matcher=matcher)
+                                          concurrent=not args.serial, matcher=matcher,
+                                          capture_collectives=args.capture_collectives)
     pipe.bind_host(inp)
     B, P, K, M = wl["batch"], wl["batch"] * wl["per_frame"], wl["joints"], wl["batch"] * wl["per_frame"]
     A = sum(l.shape[2] * l.shape[3] for l in inp.face_levels)
@@ -283,7 +290,9 @@ def main():
         "decode_nms_face": lambda: ops.decode_nms(i.face_levels, out=pipe.out["_face"]),
         "decode_nms_person": lambda: ops.decode_nms(i.person_levels, out=pipe.out["_person"]),
         "match_top1": lambda: ops.match_top1(i.embeddings, pipe.gallery, 0.4),
-        "crop_affine": lambda: ops.crop_affine(i.frames, i.boxes, i.frame_idx, out=pipe.out["pixel_values"]),
+        "crop_affine": lambda: ops.crop_affine(i.frames, i.boxes, i.frame_idx, out=pipe.out["pixel_values"],
+                                               **({"mean": [m * 255.0 for m in (0.485, 0.456, 0.406)],
+                                                   "std": [v * 255.0 for v in (0.229, 0.224, 0.225)]} if args.frames == "u8" else {})),
         "heatmap_decode": lambda: ops.heatmap_decode(i.heatmaps, i.flipped, i.perm, i.boxes, args.decode_mode, 11,
                                                      out=(pipe.out["keypoints"], pipe.out["scores"], pipe.out["argmax"])),
     }
@@ -319,7 +328,7 @@ def main():
     hm_bytes = P * (K * 64 * 48 * 4 * (2 if i.flipped is not None else 1) + K * 16)
     n_cand = float(pipe.out["_face"].count.abs().sum())   # kept rows; candidates are a small multiple
     det_full_bytes = B * ((64 + nc) * A * 4 + 300 * 6 * 4 + 4)
-    crop_bytes = P * 3 * 256 * 192 * 4 + roi_bytes(inp.boxes, wl["height"], wl["width"])
+    crop_bytes = P * 3 * 256 * 192 * 4 + roi_bytes(inp.boxes, wl["height"], wl["width"]) * (0.25 if args.frames == "u8" else 1.0)
     match_flops = 2.0 * M * wl["gallery"] * 512
     kernels = {
         "heatmap_decode": dict(bound="hbm", us=kern_us["heatmap_decode"], bytes=hm_bytes),
@@ -367,6 +376,7 @@ def main():
             "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (bf16 tensor-core candidates + fp32 re-score in the match)", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {wl['desc']}", "frames_per_gpu": B, "crops_per_gpu": P,
+                       "frames_dtype": args.frames,
                        "decode_mode": args.decode_mode, "parallelism": f"dp{world}: frames/crops/heatmaps sharded with no collective" + (
                            f"; gallery of {world * wl['gallery']} ids sharded by rows, probes all-gathered, NCCL all_reduce(MAX) "
                            "of packed (sim,id) keys" if world > 1 else ""),
@@ -398,6 +408,8 @@ def run_reference(args, wl, rank, world, pipeline, emit):
     inp = pipeline.synthetic_inputs(wl["batch"], wl["height"], wl["width"], wl["per_frame"], wl["joints"], seed=0)
     ms = spp.synth.make_match_set(wl["batch"] * wl["per_frame"], wl["gallery"], seed=1000)
     inp.embeddings = ms.embeddings
+    if args.frames == "u8":
+        inp.frames = (inp.frames * 255.0).round().clamp(0, 255).to(torch.uint8)
     steps, warm = max(1, args.steps), max(0, args.warmup)
     n, times = time_cpu_reference(inp, ms.gallery, wl["batch"], wl["per_frame"], budget_s=150.0, reps=steps, warm=warm)
     total = sum(times)
@@ -409,6 +421,7 @@ def run_reference(args, wl, rank, world, pipeline, emit):
         "ms_per_step": round(1e3 * total / len(times), 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {wl['desc']}", "frames_per_step": n, "crops_per_step": n * wl["per_frame"],
+                   "frames_dtype": args.frames,
                    "decode_mode": "dark"},
         "cpu_baseline": {"value": round(fps, 3), "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                          "sample": f"each step = the first {n} of {wl['batch']} frames of {args.workload} "

@@ -135,6 +135,14 @@ int spp_crop_affine(const float *frames, int num_frames, int frame_h, int frame_
                     const int *frame_idx, int p, int out_h, int out_w, const float *mean, const float *std,
                     int variant, float *out, spp_stream_t stream);
 
+/* Same for uint8 frames [num_frames, 3, frame_h, frame_w] (what HF does when handed uint8 images: the
+ * interpolated value is rounded half-up to uint8 by scipy before rescale / normalise; here the
+ * interpolation runs in fp64 so the rounding agrees).  mean/std are in 0..255 units (HF folds the 1/255
+ * rescale into them, image_processing_backends.py:301-305). */
+int spp_crop_affine_u8(const uint8_t *frames, int num_frames, int frame_h, int frame_w, const float *boxes,
+                       const int *frame_idx, int p, int out_h, int out_w, const float *mean, const float *std,
+                       int variant, float *out, spp_stream_t stream);
+
 /* ------------------------------------------------------------------ heatmap decode ----------- */
 
 #define SPP_DECODE_DARK 0        /* HF post_process_pose_estimation: argmax + DARK + UDP back-projection */

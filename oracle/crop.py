@@ -103,14 +103,19 @@ def crop_affine_hf(frames: np.ndarray, boxes: Sequence[Sequence[float]], frame_i
                    rescale_factor=None) -> np.ndarray:
     """HF:403-448 ``_preprocess`` — for every box: centre/scale, UDP warp, bilinear sample (fp64,
     rounded to fp32 as scipy does for a float32 channel), then ``(x - mean) / std`` in fp32.
-    ``frames`` [B, 3, H, W] fp32; returns ``[P, 3, out_h, out_w]`` fp32."""
+    ``frames`` [B, 3, H, W] fp32 or uint8 (uint8: the warped crop is uint8 too, as in HF); returns
+    ``[P, 3, out_h, out_w]`` fp32."""
     out_h, out_w = out_hw
     m_, s_ = fused_mean_std(mean, std, rescale_factor)
     res = np.empty((len(boxes), frames.shape[1], out_h, out_w), np.float32)
     for p, (box, fi) in enumerate(zip(boxes, frame_idx)):
         c, s = box_to_center_and_scale(box, out_w, out_h)
         xs, ys = source_coords(warp_matrix(c, s, out_w, out_h), out_w, out_h)
-        v = sample_bilinear_zero_outside(frames[int(fi)], xs, ys).astype(np.float32)
+        v = sample_bilinear_zero_outside(frames[int(fi)], xs, ys)
+        if frames.dtype == np.uint8:
+            # scipy writes the fp64 sample into a uint8 output array: round half up, clamp (ni_interpolation.c)
+            v = np.clip(np.floor(v + 0.5), 0, 255).astype(np.uint8)
+        v = v.astype(np.float32)
         res[p] = (v - m_[:, None, None]) / s_[:, None, None]
     return res
 

@@ -34,6 +34,8 @@ SIGNATURES = {
     "spp_match_unpack_keys": (c_int, [_P, c_int, c_float, _P, _P, _P]),
     "spp_crop_affine": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float),
                                 c_int, _P, _P]),
+    "spp_crop_affine_u8": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float),
+                                   c_int, _P, _P]),
     "spp_heatmap_decode": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P,
                                    _P, _P]),
     # test hook (include/spp_internal.h)

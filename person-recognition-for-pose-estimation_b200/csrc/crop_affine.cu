@@ -16,11 +16,13 @@
 // thread per row.  HBM-bound: 4 B written per output element + the source ROI read once.
 #include "spp_common.cuh"
 
+#include <type_traits>
+
 namespace spp {
 namespace {
 
 struct CropParams {
-    const float *frames;
+    const void *frames;         // [num_frames, 3, fh, fw] fp32 or uint8
     const float *boxes;
     const int *frame_idx;
     float *out;
@@ -70,25 +72,46 @@ __device__ __forceinline__ AxisMap crop_axis_map(const float4 box, int ow, int o
 
 // (i0, t): sample = v[i0]*(1-t) + v[i0+1]*t with i0 + 1 always inside the axis (at the far edge the pair
 // (n-2, t=1) stands for (n-1, t=0)); i0 < 0 marks "outside the frame -> 0".  n >= 2.
+// Weight type: fp32 for float frames, fp64 for uint8 frames (whose result is rounded to an integer, so
+// the interpolation itself has to be as exact as scipy's).
+template <typename W>
 struct AxisEntry {
     int i0;
-    float t;
+    W t;
 };
-__device__ __forceinline__ AxisEntry axis_entry(double s, int n) {
-    AxisEntry e;
+template <typename W>
+__device__ __forceinline__ AxisEntry<W> axis_entry(double s, int n) {
+    AxisEntry<W> e;
     if (!(s >= 0.0 && s <= (double)(n - 1))) {
         e.i0 = -1;
-        e.t = 0.f;
+        e.t = (W)0;
         return e;
     }
     const double f = floor(s);
     e.i0 = (int)f;
-    e.t = (float)(s - f);
+    e.t = (W)(s - f);
     if (e.i0 >= n - 1) {
         e.i0 = n - 2;
-        e.t = 1.0f;
+        e.t = (W)1;
     }
     return e;
+}
+
+// bilinear sample + normalisation.  float frames: fp32 lerps.  uint8 frames: fp64 lerps, then scipy's
+// integer output conversion (round half up, clamp to 0..255) before (q - mean) / std.
+__device__ __forceinline__ float sample_px(float p00, float p01, float p10, float p11, float wx, float wy, float inv_sd, float nmean) {
+    const float top = fmaf(p01 - p00, wx, p00);
+    const float bot = fmaf(p11 - p10, wx, p10);
+    return fmaf(fmaf(bot - top, wy, top), inv_sd, nmean);
+}
+__device__ __forceinline__ float sample_px(unsigned char p00, unsigned char p01, unsigned char p10, unsigned char p11, double wx,
+                                           double wy, float inv_sd, float nmean) {
+    const double a = (double)p00, b = (double)p01, c = (double)p10, d = (double)p11;
+    const double top = fma(b - a, wx, a);
+    const double bot = fma(d - c, wx, c);
+    double v = fma(bot - top, wy, top) + 0.5;
+    v = v > 255.0 ? 255.0 : v;
+    return fmaf((float)(int)v, inv_sd, nmean);        // v >= 0.5: truncation == floor
 }
 
 constexpr int kStageBytes = 40 * 1024;   // source band buffer per CTA -> 4-5 CTAs per SM
@@ -103,12 +126,16 @@ constexpr int kStageBytes = 40 * 1024;   // source band buffer per CTA -> 4-5 CT
 //     ops (bilinear + (v - mean)/std as one FMA) and one coalesced 4-byte streaming store.
 // `staged == 0` (frame width not a multiple of 4, unaligned base, or a band that cannot fit): the same
 // loop gathers straight from global memory.
+template <typename T>
 __global__ void __launch_bounds__(256) crop_affine_kernel(const CropParams prm, int staged) {
+    using W = typename std::conditional<std::is_same<T, float>::value, float, double>::type;
+    using Entry = AxisEntry<W>;
+    constexpr int kAlign = 16 / (int)sizeof(T);                                          // elements per 16 bytes
     extern __shared__ __align__(128) unsigned char crop_smem[];
     const int ow = prm.ow, oh = prm.oh;
-    float *buf = reinterpret_cast<float *>(crop_smem);                                   // [kStageBytes]
-    AxisEntry *xt = reinterpret_cast<AxisEntry *>(crop_smem + kStageBytes);              // [ow]
-    AxisEntry *yt = xt + ow;                                                             // [oh]
+    T *buf = reinterpret_cast<T *>(crop_smem);                                           // [kStageBytes]
+    Entry *xt = reinterpret_cast<Entry *>(crop_smem + kStageBytes);                      // [ow]
+    Entry *yt = xt + ow;                                                                 // [oh]
     uint64_t *bar = reinterpret_cast<uint64_t *>(yt + oh);
     __shared__ int s_v[4];   // first/last valid column, first/last valid row
 
@@ -125,12 +152,12 @@ __global__ void __launch_bounds__(256) crop_affine_kernel(const CropParams prm, 
     __syncthreads();
     for (int i = tid; i < ow + oh; i += nthreads) {
         if (i < ow) {
-            const AxisEntry e = axis_entry(m.ax * (double)i + m.bx, prm.fw);
+            const Entry e = axis_entry<W>(m.ax * (double)i + m.bx, prm.fw);
             xt[i] = e;
             if (e.i0 >= 0) { atomicMin(&s_v[0], i); atomicMax(&s_v[1], i); }
         } else {
             const int y = i - ow;
-            const AxisEntry e = axis_entry(m.ay * (double)y + m.by, prm.fh);
+            const Entry e = axis_entry<W>(m.ay * (double)y + m.by, prm.fh);
             yt[y] = e;
             if (e.i0 >= 0) { atomicMin(&s_v[2], y); atomicMax(&s_v[3], y); }
         }
@@ -140,7 +167,7 @@ __global__ void __launch_bounds__(256) crop_affine_kernel(const CropParams prm, 
 
     int f = __ldg(prm.frame_idx + p);
     f = f < 0 ? 0 : (f >= prm.num_frames ? prm.num_frames - 1 : f);
-    const float *src = prm.frames + ((size_t)f * 3 + c) * prm.fh * prm.fw;
+    const T *src = static_cast<const T *>(prm.frames) + ((size_t)f * 3 + c) * prm.fh * prm.fw;
     float *dst = prm.out + ((size_t)p * 3 + c) * oh * ow;
     const float mean = c == 0 ? prm.mean[0] : (c == 1 ? prm.mean[1] : prm.mean[2]);     // constant-bank selects
     const float inv_sd = 1.0f / (c == 0 ? prm.stdv[0] : (c == 1 ? prm.stdv[1] : prm.stdv[2]));
@@ -156,11 +183,11 @@ __global__ void __launch_bounds__(256) crop_affine_kernel(const CropParams prm, 
     if (!any) return;
 
     // source column window, 16-byte aligned; xt[].i0 + 1 is always a valid column
-    const int cx0 = xt[vx0].i0 & ~3;
-    int cx1 = (xt[vx1].i0 + 2 + 3) & ~3;             // exclusive
+    const int cx0 = xt[vx0].i0 & ~(kAlign - 1);
+    int cx1 = (xt[vx1].i0 + 2 + kAlign - 1) & ~(kAlign - 1);      // exclusive
     if (cx1 > prm.fw) cx1 = prm.fw;
     const int row_elems = cx1 - cx0;
-    const int rows_cap = kStageBytes / (row_elems * 4);
+    const int rows_cap = kStageBytes / (row_elems * (int)sizeof(T));
     const bool use_stage = staged && rows_cap >= 3;
     int band = oh;
     if (use_stage) {
@@ -177,47 +204,40 @@ __global__ void __launch_bounds__(256) crop_affine_kernel(const CropParams prm, 
         if (use_stage) {
             const int nrows = yt[r1].i0 + 1 - sy_lo + 1;
             if (warp == 0) {
-                if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(nrows * row_elems * 4));
+                if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(nrows * row_elems * (int)sizeof(T)));
                 for (int r = lane; r < nrows; r += 32)
-                    bulk_g2s(buf + (size_t)r * row_elems, src + (size_t)(sy_lo + r) * prm.fw + cx0, (uint32_t)(row_elems * 4), bar);
+                    bulk_g2s(buf + (size_t)r * row_elems, src + (size_t)(sy_lo + r) * prm.fw + cx0,
+                             (uint32_t)(row_elems * (int)sizeof(T)), bar);
             }
             mbar_wait(bar, parity);
             parity ^= 1;
         }
         for (int x = tid; x < ow; x += nthreads) {
-            const AxisEntry ex = xt[x];
+            const Entry ex = xt[x];
             float *o = dst + (size_t)r0 * ow + x;
             if (ex.i0 < 0) {
                 for (int y = r0; y <= r1; ++y, o += ow) __stcs(o, zero_out);
                 continue;
             }
-            const float wx = ex.t;
+            const W wx = ex.t;
             if (use_stage) {
                 // shared-memory tile: element (iy, ix) at buf[(iy - sy_lo) * row_elems + (ix - cx0)], 32-bit indices
                 const int colbase = ex.i0 - cx0 - sy_lo * row_elems;
 #pragma unroll 4
                 for (int y = r0; y <= r1; ++y, o += ow) {
-                    const AxisEntry ey = yt[y];
+                    const Entry ey = yt[y];
                     const int ia = ey.i0 * row_elems + colbase;
                     const int ib = ia + row_elems;
-                    const float p00 = buf[ia], p01 = buf[ia + 1], p10 = buf[ib], p11 = buf[ib + 1];
-                    const float top = fmaf(p01 - p00, wx, p00);
-                    const float bot = fmaf(p11 - p10, wx, p10);
-                    const float v = fmaf(bot - top, ey.t, top);
-                    __stcs(o, fmaf(v, inv_sd, nmean));
+                    __stcs(o, sample_px(buf[ia], buf[ia + 1], buf[ib], buf[ib + 1], wx, ey.t, inv_sd, nmean));
                 }
             } else {
-                const float *col = src + ex.i0;
+                const T *col = src + ex.i0;
 #pragma unroll 4
                 for (int y = r0; y <= r1; ++y, o += ow) {
-                    const AxisEntry ey = yt[y];
-                    const float *ra = col + (size_t)ey.i0 * prm.fw;
-                    const float *rb = ra + prm.fw;
-                    const float p00 = __ldg(ra), p01 = __ldg(ra + 1), p10 = __ldg(rb), p11 = __ldg(rb + 1);
-                    const float top = fmaf(p01 - p00, wx, p00);
-                    const float bot = fmaf(p11 - p10, wx, p10);
-                    const float v = fmaf(bot - top, ey.t, top);
-                    __stcs(o, fmaf(v, inv_sd, nmean));
+                    const Entry ey = yt[y];
+                    const T *ra = col + (size_t)ey.i0 * prm.fw;
+                    const T *rb = ra + prm.fw;
+                    __stcs(o, sample_px(__ldg(ra), __ldg(ra + 1), __ldg(rb), __ldg(rb + 1), wx, ey.t, inv_sd, nmean));
                 }
             }
         }
@@ -228,10 +248,11 @@ __global__ void __launch_bounds__(256) crop_affine_kernel(const CropParams prm, 
 }  // namespace
 }  // namespace spp
 
-extern "C" int spp_crop_affine(const float *frames, int num_frames, int frame_h, int frame_w, const float *boxes,
-                               const int *frame_idx, int p, int out_h, int out_w, const float *mean, const float *std,
-                               int variant, float *out, spp_stream_t stream) {
-    using namespace spp;
+namespace spp {
+namespace {
+template <typename T>
+int launch_crop(const void *frames, int num_frames, int frame_h, int frame_w, const float *boxes, const int *frame_idx, int p,
+                int out_h, int out_w, const float *mean, const float *std, int variant, float *out, spp_stream_t stream) {
     SPP_CHECK_ARG(frames && boxes && frame_idx && out && mean && std, "crop_affine: null pointer");
     SPP_CHECK_ARG(num_frames > 0 && frame_h >= 2 && frame_w >= 2 && p >= 0, "crop_affine: frames must be at least 2x2");
     SPP_CHECK_ARG(out_h > 0 && out_w > 0 && out_w <= 2048 && out_h <= 2048, "crop_affine: output size must be within 2048 x 2048");
@@ -243,18 +264,34 @@ extern "C" int spp_crop_affine(const float *frames, int num_frames, int frame_h,
     prm.num_frames = num_frames; prm.fh = frame_h; prm.fw = frame_w; prm.P = p; prm.oh = out_h; prm.ow = out_w;
     prm.variant = variant;
     for (int c = 0; c < 3; ++c) { prm.mean[c] = mean[c]; prm.stdv[c] = std[c]; }
-    const int staged = (frame_w % 4 == 0) && ((reinterpret_cast<uintptr_t>(frames) & 15) == 0);
-    const size_t smem = (size_t)kStageBytes + (size_t)(out_w + out_h) * 8 + 16;
+    // bulk-TMA row copies need 16-byte aligned row segments: base and row pitch multiples of 16 bytes
+    const int staged = ((size_t)frame_w * sizeof(T) % 16 == 0) && ((reinterpret_cast<uintptr_t>(frames) & 15) == 0);
+    using W = typename std::conditional<std::is_same<T, float>::value, float, double>::type;
+    const size_t smem = (size_t)kStageBytes + (size_t)(out_w + out_h) * sizeof(AxisEntry<W>) + 16;
     int threads = (out_w + 31) / 32 * 32;
     if (threads > 256) threads = 256;
     static bool configured = false;
     if (!configured) {
-        SPP_CHECK_CUDA(cudaFuncSetAttribute(crop_affine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        SPP_CHECK_CUDA(cudaFuncSetAttribute(crop_affine_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         configured = true;
     }
     SPP_CHECK_ARG(smem <= 100 * 1024, "crop_affine: output size too large");
     dim3 grid(p, 3);
-    crop_affine_kernel<<<grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(prm, staged);
+    crop_affine_kernel<T><<<grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(prm, staged);
     SPP_CHECK_LAUNCH();
     return SPP_OK;
+}
+}  // namespace
+}  // namespace spp
+
+extern "C" int spp_crop_affine(const float *frames, int num_frames, int frame_h, int frame_w, const float *boxes,
+                               const int *frame_idx, int p, int out_h, int out_w, const float *mean, const float *std,
+                               int variant, float *out, spp_stream_t stream) {
+    return spp::launch_crop<float>(frames, num_frames, frame_h, frame_w, boxes, frame_idx, p, out_h, out_w, mean, std, variant, out, stream);
+}
+
+extern "C" int spp_crop_affine_u8(const uint8_t *frames, int num_frames, int frame_h, int frame_w, const float *boxes,
+                                  const int *frame_idx, int p, int out_h, int out_w, const float *mean, const float *std,
+                                  int variant, float *out, spp_stream_t stream) {
+    return spp::launch_crop<unsigned char>(frames, num_frames, frame_h, frame_w, boxes, frame_idx, p, out_h, out_w, mean, std, variant, out, stream);
 }

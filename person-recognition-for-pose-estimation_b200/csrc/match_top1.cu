@@ -443,9 +443,12 @@ MatchPlan plan_match(int m, int n) {
     p.tiles_n = (n + BN - 1) / BN;
     int sms = sm_count();
     if (sms <= 0) sms = 148;
+    // N-splits per M-tile: at most one CTA per SM in total, but no more CTAs than give each of them ~8
+    // gallery tiles — every CTA first loads its 128 KB probe tile and needs a whole SM (225 KB smem), so
+    // a small problem should occupy few SMs and leave the rest to the kernels running beside it.
     int ns = sms / (p.m_tiles > 0 ? p.m_tiles : 1);
-    if (ns < 1) ns = 1;
-    if (ns > p.tiles_n) ns = p.tiles_n;
+    const int want = (p.tiles_n + 7) / 8;
+    if (ns > want) ns = want;
     if (ns < 1) ns = 1;
     p.nsplit = ns;
     size_t off = 0;

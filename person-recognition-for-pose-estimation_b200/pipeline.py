@@ -77,7 +77,7 @@ class SelectivePosePipeline:
 
     def __init__(self, inputs: StepInputs, gallery_bf16: torch.Tensor, device: torch.device, threshold: float = 0.4,
                  conf_thres: float = 0.001, iou_thres: float = 0.65, decode_mode: str = "dark", use_graph: bool = True,
-                 id_offset: int = 0, concurrent: bool = True, matcher=None):
+                 id_offset: int = 0, concurrent: bool = True, matcher=None, capture_collectives: bool = False):
         self.device = device
         self.threshold, self.conf, self.iou, self.mode = threshold, conf_thres, iou_thres, decode_mode
         self.id_offset = id_offset
@@ -90,8 +90,13 @@ class SelectivePosePipeline:
         self.concurrent = concurrent
         # multi-GPU: a dist.ShardedGalleryMatcher replaces the local match chain; its NCCL collectives run
         # eagerly on a side stream next to the graph (they are not captured)
+        # The NCCL collectives run eagerly on a high-priority side stream beside the graph.
+        # capture_collectives=True would capture them into the graph instead — NOT the default: on B200 /
+        # NCCL 2.28.9 / torch 2.11 a multi-branch capture containing the two collectives hung at replay.
         self.matcher = matcher
-        self._match_stream = torch.cuda.Stream(device) if matcher is not None else None
+        self.capture_collectives = capture_collectives and use_graph
+        self._eager_match = matcher is not None and not self.capture_collectives
+        self._match_stream = torch.cuda.Stream(device, priority=-1) if self._eager_match else None
         self._side = [torch.cuda.Stream(device) for _ in range(3)]
         with torch.cuda.stream(self._stream):
             if matcher is not None:
@@ -128,10 +133,19 @@ class SelectivePosePipeline:
             with torch.cuda.stream(sides[2]):
                 ids, sims, keys = ops.match_top1(i.embeddings, self.gallery, self.threshold, self.id_offset, want_keys=True)
             n += 3          # normalise, tcgen05 GEMM + top-2, fp32 re-score
-        else:
+        elif self._eager_match:
             ids, sims, keys = self.out.get("ids"), self.out.get("sims"), None
             n += 4          # (eager, in step()) normalise, GEMM + top-2, re-score, key unpack
-        pix = ops.crop_affine(i.frames, i.boxes, i.frame_idx, out=self.out.get("pixel_values"))
+        else:
+            with torch.cuda.stream(sides[2]):
+                ids, sims = self.matcher.match(i.embeddings)      # all_gather -> local top-1 -> all_reduce(MAX) -> unpack
+            keys = None
+            n += 4
+        if i.frames.dtype == torch.uint8:     # HF default for uint8 images: 1/255 rescale folded into mean / std
+            mean, std = [m * 255.0 for m in (0.485, 0.456, 0.406)], [s * 255.0 for s in (0.229, 0.224, 0.225)]
+            pix = ops.crop_affine(i.frames, i.boxes, i.frame_idx, mean=mean, std=std, out=self.out.get("pixel_values"))
+        else:
+            pix = ops.crop_affine(i.frames, i.boxes, i.frame_idx, out=self.out.get("pixel_values"))
         n += 1
         flags = (ops.FLAG_SCALE_SCORE | ops.FLAG_BACKPROJECT) if self.mode == "softargmax" else 0
         kp = ops.heatmap_decode(i.heatmaps, i.flipped, i.perm, i.boxes, self.mode, 11, flags,
@@ -155,14 +169,14 @@ class SelectivePosePipeline:
 
     def _launch(self) -> None:
         main = torch.cuda.current_stream(self.device)
-        if self.matcher is not None:
+        if self._eager_match:
             fork = torch.cuda.Event()
             fork.record(main)
         if self.graph is not None:
             self.graph.replay()
         else:
             self._enqueue()
-        if self.matcher is not None:
+        if self._eager_match:
             # gallery-sharded match: all_gather -> local top-1 -> all_reduce(MAX).  Enqueued AFTER the graph
             # launch so the host issues these eager calls while the device is busy with the graph; on the
             # device the chain runs beside the graph on its own stream.

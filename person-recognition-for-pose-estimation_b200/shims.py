@@ -128,7 +128,9 @@ class VitPoseImageProcessor:
         b, idx = _flatten_boxes(boxes, frames.device)
         mean, std = self._mean_std(self.do_rescale if do_rescale is None else do_rescale,
                                    self.do_normalize if do_normalize is None else do_normalize)
-        pix = ops.crop_affine(frames.float(), b, idx, (self.size["height"], self.size["width"]), mean, std, "hf")
+        if frames.dtype != torch.uint8:
+            frames = frames.float()
+        pix = ops.crop_affine(frames, b, idx, (self.size["height"], self.size["width"]), mean, std, "hf")
         return {"pixel_values": pix}
 
     def post_process_pose_estimation(self, outputs, boxes, kernel_size: int = 11, threshold: Optional[float] = None,

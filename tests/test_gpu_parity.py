@@ -196,6 +196,29 @@ def test_crop_vs_oracle(spp, synth, dev):
     assert float(np.abs(out.cpu().numpy() - ref).max()) < 2e-5
 
 
+def test_crop_uint8_vs_oracle(spp, synth, dev):
+    cs = synth.make_crop_set(2, 360, 480, per_frame=6, seed=12)
+    fr8 = (cs.frames * 255.0).round().clamp(0, 255).to(torch.uint8)
+    ref = ocrop.crop_affine_hf(fr8.numpy(), cs.boxes.tolist(), cs.frame_idx.tolist(), rescale_factor=1 / 255)
+    m, s = ocrop.fused_mean_std(rescale_factor=1 / 255)
+    out = spp.crop_affine(fr8.to(dev), cs.boxes.to(dev), cs.frame_idx.to(dev), mean=m.tolist(), std=s.tolist())
+    diff = np.abs(out.cpu().numpy() - ref)
+    assert float(diff.max()) < 2e-5, f"{(diff > 2e-5).sum()} pixels differ (a flipped uint8 rounding shows up as ~0.017)"
+    proc = spp.VitPoseImageProcessor()
+    boxes = [[[float(v) for v in b] for b in cs.boxes[:6]], [[float(v) for v in b] for b in cs.boxes[6:]]]
+    pix = proc.preprocess(fr8.to(dev), boxes)["pixel_values"]
+    assert float(np.abs(pix.cpu().numpy() - ref).max()) < 2e-5
+    # unaligned frame width: bulk-TMA staging is not possible, the direct path must agree
+    fr8b = fr8[:, :, :, :478].contiguous()
+    ref = ocrop.crop_affine_hf(fr8b.numpy(), cs.boxes.tolist(), cs.frame_idx.tolist(), rescale_factor=1 / 255)
+    out = spp.crop_affine(fr8b.to(dev), cs.boxes.to(dev), cs.frame_idx.to(dev), mean=m.tolist(), std=s.tolist())
+    assert float(np.abs(out.cpu().numpy() - ref).max()) < 2e-5
+    frb = cs.frames[:, :, :, :478].contiguous()
+    ref = ocrop.crop_affine_hf(frb.numpy(), cs.boxes.tolist(), cs.frame_idx.tolist())
+    out = spp.crop_affine(frb.to(dev), cs.boxes.to(dev), cs.frame_idx.to(dev))
+    assert float(np.abs(out.cpu().numpy() - ref).max()) < 2e-5
+
+
 def test_crop_golden_and_processor_shim(spp, golden, dev):
     g = golden("pose_hf.npz")
     proc = spp.VitPoseImageProcessor()

@@ -121,6 +121,17 @@ def test_oracle_against_installed_hf(synth):
     np.testing.assert_allclose(pix, pix_hf.numpy(), rtol=1e-5, atol=2e-5)
 
 
+def test_oracle_crop_uint8_against_installed_hf(synth):
+    from transformers import VitPoseImageProcessor
+    proc = VitPoseImageProcessor()
+    cs = synth.make_crop_set(1, 200, 256, per_frame=3, seed=33)
+    fr8 = (cs.frames * 255.0).round().clamp(0, 255).to(torch.uint8)
+    boxes = [[float(v) for v in b] for b in cs.boxes]
+    pix_hf = proc.preprocess([fr8[0]], boxes=[boxes], return_tensors="pt")["pixel_values"]
+    pix = ocrop.crop_affine_hf(fr8.numpy(), boxes, [0, 0, 0], rescale_factor=1 / 255)
+    np.testing.assert_allclose(pix, pix_hf.numpy(), rtol=1e-5, atol=2e-5)
+
+
 def test_quarter_offset_hand_made():
     hm = np.zeros((1, 2, 8, 6), np.float32)
     hm[0, 0, 3, 2] = 1.0; hm[0, 0, 3, 3] = 0.5; hm[0, 0, 2, 2] = 0.25     # peak (2,3): right>left, up>down
