@@ -142,8 +142,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 // ------------------------------------------------------------------------------------------------
 struct GemmParams {
     int m, n;
-    int tiles_n, nsplit;
-    Cand *part;  // [m_tiles*BM, nsplit, 2]
+    int tiles_n, nsplit;   // every M-tile is cut into nsplit chunks of gallery tiles; work item = (M-tile, chunk)
+    int items;             // m_tiles * nsplit, distributed round-robin over the persistent CTAs
+    Cand *part;            // [m_tiles*BM, nsplit, 2]
 };
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -153,19 +154,21 @@ match_gemm_top2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     unsigned char *smem_a = smem;                                         // [8][128 x 64] bf16, SW128
     unsigned char *smem_b = smem + (size_t)kKBlocks * kABytes;            // [stages][256 x 64] bf16, SW128
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_b + (size_t)kStages * kBBytes);
-    uint64_t *full = bars;                  // [kStages]
-    uint64_t *empty = bars + kStages;       // [kStages]
-    uint64_t *a_full = bars + 2 * kStages;  // [1]
-    uint64_t *t_full = a_full + 1;          // [2]
-    uint64_t *t_empty = t_full + 2;         // [2]
+    uint64_t *full = bars;                  // [kStages]  B stage landed
+    uint64_t *empty = bars + kStages;       // [kStages]  B stage consumed by the MMAs
+    uint64_t *a_full = bars + 2 * kStages;  // [1]        probe tile landed
+    uint64_t *a_empty = a_full + 1;         // [1]        probe tile no longer read (item finished)
+    uint64_t *t_full = a_empty + 1;         // [2]        accumulator complete
+    uint64_t *t_empty = t_full + 2;         // [2]        accumulator drained by the epilogue
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mt = blockIdx.x / prm.nsplit, sp = blockIdx.x - mt * prm.nsplit;
-    // contiguous range of N tiles for this split
     const int per = prm.tiles_n / prm.nsplit, rem = prm.tiles_n - per * prm.nsplit;
-    const int nt0 = sp * per + (sp < rem ? sp : rem);
-    const int ntiles = per + (sp < rem ? 1 : 0);
+    // chunk sp of an M-tile covers gallery tiles [nt0, nt0 + ntiles)
+    auto chunk_range = [&](int sp, int &nt0, int &ntiles) {
+        nt0 = sp * per + (sp < rem ? sp : rem);
+        ntiles = per + (sp < rem ? 1 : 0);
+    };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -173,6 +176,7 @@ match_gemm_top2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             mbar_init(&empty[s], 1);
         }
         mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
         for (int a = 0; a < 2; ++a) {
             mbar_init(&t_full[a], 1);
             mbar_init(&t_empty[a], 4);
@@ -192,17 +196,23 @@ match_gemm_top2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            mbar_arrive_expect_tx(a_full, kKBlocks * kABytes);
-            for (int kb = 0; kb < kKBlocks; ++kb) tma_load_2d(smem_a + (size_t)kb * kABytes, &tmap_a, a_full, kb * BK, mt * BM);
             int stage = 0;
-            uint32_t phase = 0;
-            for (int t = 0; t < ntiles; ++t) {
-                const int n0 = (nt0 + t) * BN;
-                for (int kb = 0; kb < kKBlocks; ++kb) {
-                    mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full[stage], kBBytes);
-                    tma_load_2d(smem_b + (size_t)stage * kBBytes, &tmap_b, &full[stage], kb * BK, n0);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+            uint32_t phase = 0, it = 0;
+            for (int item = blockIdx.x; item < prm.items; item += gridDim.x, ++it) {
+                const int mt = item / prm.nsplit, sp = item - mt * prm.nsplit;
+                int nt0, ntiles;
+                chunk_range(sp, nt0, ntiles);
+                mbar_wait(a_empty, (it & 1) ^ 1);            // previous item's MMAs are done with the probe tile
+                mbar_arrive_expect_tx(a_full, kKBlocks * kABytes);
+                for (int kb = 0; kb < kKBlocks; ++kb) tma_load_2d(smem_a + (size_t)kb * kABytes, &tmap_a, a_full, kb * BK, mt * BM);
+                for (int t = 0; t < ntiles; ++t) {
+                    const int n0 = (nt0 + t) * BN;
+                    for (int kb = 0; kb < kKBlocks; ++kb) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&full[stage], kBBytes);
+                        tma_load_2d(smem_b + (size_t)stage * kBBytes, &tmap_b, &full[stage], kb * BK, n0);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
                 }
             }
         }
@@ -212,70 +222,82 @@ match_gemm_top2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             // instruction descriptor: fp32 accumulate, bf16 x bf16, both K-major, M=128, N=256
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             const uint32_t a_addr = smem_u32(smem_a), b_addr = smem_u32(smem_b);
-            mbar_wait(a_full, 0);
             int stage = 0;
-            uint32_t phase = 0;
-            for (int t = 0; t < ntiles; ++t) {
-                const int acc = t & 1;
-                const uint32_t acc_phase = (uint32_t)((t >> 1) & 1);
-                mbar_wait(&t_empty[acc], acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t d_addr = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = 0; kb < kKBlocks; ++kb) {
-                    mbar_wait(&full[stage], phase);
+            uint32_t phase = 0, it = 0, tcount = 0;          // tcount: tiles issued by this CTA (accumulator ring)
+            for (int item = blockIdx.x; item < prm.items; item += gridDim.x, ++it) {
+                const int sp = item % prm.nsplit;
+                int nt0, ntiles;
+                chunk_range(sp, nt0, ntiles);
+                mbar_wait(a_full, it & 1);
+                for (int t = 0; t < ntiles; ++t, ++tcount) {
+                    const int acc = tcount & 1;
+                    const uint32_t acc_phase = (tcount >> 1) & 1;
+                    mbar_wait(&t_empty[acc], acc_phase ^ 1);
                     tc_fence_after();
+                    const uint32_t d_addr = tmem_base + (uint32_t)(acc * BN);
+                    for (int kb = 0; kb < kKBlocks; ++kb) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t ad = umma_desc_sw128(a_addr + kb * kABytes + k * 32);
-                        const uint64_t bd = umma_desc_sw128(b_addr + stage * kBBytes + k * 32);
-                        umma_bf16(d_addr, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint64_t ad = umma_desc_sw128(a_addr + kb * kABytes + k * 32);
+                            const uint64_t bd = umma_desc_sw128(b_addr + stage * kBBytes + k * 32);
+                            umma_bf16(d_addr, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                        }
+                        umma_commit(&empty[stage]);          // frees the B stage once these MMAs have read it
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(&empty[stage]);          // frees the B stage once these MMAs have read it
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    umma_commit(&t_full[acc]);               // accumulator complete
                 }
-                umma_commit(&t_full[acc]);               // accumulator complete
+                umma_commit(a_empty);                        // all MMAs of this item have read the probe tile
             }
         }
     } else {
         // ===== epilogue: TMEM -> registers -> running top-2 per probe row =====
         const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
         const int row_in_tile = quarter * 32 + lane;
-        float v1 = -INFINITY, v2 = -INFINITY;
-        int i1 = 0x7fffffff, i2 = 0x7fffffff;
-        for (int t = 0; t < ntiles; ++t) {
-            const int acc = t & 1;
-            const uint32_t acc_phase = (uint32_t)((t >> 1) & 1);
-            mbar_wait(&t_full[acc], acc_phase);
-            tc_fence_after();
-            const int n0 = (nt0 + t) * BN;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+        uint32_t tcount = 0;
+        for (int item = blockIdx.x; item < prm.items; item += gridDim.x) {
+            const int mt = item / prm.nsplit, sp = item - mt * prm.nsplit;
+            int nt0, ntiles;
+            chunk_range(sp, nt0, ntiles);
+            float v1 = -INFINITY, v2 = -INFINITY;
+            int i1 = 0x7fffffff, i2 = 0x7fffffff;
+            for (int t = 0; t < ntiles; ++t, ++tcount) {
+                const int acc = tcount & 1;
+                const uint32_t acc_phase = (tcount >> 1) & 1;
+                mbar_wait(&t_full[acc], acc_phase);
+                tc_fence_after();
+                const int n0 = (nt0 + t) * BN;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                float v[32];
-                tmem_ld32(taddr + c * 32, v);
-                float mx = v[0];
+                for (int c = 0; c < BN / 32; ++c) {
+                    float v[32];
+                    tmem_ld32(taddr + c * 32, v);
+                    float mx = v[0];
 #pragma unroll
-                for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
-                if (mx > v2) {                          // rare after the first tiles
-                    const int nb = n0 + c * 32;
+                    for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+                    if (mx > v2) {                          // rare after the first tiles
+                        const int nb = n0 + c * 32;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float x = v[j];
-                        const int n = nb + j;
-                        if (n < prm.n) {
-                            if (x > v1) { v2 = v1; i2 = i1; v1 = x; i1 = n; }
-                            else if (x > v2) { v2 = x; i2 = n; }
+                        for (int j = 0; j < 32; ++j) {
+                            const float x = v[j];
+                            const int n = nb + j;
+                            if (n < prm.n) {
+                                if (x > v1) { v2 = v1; i2 = i1; v1 = x; i1 = n; }
+                                else if (x > v2) { v2 = x; i2 = n; }
+                            }
                         }
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&t_empty[acc]);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&t_empty[acc]);
+            Cand *o = prm.part + ((size_t)(mt * BM + row_in_tile) * prm.nsplit + sp) * 2;
+            o[0] = Cand{v1, i1};
+            o[1] = Cand{v2, i2};
         }
-        Cand *o = prm.part + ((size_t)(mt * BM + row_in_tile) * prm.nsplit + sp) * 2;
-        o[0] = Cand{v1, i1};
-        o[1] = Cand{v2, i2};
     }
 
     tc_fence_before();
@@ -433,7 +455,7 @@ int make_tmap(CUtensorMap *map, const void *base, int rows, int box_rows) {
 }
 
 struct MatchPlan {
-    int m_tiles, tiles_n, nsplit;
+    int m_tiles, tiles_n, nsplit, sms;
     size_t off_qn, off_qb, off_part, bytes;
 };
 
@@ -443,14 +465,30 @@ MatchPlan plan_match(int m, int n) {
     p.tiles_n = (n + BN - 1) / BN;
     int sms = sm_count();
     if (sms <= 0) sms = 148;
-    // N-splits per M-tile: at most one CTA per SM in total, but no more CTAs than give each of them ~8
-    // gallery tiles — every CTA first loads its 128 KB probe tile and needs a whole SM (225 KB smem), so
-    // a small problem should occupy few SMs and leave the rest to the kernels running beside it.
-    int ns = sms / (p.m_tiles > 0 ? p.m_tiles : 1);
-    const int want = (p.tiles_n + 7) / 8;
-    if (ns > want) ns = want;
-    if (ns < 1) ns = 1;
+    // Work items = (M-tile, chunk of gallery tiles).  Small problems: one item per CTA, and no more CTAs than
+    // give each ~8 gallery tiles (every CTA loads a 128 KB probe tile and needs a whole SM, so a small match
+    // should leave SMs to the kernels running beside it).  Large problems: the grid is one persistent CTA
+    // per SM and the chunk count is chosen so that items ~ r * SMs (balanced rounds, <= 8 of them).
+    const int want = (p.tiles_n + 7) / 8 > 0 ? (p.tiles_n + 7) / 8 : 1;
+    int ns;
+    if ((long long)p.m_tiles * want <= sms) {
+        ns = want;
+    } else {
+        ns = 1;
+        double best = 0.0;
+        for (int r = 1; r <= 8; ++r) {
+            int c = (int)((long long)sms * r / p.m_tiles);
+            if (c < 1) continue;
+            if (c > want) c = want;
+            const long long items = (long long)p.m_tiles * c;
+            const long long rounds = (items + sms - 1) / sms;
+            const double util = (double)items / (double)(rounds * sms);
+            if (util > best + 1e-9) { best = util; ns = c; }
+            if (util >= 0.94) break;      // fewest rounds that balance well: every extra round reloads the probe tile
+        }
+    }
     p.nsplit = ns;
+    p.sms = sms;
     size_t off = 0;
     p.off_qn = off;   off += align_up((size_t)m * kDim * 4, 1024);
     p.off_qb = off;   off += align_up((size_t)m * kDim * 2, 1024);
@@ -529,8 +567,9 @@ static int match_common(const float *emb, const uint16_t *gallery, int m, int n,
             SPP_CHECK_CUDA(cudaFuncSetAttribute(match_gemm_top2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
             configured = true;
         }
-        GemmParams gp{m, n, p.tiles_n, p.nsplit, part};
-        match_gemm_top2_kernel<<<p.m_tiles * p.nsplit, kGemmThreads, kGemmSmem, st>>>(ta, tb, gp);
+        const int items = p.m_tiles * p.nsplit;
+        GemmParams gp{m, n, p.tiles_n, p.nsplit, items, part};
+        match_gemm_top2_kernel<<<items < p.sms ? items : p.sms, kGemmThreads, kGemmSmem, st>>>(ta, tb, gp);
         SPP_CHECK_LAUNCH();
     }
     match_finalize_kernel<<<(m + 7) / 8, 256, 0, st>>>(qn, gal, part, m, n, p.nsplit * 2, threshold, id_offset, out_id, out_sim,
