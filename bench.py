@@ -374,9 +374,10 @@ def main():
             "metric": "frames/sec post-backbone selective-pose pipeline (batch 64, 1/2/4/8 B200)",
             "value": round(frames_per_s, 1), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (bf16 tensor-core candidates + fp32 re-score in the match)", "data": "synthetic",
+            "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {wl['desc']}", "frames_per_gpu": B, "crops_per_gpu": P,
                        "frames_dtype": args.frames,
+                       "arithmetic": "fp32 throughout; gallery match = bf16 tcgen05 candidates re-scored in exact fp32",
                        "decode_mode": args.decode_mode, "parallelism": f"dp{world}: frames/crops/heatmaps sharded with no collective" + (
                            f"; gallery of {world * wl['gallery']} ids sharded by rows, probes all-gathered, NCCL all_reduce(MAX) "
                            "of packed (sim,id) keys" if world > 1 else ""),

@@ -128,7 +128,7 @@ class SelectivePosePipeline:
             face = ops.decode_nms(i.face_levels, conf_thres=self.conf, iou_thres=self.iou, out=self.out.get("_face"))
         with torch.cuda.stream(sides[1]):
             person = ops.decode_nms(i.person_levels, conf_thres=self.conf, iou_thres=self.iou, out=self.out.get("_person"))
-        n += 2 * 4      # memset + candidate scan + candidate decode + NMS kernel per head
+        n += 2 * 3      # candidate scan + candidate decode + NMS kernel per head (the count memset is not a kernel)
         if self.matcher is None:
             with torch.cuda.stream(sides[2]):
                 ids, sims, keys = ops.match_top1(i.embeddings, self.gallery, self.threshold, self.id_offset, want_keys=True)
