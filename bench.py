@@ -182,6 +182,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--frames", default="f32", choices=["f32", "u8"],
                     help="frame dtype: f32 in [0,1] (SURVEY 8d, default) or uint8 as a video decoder delivers them")
+    ap.add_argument("--gallery-ids", type=int, default=0, help="override the workload's gallery size")
+    ap.add_argument("--shard-gallery", default="auto", choices=["auto", "yes", "no"],
+                    help="N>1: shard the gallery by rows (NCCL top-1 reduce) or replicate it; auto = shard above 100k ids")
     ap.add_argument("--capture-collectives", action="store_true", help="N>1: capture the NCCL calls into the CUDA graph (hung in testing)")
     ap.add_argument("--serial", action="store_true", help="run the four chains back to back instead of on forked streams")
     args = ap.parse_args()
@@ -202,7 +205,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.gallery_ids > 0:
+        wl["gallery"] = args.gallery_ids
+        wl["desc"] += f" [gallery overridden to {args.gallery_ids} ids]"
     spp = importlib.import_module(PKG)
     pipeline = importlib.import_module(PKG + ".pipeline")
 
@@ -221,14 +227,21 @@ def main():
 
     # ---- inputs (per-rank shard: every rank owns `batch` frames; weak scaling) ------------------
     inp = pipeline.synthetic_inputs(wl["batch"], wl["height"], wl["width"], wl["per_frame"], wl["joints"], seed=rank)
-    ms = spp.synth.make_match_set(wl["batch"] * wl["per_frame"], wl["gallery"], seed=1000 + rank)
-    inp.embeddings = ms.embeddings
+    # One gallery for the whole job (same seed on every rank); with N > 1 it is sharded by rows.  Every rank's
+    # probes are planted from the full gallery.
+    ms = spp.synth.make_match_set(world * wl["batch"] * wl["per_frame"], wl["gallery"], seed=1000)
+    m_local = wl["batch"] * wl["per_frame"]
+    inp.embeddings = ms.embeddings[rank * m_local:(rank + 1) * m_local].contiguous()
     if args.frames == "u8":
         inp.frames = (inp.frames * 255.0).round().clamp(0, 255).to(torch.uint8)
     gallery_bf16 = ms.gallery.to(torch.bfloat16)
+    shard_lo, shard_hi = spp.dist.shard_bounds(wl["gallery"], world, rank)
     matcher = None
-    if world > 1:      # gallery sharded by rows: this rank holds ids [rank*N, (rank+1)*N); NCCL top-1 (value,index) reduce
-        matcher = spp.dist.gpu_matcher(gallery_bf16.to(dev).contiguous(), rank * wl["gallery"], 0.4)
+    # Placement policy: a gallery of <= 100k ids (<= 102 MB bf16) is replicated on every GPU and
+    # the step has no collective at all; larger galleries are sharded by rows and reduced over NCCL.
+    shard = world > 1 and (args.shard_gallery == "yes" or (args.shard_gallery == "auto" and wl["gallery"] > 100_000))
+    if shard:          # this rank holds ids [shard_lo, shard_hi); NCCL top-1 (value,index) reduce
+        matcher = spp.dist.gpu_matcher(gallery_bf16[shard_lo:shard_hi].to(dev).contiguous(), shard_lo, 0.4)
     pipe = pipeline.SelectivePosePipeline(inp, gallery_bf16, dev, decode_mode=args.decode_mode, use_graph=not args.no_graph,
                                           concurrent=not args.serial, matcher=matcher,
                                           capture_collectives=args.capture_collectives)
@@ -379,8 +392,8 @@ def main():
                        "frames_dtype": args.frames,
                        "arithmetic": "fp32 throughout; gallery match = bf16 tcgen05 candidates re-scored in exact fp32",
                        "decode_mode": args.decode_mode, "parallelism": f"dp{world}: frames/crops/heatmaps sharded with no collective" + (
-                           f"; gallery of {world * wl['gallery']} ids sharded by rows, probes all-gathered, NCCL all_reduce(MAX) "
-                           "of packed (sim,id) keys" if world > 1 else ""),
+                           f"; the {wl['gallery']}-id gallery sharded by rows ({wl['gallery'] // world} per GPU), probes all-gathered, NCCL all_reduce(MAX) "
+                           "of packed (sim,id) keys" if shard else (f"; the {wl['gallery']}-id gallery replicated per GPU (policy: shard above 100k ids)" if world > 1 else "")),
                        "l2": "step region: inputs (1.6 GB per step) are larger than the 126 MB L2, no flush; "
                              "per-kernel region: a 256 MB read between launches evicts L2 (cold, clean)",
                        "cuda_graph": not args.no_graph,
