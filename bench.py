@@ -182,6 +182,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--frames", default="f32", choices=["f32", "u8"],
                     help="frame dtype: f32 in [0,1] (SURVEY 8d, default) or uint8 as a video decoder delivers them")
+    ap.add_argument("--select-on-device", action="store_true",
+                    help="crop list = persons containing a matched face (ops.associate on the NMS output) instead of the synthetic boxes")
     ap.add_argument("--gallery-ids", type=int, default=0, help="override the workload's gallery size")
     ap.add_argument("--shard-gallery", default="auto", choices=["auto", "yes", "no"],
                     help="N>1: shard the gallery by rows (NCCL top-1 reduce) or replicate it; auto = shard above 100k ids")
@@ -244,7 +246,7 @@ def main():
         matcher = spp.dist.gpu_matcher(gallery_bf16[shard_lo:shard_hi].to(dev).contiguous(), shard_lo, 0.4)
     pipe = pipeline.SelectivePosePipeline(inp, gallery_bf16, dev, decode_mode=args.decode_mode, use_graph=not args.no_graph,
                                           concurrent=not args.serial, matcher=matcher,
-                                          capture_collectives=args.capture_collectives)
+                                          capture_collectives=args.capture_collectives, select_on_device=args.select_on_device)
     pipe.bind_host(inp)
     B, P, K, M = wl["batch"], wl["batch"] * wl["per_frame"], wl["joints"], wl["batch"] * wl["per_frame"]
     A = sum(l.shape[2] * l.shape[3] for l in inp.face_levels)
@@ -396,7 +398,7 @@ def main():
                            "of packed (sim,id) keys" if shard else (f"; the {wl['gallery']}-id gallery replicated per GPU (policy: shard above 100k ids)" if world > 1 else "")),
                        "l2": "step region: inputs (1.6 GB per step) are larger than the 126 MB L2, no flush; "
                              "per-kernel region: a 256 MB read between launches evicts L2 (cold, clean)",
-                       "cuda_graph": not args.no_graph,
+                       "cuda_graph": not args.no_graph, "crop_boxes": "selected on the device from the detections" if args.select_on_device else "synthetic input boxes",
                        "streams": "serial" if args.serial else "4 forked chains (crop->heatmap | det face | det person | match)"},
             "crops_per_s": round(world * P * args.steps / (dev_ms / 1e3), 1),
             "e2e": {"value": round(e2e_fps, 1), "unit": "frames/s", "h2d_bytes_per_step": pipe.h2d_bytes,

@@ -115,6 +115,24 @@ int spp_match_top1(const float *emb, const uint16_t *gallery, int m, int n, int 
 int spp_match_unpack_keys(const unsigned long long *keys, int m, float threshold, int *out_id, float *out_sim,
                           spp_stream_t stream);
 
+/* ------------------------------------------------------------------ face -> person association */
+
+/* The "selective" step between match and crop.  NOT in the reference (scripts/modify_models.py:71-76 is a
+ * TODO): builder-defined, parity unpinned (restated in oracle/assoc.py).  Per frame: every
+ * face detection with a matched identity picks the person detection that contains its centre and covers most
+ * of it; persons picked by at least one face are emitted, in row order, as COCO boxes for the crop.
+ *   face_dets    DEVICE [batch, face_cap, 6]   rows of spp_decode_nms (x1, y1, x2, y2, conf, cls)
+ *   face_count   DEVICE [batch] int32;  face_ids DEVICE [batch, face_cap] int32 (identity per row, -1 = none)
+ *   person_dets  DEVICE [batch, person_cap, 6]; person_count DEVICE [batch] int32
+ *   out_boxes    DEVICE [batch, cap, 4] fp32 COCO (x, y, w, h), zero padding
+ *   out_ident    DEVICE [batch, cap] int32 identity of each selected person (-1 padding)
+ *   out_row      DEVICE [batch, cap] int32 person row of each selected person (may be NULL)
+ *   out_count    DEVICE [batch] int32 selected persons per frame (<= cap)
+ */
+int spp_associate(const float *face_dets, const int *face_count, const int *face_ids, int face_cap,
+                  const float *person_dets, const int *person_count, int person_cap, int batch, int cap,
+                  float *out_boxes, int *out_ident, int *out_row, int *out_count, spp_stream_t stream);
+
 /* ------------------------------------------------------------------ crop --------------------- */
 
 #define SPP_CROP_HF_UDP 0   /* HF VitPoseImageProcessor (box_to_center_and_scale + get_warp_matrix) */

@@ -22,4 +22,4 @@ Pinning (how this oracle is tied to the reference):
   installed) and the similarity threshold gate (a8 — not in the reference).  Their restatements
   follow the published Simple-Baselines/HRNet formulas and are marked as such.
 """
-from . import det, match, crop, pose  # noqa: F401
+from . import det, match, crop, pose, assoc  # noqa: F401

@@ -7,7 +7,7 @@ therefore imported by string; ``import spp`` (repo-root shim) gives the same pac
 from . import _lib, ops, shims, synth, hostmath, pipeline, dist  # noqa: F401
 from ._lib import SppError, build  # noqa: F401
 from .ops import (  # noqa: F401
-    crop_affine, decode_nms, head_decode, heatmap_decode, l2_normalize, match_top1, match_unpack_keys, nms_decoded,
+    associate, crop_affine, decode_nms, head_decode, heatmap_decode, l2_normalize, match_top1, match_unpack_keys, nms_decoded,
     to_bf16, NmsResult,
 )
 from .shims import (  # noqa: F401
@@ -17,7 +17,7 @@ from .shims import (  # noqa: F401
 
 __all__ = [
     "SppError", "build", "ops", "shims", "synth",
-    "crop_affine", "decode_nms", "head_decode", "heatmap_decode", "l2_normalize", "match_top1", "match_unpack_keys",
+    "associate", "crop_affine", "decode_nms", "head_decode", "heatmap_decode", "l2_normalize", "match_top1", "match_unpack_keys",
     "nms_decoded", "to_bf16", "NmsResult",
     "Gallery", "VitPoseImageProcessor", "backbone_tail", "detect", "flip_test_keypoints", "get_final_preds",
     "get_keypoints_from_heatmaps", "head_forward", "l2_norm", "non_max_suppression",

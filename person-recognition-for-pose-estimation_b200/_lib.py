@@ -32,6 +32,7 @@ SIGNATURES = {
     "spp_match_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "spp_match_top1": (c_int, [_P, _P, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
     "spp_match_unpack_keys": (c_int, [_P, c_int, c_float, _P, _P, _P]),
+    "spp_associate": (c_int, [_P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "spp_crop_affine": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float),
                                 c_int, _P, _P]),
     "spp_crop_affine_u8": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float),

@@ -224,6 +224,30 @@ def match_unpack_keys(keys: torch.Tensor, threshold: Optional[float] = None):
 
 
 # ------------------------------------------------------------------------------------------------
+# face -> person association (the "selective" step; not in the reference, see include/spp.h)
+# ------------------------------------------------------------------------------------------------
+
+def associate(face: "NmsResult", face_ids: torch.Tensor, person: "NmsResult", cap: int = 16):
+    """Persons that contain a face with a matched identity.  ``face_ids [B, face_cap]`` int32 holds the
+    identity of every face-detection row (-1 = unknown / gated / padding).  Returns
+    ``(boxes [B, cap, 4] COCO xywh, ident [B, cap] int32, rows [B, cap] int32, count [B] int32)``."""
+    _need_cuda("associate", face.dets, face.count, face_ids, person.dets, person.count)
+    b, fc = face.dets.shape[0], face.dets.shape[1]
+    pc = person.dets.shape[1]
+    if face_ids.dtype != torch.int32 or tuple(face_ids.shape) != (b, fc):
+        raise ValueError(f"associate: face_ids must be int32 [{b}, {fc}]")
+    dev = face.dets.device
+    boxes = torch.empty((b, cap, 4), dtype=torch.float32, device=dev)
+    ident = torch.empty((b, cap), dtype=torch.int32, device=dev)
+    rows = torch.empty((b, cap), dtype=torch.int32, device=dev)
+    count = torch.empty((b,), dtype=torch.int32, device=dev)
+    _lib.check(_lib.lib().spp_associate(_ptr(face.dets), _ptr(face.count), _ptr(face_ids.contiguous()), fc, _ptr(person.dets),
+                                        _ptr(person.count), pc, b, cap, _ptr(boxes), _ptr(ident), _ptr(rows), _ptr(count),
+                                        _stream(boxes)), "spp_associate")
+    return boxes, ident, rows, count
+
+
+# ------------------------------------------------------------------------------------------------
 # crop
 # ------------------------------------------------------------------------------------------------
 

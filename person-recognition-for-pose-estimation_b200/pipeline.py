@@ -77,7 +77,8 @@ class SelectivePosePipeline:
 
     def __init__(self, inputs: StepInputs, gallery_bf16: torch.Tensor, device: torch.device, threshold: float = 0.4,
                  conf_thres: float = 0.001, iou_thres: float = 0.65, decode_mode: str = "dark", use_graph: bool = True,
-                 id_offset: int = 0, concurrent: bool = True, matcher=None, capture_collectives: bool = False):
+                 id_offset: int = 0, concurrent: bool = True, matcher=None, capture_collectives: bool = False,
+                 select_on_device: bool = False):
         self.device = device
         self.threshold, self.conf, self.iou, self.mode = threshold, conf_thres, iou_thres, decode_mode
         self.id_offset = id_offset
@@ -88,6 +89,16 @@ class SelectivePosePipeline:
         self.launches_per_step = 0
         self._stream = torch.cuda.Stream(device)
         self.concurrent = concurrent
+        # select_on_device: the crop list is not an input but comes from the detections — persons that contain
+        # a face with a matched identity (ops.associate), at most `per_frame` per frame, no host round-trip.
+        self.select_on_device = select_on_device
+        if select_on_device:
+            assert matcher is None or capture_collectives, "select_on_device needs the match inside the step"
+            b = self.inp.frames.shape[0]
+            self.sel_cap = self.inp.boxes.shape[0] // b
+            assert self.sel_cap * b == self.inp.boxes.shape[0], "select_on_device needs the same crop capacity per frame"
+            self._face_ids = torch.full((b, 300), -1, dtype=torch.int32, device=device)
+            self._sel_frame_idx = torch.arange(b, dtype=torch.int32, device=device).repeat_interleave(self.sel_cap).contiguous()
         # multi-GPU: a dist.ShardedGalleryMatcher replaces the local match chain; its NCCL collectives run
         # eagerly on a side stream next to the graph (they are not captured)
         # The NCCL collectives run eagerly on a high-priority side stream beside the graph.
@@ -141,14 +152,27 @@ class SelectivePosePipeline:
                 ids, sims = self.matcher.match(i.embeddings)      # all_gather -> local top-1 -> all_reduce(MAX) -> unpack
             keys = None
             n += 4
+        boxes, frame_idx = i.boxes, i.frame_idx
+        if self.select_on_device:
+            if self.concurrent:              # the selection needs both detection chains and the match
+                for s in self._side:
+                    e = torch.cuda.Event()
+                    e.record(s)
+                    main.wait_event(e)
+            pf = min(self.sel_cap, ids.shape[0] // self._face_ids.shape[0])
+            self._face_ids[:, :pf] = ids.view(self._face_ids.shape[0], -1)[:, :pf].to(torch.int32)
+            sel_boxes, sel_ident, sel_rows, sel_count = ops.associate(face, self._face_ids, person, self.sel_cap)
+            boxes, frame_idx = sel_boxes.view(-1, 4), self._sel_frame_idx
+            self.out.update(sel_boxes=sel_boxes, sel_ident=sel_ident, sel_count=sel_count)
+            n += 2
         if i.frames.dtype == torch.uint8:     # HF default for uint8 images: 1/255 rescale folded into mean / std
             mean, std = [m * 255.0 for m in (0.485, 0.456, 0.406)], [s * 255.0 for s in (0.229, 0.224, 0.225)]
-            pix = ops.crop_affine(i.frames, i.boxes, i.frame_idx, mean=mean, std=std, out=self.out.get("pixel_values"))
+            pix = ops.crop_affine(i.frames, boxes, frame_idx, mean=mean, std=std, out=self.out.get("pixel_values"))
         else:
-            pix = ops.crop_affine(i.frames, i.boxes, i.frame_idx, out=self.out.get("pixel_values"))
+            pix = ops.crop_affine(i.frames, boxes, frame_idx, out=self.out.get("pixel_values"))
         n += 1
         flags = (ops.FLAG_SCALE_SCORE | ops.FLAG_BACKPROJECT) if self.mode == "softargmax" else 0
-        kp = ops.heatmap_decode(i.heatmaps, i.flipped, i.perm, i.boxes, self.mode, 11, flags,
+        kp = ops.heatmap_decode(i.heatmaps, i.flipped, i.perm, boxes, self.mode, 11, flags,
                                 out=(self.out["keypoints"], self.out["scores"], self.out["argmax"]) if "keypoints" in self.out else None)
         n += 1
         if self.concurrent:

@@ -301,6 +301,92 @@ def test_match_reference_fixture_and_keys(spp, golden, dev):
 
 
 # ------------------------------------------------------------------------------------------------
+# face -> person association (not in the reference; parity against the builder's own oracle)
+# ------------------------------------------------------------------------------------------------
+
+def test_associate_vs_oracle(spp, synth, dev):
+    from oracle import assoc as oassoc
+    g = torch.Generator().manual_seed(5)
+    b, fcap, pcap, cap = 6, 300, 300, 8
+    face = spp.NmsResult(torch.zeros(b, fcap, 6), torch.zeros(b, dtype=torch.int32), torch.zeros(b, fcap, dtype=torch.int32))
+    person = spp.NmsResult(torch.zeros(b, pcap, 6), torch.zeros(b, dtype=torch.int32), torch.zeros(b, pcap, dtype=torch.int32))
+    ids = torch.full((b, fcap), -1, dtype=torch.int32)
+    for i in range(b):
+        npers, nface = int(torch.randint(0, 14, (1,), generator=g)), int(torch.randint(0, 20, (1,), generator=g))
+        xy = torch.rand(npers, 2, generator=g) * torch.tensor([1000.0, 400.0])
+        wh = torch.rand(npers, 2, generator=g) * torch.tensor([200.0, 300.0]) + 40
+        person.dets[i, :npers, :4] = torch.cat([xy, xy + wh], 1)
+        person.dets[i, :npers, 4] = torch.linspace(0.9, 0.2, npers) if npers else torch.zeros(0)
+        person.count[i] = npers
+        fxy = torch.rand(nface, 2, generator=g) * torch.tensor([1200.0, 600.0])
+        if npers and nface:       # put most faces at the head of a random person
+            own = torch.randint(0, npers, (nface,), generator=g)
+            inside = torch.rand(nface, generator=g) < 0.8
+            hx = person.dets[i, own, 0] + 0.5 * (person.dets[i, own, 2] - person.dets[i, own, 0])
+            hy = person.dets[i, own, 1] + 0.1 * (person.dets[i, own, 3] - person.dets[i, own, 1])
+            fxy = torch.where(inside[:, None], torch.stack([hx, hy], 1), fxy)
+        fwh = torch.rand(nface, 2, generator=g) * 40 + 16
+        face.dets[i, :nface, :4] = torch.cat([fxy - fwh / 2, fxy + fwh / 2], 1)
+        face.count[i] = nface
+        ids[i, :nface] = torch.where(torch.rand(nface, generator=g) < 0.7, torch.randint(0, 10000, (nface,), generator=g), -1).int()
+    ref_boxes, ref_ident, ref_rows = oassoc.associate([face.dets[i, :face.count[i]].numpy() for i in range(b)],
+                                                      [ids[i, :face.count[i]].numpy() for i in range(b)],
+                                                      [person.dets[i, :person.count[i]].numpy() for i in range(b)], cap)
+    fg = spp.NmsResult(face.dets.to(dev), face.count.to(dev), face.keys.to(dev))
+    pg = spp.NmsResult(person.dets.to(dev), person.count.to(dev), person.keys.to(dev))
+    boxes, ident, rows, count = spp.associate(fg, ids.to(dev), pg, cap)
+    assert count.tolist() == [len(r) for r in ref_rows]
+    assert sum(count.tolist()) > 5
+    for i in range(b):
+        k = len(ref_rows[i])
+        np.testing.assert_array_equal(rows[i, :k].cpu().numpy(), ref_rows[i])
+        np.testing.assert_array_equal(ident[i, :k].cpu().numpy(), ref_ident[i])
+        np.testing.assert_array_equal(boxes[i, :k].cpu().numpy(), ref_boxes[i])
+        assert (ident[i, k:] == -1).all() and (boxes[i, k:] == 0).all()
+
+
+def test_pipeline_graph_vs_eager_and_device_selection(spp, synth, dev):
+    """The CUDA-graphed 4-branch pipeline gives the same tensors as eager serial launches, and in
+    select_on_device mode the crops / keypoints are those of the persons the association oracle picks."""
+    from oracle import assoc as oassoc
+    pipeline = spp.pipeline
+    b, pf = 4, 6
+    inp = pipeline.synthetic_inputs(b, 360, 480, pf, 17, seed=3)
+    ms = synth.make_match_set(b * pf, 500, seed=9)
+    inp.embeddings = ms.embeddings
+    gal = ms.gallery.to(torch.bfloat16)
+    a = pipeline.SelectivePosePipeline(inp, gal, dev, use_graph=True, concurrent=True)
+    e = pipeline.SelectivePosePipeline(inp, gal, dev, use_graph=False, concurrent=False)
+    for _ in range(3):
+        a.step(); e.step()
+    a.stream.synchronize(); e.stream.synchronize()
+    for k in ("face_dets", "face_count", "person_dets", "person_count", "ids", "sims", "pixel_values", "keypoints", "scores", "argmax"):
+        assert torch.equal(a.out[k], e.out[k]), k
+    host = a.bind_host(inp) or a.run_host()
+    a.stream.synchronize()
+    assert torch.equal(host["keypoints"], a.out["keypoints"].cpu()) and torch.equal(host["ids"], a.out["ids"].cpu())
+    # crop boxes selected on the device
+    s = pipeline.SelectivePosePipeline(inp, gal, dev, use_graph=True, select_on_device=True)
+    s.step(); s.stream.synchronize()
+    face_rows, person_rows = s.out["_face"].to_list(), s.out["_person"].to_list()
+    ids = s.out["ids"].view(b, pf).cpu().numpy()
+    fids = []
+    for i in range(b):
+        f = np.full(face_rows[i].shape[0], -1, np.int64)
+        f[:min(pf, len(f))] = ids[i, :min(pf, len(f))]
+        fids.append(f)
+    rb, ri, rr = oassoc.associate([r.cpu().numpy() for r in face_rows], fids, [r.cpu().numpy() for r in person_rows], pf)
+    assert s.out["sel_count"].tolist() == [len(x) for x in rr]
+    sel = s.out["sel_boxes"].cpu().numpy()
+    for i in range(b):
+        np.testing.assert_array_equal(sel[i, :len(rr[i])], rb[i])
+        np.testing.assert_array_equal(s.out["sel_ident"][i, :len(rr[i])].cpu().numpy(), ri[i])
+    boxes = s.out["sel_boxes"].view(-1, 4)
+    fidx = torch.arange(b, dtype=torch.int32, device=dev).repeat_interleave(pf)
+    assert torch.equal(s.out["pixel_values"], spp.crop_affine(s.inp.frames, boxes, fidx))
+
+
+# ------------------------------------------------------------------------------------------------
 # multi-GPU: gallery sharded by rows, NCCL top-1 (value, index) reduction  (needs >= 2 GPUs)
 # ------------------------------------------------------------------------------------------------
 
