@@ -534,6 +534,7 @@ int launch_nms(const NmsParams &prm, int batch, cudaStream_t st) {
 int check_nms_args(int batch, int nc, float iou, int max_det, int max_nms, const float *out_dets, const int *out_count,
                    const void *ws) {
     SPP_CHECK_ARG(batch >= 0 && batch <= 8192 && nc >= 1, "nms: need 0 <= batch <= 8192 and nc >= 1 (got %d / %d)", batch, nc);
+    if (batch == 0) return SPP_OK;
     SPP_CHECK_ARG(max_det >= 1 && max_det <= 4096 && max_nms >= 1 && max_nms <= kAliveWords * 32,
                   "nms: need 1 <= max_det <= 4096 and 1 <= max_nms <= %d (got %d / %d)", kAliveWords * 32, max_det, max_nms);
     SPP_CHECK_ARG(out_dets && out_count && ws, "nms: null output / workspace");
@@ -548,6 +549,7 @@ using namespace spp;
 
 extern "C" int spp_head_decode(const float *const *levels, const int *level_h, const int *level_w, const float *strides,
                                int num_levels, int batch, int nc, float *out, spp_stream_t stream) {
+    if (batch == 0) return SPP_OK;
     Levels lv{};
     int rc = fill_levels(lv, levels, level_h, level_w, strides, num_levels);
     if (rc) return rc;
@@ -569,8 +571,8 @@ extern "C" int spp_nms_decoded(const float *pred, int batch, int nc, int num_anc
                                int *out_keys, void *workspace, size_t workspace_bytes, spp_stream_t stream) {
     int rc = check_nms_args(batch, nc, iou_thres, max_det, max_nms, out_dets, out_count, workspace);
     if (rc) return rc;
-    SPP_CHECK_ARG(pred && num_anchors >= 1, "nms_decoded: bad pred / num_anchors");
     if (batch == 0) return SPP_OK;
+    SPP_CHECK_ARG(pred && num_anchors >= 1, "nms_decoded: bad pred / num_anchors");
     Workspace w = carve(workspace, batch, num_anchors, nc, max_candidates);
     if (workspace_bytes < w.bytes) {
         set_error("nms_decoded: workspace %zu < required %zu bytes", workspace_bytes, w.bytes);
@@ -593,6 +595,7 @@ extern "C" int spp_decode_nms(const float *const *levels, const int *level_h, co
                               int num_levels, int batch, int nc, float conf_thres, float iou_thres, int max_det,
                               int max_nms, float max_wh, int max_candidates, float *out_dets, int *out_count,
                               int *out_keys, void *workspace, size_t workspace_bytes, spp_stream_t stream) {
+    if (batch == 0) return SPP_OK;
     Levels lv{};
     int rc = fill_levels(lv, levels, level_h, level_w, strides, num_levels);
     if (rc) return rc;

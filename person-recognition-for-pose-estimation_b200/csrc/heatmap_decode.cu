@@ -452,8 +452,8 @@ extern "C" int spp_heatmap_decode(const float *hm, const float *hm_flipped, cons
                                   const float *boxes, int mode, int flags, int kernel, int crop_h, int crop_w,
                                   float *keypoints, float *scores, int *argmax, spp_stream_t stream) {
     using namespace spp;
-    SPP_CHECK_ARG(hm && keypoints && scores, "heatmap_decode: hm, keypoints and scores must be non-null");
     SPP_CHECK_ARG(p >= 0 && k > 0 && h > 0 && w > 0, "heatmap_decode: bad shape p=%d k=%d h=%d w=%d", p, k, h, w);
+    SPP_CHECK_ARG(p == 0 || (hm && keypoints && scores), "heatmap_decode: hm, keypoints and scores must be non-null");
     SPP_CHECK_ARG(w % 4 == 0, "heatmap_decode: heatmap width must be a multiple of 4 (got %d)", w);
     SPP_CHECK_ARG((mode >= SPP_DECODE_DARK && mode <= SPP_DECODE_QUARTER) || mode == kModeCopyOnly, "heatmap_decode: unknown mode %d", mode);
     SPP_CHECK_ARG(kernel >= 3 && kernel <= 2 * kMaxRadius + 1 && (kernel & 1), "heatmap_decode: kernel must be odd in 3..%d (got %d)",

@@ -504,6 +504,7 @@ using namespace spp;
 
 extern "C" int spp_l2_normalize(const float *x, int m, int dim, int mode, float eps, float *out, float *norm,
                                 uint16_t *out_bf16, spp_stream_t stream) {
+    if (m == 0) return SPP_OK;
     SPP_CHECK_ARG(x && m >= 0 && dim > 0, "l2_normalize: bad arguments");
     SPP_CHECK_ARG(mode == 0 || mode == 1, "l2_normalize: mode must be 0 (x/||x||) or 1 (F.normalize)");
     if (m == 0) return SPP_OK;
@@ -531,6 +532,7 @@ extern "C" size_t spp_match_workspace_bytes(int m, int n, int dim) {
 static int match_common(const float *emb, const uint16_t *gallery, int m, int n, int dim, float threshold, int id_offset,
                         int *out_id, float *out_sim, unsigned long long *out_key, void *workspace, size_t workspace_bytes,
                         spp_stream_t stream, bool simt) {
+    if (m == 0) return SPP_OK;
     SPP_CHECK_ARG(emb && gallery && workspace, "match_top1: null pointer");
     SPP_CHECK_ARG(dim == kDim, "match_top1: embedding dimension must be %d (got %d)", kDim, dim);
     SPP_CHECK_ARG(m >= 0 && n >= 1, "match_top1: bad m=%d n=%d", m, n);

@@ -423,3 +423,98 @@ def test_sharded_gallery_match_nccl(dev):
         out = mgr.dict()
         mp.spawn(_nccl_worker, args=(world, port, 5000, 96, out), nprocs=world, join=True)
         assert dict(out) == {0: True, 1: True}
+
+
+# ------------------------------------------------------------------------------------------------
+# edge cases: empty and ragged inputs, other shapes, error behaviour
+# ------------------------------------------------------------------------------------------------
+
+def test_empty_inputs(spp, dev):
+    kp, sc, am = spp.heatmap_decode(torch.zeros(0, 17, 64, 48, device=dev))
+    assert kp.shape == (0, 17, 2) and sc.shape == (0, 17) and am.shape == (0, 17)
+    out = spp.crop_affine(torch.zeros(1, 3, 32, 32, device=dev), torch.zeros(0, 4, device=dev), torch.zeros(0, dtype=torch.int32, device=dev))
+    assert out.shape == (0, 3, 256, 192)
+    ids, sims = spp.match_top1(torch.zeros(0, 512, device=dev), torch.zeros(4, 512, device=dev, dtype=torch.bfloat16))
+    assert ids.shape == (0,) and sims.shape == (0,)
+    dets = spp.non_max_suppression(torch.zeros(0, 5, 100, device=dev))
+    assert dets == []
+    # all-zero decoded tensor: no candidate survives conf > 0.001
+    dets = spp.non_max_suppression(torch.zeros(3, 5, 100, device=dev))
+    assert [d.shape for d in dets] == [(0, 6)] * 3
+
+
+@pytest.mark.parametrize("k,h,w", [(133, 64, 48), (17, 96, 72), (3, 32, 24), (1, 16, 12)])
+def test_heatmap_other_shapes(spp, synth, dev, k, h, w):
+    hs = synth.make_heatmaps(3, k, h, w, seed=k + h, negative_frac=0.05, pairs=synth.wholebody_flip_pairs(k) if k > 17 else None)
+    cs = synth.make_crop_set(1, 480, 640, per_frame=3, seed=1)
+    avg = opose.flip_average(hs.heatmaps, hs.flipped, hs.perm)
+    kp_o, sc_o, idx_o = opose.hf_dark_decode(avg.numpy(), cs.boxes.tolist())
+    kp, sc, am = spp.heatmap_decode(hs.heatmaps.to(dev), hs.flipped.to(dev), hs.perm.to(dev), cs.boxes.to(dev), "dark", 11)
+    np.testing.assert_array_equal(am.cpu().numpy(), idx_o)
+    np.testing.assert_array_equal(sc.cpu().numpy(), sc_o)
+    valid = sc_o > 0
+    _close(kp.cpu().numpy()[valid], kp_o[valid], what=f"DARK keypoints K={k} {h}x{w}")
+    c_o, s_o = opose.soft_argmax_decode(avg)
+    c, s_, _ = spp.heatmap_decode(hs.heatmaps.to(dev), hs.flipped.to(dev), hs.perm.to(dev), None, "softargmax")
+    _close(c.cpu().numpy(), c_o.numpy(), what="softargmax coords")
+    _close(s_.cpu().numpy(), s_o.numpy(), what="softargmax scores")
+
+
+def test_heatmap_ties_and_constant_maps(spp, dev):
+    hm = torch.zeros(2, 3, 64, 48)
+    hm[0, 0, 10, 5] = hm[0, 0, 10, 6] = hm[0, 0, 40, 1] = 2.0          # three equal maxima: the first one wins
+    hm[0, 1] = 0.7                                                      # constant map: index 0
+    hm[0, 2] = -1.0
+    hm[1, 0, 63, 47] = 1.0                                              # last element
+    hm[1, 1, 0, 0] = 1.0                                                # first element
+    hm[1, 2] = float("-inf")                                            # np.argmax of all -inf is 0
+    kp, sc, am = spp.heatmap_decode(hm.to(dev), mode="quarter")
+    ref = hm.flatten(2).argmax(2)
+    assert torch.equal(am.cpu().long(), ref)
+    assert torch.equal(sc.cpu(), hm.flatten(2).max(2).values)
+
+
+def test_nms_multilabel_many_classes(spp, dev):
+    g = torch.Generator().manual_seed(2)
+    b, nc, a = 2, 80, 600
+    pred = torch.zeros(b, 4 + nc, a)
+    pred[:, 0] = torch.rand(b, a, generator=g) * 600
+    pred[:, 1] = torch.rand(b, a, generator=g) * 400
+    pred[:, 2:4] = torch.rand(b, 2, a, generator=g) * 80 + 10
+    pred[:, 4:] = torch.rand(b, nc, a, generator=g) ** 8                 # a few confident classes per anchor
+    ref_rows, ref_keys = odet.non_max_suppression(pred, 0.25, 0.45, return_index=True)
+    res = spp.nms_decoded(pred.to(dev), 0.25, 0.45)
+    assert res.count.tolist() == [r.shape[0] for r in ref_rows]
+    for rows, keys, rr, rk in zip(res.to_list(), res.keys_list(), ref_rows, ref_keys):
+        np.testing.assert_array_equal(keys.cpu().numpy(), rk.numpy())
+        np.testing.assert_array_equal(rows.cpu().numpy(), rr.numpy())
+
+
+def test_nms_thousands_of_candidates(spp, dev):
+    """More candidates than the shared-memory sort holds (8192): the workspace path."""
+    g = torch.Generator().manual_seed(3)
+    a = 12000
+    pred = torch.zeros(1, 5, a)
+    pred[0, 0] = torch.rand(a, generator=g) * 1200
+    pred[0, 1] = torch.rand(a, generator=g) * 700
+    pred[0, 2:4] = torch.rand(2, a, generator=g) * 60 + 8
+    pred[0, 4] = torch.rand(a, generator=g) * 0.9 + 0.05
+    ref_rows, ref_keys = odet.non_max_suppression(pred, 0.001, 0.65, return_index=True)
+    res = spp.nms_decoded(pred.to(dev))
+    np.testing.assert_array_equal(res.keys_list()[0].cpu().numpy(), ref_keys[0].numpy())
+    np.testing.assert_array_equal(res.to_list()[0].cpu().numpy(), ref_rows[0].numpy())
+
+
+def test_argument_errors(spp, dev):
+    with pytest.raises((ValueError, RuntimeError)):
+        spp.heatmap_decode(torch.zeros(1, 17, 64, 46, device=dev))          # width not a multiple of 4
+    with pytest.raises((ValueError, RuntimeError)):
+        spp.heatmap_decode(torch.zeros(1, 17, 64, 48, device=dev), kernel=10)
+    with pytest.raises((ValueError, TypeError, RuntimeError)):
+        spp.match_top1(torch.zeros(2, 256, device=dev), torch.zeros(4, 256, device=dev, dtype=torch.bfloat16))
+    with pytest.raises(TypeError):
+        spp.match_top1(torch.zeros(2, 512, device=dev), torch.zeros(4, 512, device=dev))   # gallery must be bf16
+    with pytest.raises(ValueError):
+        spp.non_max_suppression(torch.zeros(1, 4, 10, device=dev))           # no class channel
+    with pytest.raises(ValueError):
+        spp.crop_affine(torch.zeros(1, 1, 8, 8, device=dev), torch.zeros(1, 4, device=dev), torch.zeros(1, dtype=torch.int32, device=dev))
