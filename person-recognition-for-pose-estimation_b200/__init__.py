@@ -4,7 +4,7 @@ heatmap decode) behind the reference's own call signatures.
 The directory name carries the project name (``person-recognition-for-pose-estimation_b200``) and is
 therefore imported by string; ``import spp`` (repo-root shim) gives the same package.
 """
-from . import _lib, ops, shims, synth, hostmath, pipeline, dist  # noqa: F401
+from . import _lib, ops, shims, synth, hostmath, pipeline, dist, torch_ops  # noqa: F401
 from ._lib import SppError, build  # noqa: F401
 from .ops import (  # noqa: F401
     associate, crop_affine, decode_nms, head_decode, heatmap_decode, l2_normalize, match_top1, match_unpack_keys, nms_decoded,

@@ -110,3 +110,25 @@ def test_synthetic_inputs_are_deterministic(synth):
     assert synth.num_anchors(736, 1280) == 19320 and synth.num_anchors(640, 640) == 8400
     hm = synth.make_head_maps(1, 64, 96, n_obj=2, seed=1)
     assert [tuple(l.shape) for l in hm.levels] == [(1, 65, 8, 12), (1, 65, 4, 6), (1, 65, 2, 3)]
+
+
+def test_torch_ops_registered_with_fake_kernels(spp):
+    """torch.ops.spp.* exist, infer shapes without a GPU (fake tensors), and have no CPU implementation."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    for name in ("head_decode", "nms_decoded", "decode_nms", "l2_normalize", "match_top1", "crop_affine", "heatmap_decode"):
+        assert hasattr(torch.ops.spp, name)
+    with FakeTensorMode():
+        hm = torch.empty(7, 17, 64, 48)
+        kp, sc, am = torch.ops.spp.heatmap_decode(hm, None, None, None, "dark", 11, 0)
+        assert kp.shape == (7, 17, 2) and sc.shape == (7, 17) and am.dtype == torch.int32
+        levels = [torch.empty(2, 65, 32, 40), torch.empty(2, 65, 16, 20), torch.empty(2, 65, 8, 10)]
+        assert torch.ops.spp.head_decode(levels, [8.0, 16.0, 32.0]).shape == (2, 5, 1680)
+        dets, cnt, keys = torch.ops.spp.decode_nms(levels, [8.0, 16.0, 32.0], 0.001, 0.65, 300)
+        assert dets.shape == (2, 300, 6) and cnt.shape == (2,) and keys.shape == (2, 300)
+        ids, sims = torch.ops.spp.match_top1(torch.empty(5, 512), torch.empty(100, 512, dtype=torch.bfloat16), 0.4, 0)
+        assert ids.shape == (5,) and ids.dtype == torch.int32 and sims.shape == (5,)
+        pix = torch.ops.spp.crop_affine(torch.empty(1, 3, 64, 64), torch.empty(3, 4), torch.empty(3, dtype=torch.int32), 256, 192,
+                                        [0.485, 0.456, 0.406], [0.229, 0.224, 0.225])
+        assert pix.shape == (3, 3, 256, 192)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.spp.l2_normalize(torch.zeros(2, 512))          # CPU tensors: no kernel registered

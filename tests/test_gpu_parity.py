@@ -518,3 +518,18 @@ def test_argument_errors(spp, dev):
         spp.non_max_suppression(torch.zeros(1, 4, 10, device=dev))           # no class channel
     with pytest.raises(ValueError):
         spp.crop_affine(torch.zeros(1, 1, 8, 8, device=dev), torch.zeros(1, 4, device=dev), torch.zeros(1, dtype=torch.int32, device=dev))
+
+
+def test_torch_ops_dispatch_to_the_kernels(spp, synth, dev):
+    hs = synth.make_heatmaps(3, 17, seed=4)
+    a = torch.ops.spp.heatmap_decode(hs.heatmaps.to(dev), hs.flipped.to(dev), hs.perm.to(dev), None, "dark", 11, 0)
+    b = spp.heatmap_decode(hs.heatmaps.to(dev), hs.flipped.to(dev), hs.perm.to(dev), None, "dark", 11)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    hm = synth.make_head_maps(2, 128, 160, n_obj=3, seed=2)
+    lv = [l.to(dev) for l in hm.levels]
+    dets, cnt, keys = torch.ops.spp.decode_nms(lv, [8.0, 16.0, 32.0], 0.001, 0.65, 300)
+    ref = spp.decode_nms(lv)
+    assert torch.equal(dets, ref.dets) and torch.equal(cnt, ref.count) and torch.equal(keys, ref.keys)
+    dec = torch.ops.spp.head_decode(lv, [8.0, 16.0, 32.0])
+    d2, c2, k2 = torch.ops.spp.nms_decoded(dec, 0.001, 0.65, 300)
+    assert torch.equal(c2, cnt) and torch.equal(k2, keys)
