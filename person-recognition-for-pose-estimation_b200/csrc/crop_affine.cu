@@ -16,6 +16,7 @@
 // thread per row.  HBM-bound: 4 B written per output element + the source ROI read once.
 #include "spp_common.cuh"
 
+#include <cstdlib>
 #include <type_traits>
 
 namespace spp {
@@ -27,6 +28,7 @@ struct CropParams {
     const int *frame_idx;
     float *out;
     int num_frames, fh, fw, P, oh, ow, variant;
+    int stage_bytes;            // size of the shared-memory band buffer
     float mean[3], stdv[3];
 };
 
@@ -114,7 +116,7 @@ __device__ __forceinline__ float sample_px(unsigned char p00, unsigned char p01,
     return fmaf((float)(int)v, inv_sd, nmean);        // v >= 0.5: truncation == floor
 }
 
-constexpr int kStageBytes = 40 * 1024;   // source band buffer per CTA -> 4-5 CTAs per SM
+constexpr int kStageBytesDefault = 40 * 1024;   // source band buffer per CTA -> 4-5 CTAs per SM
 
 // One CTA per (crop, channel), one thread per output column.
 //   * coordinate tables (fp64 -> index + fp32 weight) for the out_w columns and out_h rows in smem;
@@ -133,7 +135,8 @@ __global__ void __launch_bounds__(256) crop_affine_kernel(const CropParams prm, 
     constexpr int kAlign = 16 / (int)sizeof(T);                                          // elements per 16 bytes
     extern __shared__ __align__(128) unsigned char crop_smem[];
     const int ow = prm.ow, oh = prm.oh;
-    T *buf = reinterpret_cast<T *>(crop_smem);                                           // [kStageBytes]
+    const int kStageBytes = prm.stage_bytes;
+    T *buf = reinterpret_cast<T *>(crop_smem);                                           // [stage_bytes]
     Entry *xt = reinterpret_cast<Entry *>(crop_smem + kStageBytes);                      // [ow]
     Entry *yt = xt + ow;                                                                 // [oh]
     uint64_t *bar = reinterpret_cast<uint64_t *>(yt + oh);
@@ -268,7 +271,14 @@ int launch_crop(const void *frames, int num_frames, int frame_h, int frame_w, co
     // bulk-TMA row copies need 16-byte aligned row segments: base and row pitch multiples of 16 bytes
     const int staged = ((size_t)frame_w * sizeof(T) % 16 == 0) && ((reinterpret_cast<uintptr_t>(frames) & 15) == 0);
     using W = typename std::conditional<std::is_same<T, float>::value, float, double>::type;
-    const size_t smem = (size_t)kStageBytes + (size_t)(out_w + out_h) * sizeof(AxisEntry<W>) + 16;
+    static int stage_kb = 0;
+    if (stage_kb == 0) {                         // tuning knob; default 40 KB
+        const char *e = getenv("SPP_CROP_STAGE_KB");
+        stage_kb = e ? atoi(e) : kStageBytesDefault / 1024;
+        if (stage_kb < 4 || stage_kb > 96) stage_kb = kStageBytesDefault / 1024;
+    }
+    prm.stage_bytes = stage_kb * 1024;
+    const size_t smem = (size_t)prm.stage_bytes + (size_t)(out_w + out_h) * sizeof(AxisEntry<W>) + 16;
     int threads = (out_w + 31) / 32 * 32;
     if (threads > 256) threads = 256;
     static bool configured = false;

@@ -23,6 +23,7 @@
 #include "spp_common.cuh"
 
 #include <cfloat>
+#include <cstdlib>
 #include <climits>
 #include <cmath>
 
@@ -491,6 +492,15 @@ extern "C" int spp_heatmap_decode(const float *hm, const float *hm_flipped, cons
     int warps = slots < max_warps ? slots : max_warps;
     int stages = slots / warps;
     if (stages > 4) stages = 4;
+    {   // tuning knobs (profiling only): SPP_HM_WARPS / SPP_HM_STAGES override the split of the slots
+        static int env_w = -1, env_s = -1;
+        if (env_w < 0) {
+            const char *ew = getenv("SPP_HM_WARPS"), *es = getenv("SPP_HM_STAGES");
+            env_w = ew ? atoi(ew) : 0;
+            env_s = es ? atoi(es) : 0;
+        }
+        if (env_w > 0 && env_s > 0 && env_w * env_s <= slots && env_w <= max_warps) { warps = env_w; stages = env_s; }
+    }
     prm.warps = warps; prm.stages = stages;
     {   // q / W4 by multiply-shift, verified for every quad index of a map
         const unsigned w4 = (unsigned)(w / 4), n4 = (unsigned)(h * w / 4);
