@@ -84,6 +84,29 @@ class Gallery:
     def __len__(self) -> int:
         return self.rows.shape[0]
 
+    # ---- storage: a plain [N, 512] bf16 matrix; a shard is a contiguous row range ----
+    def save(self, path: str) -> None:
+        """Raw little-endian bf16 rows (``N * 1024`` bytes) + a tiny JSON header beside it."""
+        import json
+        import numpy as np
+        self.rows.cpu().view(torch.int16).numpy().tofile(path)
+        with open(path + ".json", "w") as f:
+            json.dump({"ids": int(self.rows.shape[0]), "dim": int(self.rows.shape[1]), "dtype": "bfloat16",
+                       "id_offset": self.id_offset, "layout": "row-major, rows unit-norm"}, f)
+
+    @classmethod
+    def load(cls, path: str, device, world: int = 1, rank: int = 0) -> "Gallery":
+        """Memory-map the file and upload only this rank's contiguous row shard (``dist.shard_bounds``)."""
+        import json
+        import numpy as np
+        from .dist import shard_bounds
+        with open(path + ".json") as f:
+            meta = json.load(f)
+        lo, hi = shard_bounds(meta["ids"], world, rank)
+        mm = np.memmap(path, dtype=np.int16, mode="r", shape=(meta["ids"], meta["dim"]))
+        rows = torch.from_numpy(np.array(mm[lo:hi])).view(torch.bfloat16).to(device)
+        return cls(rows, id_offset=meta.get("id_offset", 0) + lo)
+
     def match(self, embeddings: torch.Tensor, threshold: Optional[float] = None):
         """``pred = (F.linear(F.normalize(emb), G) * s).max(1)[1]`` (face_recognition/module.py:136-145) plus the
         optional similarity gate; returns ``(ids int64 [M], sims fp32 [M])``, ``ids == -1`` where gated."""

@@ -533,3 +533,20 @@ def test_torch_ops_dispatch_to_the_kernels(spp, synth, dev):
     dec = torch.ops.spp.head_decode(lv, [8.0, 16.0, 32.0])
     d2, c2, k2 = torch.ops.spp.nms_decoded(dec, 0.001, 0.65, 300)
     assert torch.equal(c2, cnt) and torch.equal(k2, keys)
+
+
+def test_gallery_save_load_shards(spp, synth, dev, tmp_path):
+    ms = synth.make_match_set(32, 1000, seed=6)
+    gal = spp.Gallery.from_rows(ms.gallery.to(dev))
+    path = str(tmp_path / "gallery.bf16")
+    gal.save(path)
+    full = spp.Gallery.load(path, dev)
+    assert torch.equal(full.rows, gal.rows)
+    ids_full, sims_full = full.match(ms.embeddings.to(dev), threshold=0.4)
+    keys = None
+    for r in range(3):                                   # three shards, reduced with an integer max
+        sh = spp.Gallery.load(path, dev, world=3, rank=r)
+        k = spp.match_top1(ms.embeddings.to(dev), sh.rows, None, sh.id_offset, want_keys=True)[2]
+        keys = k if keys is None else torch.maximum(keys, k)
+    ids, sims = spp.match_unpack_keys(keys, 0.4)
+    assert torch.equal(ids.long(), ids_full) and torch.equal(sims, sims_full)
