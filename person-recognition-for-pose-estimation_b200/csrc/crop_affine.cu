@@ -9,13 +9,15 @@
 //              get_affine_transform + warpAffine; exact bilinear here, no 1/32-px quantisation)
 //
 // The warp has no rotation, so source coordinates are separable: x_s depends only on the output
-// column, y_s only on the output row.  One CTA per (crop, channel) computes both coordinate tables
-// ONCE in fp64 (the oracle inverts the fp32 matrix in fp64 and samples in fp64; an fp32 coordinate
-// at x ~ 1000 px would already be off by 6e-5 px) and keeps (index, fp32 weight) pairs in shared
-// memory; the sampling loop is fp32, four output pixels per thread, one 128-bit streaming store per
-// thread per row.  HBM-bound: 4 B written per output element + the source ROI read once.
+// column, y_s only on the output row.  One CTA per (crop, channel, slab of output rows) computes both
+// coordinate tables ONCE in fp64 (the oracle inverts the fp32 matrix in fp64 and samples in fp64; an fp32
+// coordinate at x ~ 1000 px would already be off by 6e-5 px) and keeps (index, weight) pairs in shared
+// memory.  A producer warp streams the needed source rows into shared-memory band buffers with bulk TMA
+// (full / empty mbarriers, no block barrier in the main loop); six consumer warps sample them in fp32.
+// HBM-bound: 4 B written per output element + the source ROI read once.
 #include "spp_common.cuh"
 
+#include <climits>
 #include <cstdlib>
 #include <type_traits>
 
@@ -28,7 +30,9 @@ struct CropParams {
     const int *frame_idx;
     float *out;
     int num_frames, fh, fw, P, oh, ow, variant;
-    int stage_bytes;            // size of the shared-memory band buffer
+    int stage_bytes;            // size of one shared-memory band buffer
+    int stages;                 // band buffers per CTA
+    int ncc, rg;                // staged kernel: column chunks (of 32 C columns) x row groups = warps per CTA
     float mean[3], stdv[3];
 };
 
@@ -74,40 +78,50 @@ __device__ __forceinline__ AxisMap crop_axis_map(const float4 box, int ow, int o
 
 // (i0, t): sample = v[i0]*(1-t) + v[i0+1]*t with i0 + 1 always inside the axis (at the far edge the pair
 // (n-2, t=1) stands for (n-1, t=0)); i0 < 0 marks "outside the frame -> 0".  n >= 2.
-// Weight type: fp32 for float frames, fp64 for uint8 frames (whose result is rounded to an integer, so
-// the interpolation itself has to be as exact as scipy's).
-template <typename W>
-struct AxisEntry {
+// fp32 frames keep an fp32 weight.  uint8 frames (whose result is rounded to an integer, so the decisive
+// interpolation has to be as exact as scipy's fp64) keep the fp64 weight next to its fp32 rounding.
+template <typename T>
+struct AxisEntry;
+template <>
+struct AxisEntry<float> {
     int i0;
-    W t;
+    float t;
+    __device__ __forceinline__ void set(int i, double w) { i0 = i; t = (float)w; }
 };
-template <typename W>
-__device__ __forceinline__ AxisEntry<W> axis_entry(double s, int n) {
-    AxisEntry<W> e;
+template <>
+struct __align__(16) AxisEntry<unsigned char> {
+    int i0;
+    float t;
+    double td;
+    __device__ __forceinline__ void set(int i, double w) { i0 = i; t = (float)w; td = w; }
+};
+template <typename T>
+__device__ __forceinline__ AxisEntry<T> axis_entry(double s, int n) {
+    AxisEntry<T> e;
     if (!(s >= 0.0 && s <= (double)(n - 1))) {
-        e.i0 = -1;
-        e.t = (W)0;
+        e.set(-1, 0.0);
         return e;
     }
     const double f = floor(s);
-    e.i0 = (int)f;
-    e.t = (W)(s - f);
-    if (e.i0 >= n - 1) {
-        e.i0 = n - 2;
-        e.t = (W)1;
+    int i0 = (int)f;
+    double t = s - f;
+    if (i0 >= n - 1) {
+        i0 = n - 2;
+        t = 1.0;
     }
+    e.set(i0, t);
     return e;
 }
 
-// bilinear sample + normalisation.  float frames: fp32 lerps.  uint8 frames: fp64 lerps, then scipy's
-// integer output conversion (round half up, clamp to 0..255) before (q - mean) / std.
-__device__ __forceinline__ float sample_px(float p00, float p01, float p10, float p11, float wx, float wy, float inv_sd, float nmean) {
-    const float top = fmaf(p01 - p00, wx, p00);
-    const float bot = fmaf(p11 - p10, wx, p10);
+// ---- per-pixel arithmetic ---------------------------------------------------------------------------
+// float frames: vertical lerp + (v - mean)/std as one FMA
+__device__ __forceinline__ float finish_px(float top, float bot, float wy, float inv_sd, float nmean) {
     return fmaf(fmaf(bot - top, wy, top), inv_sd, nmean);
 }
-__device__ __forceinline__ float sample_px(unsigned char p00, unsigned char p01, unsigned char p10, unsigned char p11, double wx,
-                                           double wy, float inv_sd, float nmean) {
+// uint8 frames, exact path: fp64 lerps, then scipy's integer output conversion (round half up, clamp to
+// 0..255) before (q - mean) / std.
+__device__ __forceinline__ float exact_px_u8(unsigned p00, unsigned p01, unsigned p10, unsigned p11, double wx, double wy,
+                                             float inv_sd, float nmean) {
     const double a = (double)p00, b = (double)p01, c = (double)p10, d = (double)p11;
     const double top = fma(b - a, wx, a);
     const double bot = fma(d - c, wx, c);
@@ -115,32 +129,112 @@ __device__ __forceinline__ float sample_px(unsigned char p00, unsigned char p01,
     v = v > 255.0 ? 255.0 : v;
     return fmaf((float)(int)v, inv_sd, nmean);        // v >= 0.5: truncation == floor
 }
+// uint8 frames, fast path.  The fp32 estimate v of the interpolated value is within 1e-4 of the fp64 one
+// (|v| <= 255: four fp32 roundings of <= 1.6e-5 each plus the fp32 weights).  r = nearest integer (2^23
+// trick, two FADDs); unless v is within kU8Guard of a tie (x.5), r == floor(exact + 0.5) and the fp32 result
+// IS scipy's.  Near a tie (2 * kU8Guard of the pixels on noise; every pixel of e.g. an exact 2x upscale)
+// the caller recomputes in fp64.
+constexpr float kU8Guard = 1.0f / 1024.0f;
+__device__ __forceinline__ bool fast_px_u8(float top, float bot, float wy, float inv_sd, float nmean, float &out) {
+    const float v = fmaf(bot - top, wy, top);
+    const float r = __fsub_rn(__fadd_rn(v, 8388608.0f), 8388608.0f);
+    const float fr = fabsf(v - r);
+    out = fmaf(fminf(r, 255.0f), inv_sd, nmean);
+    return fr < 0.5f - kU8Guard;
+}
 
-constexpr int kStageBytesDefault = 40 * 1024;   // source band buffer per CTA -> 4-5 CTAs per SM
-
-// One CTA per (crop, channel), one thread per output column.
-//   * coordinate tables (fp64 -> index + fp32 weight) for the out_w columns and out_h rows in smem;
-//   * the valid output rows are processed in bands; for each band the needed source rows, restricted to
-//     the needed (16 B aligned) column range, are copied into shared memory by bulk-TMA row copies
-//     (cp.async.bulk, issued by warp 0, all completing on one mbarrier) — coalesced full-line HBM reads
-//     instead of four scattered 4-byte gathers per output pixel;
-//   * per pixel: one 8-byte table read, 4 shared-memory reads at fixed offsets from one address, 7 FP
-//     ops (bilinear + (v - mean)/std as one FMA) and one coalesced 4-byte streaming store.
-// `staged == 0` (frame width not a multiple of 4, unaligned base, or a band that cannot fit): the same
-// loop gathers straight from global memory.
+// shared-memory loads by 32-bit address (volatile: never moved across the mbarrier waits / block barriers)
+__device__ __forceinline__ float lds_px(uint32_t addr, float) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds_px1(uint32_t addr, float) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(v) : "r"(addr));
+    return v;
+}
+// uint8: widened with the 2^23 trick (one logic op + one FADD instead of a quarter-rate I2F)
+__device__ __forceinline__ float lds_px(uint32_t addr, unsigned char) {
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return __int_as_float(0x4B000000 | (int)v) - 8388608.0f;
+}
+__device__ __forceinline__ float lds_px1(uint32_t addr, unsigned char) {
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(v) : "r"(addr));
+    return __int_as_float(0x4B000000 | (int)v) - 8388608.0f;
+}
+__device__ __forceinline__ unsigned lds_u8(uint32_t addr) {
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 template <typename T>
-__global__ void __launch_bounds__(256) crop_affine_kernel(const CropParams prm, int staged) {
-    using W = typename std::conditional<std::is_same<T, float>::value, float, double>::type;
-    using Entry = AxisEntry<W>;
+__device__ __forceinline__ float hlerp_s(uint32_t addr, float wx) {
+    const float a = lds_px(addr, T()), b = lds_px1(addr, T());
+    return fmaf(b - a, wx, a);
+}
+
+constexpr int kStageBytesDefault = 20 * 1024;   // one source band buffer of a CTA, fp32 frames
+constexpr int kStageBytesDefaultU8 = 12 * 1024; // uint8 frames (rows are a quarter of the bytes)
+constexpr int kCropWarps = 6;                   // warps per CTA = column chunks x row groups
+
+// Coordinate tables of one CTA: xt[0..ow), yt[ry0..ry1] (indexed by output row), and the valid ranges
+// s_v = {first, last valid column, first, last valid row}.  Ends with a block barrier.
+template <typename T>
+__device__ __forceinline__ void build_tables(const AxisMap &m, const CropParams &prm, AxisEntry<T> *xt, AxisEntry<T> *yt, int ry0, int ry1,
+                                             int *s_v) {
+    const int tid = threadIdx.x, nthreads = blockDim.x, ow = prm.ow;
+    for (int i = tid; i < ow + (ry1 - ry0 + 1); i += nthreads) {
+        if (i < ow) {
+            const AxisEntry<T> e = axis_entry<T>(m.ax * (double)i + m.bx, prm.fw);
+            xt[i] = e;
+            if (e.i0 >= 0) { atomicMin(&s_v[0], i); atomicMax(&s_v[1], i); }
+        } else {
+            const int y = ry0 + i - ow;
+            const AxisEntry<T> e = axis_entry<T>(m.ay * (double)y + m.by, prm.fh);
+            yt[y] = e;
+            if (e.i0 >= 0) { atomicMin(&s_v[2], y); atomicMax(&s_v[3], y); }
+        }
+    }
+    __syncthreads();
+}
+
+// One CTA per (crop, channel, slab of output rows).
+//   * coordinate tables (fp64 -> index + weight) for the out_w columns and the slab's rows in smem;
+//   * the valid output rows are processed in bands; for each band the needed source rows, restricted to
+//     the needed (16 B aligned) column range, are copied into a shared-memory band buffer by bulk-TMA row
+//     copies (cp.async.bulk) issued by a dedicated PRODUCER warp — coalesced full-line HBM reads instead of
+//     four scattered gathers per output pixel.  `stages` band buffers form a ring: full[s] (transaction
+//     mbarrier) tells the consumers the band has landed, empty[s] (one arrival per consumer warp) tells the
+//     producer the buffer can be refilled; there is no block-wide barrier after the tables are built;
+//   * a CONSUMER warp owns a chunk of 32*C output columns (lane + 32 j, j < C) and one of the row groups of
+//     every band: the per-row work (table read, row address, loop) is paid once per C pixels.  The source
+//     row index is warp-uniform, so the horizontal lerps of a source row are carried in registers from one
+//     output row to the next whenever consecutive output rows share it;
+//   * one coalesced 4-byte streaming store per pixel.
+// Measured on B200 (cfg2, 640 crops): more resident CTAs beat deeper rings (per-CTA start-up = box load +
+// fp64 tables + first band), hence 2 stages of 20 KB (fp32) / 12 KB (uint8) -> 5-7 CTAs per SM.
+// Needs 16-byte aligned source rows (bulk TMA) and room for 2 source rows of the widest window in a band
+// buffer; anything else goes to crop_affine_direct_kernel.
+template <typename T, int C>
+__global__ void __launch_bounds__(32 * (kCropWarps + 1)) crop_affine_kernel(const CropParams prm) {
+    using Entry = AxisEntry<T>;
+    constexpr bool kU8 = std::is_same<T, unsigned char>::value;
     constexpr int kAlign = 16 / (int)sizeof(T);                                          // elements per 16 bytes
     extern __shared__ __align__(128) unsigned char crop_smem[];
     const int ow = prm.ow, oh = prm.oh;
     const int kStageBytes = prm.stage_bytes;
-    T *buf = reinterpret_cast<T *>(crop_smem);                                           // [stage_bytes]
-    Entry *xt = reinterpret_cast<Entry *>(crop_smem + kStageBytes);                      // [ow]
-    Entry *yt = xt + ow;                                                                 // [oh]
-    uint64_t *bar = reinterpret_cast<uint64_t *>(yt + oh);
-    __shared__ int s_v[4];   // first/last valid column, first/last valid row
+    const int slab = (oh + (int)gridDim.z - 1) / (int)gridDim.z;
+    const int ry0 = (int)blockIdx.z * slab;
+    const int ry1 = (ry0 + slab < oh ? ry0 + slab : oh) - 1;                             // inclusive
+    if (ry0 > ry1) return;
+    Entry *xt = reinterpret_cast<Entry *>(crop_smem + (size_t)prm.stages * kStageBytes); // [ow]
+    Entry *yt = xt + ow - ry0;                                                           // [slab], indexed by output row
+    uint64_t *full = reinterpret_cast<uint64_t *>(xt + ow + slab);                       // [stages] band landed
+    uint64_t *empty = full + prm.stages;                                                 // [stages] band released by the consumers
+    __shared__ int s_v[4];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
     const int p = blockIdx.x, c = blockIdx.y;
@@ -148,24 +242,15 @@ __global__ void __launch_bounds__(256) crop_affine_kernel(const CropParams prm, 
     const AxisMap m = crop_axis_map(box, ow, oh, prm.variant);
     if (tid == 0) {
         s_v[0] = ow; s_v[1] = -1; s_v[2] = oh; s_v[3] = -1;
-        mbar_init(bar, 1);
+        for (int i = 0; i < prm.stages; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], prm.ncc * prm.rg);
+        }
         mbar_fence_init();
         fence_proxy_async();
     }
     __syncthreads();
-    for (int i = tid; i < ow + oh; i += nthreads) {
-        if (i < ow) {
-            const Entry e = axis_entry<W>(m.ax * (double)i + m.bx, prm.fw);
-            xt[i] = e;
-            if (e.i0 >= 0) { atomicMin(&s_v[0], i); atomicMax(&s_v[1], i); }
-        } else {
-            const int y = i - ow;
-            const Entry e = axis_entry<W>(m.ay * (double)y + m.by, prm.fh);
-            yt[y] = e;
-            if (e.i0 >= 0) { atomicMin(&s_v[2], y); atomicMax(&s_v[3], y); }
-        }
-    }
-    __syncthreads();
+    build_tables<T>(m, prm, xt, yt, ry0, ry1, s_v);
     const int vx0 = s_v[0], vx1 = s_v[1], vy0 = s_v[2], vy1 = s_v[3];
 
     int f = __ldg(prm.frame_idx + p);
@@ -179,7 +264,7 @@ __global__ void __launch_bounds__(256) crop_affine_kernel(const CropParams prm, 
 
     const bool any = vx1 >= vx0 && vy1 >= vy0;
     // rows with no valid source: constant
-    for (int y = warp; y < oh; y += nthreads / 32) {
+    for (int y = ry0 + warp; y <= ry1; y += nthreads / 32) {
         if (any && y >= vy0 && y <= vy1) continue;
         for (int x = lane; x < ow; x += 32) __stcs(dst + (size_t)y * ow + x, zero_out);
     }
@@ -190,61 +275,154 @@ __global__ void __launch_bounds__(256) crop_affine_kernel(const CropParams prm, 
     int cx1 = (xt[vx1].i0 + 2 + kAlign - 1) & ~(kAlign - 1);      // exclusive
     if (cx1 > prm.fw) cx1 = prm.fw;
     const int row_elems = cx1 - cx0;
-    const int rows_cap = kStageBytes / (row_elems * (int)sizeof(T));
-    const bool use_stage = staged && rows_cap >= 3;
-    int band = oh;
-    if (use_stage) {
+    const int pitch = row_elems * (int)sizeof(T);                 // bytes
+    const int rows_cap = kStageBytes / pitch;                     // >= 2 (checked on the host for the widest window)
+    const int ncc = prm.ncc, rg = prm.rg;                         // column chunks x row groups = warps of the CTA
+    int band;
+    {
         const double per = m.ay > 0.0 ? m.ay : 1.0;
-        double br = floor((double)(rows_cap - 3) / per) + 1.0;
-        band = br > (double)oh ? oh : (int)br;
+        const double br = floor((double)(rows_cap - 3) / per) + 1.0;
+        band = br > (double)(ry1 - ry0 + 1) ? ry1 - ry0 + 1 : (int)br;
+        if (band > rg) band = band / rg * rg;                     // whole row groups
         if (band < 1) band = 1;
     }
+    const int nbands = (vy1 - vy0 + band) / band;
+    const int rpg = (band + rg - 1) / rg;                         // rows per group
 
-    uint32_t parity = 0;
-    for (int r0 = vy0; r0 <= vy1; r0 += band) {
-        const int r1 = (r0 + band - 1) < vy1 ? (r0 + band - 1) : vy1;
-        const int sy_lo = yt[r0].i0;
-        if (use_stage) {
+    // ---- producer warp: bulk-copy the source rows of band b into buffer b % S once its previous tenant
+    //      (band b - S) has been released by every consumer warp ---------------------------------------------
+    const int S = prm.stages;
+    if (warp == ncc * rg) {
+        for (int b = 0; b < nbands; ++b) {
+            const int s = b % S;
+            if (b >= S) mbar_wait(&empty[s], (uint32_t)((b / S - 1) & 1));
+            const int r0 = vy0 + b * band;
+            const int r1 = (r0 + band - 1) < vy1 ? (r0 + band - 1) : vy1;
+            const int sy_lo = yt[r0].i0;
             const int nrows = yt[r1].i0 + 1 - sy_lo + 1;
-            if (warp == 0) {
-                if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)(nrows * row_elems * (int)sizeof(T)));
-                for (int r = lane; r < nrows; r += 32)
-                    bulk_g2s(buf + (size_t)r * row_elems, src + (size_t)(sy_lo + r) * prm.fw + cx0,
-                             (uint32_t)(row_elems * (int)sizeof(T)), bar);
-            }
-            mbar_wait(bar, parity);
-            parity ^= 1;
+            unsigned char *buf = crop_smem + (size_t)s * kStageBytes;
+            if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(nrows * pitch));
+            __syncwarp();
+            for (int r = lane; r < nrows; r += 32)
+                bulk_g2s(buf + (size_t)r * pitch, src + (size_t)(sy_lo + r) * prm.fw + cx0, (uint32_t)pitch, &full[s]);
         }
-        for (int x = tid; x < ow; x += nthreads) {
-            const Entry ex = xt[x];
-            float *o = dst + (size_t)r0 * ow + x;
-            if (ex.i0 < 0) {
-                for (int y = r0; y <= r1; ++y, o += ow) __stcs(o, zero_out);
-                continue;
+        return;
+    }
+
+    // ---- consumer warps ----------------------------------------------------------------------------------------
+    // this warp's columns (fixed for the whole slab): byte offset inside a staged row, weight, liveness
+    const int cc = warp % ncc, grp = warp / ncc;
+    uint32_t coff[C];
+    float wx[C];
+    bool live[C];
+    const int xbase = cc * 32 * C + lane;
+    const int safe_col = xt[vx0].i0;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+        const int x = xbase + 32 * j;
+        const Entry ex = xt[x < ow ? x : ow - 1];
+        live[j] = ex.i0 >= 0;
+        coff[j] = (uint32_t)(((live[j] ? ex.i0 : safe_col) - cx0) * (int)sizeof(T));   // dead columns read a staged address
+        wx[j] = ex.t;
+    }
+
+    const uint32_t smem_base = smem_u32(crop_smem);
+    for (int b = 0; b < nbands; ++b) {
+        const int s = b % S;
+        const int r0 = vy0 + b * band;
+        const int r1 = (r0 + band - 1) < vy1 ? (r0 + band - 1) : vy1;
+        mbar_wait(&full[s], (uint32_t)((b / S) & 1));
+
+        const int ya = r0 + grp * rpg;
+        const int yb = (ya + rpg - 1) < r1 ? (ya + rpg - 1) : r1;
+        // byte address of source row 0 of the plane as if the whole plane were staged
+        const uint32_t tile = smem_base + (uint32_t)(s * kStageBytes) - (uint32_t)(yt[r0].i0 * pitch);
+        float top[C], bot[C];
+        int prev = INT_MIN;
+        float *o = dst + (size_t)ya * ow + xbase;
+        for (int y = ya; y <= yb; ++y, o += ow) {
+            const Entry ey = yt[y];
+            const uint32_t ra = tile + (uint32_t)(ey.i0 * pitch);
+            const uint32_t rb = ra + (uint32_t)pitch;
+            if (ey.i0 == prev + 1) {
+#pragma unroll
+                for (int j = 0; j < C; ++j) {
+                    top[j] = bot[j];
+                    bot[j] = hlerp_s<T>(rb + coff[j], wx[j]);
+                }
+            } else if (ey.i0 != prev) {
+#pragma unroll
+                for (int j = 0; j < C; ++j) {
+                    top[j] = hlerp_s<T>(ra + coff[j], wx[j]);
+                    bot[j] = hlerp_s<T>(rb + coff[j], wx[j]);
+                }
             }
-            const W wx = ex.t;
-            if (use_stage) {
-                // shared-memory tile: element (iy, ix) at buf[(iy - sy_lo) * row_elems + (ix - cx0)], 32-bit indices
-                const int colbase = ex.i0 - cx0 - sy_lo * row_elems;
-#pragma unroll 4
-                for (int y = r0; y <= r1; ++y, o += ow) {
-                    const Entry ey = yt[y];
-                    const int ia = ey.i0 * row_elems + colbase;
-                    const int ib = ia + row_elems;
-                    __stcs(o, sample_px(buf[ia], buf[ia + 1], buf[ib], buf[ib + 1], wx, ey.t, inv_sd, nmean));
+            prev = ey.i0;
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                float v;
+                if constexpr (kU8) {
+                    if (!fast_px_u8(top[j], bot[j], ey.t, inv_sd, nmean, v)) {
+                        const int x = xbase + 32 * j;
+                        const uint32_t a0 = ra + coff[j], a1 = rb + coff[j];
+                        v = exact_px_u8(lds_u8(a0), lds_u8(a0 + 1), lds_u8(a1), lds_u8(a1 + 1), xt[x < ow ? x : ow - 1].td, ey.td,
+                                        inv_sd, nmean);
+                    }
+                } else {
+                    v = finish_px(top[j], bot[j], ey.t, inv_sd, nmean);
                 }
-            } else {
-                const T *col = src + ex.i0;
-#pragma unroll 4
-                for (int y = r0; y <= r1; ++y, o += ow) {
-                    const Entry ey = yt[y];
-                    const T *ra = col + (size_t)ey.i0 * prm.fw;
-                    const T *rb = ra + prm.fw;
-                    __stcs(o, sample_px(__ldg(ra), __ldg(ra + 1), __ldg(rb), __ldg(rb + 1), wx, ey.t, inv_sd, nmean));
-                }
+                if (xbase + 32 * j < ow) __stcs(o + 32 * j, live[j] ? v : zero_out);
             }
         }
-        if (use_stage) __syncthreads();              // the band buffer is refilled next
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);       // this warp is done with the buffer
+    }
+}
+
+// Fallback without staging (frame rows not 16-byte aligned, or a source window too wide for a band buffer):
+// the same tables, direct global gathers, one thread per output column.
+template <typename T>
+__global__ void __launch_bounds__(256) crop_affine_direct_kernel(const CropParams prm) {
+    using Entry = AxisEntry<T>;
+    constexpr bool kU8 = std::is_same<T, unsigned char>::value;
+    extern __shared__ __align__(128) unsigned char crop_smem[];
+    const int ow = prm.ow, oh = prm.oh;
+    Entry *xt = reinterpret_cast<Entry *>(crop_smem);
+    Entry *yt = xt + ow;
+    __shared__ int s_v[4];
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int p = blockIdx.x, c = blockIdx.y;
+    const float4 box = __ldg(reinterpret_cast<const float4 *>(prm.boxes) + p);
+    const AxisMap m = crop_axis_map(box, ow, oh, prm.variant);
+    if (tid == 0) { s_v[0] = ow; s_v[1] = -1; s_v[2] = oh; s_v[3] = -1; }
+    __syncthreads();
+    build_tables<T>(m, prm, xt, yt, 0, oh - 1, s_v);
+    int f = __ldg(prm.frame_idx + p);
+    f = f < 0 ? 0 : (f >= prm.num_frames ? prm.num_frames - 1 : f);
+    const T *src = static_cast<const T *>(prm.frames) + ((size_t)f * 3 + c) * prm.fh * prm.fw;
+    float *dst = prm.out + ((size_t)p * 3 + c) * oh * ow;
+    const float mean = c == 0 ? prm.mean[0] : (c == 1 ? prm.mean[1] : prm.mean[2]);
+    const float inv_sd = 1.0f / (c == 0 ? prm.stdv[0] : (c == 1 ? prm.stdv[1] : prm.stdv[2]));
+    const float nmean = -mean * inv_sd;
+    for (int x = tid; x < ow; x += nthreads) {
+        const Entry ex = xt[x];
+        float *o = dst + x;
+        for (int y = 0; y < oh; ++y, o += ow) {
+            const Entry ey = yt[y];
+            float v = nmean;
+            if (ex.i0 >= 0 && ey.i0 >= 0) {
+                const T *ra = src + (size_t)ey.i0 * prm.fw + ex.i0;
+                const T *rb = ra + prm.fw;
+                const T p00 = __ldg(ra), p01 = __ldg(ra + 1), p10 = __ldg(rb), p11 = __ldg(rb + 1);
+                if constexpr (kU8) {
+                    v = exact_px_u8(p00, p01, p10, p11, ex.td, ey.td, inv_sd, nmean);
+                } else {
+                    const float top = fmaf(p01 - p00, ex.t, p00), bot = fmaf(p11 - p10, ex.t, p10);
+                    v = finish_px(top, bot, ey.t, inv_sd, nmean);
+                }
+            }
+            __stcs(o, v);
+        }
     }
 }
 
@@ -253,6 +431,25 @@ __global__ void __launch_bounds__(256) crop_affine_kernel(const CropParams prm, 
 
 namespace spp {
 namespace {
+int env_int(const char *name, int dflt, int lo, int hi) {
+    const char *e = getenv(name);
+    if (!e) return dflt;
+    const int v = atoi(e);
+    return (v < lo || v > hi) ? dflt : v;
+}
+
+template <typename T, int C>
+int launch_staged(const CropParams &prm, dim3 grid, size_t smem, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        SPP_CHECK_CUDA(cudaFuncSetAttribute(crop_affine_kernel<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    crop_affine_kernel<T, C><<<grid, 32 * (prm.ncc * prm.rg + 1), smem, st>>>(prm);
+    SPP_CHECK_LAUNCH();
+    return SPP_OK;
+}
+
 template <typename T>
 int launch_crop(const void *frames, int num_frames, int frame_h, int frame_w, const float *boxes, const int *frame_idx, int p,
                 int out_h, int out_w, const float *mean, const float *std, int variant, float *out, spp_stream_t stream) {
@@ -262,35 +459,54 @@ int launch_crop(const void *frames, int num_frames, int frame_h, int frame_w, co
     SPP_CHECK_ARG(out_h > 0 && out_w > 0 && out_w <= 2048 && out_h <= 2048, "crop_affine: output size must be within 2048 x 2048");
     SPP_CHECK_ARG(variant == SPP_CROP_HF_UDP || variant == SPP_CROP_GLUONCV, "crop_affine: unknown variant %d", variant);
     SPP_CHECK_ARG((reinterpret_cast<uintptr_t>(boxes) & 15) == 0, "crop_affine: boxes must be 16-byte aligned");
-    if (p == 0) return SPP_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
     CropParams prm{};
     prm.frames = frames; prm.boxes = boxes; prm.frame_idx = frame_idx; prm.out = out;
     prm.num_frames = num_frames; prm.fh = frame_h; prm.fw = frame_w; prm.P = p; prm.oh = out_h; prm.ow = out_w;
     prm.variant = variant;
     for (int c = 0; c < 3; ++c) { prm.mean[c] = mean[c]; prm.stdv[c] = std[c]; }
-    // bulk-TMA row copies need 16-byte aligned row segments: base and row pitch multiples of 16 bytes
-    const int staged = ((size_t)frame_w * sizeof(T) % 16 == 0) && ((reinterpret_cast<uintptr_t>(frames) & 15) == 0);
-    using W = typename std::conditional<std::is_same<T, float>::value, float, double>::type;
-    static int stage_kb = 0;
-    if (stage_kb == 0) {                         // tuning knob; default 40 KB
-        const char *e = getenv("SPP_CROP_STAGE_KB");
-        stage_kb = e ? atoi(e) : kStageBytesDefault / 1024;
-        if (stage_kb < 4 || stage_kb > 96) stage_kb = kStageBytesDefault / 1024;
-    }
+    // tuning knobs: SPP_CROP_STAGE_KB (one band buffer; a CTA has two), SPP_CROP_SPLIT (row slabs per crop channel),
+    // SPP_CROP_COLS (output columns per lane)
+    static const int stage_kb = env_int("SPP_CROP_STAGE_KB", (sizeof(T) == 1 ? kStageBytesDefaultU8 : kStageBytesDefault) / 1024, 2, 80);
+    static const int split_env = env_int("SPP_CROP_SPLIT", 0, 1, 64);
+    static const int cols = env_int("SPP_CROP_COLS", 3, 3, 6) == 6 ? 6 : 3;
+    static const int stages = env_int("SPP_CROP_STAGES", 2, 2, 8);
     prm.stage_bytes = stage_kb * 1024;
-    const size_t smem = (size_t)prm.stage_bytes + (size_t)(out_w + out_h) * sizeof(AxisEntry<W>) + 16;
-    int threads = (out_w + 31) / 32 * 32;
-    if (threads > 256) threads = 256;
-    static bool configured = false;
-    if (!configured) {
-        SPP_CHECK_CUDA(cudaFuncSetAttribute(crop_affine_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        configured = true;
+    prm.stages = stages;
+    // Bulk-TMA row copies need 16-byte aligned row segments (base and row pitch multiples of 16 bytes), and the widest
+    // possible source window (the whole frame width) has to leave room for the 2 source rows of a 1-row band.
+    prm.ncc = (out_w + 32 * cols - 1) / (32 * cols);
+    prm.rg = prm.ncc <= kCropWarps ? kCropWarps / prm.ncc : 1;
+    const bool staged = ((size_t)frame_w * sizeof(T) % 16 == 0) && ((reinterpret_cast<uintptr_t>(frames) & 15) == 0) &&
+                        ((size_t)prm.stage_bytes / ((size_t)frame_w * sizeof(T)) >= 2) && prm.ncc <= kCropWarps;
+    if (!staged) {
+        static bool configured = false;
+        const size_t smem = (size_t)(out_w + out_h) * sizeof(AxisEntry<T>);
+        SPP_CHECK_ARG(smem <= 160 * 1024, "crop_affine: output size too large");
+        if (!configured) {
+            SPP_CHECK_CUDA(cudaFuncSetAttribute(crop_affine_direct_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            configured = true;
+        }
+        int threads = (out_w + 31) / 32 * 32;
+        if (threads > 256) threads = 256;
+        crop_affine_direct_kernel<T><<<dim3(p, 3), threads, smem, st>>>(prm);
+        SPP_CHECK_LAUNCH();
+        return SPP_OK;
     }
-    SPP_CHECK_ARG(smem <= 100 * 1024, "crop_affine: output size too large");
-    dim3 grid(p, 3);
-    crop_affine_kernel<T><<<grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(prm, staged);
-    SPP_CHECK_LAUNCH();
-    return SPP_OK;
+    // Slabs of output rows: enough CTAs that the last wave is a small part of the launch, but never slabs shorter
+    // than 64 rows (the tables and the first band are per-CTA overhead).
+    int split = split_env;
+    if (split == 0) {
+        const int sms = sm_count() > 0 ? sm_count() : 148;
+        split = 1;
+        while (split < 8 && (long long)p * 3 * split < 16LL * sms && out_h / (split * 2) >= 64) split *= 2;
+    }
+    if (split > out_h) split = out_h;
+    const int slab = (out_h + split - 1) / split;
+    const size_t smem = (size_t)prm.stages * prm.stage_bytes + (size_t)(out_w + slab) * sizeof(AxisEntry<T>) + 16 * (size_t)prm.stages;
+    SPP_CHECK_ARG(smem <= 200 * 1024, "crop_affine: output size too large");
+    dim3 grid(p, 3, split);
+    return cols == 3 ? launch_staged<T, 3>(prm, grid, smem, st) : launch_staged<T, 6>(prm, grid, smem, st);
 }
 }  // namespace
 }  // namespace spp

@@ -208,6 +208,16 @@ def test_crop_uint8_vs_oracle(spp, synth, dev):
     boxes = [[[float(v) for v in b] for b in cs.boxes[:6]], [[float(v) for v in b] for b in cs.boxes[6:]]]
     pix = proc.preprocess(fr8.to(dev), boxes)["pixel_values"]
     assert float(np.abs(pix.cpu().numpy() - ref).max()) < 2e-5
+    # near-ties: a ~2x upscale of a low-amplitude image puts most interpolated values within the fast path's
+    # guard band of x.5, so nearly every pixel takes the fp64 re-computation
+    g = torch.Generator().manual_seed(5)
+    lo8 = torch.randint(0, 8, (1, 3, 360, 480), generator=g, dtype=torch.uint8)
+    tb = [[100.1625, 60.55, 57.3, 76.4], [200.55, 100.7333, 76.4, 101.8667], [-20.0875, 300.55, 57.3, 76.4]]
+    ref = ocrop.crop_affine_hf(lo8.numpy(), tb, [0, 0, 0], rescale_factor=1 / 255)
+    out = spp.crop_affine(lo8.to(dev), torch.tensor(tb, device=dev), torch.zeros(3, dtype=torch.int32, device=dev),
+                          mean=m.tolist(), std=s.tolist())
+    diff = np.abs(out.cpu().numpy() - ref)
+    assert float(diff.max()) < 2e-5, f"{(diff > 2e-5).sum()} near-tie pixels differ"
     # unaligned frame width: bulk-TMA staging is not possible, the direct path must agree
     fr8b = fr8[:, :, :, :478].contiguous()
     ref = ocrop.crop_affine_hf(fr8b.numpy(), cs.boxes.tolist(), cs.frame_idx.tolist(), rescale_factor=1 / 255)
