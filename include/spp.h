@@ -79,6 +79,18 @@ int spp_decode_nms(const float *const *levels, const int *level_h, const int *le
                    float max_wh, int max_candidates, float *out_dets, int *out_count, int *out_keys,
                    void *workspace, size_t workspace_bytes, spp_stream_t stream);
 
+/* The same two entry points on the head's conv outputs BEFORE the per-level torch.cat of nn.py:257
+ * (SURVEY.md 8f-1): box_levels[l] DEVICE [batch, 64, level_h[l], level_w[l]] (self.box[i](x[i])) and
+ * cls_levels[l] DEVICE [batch, nc, level_h[l], level_w[l]] (self.cls[i](x[i])), NCHW contiguous fp32.
+ * Identical results; the concatenated copy (5 MB per 720p frame) is never made. */
+int spp_head_decode_split(const float *const *box_levels, const float *const *cls_levels, const int *level_h,
+                          const int *level_w, const float *strides, int num_levels, int batch, int nc, float *out,
+                          spp_stream_t stream);
+int spp_decode_nms_split(const float *const *box_levels, const float *const *cls_levels, const int *level_h,
+                         const int *level_w, const float *strides, int num_levels, int batch, int nc, float conf_thres,
+                         float iou_thres, int max_det, int max_nms, float max_wh, int max_candidates, float *out_dets,
+                         int *out_count, int *out_keys, void *workspace, size_t workspace_bytes, spp_stream_t stream);
+
 /* ------------------------------------------------------------------ embedding + gallery match - */
 
 /* Replaces the tail of Backbone.forward — libs/net_adaface.py:334-337 (mode 0: x / ||x||, no eps)
@@ -188,6 +200,30 @@ int spp_crop_affine_u8(const uint8_t *frames, int num_frames, int frame_h, int f
 int spp_heatmap_decode(const float *hm, const float *hm_flipped, const int *perm, int p, int k, int h, int w,
                        const float *boxes, int mode, int flags, int kernel, int crop_h, int crop_w,
                        float *keypoints, float *scores, int *argmax, spp_stream_t stream);
+
+/* ------------------------------------------------------------------ pose results ------------- */
+
+/* Replaces the result loop of PoseEstimationModule.validation_step, training/lightning/pose_estimation/
+ * module.py:534-549: COCO keypoint rows (x, y, v) and the instance score.
+ *   keypoints   DEVICE [p, k, 2] fp32: normalised (kx, ky) when boxes_xyxy is given, image pixels otherwise
+ *   scores      DEVICE [p, k] fp32
+ *   boxes_xyxy  DEVICE [p, 4] fp32 (x1, y1, x2, y2) or NULL:  x = kx * (x2 - x1) + x1,  y = ky * (y2 - y1) + y1
+ *   keypoint_thresh  v = 2 if score > thresh else 1 (module.py:172 keypoint_thresh, default 0.3)
+ *   out_keypoints        DEVICE [p, k, 3] fp32 (x, y, v) — the "keypoints" list of a COCO result, row-major
+ *   out_instance_score   DEVICE [p] fp32 mean of the keypoint scores (may be NULL)
+ */
+int spp_pose_results(const float *keypoints, const float *scores, const float *boxes_xyxy, int p, int k,
+                     float keypoint_thresh, float *out_keypoints, float *out_instance_score, spp_stream_t stream);
+
+/* Object keypoint similarity of explicit (prediction, ground truth) pairs: pycocotools COCOeval.computeOks
+ * (third-party, not in the reference tree; driven from module.py:598-615).  PARITY UNPINNED.
+ *   pred           DEVICE [p, k, pred_stride] fp32, pred_stride 2 or 3 (x, y[, v])
+ *   gt             DEVICE [p, k, 3] fp32 (x, y, v);  gt_boxes_xywh DEVICE [p, 4] or NULL (used when no joint is labelled)
+ *   gt_area        DEVICE [p] fp32;  sigmas DEVICE [k] fp32 (COCO_SIGMAS, datamodule.py:36-40)
+ *   out_oks        DEVICE [p] fp32
+ */
+int spp_pose_oks(const float *pred, int pred_stride, const float *gt, const float *gt_boxes_xywh, const float *gt_area,
+                 const float *sigmas, int p, int k, float *out_oks, spp_stream_t stream);
 
 #ifdef __cplusplus
 }

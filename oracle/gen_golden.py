@@ -189,9 +189,71 @@ def gen_pose_hf():
     print("pose_hf ok", kp.shape, pix.shape)
 
 
+def gen_pose_results():
+    """a15 / 8f-3: the reference's own validation_step result loop (module.py:451-560), run on a fake
+    ``self`` whose model returns seeded heatmaps.  Batch size 1 per call: there the live flip-back
+    (quirk Q1, ``.flip(0)`` over the batch axis) is the identity, i.e. the flipped heatmaps are mirrored
+    but NOT channel-swapped (= the ``perm=None`` mode of the kernel)."""
+    _stub_modules()
+    sys.path.insert(0, os.path.join(REF, "training"))
+    from lightning.pose_estimation.module import PoseEstimationModule
+
+    hs = synth.make_heatmaps(3, 17, seed=31)
+    g = torch.Generator().manual_seed(32)
+    n_inst = 3
+    xy = torch.rand(3, n_inst, 2, generator=g) * 300
+    wh = torch.rand(3, n_inst, 2, generator=g) * 250 + 20
+    boxes = torch.cat([xy, xy + wh], -1)                                           # [B, N, 4] xyxy
+    areas = (wh[..., 0] * wh[..., 1]) * 0.6
+    masks = torch.tensor([[True, True, True], [True, True, False], [True, False, False]])
+    is_crowd = torch.tensor([[False, True, False], [False, False, False], [False, False, False]])
+    image_ids = [101, 202, 303]
+    preds = []
+    coords, scores = [], []
+    for b in range(3):
+        calls = []
+
+        def model(images, b=b, calls=calls):
+            calls.append(1)
+            hm = hs.heatmaps[b:b + 1] if len(calls) == 1 else hs.flipped[b:b + 1]
+            return types.SimpleNamespace(heatmaps=hm.clone())
+
+        fake = types.SimpleNamespace()
+        fake.model = model
+        fake._generate_target_heatmap = lambda c, v, a: (None, None)
+        fake.heatmap_loss = lambda *a, **k: torch.zeros(())
+        real = PoseEstimationModule._get_keypoints_from_heatmaps
+
+        def get_kp(hm, boxes=None, fake=fake):
+            c, s = real(fake, hm, boxes=boxes)
+            coords.append(c.numpy().copy())
+            scores.append(s.numpy().copy())
+            return c, s
+
+        fake._get_keypoints_from_heatmaps = get_kp
+        fake._eval_cache = {"image_ids": set()}
+        fake.keypoint_thresh = 0.3
+        fake.eval_predictions = preds
+        fake.log = lambda *a, **k: None
+        fake.print = print
+        batch = {"images": torch.zeros(1, 3, 8, 8), "keypoints": torch.zeros(1, n_inst, 17, 3), "boxes": boxes[b:b + 1],
+                 "areas": areas[b:b + 1], "masks": masks[b:b + 1], "is_crowd": is_crowd[b:b + 1], "image_ids": [image_ids[b]]}
+        PoseEstimationModule.validation_step(fake, batch, b)
+    np.savez_compressed(
+        os.path.join(OUT, "pose_results.npz"),
+        hm=hs.heatmaps.numpy(), flipped=hs.flipped.numpy(), boxes=boxes.numpy(), areas=areas.numpy(), masks=masks.numpy(),
+        is_crowd=is_crowd.numpy(), image_ids=np.array(image_ids),
+        coords=np.concatenate(coords, 0), scores=np.concatenate(scores, 0),
+        res_image_id=np.array([p["image_id"] for p in preds]), res_keypoints=np.array([p["keypoints"] for p in preds], np.float64),
+        res_score=np.array([p["score"] for p in preds], np.float64), res_bbox=np.array([p["bbox"] for p in preds], np.float64),
+        res_area=np.array([p["area"] for p in preds], np.float64))
+    print("pose_results ok:", len(preds), "rows")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gen_det()
     gen_match()
     gen_pose_live()
     gen_pose_hf()
+    gen_pose_results()

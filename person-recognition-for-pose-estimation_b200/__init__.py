@@ -8,17 +8,18 @@ from . import _lib, ops, shims, synth, hostmath, pipeline, dist, torch_ops  # no
 from ._lib import SppError, build  # noqa: F401
 from .ops import (  # noqa: F401
     associate, crop_affine, decode_nms, head_decode, heatmap_decode, l2_normalize, match_top1, match_unpack_keys, nms_decoded,
-    to_bf16, NmsResult,
+    pose_oks, pose_results, to_bf16, NmsResult,
 )
 from .shims import (  # noqa: F401
     Gallery, VitPoseImageProcessor, backbone_tail, detect, flip_test_keypoints, get_final_preds,
-    get_keypoints_from_heatmaps, head_forward, l2_norm, non_max_suppression,
+    coco_keypoint_results, get_keypoints_from_heatmaps, head_conv_outputs, head_eval_forward, head_forward, l2_norm,
+    non_max_suppression,
 )
 
 __all__ = [
     "SppError", "build", "ops", "shims", "synth",
     "associate", "crop_affine", "decode_nms", "head_decode", "heatmap_decode", "l2_normalize", "match_top1", "match_unpack_keys",
-    "nms_decoded", "to_bf16", "NmsResult",
+    "nms_decoded", "pose_oks", "pose_results", "to_bf16", "NmsResult",
     "Gallery", "VitPoseImageProcessor", "backbone_tail", "detect", "flip_test_keypoints", "get_final_preds",
-    "get_keypoints_from_heatmaps", "head_forward", "l2_norm", "non_max_suppression",
+    "coco_keypoint_results", "get_keypoints_from_heatmaps", "head_conv_outputs", "head_eval_forward", "head_forward", "l2_norm", "non_max_suppression",
 ]

@@ -22,6 +22,10 @@ SIGNATURES = {
     "spp_last_error": (c_char_p, []),
     "spp_device_sm_count": (c_int, []),
     "spp_head_decode": (c_int, [POINTER(_P), POINTER(c_int), POINTER(c_int), POINTER(c_float), c_int, c_int, c_int, _P, _P]),
+    "spp_head_decode_split": (c_int, [POINTER(_P), POINTER(_P), POINTER(c_int), POINTER(c_int), POINTER(c_float), c_int, c_int, c_int,
+                                      _P, _P]),
+    "spp_decode_nms_split": (c_int, [POINTER(_P), POINTER(_P), POINTER(c_int), POINTER(c_int), POINTER(c_float), c_int, c_int,
+                                     c_int, c_float, c_float, c_int, c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
     "spp_nms_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "spp_nms_decoded": (c_int, [_P, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_float, c_int, _P, _P, _P, _P,
                                 c_size_t, _P]),
@@ -39,6 +43,8 @@ SIGNATURES = {
                                    c_int, _P, _P]),
     "spp_heatmap_decode": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P,
                                    _P, _P]),
+    "spp_pose_results": (c_int, [_P, _P, _P, c_int, c_int, c_float, _P, _P, _P]),
+    "spp_pose_oks": (c_int, [_P, c_int, _P, _P, _P, _P, c_int, c_int, _P, _P]),
     # test hook (include/spp_internal.h)
     "spp_debug_match_top1_simt": (c_int, [_P, _P, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
 }

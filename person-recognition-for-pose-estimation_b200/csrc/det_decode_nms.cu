@@ -37,8 +37,14 @@ constexpr int kSortSmemMax = 8192;  // keys sorted in shared memory up to this (
 constexpr int kBoxSmemMax = 2048;   // sorted boxes kept in shared memory (the rest is re-gathered)
 constexpr int kAliveWords = 1024;   // one alive bit per candidate: max_nms <= 32768
 
+// Per level: the 64 DFL planes and the nc class planes of image b start at box[l] + b * bs_box[l] and
+// cls[l] + b * bs_cls[l] (elements).  One concatenated map [B, 64+nc, H, W] (nn.py:257) gives
+// cls = box + 64*H*W, bs_box = bs_cls = (64+nc)*H*W; the un-concatenated conv outputs of nn.py:256-257
+// ([B, 64, H, W] and [B, nc, H, W]) give bs_box = 64*H*W, bs_cls = nc*H*W.
 struct Levels {
-    const float *ptr[SPP_MAX_LEVELS];
+    const float *box[SPP_MAX_LEVELS];
+    const float *cls[SPP_MAX_LEVELS];
+    long long bs_box[SPP_MAX_LEVELS], bs_cls[SPP_MAX_LEVELS];
     int h[SPP_MAX_LEVELS], w[SPP_MAX_LEVELS], off[SPP_MAX_LEVELS + 1];
     float stride[SPP_MAX_LEVELS];
     int n, A;
@@ -47,15 +53,18 @@ struct Levels {
 // Resolved pyramid level of one anchor.  Selected with compile-time indices only, so the by-value
 // kernel parameter stays in the constant bank (dynamic indexing would copy it to local memory per thread).
 struct LevelRef {
-    const float *ptr;
+    const float *box;
+    const float *cls;
+    long long bs_box, bs_cls;
     int w, hw, i;
     float stride;
 };
 __device__ __forceinline__ LevelRef find_level(const Levels &lv, int a) {
-    LevelRef r{lv.ptr[0], lv.w[0], lv.h[0] * lv.w[0], a, lv.stride[0]};
+    LevelRef r{lv.box[0], lv.cls[0], lv.bs_box[0], lv.bs_cls[0], lv.w[0], lv.h[0] * lv.w[0], a, lv.stride[0]};
 #pragma unroll
     for (int i = 1; i < SPP_MAX_LEVELS; ++i)
-        if (i < lv.n && a >= lv.off[i]) r = LevelRef{lv.ptr[i], lv.w[i], lv.h[i] * lv.w[i], a - lv.off[i], lv.stride[i]};
+        if (i < lv.n && a >= lv.off[i])
+            r = LevelRef{lv.box[i], lv.cls[i], lv.bs_box[i], lv.bs_cls[i], lv.w[i], lv.h[i] * lv.w[i], a - lv.off[i], lv.stride[i]};
     return r;
 }
 
@@ -113,15 +122,15 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const Levels lv, int n
     const LevelRef lr = find_level(lv, a);
     const int i = lr.i, w = lr.w, hw = lr.hw;
     const int y = i / w, x = i - y * w;
-    const int no = 4 * kDfl + nc;
-    const float *base = lr.ptr + (size_t)b * no * hw + i;
+    const float *base = lr.box + (size_t)b * lr.bs_box + i;
+    const float *cbase = lr.cls + (size_t)b * lr.bs_cls + i;
     const float4 box = decode_box(base, hw, (float)x + 0.5f, (float)y + 0.5f, lr.stride);
     float *o = out + (size_t)b * (4 + nc) * lv.A + a;
     o[0] = box.x;
     o[(size_t)lv.A] = box.y;
     o[(size_t)2 * lv.A] = box.z;
     o[(size_t)3 * lv.A] = box.w;
-    for (int j = 0; j < nc; ++j) o[(size_t)(4 + j) * lv.A] = sigmoidf_ref(__ldg(base + (size_t)(4 * kDfl + j) * hw));
+    for (int j = 0; j < nc; ++j) o[(size_t)(4 + j) * lv.A] = sigmoidf_ref(__ldg(cbase + (size_t)j * hw));
 }
 
 __device__ __forceinline__ unsigned long long make_sort_key(float score, unsigned cand) {
@@ -169,8 +178,7 @@ __global__ void __launch_bounds__(256) cand_scan_kernel(const Levels lv, int nc,
     const int b = blockIdx.y;
     const bool in = a < lv.A;
     const LevelRef lr = find_level(lv, in ? a : 0);
-    const int no = 4 * kDfl + nc;
-    const float *cls = lr.ptr + ((size_t)b * no + 4 * kDfl) * lr.hw + lr.i;
+    const float *cls = lr.cls + (size_t)b * lr.bs_cls + lr.i;
     unsigned long long *k = keys + (size_t)b * cap_pad;
     for (int j = 0; j < nc; ++j) {
         float s = 0.f;
@@ -204,7 +212,6 @@ __global__ void __launch_bounds__(256) cand_decode_kernel(const Levels lv, int n
     }
     __syncthreads();
     const int total = pre[batch];                                 // items = candidates of all images, back to back
-    const int no = 4 * kDfl + nc;
     // both halves of a warp iterate together (full-mask shuffles); an idle half works on a dummy item
     for (int base = (half_id & ~1); base < total; base += nhalf) {
         const int t = base + (half_id & 1);
@@ -218,7 +225,7 @@ __global__ void __launch_bounds__(256) cand_decode_kernel(const Levels lv, int n
         const unsigned cand = valid ? (unsigned)(keys[(size_t)b * cap_pad + slot] & 0xffffffffu) : 0u;
         const int anchor = (int)(cand / (unsigned)nc);
         const LevelRef lr = find_level(lv, anchor);
-        const float *basep = lr.ptr + (size_t)(valid ? b : 0) * no * lr.hw + lr.i;
+        const float *basep = lr.box + (size_t)(valid ? b : 0) * lr.bs_box + lr.i;
         float v[4];
 #pragma unroll
         for (int sd = 0; sd < 4; ++sd) v[sd] = __ldg(basep + (size_t)(sd * kDfl + sub) * lr.hw);
@@ -470,15 +477,27 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams prm) {
     if (tid == 0) prm.out_count[b] = raw_count > prm.cap ? -nk : nk;
 }
 
-int fill_levels(Levels &lv, const float *const *levels, const int *level_h, const int *level_w, const float *strides,
-                int num_levels) {
+// cls_levels == nullptr: levels[l] is the concatenated [B, 64+nc, H, W] map; else levels[l] = [B, 64, H, W] box
+// conv output and cls_levels[l] = [B, nc, H, W] class conv output.
+int fill_levels(Levels &lv, const float *const *levels, const float *const *cls_levels, const int *level_h, const int *level_w,
+                const float *strides, int num_levels, int nc) {
     SPP_CHECK_ARG(levels && level_h && level_w && strides, "detection: null level description");
     SPP_CHECK_ARG(num_levels >= 1 && num_levels <= SPP_MAX_LEVELS, "detection: num_levels must be 1..%d", SPP_MAX_LEVELS);
     lv.n = num_levels;
     lv.off[0] = 0;
     for (int l = 0; l < num_levels; ++l) {
         SPP_CHECK_ARG(levels[l] && level_h[l] > 0 && level_w[l] > 0, "detection: bad level %d", l);
-        lv.ptr[l] = levels[l];
+        const long long hw = (long long)level_h[l] * level_w[l];
+        lv.box[l] = levels[l];
+        if (cls_levels) {
+            SPP_CHECK_ARG(cls_levels[l], "detection: bad class level %d", l);
+            lv.cls[l] = cls_levels[l];
+            lv.bs_box[l] = 4 * kDfl * hw;
+            lv.bs_cls[l] = (long long)nc * hw;
+        } else {
+            lv.cls[l] = levels[l] + 4 * kDfl * hw;
+            lv.bs_box[l] = lv.bs_cls[l] = (4 * kDfl + nc) * hw;
+        }
         lv.h[l] = level_h[l];
         lv.w[l] = level_w[l];
         lv.stride[l] = strides[l];
@@ -547,18 +566,30 @@ int check_nms_args(int batch, int nc, float iou, int max_det, int max_nms, const
 
 using namespace spp;
 
-extern "C" int spp_head_decode(const float *const *levels, const int *level_h, const int *level_w, const float *strides,
-                               int num_levels, int batch, int nc, float *out, spp_stream_t stream) {
+static int head_decode_impl(const float *const *levels, const float *const *cls_levels, const int *level_h, const int *level_w,
+                            const float *strides, int num_levels, int batch, int nc, float *out, spp_stream_t stream) {
     if (batch == 0) return SPP_OK;
-    Levels lv{};
-    int rc = fill_levels(lv, levels, level_h, level_w, strides, num_levels);
-    if (rc) return rc;
     SPP_CHECK_ARG(out && batch >= 0 && nc >= 1, "head_decode: bad arguments");
+    Levels lv{};
+    int rc = fill_levels(lv, levels, cls_levels, level_h, level_w, strides, num_levels, nc);
+    if (rc) return rc;
     if (batch == 0) return SPP_OK;
     dim3 grid((lv.A + 255) / 256, batch);
     head_decode_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(lv, nc, out);
     SPP_CHECK_LAUNCH();
     return SPP_OK;
+}
+
+extern "C" int spp_head_decode(const float *const *levels, const int *level_h, const int *level_w, const float *strides,
+                               int num_levels, int batch, int nc, float *out, spp_stream_t stream) {
+    return head_decode_impl(levels, nullptr, level_h, level_w, strides, num_levels, batch, nc, out, stream);
+}
+
+extern "C" int spp_head_decode_split(const float *const *box_levels, const float *const *cls_levels, const int *level_h,
+                                     const int *level_w, const float *strides, int num_levels, int batch, int nc, float *out,
+                                     spp_stream_t stream) {
+    SPP_CHECK_ARG(batch == 0 || cls_levels, "head_decode_split: null class levels");
+    return head_decode_impl(box_levels, cls_levels, level_h, level_w, strides, num_levels, batch, nc, out, stream);
 }
 
 extern "C" size_t spp_nms_workspace_bytes(int batch, int num_anchors, int nc, int max_candidates) {
@@ -591,13 +622,14 @@ extern "C" int spp_nms_decoded(const float *pred, int batch, int nc, int num_anc
     return launch_nms<false>(prm, batch, st);
 }
 
-extern "C" int spp_decode_nms(const float *const *levels, const int *level_h, const int *level_w, const float *strides,
-                              int num_levels, int batch, int nc, float conf_thres, float iou_thres, int max_det,
-                              int max_nms, float max_wh, int max_candidates, float *out_dets, int *out_count,
-                              int *out_keys, void *workspace, size_t workspace_bytes, spp_stream_t stream) {
+static int decode_nms_impl(const float *const *levels, const float *const *cls_levels, const int *level_h, const int *level_w,
+                           const float *strides, int num_levels, int batch, int nc, float conf_thres, float iou_thres, int max_det,
+                           int max_nms, float max_wh, int max_candidates, float *out_dets, int *out_count, int *out_keys,
+                           void *workspace, size_t workspace_bytes, spp_stream_t stream) {
     if (batch == 0) return SPP_OK;
+    SPP_CHECK_ARG(nc >= 1, "decode_nms: nc must be >= 1");
     Levels lv{};
-    int rc = fill_levels(lv, levels, level_h, level_w, strides, num_levels);
+    int rc = fill_levels(lv, levels, cls_levels, level_h, level_w, strides, num_levels, nc);
     if (rc) return rc;
     rc = check_nms_args(batch, nc, iou_thres, max_det, max_nms, out_dets, out_count, workspace);
     if (rc) return rc;
@@ -628,4 +660,21 @@ extern "C" int spp_decode_nms(const float *const *levels, const int *level_h, co
     prm.iou = iou_thres; prm.max_wh = max_wh; prm.max_det = max_det; prm.max_nms = max_nms;
     prm.out_dets = out_dets; prm.out_count = out_count; prm.out_keys = out_keys;
     return launch_nms<true>(prm, batch, st);
+}
+
+extern "C" int spp_decode_nms(const float *const *levels, const int *level_h, const int *level_w, const float *strides,
+                              int num_levels, int batch, int nc, float conf_thres, float iou_thres, int max_det,
+                              int max_nms, float max_wh, int max_candidates, float *out_dets, int *out_count,
+                              int *out_keys, void *workspace, size_t workspace_bytes, spp_stream_t stream) {
+    return decode_nms_impl(levels, nullptr, level_h, level_w, strides, num_levels, batch, nc, conf_thres, iou_thres, max_det, max_nms,
+                           max_wh, max_candidates, out_dets, out_count, out_keys, workspace, workspace_bytes, stream);
+}
+
+extern "C" int spp_decode_nms_split(const float *const *box_levels, const float *const *cls_levels, const int *level_h,
+                                    const int *level_w, const float *strides, int num_levels, int batch, int nc, float conf_thres,
+                                    float iou_thres, int max_det, int max_nms, float max_wh, int max_candidates, float *out_dets,
+                                    int *out_count, int *out_keys, void *workspace, size_t workspace_bytes, spp_stream_t stream) {
+    SPP_CHECK_ARG(batch == 0 || cls_levels, "decode_nms_split: null class levels");
+    return decode_nms_impl(box_levels, cls_levels, level_h, level_w, strides, num_levels, batch, nc, conf_thres, iou_thres, max_det,
+                           max_nms, max_wh, max_candidates, out_dets, out_count, out_keys, workspace, workspace_bytes, stream);
 }

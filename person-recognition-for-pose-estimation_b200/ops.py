@@ -56,33 +56,59 @@ def _f32c(name: str, t: torch.Tensor) -> torch.Tensor:
 # detection
 # ------------------------------------------------------------------------------------------------
 
-def _levels_args(levels: Sequence[torch.Tensor], strides: Sequence[float]):
+def _levels_args(levels: Sequence, strides: Sequence[float]):
+    """``levels``: per pyramid level either the concatenated map ``[B, 64+nc, H, W]`` (nn.py:257) or the pair
+    ``(box [B, 64, H, W], cls [B, nc, H, W])`` of conv outputs before the ``cat`` (nn.py:256-257).
+    Returns (kept tensors, box ptrs, cls ptrs or None, hs, ws, strides, n, B, nc, A)."""
     if len(levels) < 1 or len(levels) > 4 or len(levels) != len(strides):
         raise ValueError("detection: need 1..4 levels and one stride per level")
-    lv = [_f32c("detection level", l) for l in levels]
-    b, no = lv[0].shape[0], lv[0].shape[1]
-    for l in lv:
-        if l.dim() != 4 or l.shape[0] != b or l.shape[1] != no:
-            raise ValueError("detection: every level must be [B, 64+nc, H, W] with the same B and channel count")
-    nc = no - 64
+    split = isinstance(levels[0], (tuple, list))
+    if any(isinstance(l, (tuple, list)) != split for l in levels):
+        raise ValueError("detection: levels must be all concatenated maps or all (box, cls) pairs")
+    if split:
+        bx = [_f32c("detection box level", l[0]) for l in levels]
+        cl = [_f32c("detection class level", l[1]) for l in levels]
+        b, nc = bx[0].shape[0], cl[0].shape[1]
+        for x, c in zip(bx, cl):
+            if x.dim() != 4 or c.dim() != 4 or x.shape[1] != 64 or c.shape[1] != nc or x.shape[0] != b or c.shape[0] != b \
+                    or x.shape[2:] != c.shape[2:]:
+                raise ValueError("detection: split levels must be ([B, 64, H, W], [B, nc, H, W]) with matching B, H, W")
+        lv = bx
+    else:
+        lv = [_f32c("detection level", l) for l in levels]
+        cl = None
+        b, no = lv[0].shape[0], lv[0].shape[1]
+        for l in lv:
+            if l.dim() != 4 or l.shape[0] != b or l.shape[1] != no:
+                raise ValueError("detection: every level must be [B, 64+nc, H, W] with the same B and channel count")
+        nc = no - 64
     if nc < 1:
-        raise ValueError(f"detection: levels have {no} channels, need 64 + nc")
+        raise ValueError("detection: need 64 box channels + nc >= 1 class channels")
     n = len(lv)
     ptrs = (ctypes.c_void_p * n)(*[l.data_ptr() for l in lv])
+    cptrs = (ctypes.c_void_p * n)(*[c.data_ptr() for c in cl]) if split else None
     hs = (ctypes.c_int * n)(*[l.shape[2] for l in lv])
     ws = (ctypes.c_int * n)(*[l.shape[3] for l in lv])
     st = (ctypes.c_float * n)(*[float(s) for s in strides])
     a = sum(l.shape[2] * l.shape[3] for l in lv)
-    return lv, ptrs, hs, ws, st, n, b, nc, a
+    return (lv, cl), ptrs, cptrs, hs, ws, st, n, b, nc, a
 
 
-def head_decode(levels: Sequence[torch.Tensor], strides: Sequence[float] = (8, 16, 32)) -> torch.Tensor:
+def _flat_levels(levels: Sequence) -> List[torch.Tensor]:
+    return [t for l in levels for t in (l if isinstance(l, (tuple, list)) else (l,))]
+
+
+def head_decode(levels: Sequence, strides: Sequence[float] = (8, 16, 32)) -> torch.Tensor:
     """``Head.forward`` eval branch (training/yolopt/nets/nn.py:255-270): raw per-level maps
-    ``[B, 64+nc, H_l, W_l]`` -> ``[B, 4+nc, A]`` (cx, cy, w, h in pixels; sigmoid scores)."""
-    _need_cuda("head_decode", *levels)
-    lv, ptrs, hs, ws, st, n, b, nc, a = _levels_args(levels, strides)
-    out = torch.empty((b, 4 + nc, a), dtype=torch.float32, device=lv[0].device)
-    _lib.check(_lib.lib().spp_head_decode(ptrs, hs, ws, st, n, b, nc, _ptr(out), _stream(out)), "spp_head_decode")
+    ``[B, 64+nc, H_l, W_l]`` (or ``(box, cls)`` pairs before the ``cat``) -> ``[B, 4+nc, A]`` (cx, cy, w, h in
+    pixels; sigmoid scores)."""
+    _need_cuda("head_decode", *_flat_levels(levels))
+    keep, ptrs, cptrs, hs, ws, st, n, b, nc, a = _levels_args(levels, strides)
+    out = torch.empty((b, 4 + nc, a), dtype=torch.float32, device=keep[0][0].device)
+    if cptrs is None:
+        _lib.check(_lib.lib().spp_head_decode(ptrs, hs, ws, st, n, b, nc, _ptr(out), _stream(out)), "spp_head_decode")
+    else:
+        _lib.check(_lib.lib().spp_head_decode_split(ptrs, cptrs, hs, ws, st, n, b, nc, _ptr(out), _stream(out)), "spp_head_decode_split")
     return out
 
 
@@ -136,13 +162,14 @@ def nms_decoded(pred: torch.Tensor, conf_thres: float = 0.001, iou_thres: float 
     return NmsResult(dets, count, keys)
 
 
-def decode_nms(levels: Sequence[torch.Tensor], strides: Sequence[float] = (8, 16, 32), conf_thres: float = 0.001,
+def decode_nms(levels: Sequence, strides: Sequence[float] = (8, 16, 32), conf_thres: float = 0.001,
                iou_thres: float = 0.65, max_det: int = MAX_DET, max_nms: int = MAX_NMS, max_wh: float = MAX_WH,
                max_candidates: int = 0, out: Optional[NmsResult] = None) -> NmsResult:
-    """Fused ``Head.forward`` (eval) + ``non_max_suppression`` from the raw per-level maps."""
-    _need_cuda("decode_nms", *levels)
-    lv, ptrs, hs, ws_, st, n, b, nc, a = _levels_args(levels, strides)
-    dev = lv[0].device
+    """Fused ``Head.forward`` (eval) + ``non_max_suppression`` from the raw per-level maps (concatenated, or
+    ``(box, cls)`` pairs straight from the head's conv stacks — no ``cat`` copy)."""
+    _need_cuda("decode_nms", *_flat_levels(levels))
+    keep, ptrs, cptrs, hs, ws_, st, n, b, nc, a = _levels_args(levels, strides)
+    dev = keep[0][0].device
     L = _lib.lib()
     if out is None:
         out = NmsResult(torch.empty((b, max_det, 6), dtype=torch.float32, device=dev),
@@ -150,9 +177,14 @@ def decode_nms(levels: Sequence[torch.Tensor], strides: Sequence[float] = (8, 16
                         torch.empty((b, max_det), dtype=torch.int32, device=dev))
     nbytes = L.spp_nms_workspace_bytes(b, a, nc, max_candidates)
     ws = _workspace(dev, nbytes, "nms")
-    _lib.check(L.spp_decode_nms(ptrs, hs, ws_, st, n, b, nc, conf_thres, iou_thres, max_det, max_nms, max_wh,
-                                max_candidates, _ptr(out.dets), _ptr(out.count), _ptr(out.keys), _ptr(ws), nbytes,
-                                _stream(out.dets)), "spp_decode_nms")
+    if cptrs is None:
+        _lib.check(L.spp_decode_nms(ptrs, hs, ws_, st, n, b, nc, conf_thres, iou_thres, max_det, max_nms, max_wh,
+                                    max_candidates, _ptr(out.dets), _ptr(out.count), _ptr(out.keys), _ptr(ws), nbytes,
+                                    _stream(out.dets)), "spp_decode_nms")
+    else:
+        _lib.check(L.spp_decode_nms_split(ptrs, cptrs, hs, ws_, st, n, b, nc, conf_thres, iou_thres, max_det, max_nms, max_wh,
+                                          max_candidates, _ptr(out.dets), _ptr(out.count), _ptr(out.keys), _ptr(ws), nbytes,
+                                          _stream(out.dets)), "spp_decode_nms_split")
     return out
 
 
@@ -323,3 +355,47 @@ def heatmap_decode(hm: torch.Tensor, hm_flipped: Optional[torch.Tensor] = None, 
                                              DECODE_MODES[mode], flags, kernel, crop_hw[0], crop_hw[1], _ptr(kp), _ptr(sc),
                                              _ptr(am), _stream(hm)), "spp_heatmap_decode")
     return kp, sc, am
+
+
+# ------------------------------------------------------------------------------------------------
+# COCO keypoint result rows + OKS
+# ------------------------------------------------------------------------------------------------
+
+def pose_results(keypoints: torch.Tensor, scores: torch.Tensor, boxes_xyxy: Optional[torch.Tensor] = None,
+                 keypoint_thresh: float = 0.3) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``keypoints [P,K,2]`` (normalised when ``boxes_xyxy [P,4]`` is given, image pixels otherwise) and
+    ``scores [P,K]`` -> ``(rows [P,K,3] = (x, y, v), instance_score [P])`` as module.py:534-549 builds them."""
+    _need_cuda("pose_results", keypoints, scores, boxes_xyxy)
+    keypoints, scores = _f32c("pose_results keypoints", keypoints), _f32c("pose_results scores", scores)
+    if keypoints.dim() != 3 or keypoints.shape[2] != 2 or tuple(scores.shape) != tuple(keypoints.shape[:2]):
+        raise ValueError("pose_results: keypoints must be [P, K, 2] and scores [P, K]")
+    p, k = scores.shape
+    if boxes_xyxy is not None:
+        boxes_xyxy = _f32c("pose_results boxes", boxes_xyxy)
+        if tuple(boxes_xyxy.shape) != (p, 4):
+            raise ValueError("pose_results: boxes must be [P, 4] (x1, y1, x2, y2)")
+    rows = torch.empty((p, k, 3), dtype=torch.float32, device=keypoints.device)
+    inst = torch.empty((p,), dtype=torch.float32, device=keypoints.device)
+    _lib.check(_lib.lib().spp_pose_results(_ptr(keypoints), _ptr(scores), _ptr(boxes_xyxy), p, k, float(keypoint_thresh), _ptr(rows),
+                                           _ptr(inst), _stream(rows)), "spp_pose_results")
+    return rows, inst
+
+
+def pose_oks(pred: torch.Tensor, gt: torch.Tensor, gt_area: torch.Tensor, sigmas: torch.Tensor,
+             gt_boxes_xywh: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Object keypoint similarity of pairs: ``pred [P,K,2|3]``, ``gt [P,K,3]`` (x, y, v), ``gt_area [P]``,
+    ``sigmas [K]`` -> ``oks [P]`` (COCOeval.computeOks; boxes are used only for pairs without a labelled joint)."""
+    _need_cuda("pose_oks", pred, gt, gt_area, sigmas, gt_boxes_xywh)
+    pred, gt = _f32c("pose_oks pred", pred), _f32c("pose_oks gt", gt)
+    gt_area, sigmas = _f32c("pose_oks area", gt_area), _f32c("pose_oks sigmas", sigmas)
+    if pred.dim() != 3 or pred.shape[2] not in (2, 3) or gt.dim() != 3 or gt.shape[2] != 3 or gt.shape[:2] != pred.shape[:2]:
+        raise ValueError("pose_oks: pred must be [P, K, 2|3] and gt [P, K, 3]")
+    p, k = gt.shape[0], gt.shape[1]
+    if gt_area.numel() != p or sigmas.numel() != k:
+        raise ValueError("pose_oks: gt_area must be [P] and sigmas [K]")
+    if gt_boxes_xywh is not None:
+        gt_boxes_xywh = _f32c("pose_oks boxes", gt_boxes_xywh)
+    out = torch.empty((p,), dtype=torch.float32, device=pred.device)
+    _lib.check(_lib.lib().spp_pose_oks(_ptr(pred), int(pred.shape[2]), _ptr(gt), _ptr(gt_boxes_xywh), _ptr(gt_area), _ptr(sigmas), p, k,
+                                       _ptr(out), _stream(out)), "spp_pose_oks")
+    return out

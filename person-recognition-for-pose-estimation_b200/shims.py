@@ -41,6 +41,20 @@ def detect(levels: Sequence[torch.Tensor], confidence_threshold: float = 0.001, 
     return ops.decode_nms(levels, strides, confidence_threshold, iou_threshold).to_list()
 
 
+def head_conv_outputs(head: torch.nn.Module, feats: Sequence[torch.Tensor]):
+    """The reference ``Head``'s conv stacks WITHOUT the per-level ``torch.cat`` of nn.py:257:
+    ``[(head.box[i](x[i]), head.cls[i](x[i]))]`` — the pairs ``head_forward`` / ``detect`` / ``ops.decode_nms``
+    consume in place of the concatenated maps.  ``head`` is the reference's own module (its weights, its convs)."""
+    return [(b(x).contiguous(), c(x).contiguous()) for b, c, x in zip(head.box, head.cls, feats)]
+
+
+def head_eval_forward(head: torch.nn.Module, feats: Sequence[torch.Tensor]) -> torch.Tensor:
+    """Drop-in for ``Head.forward(x)`` in eval mode (nn.py:255-270): same ``[B, 4+nc, A]`` result, conv stacks by
+    the reference module, everything after them (cat, anchors, DFL, dist2bbox, sigmoid) by one kernel."""
+    strides = [float(s) for s in head.stride.tolist()]
+    return ops.head_decode(head_conv_outputs(head, feats), strides)
+
+
 # ---- libs/head_adaface.py:39 / libs/net_adaface.py:334 ---------------------------------------------
 def l2_norm(input: torch.Tensor, axis: int = 1) -> torch.Tensor:  # noqa: A002 (reference's argument name)
     """``l2_norm(input, axis=1)`` — libs/head_adaface.py:39-42."""
@@ -218,3 +232,37 @@ def get_final_preds(batch_heatmaps: torch.Tensor, center: torch.Tensor, scale: t
     cs = torch.cat([center.float(), scale.float()], 1).to(batch_heatmaps.device).contiguous()
     kp, sc, _ = ops.heatmap_decode(batch_heatmaps, None, None, cs, "quarter", flags=4)
     return kp, sc[..., None]
+
+
+# ---- training/lightning/pose_estimation/module.py:505-560 (the COCO result loop of validation_step) --------
+COCO_SIGMAS = (.026, .025, .025, .035, .035, .079, .079, .072, .072, .062, .062, .107, .107, .087, .087, .089, .089)  # datamodule.py:37-40
+
+
+def coco_keypoint_results(pred_coords: torch.Tensor, pred_scores: torch.Tensor, boxes: torch.Tensor, areas: torch.Tensor,
+                          masks: torch.Tensor, is_crowd: torch.Tensor, image_ids: Sequence[int],
+                          keypoint_thresh: float = 0.3) -> list:
+    """The reference builds its COCO predictions with a triple Python loop and ``.item()`` per value
+    (module.py:505-560).  Same rows, one kernel: ``pred_coords [B,K,2]`` normalised, ``pred_scores [B,K]``,
+    ``boxes [B,N,4]`` xyxy, ``areas [B,N]``, ``masks / is_crowd [B,N]`` bool.  As in the reference, every
+    instance ``n < masks[b].sum()`` of image ``b`` that is not a crowd gets image ``b``'s keypoints scaled
+    into its own box; ``bbox`` is the xyxy box as the reference emits it.  One D2H of the packed rows."""
+    dev = pred_coords.device
+    m = masks.to("cpu").bool()
+    crowd = is_crowd.to("cpu").bool()
+    pairs = [(b, n) for b in range(len(image_ids)) for n in range(int(m[b].sum())) if not bool(crowd[b, n])]
+    if not pairs:
+        return []
+    bi = torch.tensor([b for b, _ in pairs], device=dev)
+    ni = torch.tensor([n for _, n in pairs], device=dev)
+    sel_boxes = boxes.to(dev).float()[bi, ni].contiguous()
+    rows, inst = ops.pose_results(pred_coords.float()[bi].contiguous(), pred_scores.float()[bi].contiguous(), sel_boxes,
+                                  keypoint_thresh)
+    rows, inst, sel_boxes = rows.cpu(), inst.cpu(), sel_boxes.cpu()
+    areas = areas.to("cpu")
+    out = []
+    for r, (b, n) in enumerate(pairs):
+        kp = rows[r].tolist()
+        out.append({"image_id": int(image_ids[b]), "category_id": 1,
+                    "keypoints": [v if i < 2 else int(v) for xyv in kp for i, v in enumerate(xyv)],
+                    "score": float(inst[r]), "bbox": [float(v) for v in sel_boxes[r]], "area": float(areas[b, n])})
+    return out

@@ -23,6 +23,8 @@ _LIB.define("match_top1(Tensor emb, Tensor gallery_bf16, float? threshold, int i
 _LIB.define("crop_affine(Tensor frames, Tensor boxes, Tensor frame_idx, int out_h, int out_w, float[] mean, float[] std) -> Tensor")
 _LIB.define("heatmap_decode(Tensor hm, Tensor? hm_flipped, Tensor? perm, Tensor? boxes, str mode, int kernel, int flags) "
             "-> (Tensor, Tensor, Tensor)")
+_LIB.define("pose_results(Tensor keypoints, Tensor scores, Tensor? boxes_xyxy, float keypoint_thresh) -> (Tensor, Tensor)")
+_LIB.define("pose_oks(Tensor pred, Tensor gt, Tensor gt_area, Tensor sigmas, Tensor? gt_boxes_xywh) -> Tensor")
 
 
 def _head_decode(levels: List[torch.Tensor], strides: List[float]) -> torch.Tensor:
@@ -55,7 +57,15 @@ def _heatmap_decode(hm, hm_flipped, perm, boxes, mode, kernel, flags):
     return ops.heatmap_decode(hm, hm_flipped, perm, boxes, mode, kernel, flags)
 
 
-for _name, _fn in (("head_decode", _head_decode), ("nms_decoded", _nms_decoded), ("decode_nms", _decode_nms),
+def _pose_results(keypoints, scores, boxes_xyxy, keypoint_thresh):
+    return ops.pose_results(keypoints, scores, boxes_xyxy, keypoint_thresh)
+
+
+def _pose_oks(pred, gt, gt_area, sigmas, gt_boxes_xywh):
+    return ops.pose_oks(pred, gt, gt_area, sigmas, gt_boxes_xywh)
+
+
+for _name, _fn in (("pose_results", _pose_results), ("pose_oks", _pose_oks), ("head_decode", _head_decode), ("nms_decoded", _nms_decoded), ("decode_nms", _decode_nms),
                    ("l2_normalize", _l2_normalize), ("match_top1", _match_top1), ("crop_affine", _crop_affine),
                    ("heatmap_decode", _heatmap_decode)):
     _LIB.impl(_name, _fn, "CUDA")
@@ -106,3 +116,14 @@ def _(frames, boxes, frame_idx, out_h, out_w, mean, std):
 def _(hm, hm_flipped, perm, boxes, mode, kernel, flags):
     p, k = hm.shape[0], hm.shape[1]
     return hm.new_empty((p, k, 2)), hm.new_empty((p, k)), hm.new_empty((p, k), dtype=torch.int32)
+
+
+@torch.library.register_fake("spp::pose_results")
+def _(keypoints, scores, boxes_xyxy, keypoint_thresh):
+    p, k = scores.shape
+    return scores.new_empty((p, k, 3)), scores.new_empty((p,))
+
+
+@torch.library.register_fake("spp::pose_oks")
+def _(pred, gt, gt_area, sigmas, gt_boxes_xywh):
+    return pred.new_empty((pred.shape[0],))

@@ -560,3 +560,102 @@ def test_gallery_save_load_shards(spp, synth, dev, tmp_path):
         keys = k if keys is None else torch.maximum(keys, k)
     ids, sims = spp.match_unpack_keys(keys, 0.4)
     assert torch.equal(ids.long(), ids_full) and torch.equal(sims, sims_full)
+
+
+# ------------------------------------------------------------------------------------------------
+# COCO result rows + OKS (a15 / 8f-3)
+# ------------------------------------------------------------------------------------------------
+
+def test_coco_results_vs_reference_rows(spp, golden, dev):
+    """heatmaps -> flip test (no channel swap: the reference's batch-of-1 behaviour) -> soft-argmax -> result rows,
+    against the rows the reference's own validation_step emitted."""
+    g = golden("pose_results.npz")
+    hm, fl = torch.from_numpy(g["hm"]).to(dev), torch.from_numpy(g["flipped"]).to(dev)
+    boxes = torch.from_numpy(g["boxes"]).to(dev)
+    kp, sc, _ = spp.heatmap_decode(hm, fl, None, boxes[:, 0].contiguous(), "softargmax", flags=spp.ops.FLAG_SCALE_SCORE)
+    _close(kp.cpu().numpy(), g["coords"], atol=1e-6, what="normalised coordinates")
+    _close(sc.cpu().numpy(), g["scores"], what="scores")
+    res = spp.coco_keypoint_results(kp, sc, boxes, torch.from_numpy(g["areas"]), torch.from_numpy(g["masks"]),
+                                    torch.from_numpy(g["is_crowd"]), g["image_ids"].tolist())
+    assert [r["image_id"] for r in res] == g["res_image_id"].tolist()
+    got = np.array([r["keypoints"] for r in res]).reshape(len(res), -1, 3)
+    want = g["res_keypoints"].reshape(len(res), -1, 3)
+    _close(got[..., :2], want[..., :2], what="result keypoints")
+    clear = np.abs(g["scores"][[0, 0, 1, 1, 2]] - 0.3) > 1e-3          # visibility flags away from the threshold: exact
+    assert np.array_equal(got[..., 2][clear], want[..., 2][clear])
+    _close([r["score"] for r in res], g["res_score"], what="instance score")
+    assert np.array_equal(np.array([r["bbox"] for r in res]), g["res_bbox"])
+    np.testing.assert_allclose([r["area"] for r in res], g["res_area"], rtol=0)
+    # the kernel on the reference's own decoded coordinates: bit-exact rows
+    res2 = spp.coco_keypoint_results(torch.from_numpy(g["coords"]).to(dev), torch.from_numpy(g["scores"]).to(dev), boxes,
+                                     torch.from_numpy(g["areas"]), torch.from_numpy(g["masks"]), torch.from_numpy(g["is_crowd"]),
+                                     g["image_ids"].tolist())
+    assert np.array_equal(np.array([r["keypoints"] for r in res2]), g["res_keypoints"])
+    np.testing.assert_allclose([r["score"] for r in res2], g["res_score"], rtol=1e-6)
+    assert spp.coco_keypoint_results(kp, sc, boxes, torch.from_numpy(g["areas"]), torch.zeros(3, 3, dtype=torch.bool),
+                                     torch.from_numpy(g["is_crowd"]), g["image_ids"].tolist()) == []
+
+
+def test_pose_results_and_oks_vs_oracle(spp, dev):
+    from oracle import results as ores
+    g = torch.Generator().manual_seed(9)
+    p, k = 300, 17
+    gt = torch.rand(p, k, 3, generator=g) * 200
+    gt[..., 2] = torch.randint(0, 3, (p, k), generator=g).float()
+    gt[:7, :, 2] = 0                                                     # pairs without a labelled joint
+    pred = gt[..., :2] + torch.randn(p, k, 2, generator=g) * 6
+    area = torch.rand(p, generator=g) * 20000 + 500
+    gbox = torch.cat([torch.rand(p, 2, generator=g) * 100, torch.rand(p, 2, generator=g) * 150 + 10], 1)
+    sig = torch.tensor(ores.COCO_SIGMAS)
+    oks = spp.pose_oks(pred.to(dev), gt.to(dev), area.to(dev), sig.to(dev), gbox.to(dev)).cpu().numpy()
+    want = [ores.compute_oks(pred[i].numpy(), gt[i].numpy(), float(area[i]), ores.COCO_SIGMAS, gbox[i].numpy()) for i in range(p)]
+    _close(oks, want, rtol=1e-5, atol=1e-7, what="OKS")
+    sc = torch.rand(p, k, generator=g)
+    rows, inst = spp.pose_results(pred.to(dev), sc.to(dev))            # already in image pixels: no boxes
+    assert torch.equal(rows[..., :2].cpu(), pred)
+    assert torch.equal(rows[..., 2].cpu(), torch.where(sc > 0.3, 2.0, 1.0))
+    _close(inst.cpu().numpy(), sc.mean(1).numpy(), rtol=1e-6, what="instance score")
+    rows3 = torch.cat([pred, sc[..., None]], -1).to(dev)                # [P, K, 3] predictions
+    assert np.allclose(spp.pose_oks(rows3, gt.to(dev), area.to(dev), sig.to(dev), gbox.to(dev)).cpu().numpy(), oks)
+    e_rows, e_inst = spp.pose_results(torch.zeros(0, k, 2, device=dev), torch.zeros(0, k, device=dev))
+    assert e_rows.shape == (0, k, 3) and e_inst.shape == (0,)
+
+
+# ------------------------------------------------------------------------------------------------
+# detection head consumed before the per-level cat (8f-1)
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("tag", ["nc1", "nc3"])
+def test_split_head_inputs_match_concatenated(spp, golden, dev, tag):
+    g = golden(f"det_{tag}.npz")
+    cat = [torch.from_numpy(g[k]).to(dev) for k in ("l0", "l1", "l2")]
+    pairs = [(l[:, :64].contiguous(), l[:, 64:].contiguous()) for l in cat]
+    conf = float(g["conf"])
+    assert torch.equal(spp.head_decode(pairs), spp.head_decode(cat))
+    _close(spp.head_decode(pairs).cpu().numpy(), g["decoded"], atol=1e-4, what="decoded head (split inputs) vs reference")
+    a, b = spp.decode_nms(pairs, conf_thres=conf), spp.decode_nms(cat, conf_thres=conf)
+    assert torch.equal(a.count, b.count) and torch.equal(a.keys, b.keys) and torch.equal(a.dets, b.dets)
+    assert a.count.abs().tolist() == g["n"].tolist()
+    with pytest.raises(ValueError):
+        spp.decode_nms([pairs[0], cat[1], cat[2]])
+
+
+def test_head_eval_forward_with_torch_convs(spp, dev):
+    """A Head-shaped module (box / cls ModuleLists + stride, as nn.py:228-253): the shim runs its convs and
+    replaces everything after them; compared with the plain torch restatement of nn.py:255-270."""
+    torch.manual_seed(0)
+
+    class TinyHead(torch.nn.Module):
+        def __init__(self, nc=2, filters=(8, 16, 24)):
+            super().__init__()
+            self.box = torch.nn.ModuleList(torch.nn.Conv2d(f, 64, 1) for f in filters)
+            self.cls = torch.nn.ModuleList(torch.nn.Conv2d(f, nc, 1) for f in filters)
+            self.stride = torch.tensor([8.0, 16.0, 32.0])
+
+    head = TinyHead().to(dev).eval()
+    feats = [torch.randn(2, f, s, s + 4, device=dev) for f, s in ((8, 16), (16, 8), (24, 4))]
+    with torch.no_grad():
+        out = spp.head_eval_forward(head, feats)
+        cat = [torch.cat((b(x), c(x)), 1) for b, c, x in zip(head.box, head.cls, feats)]
+    ref = odet.head_decode([l.cpu() for l in cat])
+    _close(out.cpu().numpy(), ref.numpy(), atol=1e-4, what="head_eval_forward")

@@ -142,3 +142,48 @@ def test_quarter_offset_hand_made():
     r = 60.0 / 6
     np.testing.assert_allclose(preds[0, 0], [(2 + 0.25) * r + 100 - 30, (3 - 0.25) * r + 200 - r * 4], rtol=1e-6)
     np.testing.assert_allclose(preds[0, 1], [100 - 30, 200 - r * 4], rtol=1e-6)
+
+
+def test_coco_results_oracle_matches_reference_validation_step(golden):
+    """a15 / 8f-3: the restated result loop against the rows the reference's own validation_step produced
+    (oracle/gen_golden.py:gen_pose_results)."""
+    from oracle import results as ores
+    g = golden("pose_results.npz")
+    res = ores.coco_results(g["coords"], g["scores"], g["boxes"], g["areas"], g["masks"], g["is_crowd"], g["image_ids"])
+    assert [r["image_id"] for r in res] == g["res_image_id"].tolist()
+    assert np.array_equal(np.array([r["keypoints"] for r in res]), g["res_keypoints"])       # bit-exact, incl. v
+    assert np.array_equal(np.array([r["bbox"] for r in res]), g["res_bbox"])
+    np.testing.assert_allclose([r["score"] for r in res], g["res_score"], rtol=1e-6)
+    np.testing.assert_allclose([r["area"] for r in res], g["res_area"], rtol=0)
+    # the soft-argmax oracle reproduces the coordinates the reference decoded (batch of 1: no channel swap)
+    for b in range(3):
+        avg = opose.flip_average(torch.from_numpy(g["hm"][b:b + 1]), torch.from_numpy(g["flipped"][b:b + 1]), None)
+        c, s = opose.soft_argmax_decode(avg, torch.from_numpy(g["boxes"][b:b + 1, 0]))
+        np.testing.assert_allclose(c[0].numpy(), g["coords"][b], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(s[0].numpy(), g["scores"][b], rtol=1e-5)
+
+
+def test_oks_known_answers():
+    """COCOeval.computeOks restatement (parity unpinned): closed-form cases."""
+    from oracle import results as ores
+    k = 17
+    gt = np.zeros((k, 3))
+    gt[:, 0] = np.arange(k) * 3.0
+    gt[:, 1] = 50.0
+    gt[:, 2] = 2
+    assert ores.compute_oks(gt[:, :2], gt, area=1000.0) == 1.0
+    # one joint off by d: oks = (k - 1 + exp(-d^2 / (2 * area * (2 sigma)^2))) / k
+    pred = gt[:, :2].copy()
+    pred[5, 0] += 4.0
+    want = (k - 1 + np.exp(-16.0 / (2 * 1000.0 * (2 * float(np.float32(0.079))) ** 2))) / k   # sigmas are fp32 (datamodule.py:37-40)
+    assert abs(ores.compute_oks(pred, gt, area=1000.0) - want) < 1e-12
+    # unlabelled joints do not count
+    gt2 = gt.copy()
+    gt2[5, 2] = 0
+    assert ores.compute_oks(pred, gt2, area=1000.0) == 1.0
+    # nothing labelled: distance to the doubled box
+    gt3 = gt.copy()
+    gt3[:, 2] = 0
+    inside = np.tile([[20.0, 20.0]], (k, 1))
+    assert ores.compute_oks(inside, gt3, area=1000.0, gt_box_xywh=[10, 10, 20, 20]) == 1.0
+    assert ores.compute_oks(inside + 500.0, gt3, area=1000.0, gt_box_xywh=[10, 10, 20, 20]) < 1e-6
