@@ -79,6 +79,11 @@ int spp_decode_nms(const float *const *levels, const int *level_h, const int *le
                    float max_wh, int max_candidates, float *out_dets, int *out_count, int *out_keys,
                    void *workspace, size_t workspace_bytes, spp_stream_t stream);
 
+/* Implementation choice for spp_decode_nms / spp_decode_nms_split, process-wide: 0 = three launches per call (candidate
+ * scan, candidate decode, sort + NMS; default), 1 = one fused kernel (a CTA per image does all of it; fewer launches,
+ * e.g. for tiny batches).  Results are identical bit for bit.  Returns the previous mode; any other argument only queries. */
+int spp_decode_nms_mode(int mode);
+
 /* The same two entry points on the head's conv outputs BEFORE the per-level torch.cat of nn.py:257
  * (SURVEY.md 8f-1): box_levels[l] DEVICE [batch, 64, level_h[l], level_w[l]] (self.box[i](x[i])) and
  * cls_levels[l] DEVICE [batch, nc, level_h[l], level_w[l]] (self.cls[i](x[i])), NCHW contiguous fp32.

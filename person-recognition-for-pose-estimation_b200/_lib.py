@@ -26,6 +26,7 @@ SIGNATURES = {
                                       _P, _P]),
     "spp_decode_nms_split": (c_int, [POINTER(_P), POINTER(_P), POINTER(c_int), POINTER(c_int), POINTER(c_float), c_int, c_int,
                                      c_int, c_float, c_float, c_int, c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "spp_decode_nms_mode": (c_int, [c_int]),
     "spp_nms_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "spp_nms_decoded": (c_int, [_P, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_float, c_int, _P, _P, _P, _P,
                                 c_size_t, _P]),

@@ -8,23 +8,29 @@
 // Kernels
 //   head_decode_kernel     full decode to [B, 4+nc, A] (drop-in for Head.forward); one thread per
 //                          anchor, every channel plane read as coalesced 128 B lines.
-//   cand_raw_kernel        fused path: reads ONLY the class planes for all anchors; the 64 DFL planes are
-//                          touched just for anchors that pass the confidence threshold, whose decoded
-//                          boxes are parked in a per-image [A] float4 table.  Candidates are appended with
-//                          warp-aggregated atomics as 64-bit sort keys (~score | anchor*nc+cls).
-//   cand_decoded_kernel    same candidate pass over an already decoded [B, 4+nc, A] tensor.
-//   nms_kernel             one CTA per image: bitonic sort of the keys (score descending, candidate key
-//                          ascending — a stable order), then greedy suppression in that order against
-//                          the list of boxes kept so far.  A box survives iff no earlier KEPT box has
-//                          IoU > thr, so only n * kept (<= n * max_det) IoUs are needed instead of the
-//                          n^2/2 of a full bitmask; inside each 32-box chunk the survivors are resolved
-//                          with warp ballots (each kept lane broadcasts its box, the ballot of "IoU > thr"
-//                          clears the alive mask).  The loop stops after max_det kept boxes.
+//   nms_kernel<2>          THE fused path, one CTA per image, one launch per head:
+//                          (0) candidate scan over the image's class planes only (logit pre-filter, exact fp32
+//                              sigmoid > conf), warp-aggregated append of 64-bit sort keys (~score | anchor*nc+cls);
+//                              the 64 DFL planes are touched just for the candidates (half-warp per candidate,
+//                              lane = DFL bin), whose decoded boxes are parked in a per-image [A] float4 table;
+//                          (1) bitonic sort of the keys (score descending, candidate key ascending — a stable
+//                              order);
+//                          (2) greedy suppression in that order against the boxes kept so far.  A box survives
+//                              iff no earlier KEPT box has IoU > thr, so only n * kept (<= n * max_det) IoUs are
+//                              needed instead of the n^2/2 of a full bitmask; every warp clears, with one ballot
+//                              per 32-candidate bitmask word, the later candidates the current box suppresses.
+//                              The loop stops after max_det kept boxes.
+//   cand_scan_kernel + cand_decode_kernel + nms_kernel<1>   the same work as three launches (SPP_DET_SPLIT=1; kept
+//                          as the profiling baseline: two full-machine latency-bound launches in front of the NMS).
+//   cand_decoded_kernel + nms_kernel<0>   candidate pass + NMS over an already decoded [B, 4+nc, A] tensor
+//                          (drop-in for non_max_suppression).
 // IoU arithmetic is fp32 with round-to-nearest intrinsics (never contracted to FMA): it must agree bit
 // for bit with torchvision's CPU loop, which is what the reference's keep indices come from.
 #include "spp_common.cuh"
 
+#include <atomic>
 #include <climits>
+#include <cstdlib>
 #include <cmath>
 
 namespace spp {
@@ -194,6 +200,51 @@ __global__ void __launch_bounds__(256) cand_scan_kernel(const Levels lv, int nc,
     }
 }
 
+// DFL decode of ONE candidate anchor by one half-warp (both halves of a warp call this together: the shuffles
+// use the full mask with xor offsets < 16).  Lane `sub` owns DFL bin `sub` of all four sides (4 loads in flight
+// per lane, 64 per candidate); softmax max / sum and the expectation are 16-lane xor-shuffle reductions.
+// The xyxy box is written to img_boxes[anchor] by lane 0 of the half-warp.
+__device__ __forceinline__ void decode_candidate(const Levels &lv, int b, int anchor, bool valid, int sub, float4 *img_boxes) {
+    const LevelRef lr = find_level(lv, anchor);
+    const float *basep = lr.box + (size_t)b * lr.bs_box + lr.i;
+    float v[4];
+#pragma unroll
+    for (int sd = 0; sd < 4; ++sd) v[sd] = __ldg(basep + (size_t)(sd * kDfl + sub) * lr.hw);
+    float m[4], sum[4], d[4];
+#pragma unroll
+    for (int sd = 0; sd < 4; ++sd) m[sd] = v[sd];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+        for (int sd = 0; sd < 4; ++sd) m[sd] = fmaxf(m[sd], __shfl_xor_sync(FULL, m[sd], o));
+#pragma unroll
+    for (int sd = 0; sd < 4; ++sd) {
+        sum[sd] = __expf(v[sd] - m[sd]);
+        d[sd] = (float)sub * sum[sd];
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+        for (int sd = 0; sd < 4; ++sd) {
+            sum[sd] += __shfl_xor_sync(FULL, sum[sd], o);
+            d[sd] += __shfl_xor_sync(FULL, d[sd], o);
+        }
+#pragma unroll
+    for (int sd = 0; sd < 4; ++sd) d[sd] = __fdiv_rn(d[sd], sum[sd]);      // sum_j j*e_j / sum_j e_j
+    if (valid && sub == 0) {
+        const int y = lr.i / lr.w, x = lr.i - y * lr.w;
+        const float ax = (float)x + 0.5f, ay = (float)y + 0.5f;
+        const float x1 = __fsub_rn(ax, d[0]), y1 = __fsub_rn(ay, d[1]);
+        const float x2 = __fadd_rn(ax, d[2]), y2 = __fadd_rn(ay, d[3]);
+        float4 r;
+        r.x = __fmul_rn(__fmul_rn(__fadd_rn(x1, x2), 0.5f), lr.stride);
+        r.y = __fmul_rn(__fmul_rn(__fadd_rn(y1, y2), 0.5f), lr.stride);
+        r.z = __fmul_rn(__fsub_rn(x2, x1), lr.stride);
+        r.w = __fmul_rn(__fsub_rn(y2, y1), lr.stride);
+        img_boxes[anchor] = wh2xy(r);
+    }
+}
+
 // Box decode for the candidates only: one half-warp per (image, candidate).  Lane j of the half-warp
 // owns DFL bin j of all four sides (4 loads in flight per lane, 64 per candidate); the softmax
 // max / sum and the expectation are 16-lane xor-shuffle reductions, four sides at a time.
@@ -224,50 +275,15 @@ __global__ void __launch_bounds__(256) cand_decode_kernel(const Levels lv, int n
         const int b = lo, slot = (valid ? t : 0) - pre[lo];
         const unsigned cand = valid ? (unsigned)(keys[(size_t)b * cap_pad + slot] & 0xffffffffu) : 0u;
         const int anchor = (int)(cand / (unsigned)nc);
-        const LevelRef lr = find_level(lv, anchor);
-        const float *basep = lr.box + (size_t)(valid ? b : 0) * lr.bs_box + lr.i;
-        float v[4];
-#pragma unroll
-        for (int sd = 0; sd < 4; ++sd) v[sd] = __ldg(basep + (size_t)(sd * kDfl + sub) * lr.hw);
-        float m[4], sum[4], d[4];
-#pragma unroll
-        for (int sd = 0; sd < 4; ++sd) m[sd] = v[sd];
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1)
-#pragma unroll
-            for (int sd = 0; sd < 4; ++sd) m[sd] = fmaxf(m[sd], __shfl_xor_sync(FULL, m[sd], o));
-#pragma unroll
-        for (int sd = 0; sd < 4; ++sd) {
-            sum[sd] = __expf(v[sd] - m[sd]);
-            d[sd] = (float)sub * sum[sd];
-        }
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1)
-#pragma unroll
-            for (int sd = 0; sd < 4; ++sd) {
-                sum[sd] += __shfl_xor_sync(FULL, sum[sd], o);
-                d[sd] += __shfl_xor_sync(FULL, d[sd], o);
-            }
-#pragma unroll
-        for (int sd = 0; sd < 4; ++sd) d[sd] = __fdiv_rn(d[sd], sum[sd]);      // sum_j j*e_j / sum_j e_j
-        if (valid && sub == 0) {
-            const int y = lr.i / lr.w, x = lr.i - y * lr.w;
-            const float ax = (float)x + 0.5f, ay = (float)y + 0.5f;
-            const float x1 = __fsub_rn(ax, d[0]), y1 = __fsub_rn(ay, d[1]);
-            const float x2 = __fadd_rn(ax, d[2]), y2 = __fadd_rn(ay, d[3]);
-            float4 r;
-            r.x = __fmul_rn(__fmul_rn(__fadd_rn(x1, x2), 0.5f), lr.stride);
-            r.y = __fmul_rn(__fmul_rn(__fadd_rn(y1, y2), 0.5f), lr.stride);
-            r.z = __fmul_rn(__fsub_rn(x2, x1), lr.stride);
-            r.w = __fmul_rn(__fsub_rn(y2, y1), lr.stride);
-            boxes[(size_t)b * lv.A + anchor] = wh2xy(r);
-        }
+        decode_candidate(lv, valid ? b : 0, anchor, valid, sub, boxes + (size_t)b * lv.A);
     }
 }
 
 struct NmsParams {
     const float *pred;          // decoded path
-    const float4 *boxes;        // raw path: [B, A] xyxy
+    float4 *boxes;              // raw path: [B, A] xyxy (written by cand_decode_kernel, or by the fused kernel itself)
+    Levels lv;                  // fused path: the raw head maps
+    float conf, logit_lo;       // fused path: candidate threshold and its logit pre-filter
     const int *counts;
     unsigned long long *keys;   // [B, cap_pad]
     int nc, A, cap, cap_pad;
@@ -337,8 +353,14 @@ __device__ unsigned long long block_bitonic_reg(unsigned long long key, unsigned
 //      it owns, the later candidates whose IoU with the current box exceeds the threshold, and proposes
 //      the first survivor it sees (shared-memory atomicMin) as the next box.  One block barrier per kept
 //      box, n/32/16 ballots per warp per kept box; stops after max_det.
-template <bool RAW>
+//   MODE 0: candidates from cand_decoded_kernel, boxes from the decoded [B, 4+nc, A] tensor;
+//   MODE 1: candidates from cand_scan_kernel, boxes from cand_decode_kernel's table;
+//   MODE 2: FUSED — step 0 of the CTA is the candidate scan over its image's class planes and the DFL decode of
+//           the candidates (half-warp per candidate, two in flight per half-warp): one launch per head instead
+//           of three, and one CTA per image instead of two full-machine latency-bound launches in front of it.
+template <int MODE>
 __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams prm) {
+    constexpr bool RAW = MODE != 0;
     extern __shared__ __align__(16) unsigned char nms_smem[];
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -351,9 +373,61 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams prm) {
     int *kept_idx = reinterpret_cast<int *>(alive + kAliveWords);                              // [max_det]
     __shared__ int s_next[3];
 
-    const int raw_count = prm.counts[b];
-    int n = raw_count < prm.cap ? raw_count : prm.cap;
     unsigned long long *gkeys = prm.keys + (size_t)b * prm.cap_pad;
+    int raw_count;
+    if (MODE == 2) {
+        __shared__ int s_count;
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+        const Levels &lv = prm.lv;
+        const int nc = prm.nc;
+        // ---- candidate scan: 4 anchors per thread in flight, class planes read as coalesced lines ----
+        for (int j = 0; j < nc; ++j) {
+            for (int a0 = 0; a0 < lv.A; a0 += 4 * kNmsThreads) {
+                float x[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int a = a0 + u * kNmsThreads + tid;
+                    x[u] = -INFINITY;
+                    if (a < lv.A) {
+                        const LevelRef lr = find_level(lv, a);
+                        x[u] = __ldg(lr.cls + (size_t)b * lr.bs_cls + (size_t)j * lr.hw + lr.i);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int a = a0 + u * kNmsThreads + tid;
+                    float sc = 0.f;
+                    bool c = false;
+                    if (x[u] > prm.logit_lo) {          // -inf for anchors past the end
+                        sc = sigmoidf_ref(x[u]);
+                        c = sc > prm.conf;
+                    }
+                    append_candidate(c, make_sort_key(sc, (unsigned)(a * nc + j)), &s_count, gkeys, prm.cap);
+                }
+            }
+        }
+        __syncthreads();
+        raw_count = s_count;
+        // ---- DFL decode of the candidates into this image's box table ----
+        const int nd = raw_count < prm.cap ? raw_count : prm.cap;
+        const int sub = lane & 15, half = tid >> 4;
+        constexpr int NH = kNmsThreads / 16;
+        float4 *img_boxes = prm.boxes + (size_t)b * lv.A;
+        for (int base = 0; base < nd; base += 2 * NH) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int t = base + u * NH + half;
+                const bool valid = t < nd;
+                const unsigned cand = valid ? (unsigned)(gkeys[t] & 0xffffffffu) : 0u;
+                decode_candidate(lv, b, (int)(cand / (unsigned)nc), valid, sub, img_boxes);
+            }
+        }
+        __syncthreads();                                 // keys and boxes written above are read below
+    } else {
+        raw_count = prm.counts[b];
+    }
+    int n = raw_count < prm.cap ? raw_count : prm.cap;
     unsigned long long *keys;
     if (n <= kNmsThreads) {
         const unsigned long long mine = block_bitonic_reg(tid < n ? gkeys[tid] : ~0ull, reinterpret_cast<unsigned long long *>(sbox));
@@ -536,16 +610,16 @@ Workspace carve(void *ws, int batch, int num_anchors, int nc, int max_candidates
     return w;
 }
 
-template <bool RAW>
+template <int MODE>
 int launch_nms(const NmsParams &prm, int batch, cudaStream_t st) {
     const size_t smem = (size_t)kSortSmemMax * 8 + (size_t)kBoxSmemMax * 20 + (size_t)kAliveWords * 4 + (size_t)prm.max_det * 4;
     static bool configured = false;
     if (!configured) {
-        SPP_CHECK_CUDA(cudaFuncSetAttribute(nms_kernel<RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        SPP_CHECK_CUDA(cudaFuncSetAttribute(nms_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         configured = true;
     }
     SPP_CHECK_ARG(smem <= 160 * 1024, "nms: max_det %d too large", prm.max_det);
-    nms_kernel<RAW><<<batch, kNmsThreads, smem, st>>>(prm);
+    nms_kernel<MODE><<<batch, kNmsThreads, smem, st>>>(prm);
     SPP_CHECK_LAUNCH();
     return SPP_OK;
 }
@@ -565,6 +639,13 @@ int check_nms_args(int batch, int nc, float iou, int max_det, int max_nms, const
 }  // namespace spp
 
 using namespace spp;
+
+static std::atomic<int> g_det_mode{[] { const char *e = getenv("SPP_DET_FUSED"); return (e && atoi(e) != 0) ? 1 : 0; }()};
+
+extern "C" int spp_decode_nms_mode(int mode) {
+    if (mode != 0 && mode != 1) return g_det_mode.load();
+    return g_det_mode.exchange(mode);
+}
 
 static int head_decode_impl(const float *const *levels, const float *const *cls_levels, const int *level_h, const int *level_w,
                             const float *strides, int num_levels, int batch, int nc, float *out, spp_stream_t stream) {
@@ -619,7 +700,7 @@ extern "C" int spp_nms_decoded(const float *pred, int batch, int nc, int num_anc
     prm.nc = nc; prm.A = num_anchors; prm.cap = w.cap; prm.cap_pad = w.cap_pad;
     prm.iou = iou_thres; prm.max_wh = max_wh; prm.max_det = max_det; prm.max_nms = max_nms;
     prm.out_dets = out_dets; prm.out_count = out_count; prm.out_keys = out_keys;
-    return launch_nms<false>(prm, batch, st);
+    return launch_nms<0>(prm, batch, st);
 }
 
 static int decode_nms_impl(const float *const *levels, const float *const *cls_levels, const int *level_h, const int *level_w,
@@ -640,12 +721,26 @@ static int decode_nms_impl(const float *const *levels, const float *const *cls_l
         return SPP_ERR_WORKSPACE;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    SPP_CHECK_CUDA(cudaMemsetAsync(w.counts, 0, (size_t)batch * sizeof(int), st));
-    dim3 grid((lv.A + 255) / 256, batch);
     // sigmoid(x) > conf can only hold for x > logit(conf); 0.05 of slack covers fp32 rounding
     float logit_lo = -INFINITY;
     if (conf_thres >= 1.0f) logit_lo = INFINITY;
     else if (conf_thres > 0.0f) logit_lo = (float)(std::log((double)conf_thres / (1.0 - (double)conf_thres)) - 0.05);
+    NmsParams prm{};
+    prm.pred = nullptr; prm.boxes = w.boxes; prm.counts = w.counts; prm.keys = w.keys;
+    prm.nc = nc; prm.A = lv.A; prm.cap = w.cap; prm.cap_pad = w.cap_pad;
+    prm.iou = iou_thres; prm.max_wh = max_wh; prm.max_det = max_det; prm.max_nms = max_nms;
+    prm.out_dets = out_dets; prm.out_count = out_count; prm.out_keys = out_keys;
+    // Default: three launches per head (candidate scan, candidate decode, sort + NMS).  spp_decode_nms_mode(1) / SPP_DET_FUSED=1
+    // selects ONE fused kernel per head (a CTA per image does all of it): same results bit for bit, one launch instead of
+    // three + a memset; measured on B200 at cfg2 it is slower alone (57 vs 45 us per head: one CTA serialises what two
+    // full-machine launches do in parallel) and equal inside the step, so it is the option, not the default.
+    const bool split3 = g_det_mode.load(std::memory_order_relaxed) == 0;
+    if (!split3) {
+        prm.lv = lv; prm.conf = conf_thres; prm.logit_lo = logit_lo;
+        return launch_nms<2>(prm, batch, st);
+    }
+    SPP_CHECK_CUDA(cudaMemsetAsync(w.counts, 0, (size_t)batch * sizeof(int), st));
+    dim3 grid((lv.A + 255) / 256, batch);
     cand_scan_kernel<<<grid, 256, 0, st>>>(lv, nc, conf_thres, logit_lo, w.cap, w.cap_pad, w.counts, w.keys);
     SPP_CHECK_LAUNCH();
     {
@@ -654,12 +749,7 @@ static int decode_nms_impl(const float *const *levels, const float *const *cls_l
         cand_decode_kernel<<<sms * 8, 256, (size_t)(batch + 1) * sizeof(int), st>>>(lv, nc, batch, w.cap, w.cap_pad, w.counts, w.keys, w.boxes);
         SPP_CHECK_LAUNCH();
     }
-    NmsParams prm{};
-    prm.pred = nullptr; prm.boxes = w.boxes; prm.counts = w.counts; prm.keys = w.keys;
-    prm.nc = nc; prm.A = lv.A; prm.cap = w.cap; prm.cap_pad = w.cap_pad;
-    prm.iou = iou_thres; prm.max_wh = max_wh; prm.max_det = max_det; prm.max_nms = max_nms;
-    prm.out_dets = out_dets; prm.out_count = out_count; prm.out_keys = out_keys;
-    return launch_nms<true>(prm, batch, st);
+    return launch_nms<1>(prm, batch, st);
 }
 
 extern "C" int spp_decode_nms(const float *const *levels, const int *level_h, const int *level_w, const float *strides,

@@ -20,6 +20,8 @@
 // the gate and packs the (value, index) key for the multi-GPU top-1 reduction.
 #include "spp_common.cuh"
 
+#include <cstdlib>
+
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cmath>
@@ -465,21 +467,30 @@ MatchPlan plan_match(int m, int n) {
     p.tiles_n = (n + BN - 1) / BN;
     int sms = sm_count();
     if (sms <= 0) sms = 148;
-    // Work items = (M-tile, chunk of gallery tiles).  Small problems: one item per CTA, and no more CTAs than
-    // give each ~8 gallery tiles (every CTA loads a 128 KB probe tile and needs a whole SM, so a small match
-    // should leave SMs to the kernels running beside it).  Large problems: the grid is one persistent CTA
-    // per SM and the chunk count is chosen so that items ~ r * SMs (balanced rounds, <= 8 of them).
-    const int want = (p.tiles_n + 7) / 8 > 0 ? (p.tiles_n + 7) / 8 : 1;
+    // Work items = (M-tile, chunk of gallery tiles).  Small problems (fewer items than SMs even at one gallery
+    // tile per item): one item per CTA and as many CTAs as there are SMs — every CTA pays a 128 KB probe-tile
+    // load, but the kernel is over in ~1/6 of the time 8-tile chunks take (cfg2: 145 CTAs x 1-2 tiles instead of
+    // 25 CTAs x 8; measured 72 us -> see profiles/README.md), and a short kernel is what the graph's other
+    // branches need from it.  SPP_MATCH_CHUNK_TILES=<t> restores chunks of >= t tiles (profiling knob).
+    // Large problems: the grid is one persistent CTA per SM and the chunk count is chosen so that
+    // items ~ r * SMs (balanced rounds, <= 8 of them).
+    static const int chunk_tiles = [] { const char *e = getenv("SPP_MATCH_CHUNK_TILES"); const int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();
+    const int want = (p.tiles_n + chunk_tiles - 1) / chunk_tiles > 0 ? (p.tiles_n + chunk_tiles - 1) / chunk_tiles : 1;
     int ns;
     if ((long long)p.m_tiles * want <= sms) {
         ns = want;
+    } else if ((long long)p.m_tiles * p.tiles_n <= 2LL * sms || p.tiles_n <= 8 * (sms / p.m_tiles > 0 ? sms / p.m_tiles : 1)) {
+        // at most a couple of tiles per SM: one round, chunks as even as the tile count allows
+        ns = sms / p.m_tiles > 0 ? sms / p.m_tiles : 1;
+        if (ns > want) ns = want;
     } else {
         ns = 1;
         double best = 0.0;
+        const int cap = (p.tiles_n + 7) / 8 > 0 ? (p.tiles_n + 7) / 8 : 1;      // >= 8 tiles per chunk: the probe-tile reload stays < 7 %
         for (int r = 1; r <= 8; ++r) {
             int c = (int)((long long)sms * r / p.m_tiles);
             if (c < 1) continue;
-            if (c > want) c = want;
+            if (c > cap) c = cap;
             const long long items = (long long)p.m_tiles * c;
             const long long rounds = (items + sms - 1) / sms;
             const double util = (double)items / (double)(rounds * sms);

@@ -162,6 +162,13 @@ def nms_decoded(pred: torch.Tensor, conf_thres: float = 0.001, iou_thres: float 
     return NmsResult(dets, count, keys)
 
 
+def set_decode_nms_mode(mode: str) -> str:
+    """``"split"`` (default: scan, candidate decode, sort + NMS as three launches) or ``"fused"`` (one kernel, a CTA per
+    image); identical results.  Returns the previous mode.  Call before a pipeline captures its CUDA graph."""
+    prev = _lib.lib().spp_decode_nms_mode({"split": 0, "fused": 1}[mode])
+    return "fused" if prev == 1 else "split"
+
+
 def decode_nms(levels: Sequence, strides: Sequence[float] = (8, 16, 32), conf_thres: float = 0.001,
                iou_thres: float = 0.65, max_det: int = MAX_DET, max_nms: int = MAX_NMS, max_wh: float = MAX_WH,
                max_candidates: int = 0, out: Optional[NmsResult] = None) -> NmsResult:

@@ -21,7 +21,7 @@ from typing import Dict, Optional, Sequence
 
 import torch
 
-from . import ops, synth
+from . import _lib, ops, synth
 
 
 @dataclass
@@ -139,7 +139,9 @@ class SelectivePosePipeline:
             face = ops.decode_nms(i.face_levels, conf_thres=self.conf, iou_thres=self.iou, out=self.out.get("_face"))
         with torch.cuda.stream(sides[1]):
             person = ops.decode_nms(i.person_levels, conf_thres=self.conf, iou_thres=self.iou, out=self.out.get("_person"))
-        n += 2 * 3      # candidate scan + candidate decode + NMS kernel per head (the count memset is not a kernel)
+        # candidate scan + candidate decode + NMS kernel per head (the count memset is not a kernel); one fused kernel
+        # per head after ops.set_decode_nms_mode("fused")
+        n += 2 * (1 if _lib.lib().spp_decode_nms_mode(-1) == 1 else 3)
         if self.matcher is None:
             with torch.cuda.stream(sides[2]):
                 ids, sims, keys = ops.match_top1(i.embeddings, self.gallery, self.threshold, self.id_offset, want_keys=True)

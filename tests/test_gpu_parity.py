@@ -659,3 +659,23 @@ def test_head_eval_forward_with_torch_convs(spp, dev):
         cat = [torch.cat((b(x), c(x)), 1) for b, c, x in zip(head.box, head.cls, feats)]
     ref = odet.head_decode([l.cpu() for l in cat])
     _close(out.cpu().numpy(), ref.numpy(), atol=1e-4, what="head_eval_forward")
+
+
+@pytest.mark.parametrize("tag", ["nc1", "nc3"])
+def test_fused_single_kernel_decode_nms_is_identical(spp, synth, golden, dev, tag):
+    """spp_decode_nms_mode(1): one kernel per head (scan + candidate decode + sort + NMS in one CTA per image)."""
+    g = golden(f"det_{tag}.npz")
+    cat = [torch.from_numpy(g[k]).to(dev) for k in ("l0", "l1", "l2")]
+    big = synth.make_head_maps(3, 736, 1280, n_obj=10, nc=1, seed=4)
+    try:
+        prev = spp.ops.set_decode_nms_mode("split")
+        a = spp.decode_nms(cat, conf_thres=float(g["conf"]))
+        a2 = spp.decode_nms([l.to(dev) for l in big.levels])
+        assert spp.ops.set_decode_nms_mode("fused") == "split"
+        b = spp.decode_nms(cat, conf_thres=float(g["conf"]))
+        b2 = spp.decode_nms([l.to(dev) for l in big.levels])
+    finally:
+        spp.ops.set_decode_nms_mode(prev)
+    for x, y in ((a, b), (a2, b2)):
+        assert torch.equal(x.count, y.count) and torch.equal(x.keys, y.keys) and torch.equal(x.dets, y.dets)
+    assert b.count.abs().tolist() == g["n"].tolist()

@@ -1,0 +1,45 @@
+"""Kernel timeline of one graph replay of the cfg2 step (CUPTI through torch.profiler; there is no nsys here):
+start / end of every kernel relative to the first one, so that branch overlap and tails can be read off.
+python tools/timeline.py [frames_dtype]"""
+import importlib
+import os
+import sys
+
+import torch
+from torch.profiler import ProfilerActivity, profile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+PKG = "person-recognition-for-pose-estimation_b200"
+spp = importlib.import_module(PKG)
+pipeline = importlib.import_module(PKG + ".pipeline")
+
+dev = torch.device("cuda:0")
+inp = pipeline.synthetic_inputs(64, 720, 1280, 10, 17, seed=0)
+ms = spp.synth.make_match_set(640, 10000, seed=1000)
+inp.embeddings = ms.embeddings
+if len(sys.argv) > 1 and sys.argv[1] == "u8":
+    inp.frames = (inp.frames * 255.0).round().clamp(0, 255).to(torch.uint8)
+pipe = pipeline.SelectivePosePipeline(inp, ms.gallery.to(torch.bfloat16), dev)
+for _ in range(5):
+    pipe.step()
+pipe.stream.synchronize()
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    for _ in range(4):
+        pipe.step()
+    pipe.stream.synchronize()
+ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+ev.sort(key=lambda e: e.time_range.start)
+# split into replays: a gap before a kernel whose name repeats the first kernel's name
+names = [e.name for e in ev]
+first = names[0]
+starts = [i for i, n in enumerate(names) if n == first]
+per = len(ev) // 4 if len(ev) % 4 == 0 else None
+print("kernels:", len(ev), "per replay:", per)
+if per:
+    rep = ev[2 * per:3 * per]
+    t0 = rep[0].time_range.start
+    for e in rep:
+        print(f"{(e.time_range.start - t0):9.1f} -> {(e.time_range.end - t0):9.1f} us  ({e.time_range.end - e.time_range.start:7.1f})  {e.name[:90]}")
+    nxt = ev[3 * per].time_range.start - t0
+    print(f"next replay starts at {nxt:.1f} us; this replay ends at {max(e.time_range.end for e in rep) - t0:.1f} us")
