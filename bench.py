@@ -298,6 +298,32 @@ def main():
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
     e2e_fps = world * B * e2e_steps / (e2e_ms / 1e3)
 
+    # ---- (2b) the same end-to-end pass with uint8 frames (what a video decoder delivers, and what HF's default
+    #      do_rescale=True path expects): 4x fewer frame bytes over PCIe.  Reported beside the fp32 headline. -----
+    e2e_u8 = None
+    if world == 1 and args.frames == "f32" and not args.select_on_device:
+        import copy
+        inp8 = copy.copy(inp)
+        inp8.frames = (inp.frames * 255.0).round().clamp(0, 255).to(torch.uint8)
+        pipe8 = pipeline.SelectivePosePipeline(inp8, gallery_bf16, dev, decode_mode=args.decode_mode, use_graph=not args.no_graph,
+                                               concurrent=not args.serial)
+        pipe8.bind_host(inp8)
+        for _ in range(2):
+            pipe8.run_host()
+        pipe8.stream.synchronize()
+        n8 = max(3, min(args.steps, 10))
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(pipe8.stream)
+        for _ in range(n8):
+            pipe8.run_host()
+        a1.record(pipe8.stream)
+        pipe8.stream.synchronize()
+        ms8 = a0.elapsed_time(a1) / n8
+        e2e_u8 = {"value": round(B / (ms8 / 1e3), 1), "unit": "frames/s", "frames_dtype": "u8", "h2d_bytes_per_step": pipe8.h2d_bytes,
+                  "d2h_bytes_per_step": pipe8.d2h_bytes, "ms_per_step": round(ms8, 3), "steps": n8}
+        del pipe8, inp8
+        torch.cuda.empty_cache()
+
     # ---- (3) per-kernel durations (eager launches, CUDA events around each op on its stream) ------
     ops = spp.ops
     i = pipe.inp
@@ -410,6 +436,7 @@ def main():
             "crops_per_s": round(world * P * args.steps / (dev_ms / 1e3), 1),
             "e2e": {"value": round(e2e_fps, 1), "unit": "frames/s", "h2d_bytes_per_step": pipe.h2d_bytes,
                     "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": round(e2e_ms / e2e_steps, 3), "steps": e2e_steps},
+            "e2e_u8_frames": e2e_u8,
             "gpu_launches": pipe.launches_per_step * args.steps,
             "roofline": roofline,
             "kernels": {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in d.items()} for k, d in kernels.items()},
