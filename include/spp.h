@@ -190,6 +190,12 @@ int spp_crop_affine_u8(const uint8_t *frames, int num_frames, int frame_h, int f
                                           HF keypoints_from_heatmaps(heatmaps, center, scale) (scale = size/200*1.25) and
                                           gluoncv get_final_preds(heatmaps, center, scale) (scale in pixels) */
 
+#define SPP_DECODE_FLAG_HF_F32_INDEX 8 /* DARK: reproduce HF's float32 flat tap index (image_processing_vitpose.py:248-257:
+                                          `index += stride * arange` adds in place into a float32 array).  Exact for the first
+                                          2^24 / ((w+2)(h+2)) maps of a call (5 084 maps = 299 crops x 17 joints at 64x48);
+                                          beyond that HF reads its 7 taps 1-2 padded columns off.  Default (flag clear):
+                                          the taps at their true positions for every map.  Reference quirk Q6. */
+
 /* Replaces flip-test averaging (module.py:473-484 with the correct channel swap of
  * "module copy.py":465-472 / HF modeling_vitpose.py:80-117) + the three decode variants, in one pass
  * over the heatmaps.

@@ -9,6 +9,11 @@ Three decode variants exist around the reference:
 * argmax + quarter-offset — gluoncv ``get_max_pred``/``get_final_preds`` called at
   training/lightning/pose_estimation/module_v2.py:214-222 — gluoncv is not installed/pinned:
   PARITY UNPINNED, restated from the published Simple-Baselines/HRNet formulas.
+
+Reference quirk Q6: HF's DARK addresses its taps through a float32 flat index (HF:248-250), exact only for the
+first 2^24 / ((W+2)(H+2)) maps of a call.  ``dark_refine_full`` / ``hf_dark_decode`` restate HF literally (same numpy
+in-place float32 add, so they carry the quirk); ``dark_decode_local`` is the per-joint restatement with the taps at
+their true positions.  The two are bit-identical below the limit (tests/test_oracle_golden.py).
 """
 from __future__ import annotations
 

@@ -118,6 +118,31 @@ __device__ float warp_blurred_log_single(const MapView<FLIP> &mv, int H, int y, 
     return clip_log((float)acc);
 }
 
+// Quirk Q6 helper: log(clip(blur(.))) at flat position t of HF's flattened, edge-padded batch ([P*K, H+2, W+2]); the
+// staged map (A, B in shared memory) is used when t falls into map q, global memory otherwise.  Deliberately not inlined:
+// seven call sites, opt-in path.
+template <bool FLIP>
+__device__ __noinline__ float hf_tap_value(const DecodeParams prm, const float *A, const float *B, long long q, long long t,
+                                           float *scratch, int lane) {
+    const int H = prm.H, W = prm.W, K = prm.K;
+    const long long total = (long long)prm.P * K, stride = (long long)(W + 2) * (H + 2);
+    const size_t map_elems = (size_t)H * W;
+    if (t < 0) t += total * stride;                        // numpy negative index
+    if (t >= total * stride) t = total * stride - 1;       // (numpy would raise; cannot happen for in-range arg-maxes)
+    const long long qt = t / stride;
+    const int r = (int)(t - qt * stride);
+    const int py = r / (W + 2), px = r - py * (W + 2);
+    const int ty = clampi(py - 1, 0, H - 1), tx = clampi(px - 1, 0, W - 1);
+    MapView<FLIP> mv{A, B, W};
+    if (qt != q) {
+        const long long pt = qt / K;
+        const int kt = (int)(qt - pt * K);
+        mv.A = prm.hm + qt * map_elems;
+        if (FLIP) mv.B = prm.hmf + (pt * K + (prm.perm ? __ldg(prm.perm + kt) : kt)) * map_elems;
+    }
+    return warp_blurred_log_single(mv, H, ty, tx, prm.gw, prm.radius, scratch, lane);
+}
+
 // running "first maximum" of one lane-private chain, tracked per float4 quad
 struct Best {
     float v;
@@ -128,7 +153,7 @@ struct Best {
     }
 };
 
-template <bool FLIP, int RADIUS>
+template <bool FLIP, int RADIUS, bool HFQ>
 __global__ void __launch_bounds__(FLIP ? 256 : 512, 1) heatmap_decode_kernel(const DecodeParams prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -250,7 +275,23 @@ __global__ void __launch_bounds__(FLIP ? 256 : 512, 1) heatmap_decode_kernel(con
         float c00 = 0.f, cbr = 0.f, cbl = 0.f;          // DARK, score <= 0 path
         float se = 0.f, sxe = 0.f, sye = 0.f;           // soft-argmax sums
         float qdx = 0.f, qdy = 0.f;                     // quarter-offset differences
-        if (prm.mode == SPP_DECODE_DARK) {
+        float hfL[7];                                    // quirk Q6 taps: L11, L12, L21, L22, L00, L10, L01
+        const bool hf_index = HFQ && prm.mode == SPP_DECODE_DARK;      // HFQ: separate instantiation, the default kernels carry none of it
+        if (hf_index) {
+            // HF post_dark_unbiased_data_processing (image_processing_vitpose.py:248-257) addresses its 7 taps in the
+            // flattened, edge-padded batch through a FLOAT32 index (`index += stride * arange(...)` adds in place into
+            // a float32 array): exact below 2^24, i.e. for the first 2^24 / ((W+2)(H+2)) maps of a call (5 084 maps =
+            // 299 crops of 17 joints), rounded to even / multiples of 4 beyond — the taps then sit 1-2 padded columns
+            // off.  Reproduced literally: same float32 index, same 7 offsets, each tap located by integer division
+            // in the padded batch (so shifted taps wrap rows / maps exactly as numpy's flat indexing does).
+            const float cxh = valid ? (float)ax : -1.0f, cyh = valid ? (float)ay : -1.0f;
+            const float c32 = __fadd_rn(__fadd_rn(cxh, 1.0f), __fmul_rn(__fadd_rn(cyh, 1.0f), (float)(W + 2)));
+            const long long stride = (long long)(W + 2) * (H + 2);
+            const long long idx = (long long)(float)((double)c32 + (double)(stride * q));
+            const int offs[7] = {0, 1, W + 2, W + 3, -(W + 3), -1, -(W + 2)};
+#pragma unroll
+            for (int t7 = 0; t7 < 7; ++t7) hfL[t7] = hf_tap_value<FLIP>(prm, A, B, q, idx + offs[t7], scratch, lane);
+        } else if (prm.mode == SPP_DECODE_DARK) {
             if (valid) {
                 // (2r+3)^2 window of the averaged map, 'reflect'-indexed like scipy's line extension
                 for (int t = lane; t < wn * wn; t += 32) {
@@ -308,7 +349,9 @@ __global__ void __launch_bounds__(FLIP ? 256 : 512, 1) heatmap_decode_kernel(con
             // HF get_keypoint_predictions: coordinates -1 where score <= 0
             const float cx = valid ? (float)ax : -1.0f, cy = valid ? (float)ay : -1.0f;
             float L00, L01, L10, L11, L12, L21, L22;
-            if (valid) {
+            if (hf_index) {
+                L11 = hfL[0]; L12 = hfL[1]; L21 = hfL[2]; L22 = hfL[3]; L00 = hfL[4]; L10 = hfL[5]; L01 = hfL[6];
+            } else if (valid) {
                 // vertical pass (scipy filters axis 0 first): T[r3][j] for the 3 tap rows x (2r+3) columns,
                 // two outputs per lane issued together; window row of map row u is u - (ay - r - 1)
                 const int t0 = lane, t1 = lane + 32;
@@ -433,14 +476,14 @@ __global__ void __launch_bounds__(FLIP ? 256 : 512, 1) heatmap_decode_kernel(con
     }
 }
 
-template <bool FLIP, int RADIUS>
+template <bool FLIP, int RADIUS, bool HFQ = false>
 int launch_decode(const DecodeParams &prm, unsigned grid, size_t smem, cudaStream_t st) {
     static size_t configured = 0;
     if (configured < smem) {
-        SPP_CHECK_CUDA(cudaFuncSetAttribute(heatmap_decode_kernel<FLIP, RADIUS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SPP_CHECK_CUDA(cudaFuncSetAttribute(heatmap_decode_kernel<FLIP, RADIUS, HFQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    heatmap_decode_kernel<FLIP, RADIUS><<<grid, prm.warps * 32, smem, st>>>(prm);
+    heatmap_decode_kernel<FLIP, RADIUS, HFQ><<<grid, prm.warps * 32, smem, st>>>(prm);
     SPP_CHECK_LAUNCH();
     return SPP_OK;
 }
@@ -519,6 +562,8 @@ extern "C" int spp_heatmap_decode(const float *hm, const float *hm_flipped, cons
     if (grid > sms) grid = sms;
 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (mode == SPP_DECODE_DARK && (flags & SPP_DECODE_FLAG_HF_F32_INDEX))      // quirk Q6: run-time radius, own instantiation
+        return flip ? launch_decode<true, 0, true>(prm, (unsigned)grid, smem, st) : launch_decode<false, 0, true>(prm, (unsigned)grid, smem, st);
     if (flip) return prm.radius == 5 ? launch_decode<true, 5>(prm, (unsigned)grid, smem, st) : launch_decode<true, 0>(prm, (unsigned)grid, smem, st);
     return prm.radius == 5 ? launch_decode<false, 5>(prm, (unsigned)grid, smem, st) : launch_decode<false, 0>(prm, (unsigned)grid, smem, st);
 }

@@ -327,6 +327,8 @@ def crop_affine(frames: torch.Tensor, boxes: torch.Tensor, frame_idx: torch.Tens
 
 FLAG_SCALE_SCORE = 1
 FLAG_BACKPROJECT = 2
+FLAG_CENTER_SCALE = 4
+FLAG_HF_F32_INDEX = 8     # DARK: reproduce HF's float32 flat tap index (reference quirk Q6, include/spp.h)
 
 
 def heatmap_decode(hm: torch.Tensor, hm_flipped: Optional[torch.Tensor] = None, perm: Optional[torch.Tensor] = None,

@@ -172,15 +172,20 @@ class VitPoseImageProcessor:
 
     def post_process_pose_estimation(self, outputs, boxes, kernel_size: int = 11, threshold: Optional[float] = None,
                                      flipped_heatmaps: Optional[torch.Tensor] = None,
-                                     flip_pairs: Optional[Sequence[Tuple[int, int]]] = COCO_FLIP_PAIRS):
+                                     flip_pairs: Optional[Sequence[Tuple[int, int]]] = COCO_FLIP_PAIRS,
+                                     hf_index_quirk: bool = False):
         """HF:465-535.  ``outputs`` has ``.heatmaps [P,K,H,W]`` (or is that tensor).  Extension: pass the raw
-        heatmaps of the mirrored crops as ``flipped_heatmaps`` and the flip test is fused into the decode."""
+        heatmaps of the mirrored crops as ``flipped_heatmaps`` and the flip test is fused into the decode.
+        ``hf_index_quirk=True`` reproduces HF's float32 flat tap index (quirk Q6): identical to HF for calls of ANY size;
+        the default agrees with HF for the first 2^24 / ((W+2)(H+2)) maps of a call (299 crops of 17 joints at 64x48) and
+        returns the intended DARK refinement where HF's index has lost its low bits."""
         hm = outputs.heatmaps if hasattr(outputs, "heatmaps") else outputs
         b, _ = _flatten_boxes(boxes, hm.device)
         perm = None
         if flipped_heatmaps is not None:
             perm = flip_perm(hm.shape[1], flip_pairs).to(hm.device)
         kp, sc, _ = ops.heatmap_decode(hm, flipped_heatmaps, perm, b, "dark", kernel_size,
+                                       flags=ops.FLAG_HF_F32_INDEX if hf_index_quirk else 0,
                                        crop_hw=(self.size["height"], self.size["width"]))
         kp, sc = kp.cpu(), sc.cpu()
         labels = torch.arange(0, hm.shape[1])

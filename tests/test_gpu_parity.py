@@ -679,3 +679,70 @@ def test_fused_single_kernel_decode_nms_is_identical(spp, synth, golden, dev, ta
     for x, y in ((a, b), (a2, b2)):
         assert torch.equal(x.count, y.count) and torch.equal(x.keys, y.keys) and torch.equal(x.dets, y.dets)
     assert b.count.abs().tolist() == g["n"].tolist()
+
+
+# ------------------------------------------------------------------------------------------------
+# the benchmark workload itself (BASELINE.json configs[1], full size) against the reference's CPU calls
+# ------------------------------------------------------------------------------------------------
+
+def test_cfg2_full_size_against_cpu_reference_calls(spp, synth, dev):
+    """cfg2 exactly as bench.py runs it (64 frames 1280x720, 640 faces / persons / crops, 10k-id gallery, 17 joints with
+    flip test), CUDA-graphed pipeline vs the CPU path bench.py times as the baseline: torch Head decode + torchvision
+    nms, F.normalize / F.linear / max, HF VitPoseImageProcessor.preprocess and post_process_pose_estimation."""
+    import bench
+    pipeline = spp.pipeline
+    b, pf = 64, 10
+    inp = pipeline.synthetic_inputs(b, 720, 1280, pf, 17, seed=0)
+    ms = synth.make_match_set(b * pf, 10000, seed=1000)
+    inp.embeddings = ms.embeddings
+    pipe = pipeline.SelectivePosePipeline(inp, ms.gallery.to(torch.bfloat16), dev)
+    pipe.step()
+    pipe.stream.synchronize()
+    ref = bench.cpu_reference_step(inp, ms.gallery, b, pf)
+    # detections: same number of rows per frame, same rows (boxes / scores within 1e-3, conf-descending order)
+    for name in ("face", "person"):
+        rows = pipe.out["_" + name].to_list()
+        checked = 0
+        for got, want in zip(rows, ref[name]):
+            if odet.near_threshold_pairs(want, 0.65):      # an IoU within rounding of the threshold may legitimately flip
+                continue
+            checked += 1
+            assert got.shape == want.shape, name
+            _close(got.cpu().numpy(), want.numpy(), atol=1e-3, what=f"{name} detections")
+        assert checked >= 0.9 * b, f"{name}: only {checked} of {b} frames free of borderline IoU pairs"
+    # identities: exact wherever the fp32 top-2 gap and the gate margin are not degenerate
+    gap = omatch.top2_gap(ms.embeddings, ms.gallery.to(torch.bfloat16).float())
+    ref_ids, ref_sims = omatch.match_top1(ms.embeddings, ms.gallery.to(torch.bfloat16).float(), threshold=0.4)
+    ok = (gap > 1e-5) & ((ref_sims - 0.4).abs() > 1e-5)
+    assert torch.equal(pipe.out["ids"].cpu()[ok].long(), ref_ids[ok].long())
+    _close(pipe.out["sims"].cpu().numpy(), ref_sims.numpy(), atol=1e-5, what="similarities")
+    # crops against HF's own scipy warp
+    diff = (pipe.out["pixel_values"].cpu() - ref["pixel_values"]).abs().max()
+    assert float(diff) < 2e-5, f"crop max abs diff {float(diff):.3e}"
+    # poses against HF's own post-processing.  HF addresses its DARK taps through a float32 flat index (quirk Q6):
+    # exact for the first 5 084 maps of a call = 299 crops here.  (a) HF called in chunks of 25 frames (250 crops) is
+    # the intended computation -> the default kernel; (b) HF called once on all 640 crops -> the quirk flag.
+    from transformers import VitPoseImageProcessor
+    from transformers.models.vitpose.modeling_vitpose import VitPoseEstimatorOutput
+    proc = VitPoseImageProcessor()
+    avg = opose.flip_average(inp.heatmaps, inp.flipped, inp.perm)
+    boxes = [[[float(v) for v in inp.boxes[f * pf + j]] for j in range(pf)] for f in range(b)]
+    chunks = []
+    for f0 in range(0, b, 25):
+        f1 = min(b, f0 + 25)
+        chunks += proc.post_process_pose_estimation(VitPoseEstimatorOutput(heatmaps=avg[f0 * pf:f1 * pf]), boxes=boxes[f0:f1], kernel_size=11)
+    kp = pipe.out["keypoints"].cpu().numpy()
+    sc = pipe.out["scores"].cpu().numpy()
+    want_kp = np.stack([p["keypoints"].numpy() for img in chunks for p in img])
+    want_sc = np.stack([p["scores"].numpy() for img in chunks for p in img])
+    valid = want_sc > 0
+    np.testing.assert_array_equal(sc, want_sc)                                   # max of the averaged map: bit-exact
+    _close(kp[valid], want_kp[valid], what="keypoints (image pixels) vs HF in calls of <= 299 crops")
+    once_kp = np.stack([p["keypoints"].numpy() for img in ref["poses"] for p in img])
+    assert float(np.abs(once_kp - want_kp)[299:].max()) > 1.0, "HF's float32 index quirk should be visible from crop 299 on"
+    np.testing.assert_array_equal(once_kp[:299], want_kp[:299])
+    qk, qs, _ = spp.heatmap_decode(pipe.inp.heatmaps, pipe.inp.flipped, pipe.inp.perm, pipe.inp.boxes, "dark", 11,
+                                   flags=spp.ops.FLAG_HF_F32_INDEX)
+    _close(qk.cpu().numpy()[valid], once_kp[valid], what="keypoints with the HF float32-index quirk vs HF in ONE call of 640 crops")
+    # (score <= 0 joints: both modes reproduce HF's flat-index reads there as well)
+    _close(qk.cpu().numpy()[~valid], once_kp[~valid], atol=1e-2, what="score <= 0 joints, quirk mode")

@@ -187,3 +187,20 @@ def test_oks_known_answers():
     inside = np.tile([[20.0, 20.0]], (k, 1))
     assert ores.compute_oks(inside, gt3, area=1000.0, gt_box_xywh=[10, 10, 20, 20]) == 1.0
     assert ores.compute_oks(inside + 500.0, gt3, area=1000.0, gt_box_xywh=[10, 10, 20, 20]) < 1e-6
+
+
+def test_hf_float32_index_quirk_q6(synth):
+    """Reference quirk Q6: HF's DARK taps are addressed through a float32 flat index (image_processing_vitpose.py:248-250),
+    exact only for the first 2^24 / ((W+2)(H+2)) = 5 084 maps of a call.  The literal restatement (hf_dark_decode, which
+    the GPU quirk mode is held to) and the per-joint restatement (dark_decode_local, the default kernel's target) agree
+    bit for bit before that map and part ways after it."""
+    hs = synth.make_heatmaps(44, 133, seed=5)                       # 5 852 maps: the last 768 are past the limit
+    boxes = synth.make_crop_set(4, 480, 640, per_frame=11, seed=5).boxes.tolist()
+    kp_hf, sc, _ = opose.hf_dark_decode(hs.heatmaps.numpy(), boxes)
+    kp_loc, sc2, _ = opose.dark_decode_local(hs.heatmaps.numpy(), boxes)
+    first = 2 ** 24 // (50 * 66)
+    d = np.abs(kp_hf - kp_loc).reshape(-1, 2).max(1)
+    v = (sc > 0).reshape(-1)
+    np.testing.assert_array_equal(sc, sc2)
+    assert d[:first][v[:first]].max() < 1e-3
+    assert (d[first:][v[first:]] > 1e-3).mean() > 0.3
