@@ -746,3 +746,18 @@ def test_cfg2_full_size_against_cpu_reference_calls(spp, synth, dev):
     _close(qk.cpu().numpy()[valid], once_kp[valid], what="keypoints with the HF float32-index quirk vs HF in ONE call of 640 crops")
     # (score <= 0 joints: both modes reproduce HF's flat-index reads there as well)
     _close(qk.cpu().numpy()[~valid], once_kp[~valid], atol=1e-2, what="score <= 0 joints, quirk mode")
+
+
+def test_crop_uint8_720p_against_hf_preprocess(spp, dev):
+    """uint8 1280x720 frames (HF's default do_rescale=True input) through the real HF VitPoseImageProcessor.preprocess:
+    every pixel of 160 crops, i.e. every uint8 rounding decision of the fast path / fp64 re-computation split."""
+    from transformers import VitPoseImageProcessor
+    pipeline = spp.pipeline
+    b, pf = 16, 10
+    inp = pipeline.synthetic_inputs(b, 720, 1280, pf, 17, seed=5)
+    fr8 = (inp.frames * 255.0).round().clamp(0, 255).to(torch.uint8)
+    boxes = [[[float(v) for v in inp.boxes[f * pf + j]] for j in range(pf)] for f in range(b)]
+    want = VitPoseImageProcessor().preprocess([fr8[f] for f in range(b)], boxes=boxes, return_tensors="pt")["pixel_values"]
+    got = spp.VitPoseImageProcessor().preprocess(fr8.to(dev), boxes)["pixel_values"].cpu()
+    diff = (got - want).abs()
+    assert float(diff.max()) < 2e-5, f"{int((diff > 2e-5).sum())} of {diff.numel()} pixels differ (one flipped rounding = 0.017)"
