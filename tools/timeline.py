@@ -20,7 +20,7 @@ ms = spp.synth.make_match_set(640, 10000, seed=1000)
 inp.embeddings = ms.embeddings
 if len(sys.argv) > 1 and sys.argv[1] == "u8":
     inp.frames = (inp.frames * 255.0).round().clamp(0, 255).to(torch.uint8)
-pipe = pipeline.SelectivePosePipeline(inp, ms.gallery.to(torch.bfloat16), dev)
+pipe = pipeline.SelectivePosePipeline(inp, ms.gallery.to(torch.bfloat16), dev, use_graph=os.environ.get("SPP_TL_NOGRAPH", "0") in ("", "0"))
 for _ in range(5):
     pipe.step()
 pipe.stream.synchronize()
