@@ -178,25 +178,52 @@ __global__ void __launch_bounds__(256) cand_decoded_kernel(const float *__restri
 // Candidate scan over the raw class planes only.  sigmoid is monotone, so anchors whose logit is below
 // logit(conf) - 0.05 are rejected without evaluating it; the exact fp32 test sigmoid(x) > conf decides
 // the rest.  Candidates are appended as sort keys; their boxes are decoded by cand_decode_kernel.
+constexpr int kScanPerThread = 8;        // anchors per thread: 8 independent loads in flight, 1/8 of the CTAs
 __global__ void __launch_bounds__(256) cand_scan_kernel(const Levels lv, int nc, float conf, float logit_lo, int cap, int cap_pad,
                                                         int *counts, unsigned long long *keys) {
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int a0 = blockIdx.x * (256 * kScanPerThread) + threadIdx.x;
     const int b = blockIdx.y;
-    const bool in = a < lv.A;
-    const LevelRef lr = find_level(lv, in ? a : 0);
-    const float *cls = lr.cls + (size_t)b * lr.bs_cls + lr.i;
     unsigned long long *k = keys + (size_t)b * cap_pad;
     for (int j = 0; j < nc; ++j) {
-        float s = 0.f;
-        bool c = false;
-        if (in) {
-            const float x = __ldg(cls + (size_t)j * lr.hw);
-            if (x > logit_lo) {
-                s = sigmoidf_ref(x);
-                c = s > conf;
+        float x[kScanPerThread];
+#pragma unroll
+        for (int u = 0; u < kScanPerThread; ++u) {
+            const int a = a0 + u * 256;
+            x[u] = -INFINITY;
+            if (a < lv.A) {
+                const LevelRef lr = find_level(lv, a);
+                x[u] = __ldg(lr.cls + (size_t)b * lr.bs_cls + (size_t)j * lr.hw + lr.i);
             }
         }
-        append_candidate(c, make_sort_key(s, (unsigned)(a * nc + j)), counts + b, k, cap);
+        // one warp-aggregated append for the 8 anchors of every lane: a single atomicAdd round trip per warp
+        float sc[kScanPerThread];
+        unsigned ball[kScanPerThread];
+        int total = 0;
+#pragma unroll
+        for (int u = 0; u < kScanPerThread; ++u) {
+            sc[u] = 0.f;
+            bool c = false;
+            if (x[u] > logit_lo) {               // -inf past the last anchor
+                sc[u] = sigmoidf_ref(x[u]);
+                c = sc[u] > conf;
+            }
+            ball[u] = __ballot_sync(FULL, c);
+            total += __popc(ball[u]);
+        }
+        if (total) {                             // warp-uniform
+            const int lane = threadIdx.x & 31;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(counts + b, total);
+            base = __shfl_sync(FULL, base, 0);
+#pragma unroll
+            for (int u = 0; u < kScanPerThread; ++u) {
+                if ((ball[u] >> lane) & 1u) {
+                    const int slot = base + __popc(ball[u] & ((1u << lane) - 1u));
+                    if (slot < cap) k[slot] = make_sort_key(sc[u], (unsigned)((a0 + u * 256) * nc + j));
+                }
+                base += __popc(ball[u]);
+            }
+        }
     }
 }
 
@@ -349,10 +376,9 @@ __device__ unsigned long long block_bitonic_reg(unsigned long long key, unsigned
 //      memory up to kSortSmemMax, in the workspace beyond;
 //   2. sorted, class-offset boxes + areas are staged in shared memory (first kBoxSmemMax; beyond that they
 //      are re-gathered on the fly), one "alive" bit per candidate;
-//   3. greedy loop, serial over KEPT boxes only: every warp clears, with one ballot per 32-candidate word
-//      it owns, the later candidates whose IoU with the current box exceeds the threshold, and proposes
-//      the first survivor it sees (shared-memory atomicMin) as the next box.  One block barrier per kept
-//      box, n/32/16 ballots per warp per kept box; stops after max_det.
+//   3. greedy suppression one 32-candidate word at a time: warp 0 resolves the word in sorted order with ballots and
+//      publishes the kept lanes, every warp applies those kept boxes to the later words it owns.  Two block barriers
+//      per word, one ballot per (kept box, later word); stops after max_det.
 //   MODE 0: candidates from cand_decoded_kernel, boxes from the decoded [B, 4+nc, A] tensor;
 //   MODE 1: candidates from cand_scan_kernel, boxes from cand_decode_kernel's table;
 //   MODE 2: FUSED — step 0 of the CTA is the candidate scan over its image's class planes and the DFL decode of
@@ -492,40 +518,65 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams prm) {
 
     const float thr = prm.iou;
     const int max_det = prm.max_det;
+    // Greedy suppression, one 32-candidate bitmask word at a time (two block barriers per word instead of one per kept box):
+    //   (a) warp 0 resolves the word itself in sorted order with warp ballots — the first alive lane is kept, its box is
+    //       broadcast, the ballot of "IoU > thr" clears the later lanes of the word — and publishes the kept lanes;
+    //   (b) every warp applies those kept boxes, in order, to the later words it owns (one ballot per kept box and word).
+    // A candidate is kept iff no earlier KEPT candidate suppresses it: identical to the serial loop of torchvision's CPU nms.
     int nk = 0;
-    for (int it = 0;; ++it) {
-        const int i = s_next[it % 3];
-        if (i == INT_MAX || nk >= max_det) break;
-        if (tid == 0) {
-            kept_idx[nk] = i;
-            s_next[(it + 2) % 3] = INT_MAX;   // last read in iteration it - 1, proposals start in it + 1
-        }
-        ++nk;
-        if ((i >> 5) + warp >= nwords) {          // nothing left for this warp
-            __syncthreads();
-            continue;
-        }
-        float4 bi;
-        float ai;
-        get_box(i, bi, ai);
-        int first = INT_MAX;
-        for (int wi = (i >> 5) + warp; wi < nwords; wi += NW) {
-            unsigned word = alive[wi];
-            const int j = wi * 32 + lane;
-            bool sup = false;
-            if (((word >> lane) & 1u) && j > i) {
-                float4 bj;
-                float aj;
-                get_box(j, bj, aj);
-                sup = iou_gt(bi, ai, bj, aj, thr);
+    unsigned *s_keptmask = reinterpret_cast<unsigned *>(&s_next[0]);
+    for (int w = 0; w < nwords && nk < max_det; ++w) {
+        if (alive[w] == 0u) continue;                    // uniform: every thread reads the same word
+        if (warp == 0) {
+            unsigned word = alive[w];
+            unsigned kept = 0u;
+            int cnt = nk;
+            const int j = w * 32 + lane;
+            float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
+            float aj = 0.f;
+            if (j < n) get_box(j, bj, aj);
+            while (word && cnt < max_det) {
+                const int l = __ffs(word) - 1;
+                kept |= 1u << l;
+                word &= ~(1u << l);
+                if (lane == 0) kept_idx[cnt] = w * 32 + l;
+                ++cnt;
+                const float4 bl = make_float4(__shfl_sync(FULL, bj.x, l), __shfl_sync(FULL, bj.y, l), __shfl_sync(FULL, bj.z, l),
+                                              __shfl_sync(FULL, bj.w, l));
+                const float al = __shfl_sync(FULL, aj, l);
+                const bool sup = ((word >> lane) & 1u) && iou_gt(bl, al, bj, aj, thr);
+                word &= ~__ballot_sync(FULL, sup);
             }
-            const unsigned sm = __ballot_sync(FULL, sup);
-            word &= ~sm;
-            if (wi == (i >> 5)) word &= ~((2u << (i & 31)) - 1u);        // i and everything before it is resolved
-            if (lane == 0 && (sm || wi == (i >> 5))) alive[wi] = word;
-            if (word && first == INT_MAX) first = wi * 32 + __ffs(word) - 1;
+            if (lane == 0) {
+                *s_keptmask = kept;
+                alive[w] = 0u;
+            }
         }
-        if (lane == 0 && first != INT_MAX) atomicMin(&s_next[(it + 1) % 3], first);
+        __syncthreads();
+        const unsigned kept = *s_keptmask;
+        nk += __popc(kept);
+        if (nk < max_det) {
+            for (int wi = w + 1 + warp; wi < nwords; wi += NW) {
+                unsigned word = alive[wi];
+                if (!word) continue;
+                const int j = wi * 32 + lane;
+                float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
+                float aj = 0.f;
+                const bool mine = (word >> lane) & 1u;
+                if (mine) get_box(j, bj, aj);
+                unsigned km = kept;
+                while (km && word) {
+                    const int l = __ffs(km) - 1;
+                    km &= km - 1;
+                    float4 bl;
+                    float al;
+                    get_box(w * 32 + l, bl, al);
+                    const bool sup = ((word >> lane) & 1u) && iou_gt(bl, al, bj, aj, thr);
+                    word &= ~__ballot_sync(FULL, sup);
+                }
+                if (lane == 0) alive[wi] = word;
+            }
+        }
         __syncthreads();
     }
     __syncthreads();
@@ -740,7 +791,7 @@ static int decode_nms_impl(const float *const *levels, const float *const *cls_l
         return launch_nms<2>(prm, batch, st);
     }
     SPP_CHECK_CUDA(cudaMemsetAsync(w.counts, 0, (size_t)batch * sizeof(int), st));
-    dim3 grid((lv.A + 255) / 256, batch);
+    dim3 grid((lv.A + 256 * kScanPerThread - 1) / (256 * kScanPerThread), batch);
     cand_scan_kernel<<<grid, 256, 0, st>>>(lv, nc, conf_thres, logit_lo, w.cap, w.cap_pad, w.counts, w.keys);
     SPP_CHECK_LAUNCH();
     {
