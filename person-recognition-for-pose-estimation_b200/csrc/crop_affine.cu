@@ -186,17 +186,25 @@ template <typename T>
 __device__ __forceinline__ void build_tables(const AxisMap &m, const CropParams &prm, AxisEntry<T> *xt, AxisEntry<T> *yt, int ry0, int ry1,
                                              int *s_v) {
     const int tid = threadIdx.x, nthreads = blockDim.x, ow = prm.ow;
+    int x_lo = INT_MAX, x_hi = -1, y_lo = INT_MAX, y_hi = -1;       // this thread's valid entries
     for (int i = tid; i < ow + (ry1 - ry0 + 1); i += nthreads) {
         if (i < ow) {
             const AxisEntry<T> e = axis_entry<T>(m.ax * (double)i + m.bx, prm.fw);
             xt[i] = e;
-            if (e.i0 >= 0) { atomicMin(&s_v[0], i); atomicMax(&s_v[1], i); }
+            if (e.i0 >= 0) { x_lo = min(x_lo, i); x_hi = max(x_hi, i); }
         } else {
             const int y = ry0 + i - ow;
             const AxisEntry<T> e = axis_entry<T>(m.ay * (double)y + m.by, prm.fh);
             yt[y] = e;
-            if (e.i0 >= 0) { atomicMin(&s_v[2], y); atomicMax(&s_v[3], y); }
+            if (e.i0 >= 0) { y_lo = min(y_lo, y); y_hi = max(y_hi, y); }
         }
+    }
+    // warp reductions, then one shared-memory atomic per warp and quantity (not two per table entry)
+    x_lo = __reduce_min_sync(FULL, x_lo); x_hi = __reduce_max_sync(FULL, x_hi);
+    y_lo = __reduce_min_sync(FULL, y_lo); y_hi = __reduce_max_sync(FULL, y_hi);
+    if ((tid & 31) == 0) {
+        if (x_hi >= 0) { atomicMin(&s_v[0], x_lo); atomicMax(&s_v[1], x_hi); }
+        if (y_hi >= 0) { atomicMin(&s_v[2], y_lo); atomicMax(&s_v[3], y_hi); }
     }
     __syncthreads();
 }
@@ -239,6 +247,7 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1)) crop_affine_kernel(cons
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
     const int p = blockIdx.x, c = blockIdx.y;
     const float4 box = __ldg(reinterpret_cast<const float4 *>(prm.boxes) + p);
+    int f = __ldg(prm.frame_idx + p);                 // both loads in flight before the fp64 map is built
     const AxisMap m = crop_axis_map(box, ow, oh, prm.variant);
     if (tid == 0) {
         s_v[0] = ow; s_v[1] = -1; s_v[2] = oh; s_v[3] = -1;
@@ -253,7 +262,6 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1)) crop_affine_kernel(cons
     build_tables<T>(m, prm, xt, yt, ry0, ry1, s_v);
     const int vx0 = s_v[0], vx1 = s_v[1], vy0 = s_v[2], vy1 = s_v[3];
 
-    int f = __ldg(prm.frame_idx + p);
     f = f < 0 ? 0 : (f >= prm.num_frames ? prm.num_frames - 1 : f);
     const T *src = static_cast<const T *>(prm.frames) + ((size_t)f * 3 + c) * prm.fh * prm.fw;
     float *dst = prm.out + ((size_t)p * 3 + c) * oh * ow;
