@@ -761,3 +761,29 @@ def test_crop_uint8_720p_against_hf_preprocess(spp, dev):
     got = spp.VitPoseImageProcessor().preprocess(fr8.to(dev), boxes)["pixel_values"].cpu()
     diff = (got - want).abs()
     assert float(diff.max()) < 2e-5, f"{int((diff > 2e-5).sum())} of {diff.numel()} pixels differ (one flipped rounding = 0.017)"
+
+
+def test_crop_extreme_boxes_vs_oracle(spp, dev):
+    """Boxes far from the synthetic distribution: down-scales of 3-7x (one source band per output row, source windows as wide
+    as the frame), 20x up-scales (many output rows per source row), boxes mostly or entirely outside the frame."""
+    g = torch.Generator().manual_seed(21)
+    frames = torch.rand(2, 3, 720, 1280, generator=g)
+    boxes = [[0.0, 0.0, 1280.0, 720.0], [100.0, 10.0, 1100.0, 700.0], [-300.0, -200.0, 1900.0, 1100.0], [10.0, 300.0, 1260.0, 60.0],
+             [640.0, 360.0, 8.0, 8.0], [5.5, 7.25, 3.0, 14.0], [1270.0, 710.0, 40.0, 60.0], [-500.0, -500.0, 100.0, 100.0],
+             [1279.0, 0.0, 2.0, 719.0], [300.0, -50.0, 20.0, 900.0]]
+    fidx = [0, 1, 0, 1, 0, 1, 0, 1, 0, 1]
+    ref = ocrop.crop_affine_hf(frames.numpy(), boxes, fidx)
+    out = spp.crop_affine(frames.to(dev), torch.tensor(boxes, device=dev), torch.tensor(fidx, dtype=torch.int32, device=dev))
+    diff = np.abs(out.cpu().numpy() - ref)
+    assert float(diff.max()) < 2e-5, f"max abs diff {float(diff.max()):.3e} at crop {int(np.argmax(diff.reshape(len(boxes), -1).max(1)))}"
+    fr8 = (frames * 255.0).round().clamp(0, 255).to(torch.uint8)
+    m, s = ocrop.fused_mean_std(rescale_factor=1 / 255)
+    ref8 = ocrop.crop_affine_hf(fr8.numpy(), boxes, fidx, rescale_factor=1 / 255)
+    out8 = spp.crop_affine(fr8.to(dev), torch.tensor(boxes, device=dev), torch.tensor(fidx, dtype=torch.int32, device=dev),
+                           mean=m.tolist(), std=s.tolist())
+    diff8 = np.abs(out8.cpu().numpy() - ref8)
+    assert float(diff8.max()) < 2e-5, f"uint8: {(diff8 > 2e-5).sum()} pixels differ"
+    # gluoncv-style variant on the same boxes
+    refb = ocrop.crop_affine_v2(frames.numpy(), boxes, fidx)
+    outb = spp.crop_affine(frames.to(dev), torch.tensor(boxes, device=dev), torch.tensor(fidx, dtype=torch.int32, device=dev), variant="gluoncv")
+    assert float(np.abs(outb.cpu().numpy() - refb).max()) < 2e-5
