@@ -361,9 +361,17 @@ __global__ void __launch_bounds__(256) match_finalize_kernel(const float *__rest
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= m) return;
-    float q[kDim / 32];
+    // lane owns 16 contiguous dimensions: the probe is 4 x 128-bit loads, a gallery row 2 x 128-bit loads per lane
+    constexpr int kPer = kDim / 32;                  // 16
+    float q[kPer];
+    {
+        const float4 *qp = reinterpret_cast<const float4 *>(qn + (size_t)row * kDim + lane * kPer);
 #pragma unroll
-    for (int i = 0; i < kDim / 32; ++i) q[i] = qn[(size_t)row * kDim + i * 32 + lane];
+        for (int i = 0; i < kPer / 4; ++i) {
+            const float4 v = __ldg(qp + i);
+            q[4 * i] = v.x; q[4 * i + 1] = v.y; q[4 * i + 2] = v.z; q[4 * i + 3] = v.w;
+        }
+    }
     const Cand *c = part + (size_t)row * ncand;
     float vmax = -INFINITY;
     for (int k = lane; k < ncand; k += 32) {
@@ -373,6 +381,16 @@ __global__ void __launch_bounds__(256) match_finalize_kernel(const float *__rest
     vmax = warp_max(vmax);
     float best = -INFINITY;
     int bidx = 0x7fffffff;
+    auto dot16 = [&](const uint4 &lo, const uint4 &hi) {
+        const unsigned w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {                // bf16 -> fp32 is a 16-bit shift
+            s = fmaf(q[2 * i], __uint_as_float(w[i] << 16), s);
+            s = fmaf(q[2 * i + 1], __uint_as_float(w[i] & 0xffff0000u), s);
+        }
+        return s;
+    };
     for (int k0 = 0; k0 < ncand; k0 += 32) {
         const int k = k0 + lane;
         Cand x{-INFINITY, -1};
@@ -380,15 +398,27 @@ __global__ void __launch_bounds__(256) match_finalize_kernel(const float *__rest
         const bool need = x.i >= 0 && x.i < n && x.v >= vmax - kPrune;
         unsigned todo = __ballot_sync(FULL, need);
         while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int g = __shfl_sync(FULL, x.i, src);
-            const __nv_bfloat16 *gr = gal + (size_t)g * kDim;
-            float s = 0.f;
+            // up to four candidates per round: their rows are all requested before the first dot product
+            int g[4];
+            uint4 lo[4], hi[4];
 #pragma unroll
-            for (int i = 0; i < kDim / 32; ++i) s = fmaf(q[i], __bfloat162float(gr[i * 32 + lane]), s);
-            s = warp_sum(s);
-            if (s > best || (s == best && g < bidx)) { best = s; bidx = g; }
+            for (int u = 0; u < 4; ++u) {
+                g[u] = -1;
+                if (todo) {
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    g[u] = __shfl_sync(FULL, x.i, src);
+                    const uint4 *gr = reinterpret_cast<const uint4 *>(gal + (size_t)g[u] * kDim + lane * kPer);
+                    lo[u] = __ldg(gr);
+                    hi[u] = __ldg(gr + 1);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (g[u] < 0) continue;              // warp-uniform
+                const float s = warp_sum(dot16(lo[u], hi[u]));
+                if (s > best || (s == best && g[u] < bidx)) { best = s; bidx = g[u]; }
+            }
         }
     }
     if (lane == 0) {
