@@ -301,7 +301,7 @@ def main():
     # ---- (2b) the same end-to-end pass with uint8 frames (what a video decoder delivers, and what HF's default
     #      do_rescale=True path expects): 4x fewer frame bytes over PCIe.  Reported beside the fp32 headline. -----
     e2e_u8 = None
-    if world == 1 and args.frames == "f32" and not args.select_on_device:
+    if world == 1 and args.frames == "f32" and not args.select_on_device and args.workload == "cfg2":
         import copy
         inp8 = copy.copy(inp)
         inp8.frames = (inp.frames * 255.0).round().clamp(0, 255).to(torch.uint8)
