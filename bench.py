@@ -373,7 +373,7 @@ def main():
     kern_us = {k: 1e3 * statistics.median(v) for k, v in samples.items()}
 
     hm_bytes = P * (K * 64 * 48 * 4 * (2 if i.flipped is not None else 1) + K * 16)
-    n_cand = float(pipe.out["_face"].count.abs().sum())   # kept rows; candidates are a small multiple
+    n_cand = float(pipe.out["_face"].kept().sum())   # kept rows; candidates are a small multiple
     det_full_bytes = B * ((64 + nc) * A * 4 + 300 * 6 * 4 + 4)
     crop_bytes = P * 3 * 256 * 192 * 4 + roi_bytes(inp.boxes, wl["height"], wl["width"]) * (0.25 if args.frames == "u8" else 1.0)
     match_flops = 2.0 * M * wl["gallery"] * 512

@@ -52,7 +52,7 @@ int spp_head_decode(const float *const *levels, const int *level_h, const int *l
 /* Workspace for the two NMS entry points below (bytes).  max_candidates bounds the per-image
  * candidate list: min(num_anchors * nc, max_candidates) candidates are kept per image (pass <= 0 for
  * "all of them").  Results are exact whenever the number of candidates of every image fits; beyond
- * that the surplus (arbitrary) candidates are dropped and out_count[b] is returned negated.  With
+ * that the surplus (arbitrary) candidates are dropped and out_count[b] is returned as ~kept = -(kept + 1).  With
  * nc == 1 and max_candidates <= 0 this cannot happen. */
 size_t spp_nms_workspace_bytes(int batch, int num_anchors, int nc, int max_candidates);
 
@@ -128,9 +128,73 @@ int spp_match_top1(const float *emb, const uint16_t *gallery, int m, int n, int 
                    int id_offset, int *out_id, float *out_sim, unsigned long long *out_key, void *workspace,
                    size_t workspace_bytes, spp_stream_t stream);
 
+/* spp_match_top1 with the two enrolment-time facts the exactness guarantee depends on:
+ *   gallery_f32   DEVICE [n, dim] fp32 rows the bf16 gallery was rounded from, or NULL.  When given, the surviving
+ *                 candidates are re-scored against THESE rows: ids and similarities are those of the reference's fp32
+ *                 F.linear(F.normalize(emb), gallery).max(1) (face_recognition/module.py:136-145), the bf16 copy only
+ *                 steers the candidate search.  NULL: re-score against the bf16 rows (ids / sims exact for that gallery).
+ *   max_row_norm  largest L2 norm of a gallery row (1 for a normalised gallery; > 1 e.g. for quirk Q3 enrolment).  It
+ *                 scales the band of candidate-search scores that are re-scored: |bf16 score - fp32 score| <= 2^-8 * norm.
+ * The returned id is the exact fp32 arg-max (lowest id on ties) for ANY gallery content: the GEMM epilogue keeps the best
+ * two scores per (probe, gallery chunk) plus the best score it dropped, and a chunk whose dropped scores reach the
+ * re-score band (near-duplicate enrolments, the crowded top of a 1M-id gallery) is re-scanned in exact fp32. */
+int spp_match_top1_ex(const float *emb, const uint16_t *gallery, const float *gallery_f32, float max_row_norm, int m, int n,
+                      int dim, float threshold, int id_offset, int *out_id, float *out_sim, unsigned long long *out_key,
+                      void *workspace, size_t workspace_bytes, spp_stream_t stream);
+
 /* Unpack all-reduced keys: id = -1 where sim < threshold (NaN: no gate). */
 int spp_match_unpack_keys(const unsigned long long *keys, int m, float threshold, int *out_id, float *out_sim,
                           spp_stream_t stream);
+
+/* ------------------------------------------------------------------ gallery sharded over GPUs - */
+
+/* North-star config 3: the gallery is sharded by rows over the GPUs of one box, one process per GPU.  The
+ * exchange steps that NCCL would do (all-gather of the probes, top-1 (value, index) all-reduce) are done by the match
+ * kernels themselves over NVLink peer memory: every rank owns one exchange buffer, mapped by all ranks through CUDA IPC.
+ * The reference has no multi-GPU inference path (its only collectives are training-time DDP, training/yolopt/main.py:57-60).
+ *
+ *   spp_peer_alloc   cudaMalloc + zero an exchange buffer on the current device, return its IPC handle (64 bytes, HOST)
+ *   spp_peer_open    map another process's buffer from its handle (peer access enabled lazily);  spp_peer_close unmaps
+ *   spp_peer_free    release a buffer obtained from spp_peer_alloc
+ * The host exchanges the 64-byte handles with any transport it has (torch.distributed all_gather_object in dist.py). */
+#define SPP_MAX_PEERS 16
+#define SPP_IPC_HANDLE_BYTES 64
+typedef struct spp_peer_group {
+    int world, rank;
+    int m_local;                   /* probes per rank and step — the same on every rank */
+    void *buffers[SPP_MAX_PEERS];  /* DEVICE pointers valid in THIS process; buffers[rank] is this rank's own buffer */
+} spp_peer_group;
+
+size_t spp_peer_buffer_bytes(int world, int m_local, int dim);
+int spp_peer_alloc(size_t bytes, void **dev_ptr, unsigned char *handle_out);
+int spp_peer_open(const unsigned char *handle, void **dev_ptr);
+int spp_peer_close(void *dev_ptr);
+int spp_peer_free(void *dev_ptr);
+/* 1 if the current device can map peer memory of device `other` (cudaDeviceCanAccessPeer), 0 if not, <0 on error. */
+int spp_peer_can_access(int other_device);
+
+#define SPP_SHARDED_STAGE_PUSH 1      /* F.normalize this rank's probes, store fp32 + bf16 into every rank's buffer */
+#define SPP_SHARDED_STAGE_WAIT 2      /* wait until every rank's probes of this step have landed here */
+#define SPP_SHARDED_STAGE_SEARCH 4    /* tcgen05 GEMM + top-2 of ALL world * m_local probes against the local shard */
+#define SPP_SHARDED_STAGE_FINALIZE 8  /* fp32 re-score; every probe's packed (sim, id) key is stored into its owner's buffer */
+#define SPP_SHARDED_STAGE_REDUCE 16   /* wait for all ranks' keys of MY probes, integer max, unpack + gate; advances the step */
+#define SPP_SHARDED_STAGE_ALL 31
+
+size_t spp_sharded_match_workspace_bytes(int world, int m_local, int n_shard, int dim);
+
+/* One step of the sharded match = the five kernels above, enqueued on `stream` (graph-capturable; no host
+ * synchronisation, no NCCL).  EVERY rank of the group must enqueue the same number of steps; a rank that waits more than
+ * 60 s for a peer traps (CUDA error) instead of hanging.  `stages` = SPP_SHARDED_STAGE_ALL; a subset runs only those
+ * kernels (per-stage timing in bench.py — over one step all five must still run, in order, on every rank).
+ *   emb        DEVICE [m_local, dim] fp32 raw embeddings of THIS rank's probes
+ *   shard      DEVICE [n_shard, dim] bf16 rows [id_offset, id_offset + n_shard) of the gallery; shard_f32 / max_row_norm
+ *              as in spp_match_top1_ex
+ *   out_id / out_sim / out_key   DEVICE [m_local]: global top-1 of this rank's probes over ALL shards (out_key may be NULL)
+ */
+int spp_sharded_match_top1(const spp_peer_group *group, const float *emb, const uint16_t *shard, const float *shard_f32,
+                           float max_row_norm, int n_shard, int dim, int id_offset, float threshold, int stages, int *out_id,
+                           float *out_sim, unsigned long long *out_key, void *workspace, size_t workspace_bytes,
+                           spp_stream_t stream);
 
 /* ------------------------------------------------------------------ face -> person association */
 

@@ -9,11 +9,20 @@ from __future__ import annotations
 import ctypes
 import os
 import subprocess
-from ctypes import POINTER, c_char_p, c_float, c_int, c_size_t, c_uint16, c_ulonglong, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_size_t, c_ubyte, c_uint16, c_ulonglong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libspp.so")
 CSRC = os.path.join(_HERE, "csrc")
+
+MAX_PEERS = 16            # SPP_MAX_PEERS
+IPC_HANDLE_BYTES = 64     # SPP_IPC_HANDLE_BYTES
+
+
+class PeerGroupStruct(Structure):
+    """``spp_peer_group`` of include/spp.h."""
+    _fields_ = [("world", c_int), ("rank", c_int), ("m_local", c_int), ("buffers", c_void_p * MAX_PEERS)]
+
 
 # name -> (restype, argtypes); mirrors include/spp.h and include/spp_internal.h
 _P = c_void_p
@@ -36,7 +45,17 @@ SIGNATURES = {
     "spp_f32_to_bf16": (c_int, [_P, c_size_t, _P, _P]),
     "spp_match_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "spp_match_top1": (c_int, [_P, _P, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "spp_match_top1_ex": (c_int, [_P, _P, _P, c_float, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
     "spp_match_unpack_keys": (c_int, [_P, c_int, c_float, _P, _P, _P]),
+    "spp_peer_buffer_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "spp_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p), POINTER(c_ubyte)]),
+    "spp_peer_open": (c_int, [POINTER(c_ubyte), POINTER(c_void_p)]),
+    "spp_peer_close": (c_int, [_P]),
+    "spp_peer_free": (c_int, [_P]),
+    "spp_peer_can_access": (c_int, [c_int]),
+    "spp_sharded_match_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "spp_sharded_match_top1": (c_int, [POINTER(PeerGroupStruct), _P, _P, _P, c_float, c_int, c_int, c_int, c_float, c_int, _P, _P, _P,
+                                       _P, c_size_t, _P]),
     "spp_associate": (c_int, [_P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "spp_crop_affine": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float),
                                 c_int, _P, _P]),

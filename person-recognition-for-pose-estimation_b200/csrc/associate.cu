@@ -27,8 +27,8 @@ __global__ void __launch_bounds__(kAssocThreads) associate_kernel(const float *_
     __shared__ int s_n;
     const int b = blockIdx.x, tid = threadIdx.x;
     int nf = face_count[b], np = person_count[b];
-    nf = nf < 0 ? -nf : nf;                 // a negative count flags a candidate overflow upstream; rows are still valid
-    np = np < 0 ? -np : np;
+    nf = nf < 0 ? ~nf : nf;                 // a negative count (~kept) flags a candidate overflow upstream; rows are still valid
+    np = np < 0 ? ~np : np;
     nf = nf < face_cap ? nf : face_cap;
     np = np < person_cap ? np : person_cap;
     const float *fd = face_dets + (size_t)b * face_cap * 6;

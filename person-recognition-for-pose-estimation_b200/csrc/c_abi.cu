@@ -33,6 +33,52 @@ int sm_count() {
 
 }  // namespace spp
 
-extern "C" int spp_abi_version(void) { return 1; }
+extern "C" int spp_abi_version(void) { return 2; }
 extern "C" const char *spp_last_error(void) { return spp::g_error; }
 extern "C" int spp_device_sm_count(void) { return spp::sm_count(); }
+
+// ---- exchange buffers shared between the per-GPU processes of one box (CUDA IPC) ----------------
+extern "C" int spp_peer_alloc(size_t bytes, void **dev_ptr, unsigned char *handle_out) {
+    SPP_CHECK_ARG(dev_ptr && handle_out && bytes > 0, "peer_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == SPP_IPC_HANDLE_BYTES, "IPC handle size");
+    void *p = nullptr;
+    SPP_CHECK_CUDA(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        spp::set_error("peer_alloc: %s", cudaGetErrorString(e));
+        return SPP_ERR_CUDA;
+    }
+    memcpy(handle_out, &h, sizeof(h));
+    *dev_ptr = p;
+    return SPP_OK;
+}
+
+extern "C" int spp_peer_open(const unsigned char *handle, void **dev_ptr) {
+    SPP_CHECK_ARG(handle && dev_ptr, "peer_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    SPP_CHECK_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return SPP_OK;
+}
+
+extern "C" int spp_peer_close(void *dev_ptr) {
+    if (dev_ptr) SPP_CHECK_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return SPP_OK;
+}
+
+extern "C" int spp_peer_free(void *dev_ptr) {
+    if (dev_ptr) SPP_CHECK_CUDA(cudaFree(dev_ptr));
+    return SPP_OK;
+}
+
+extern "C" int spp_peer_can_access(int other_device) {
+    int dev = 0, ok = 0;
+    SPP_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev == other_device) return 1;
+    SPP_CHECK_CUDA(cudaDeviceCanAccessPeer(&ok, dev, other_device));
+    return ok;
+}

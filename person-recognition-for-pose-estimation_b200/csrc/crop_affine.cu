@@ -209,6 +209,36 @@ __device__ __forceinline__ void build_tables(const AxisMap &m, const CropParams 
     __syncthreads();
 }
 
+// Direct global gathers for output rows [ry0, ry1] of one (crop, channel): no monotonicity assumption on the source
+// map.  Used by the staging-free fallback kernel and, inside the staged kernel, for mirrored crops (a box with negative
+// width AND height gives a negative scale on both axes; HF / scipy then produce the mirrored crop).
+template <typename T>
+__device__ __forceinline__ void direct_gather_rows(const CropParams &prm, const T *src, float *dst, const AxisEntry<T> *xt,
+                                                   const AxisEntry<T> *yt, int ry0, int ry1, float inv_sd, float nmean) {
+    constexpr bool kU8 = std::is_same<T, unsigned char>::value;
+    const int ow = prm.ow;
+    for (int x = threadIdx.x; x < ow; x += blockDim.x) {
+        const AxisEntry<T> ex = xt[x];
+        float *o = dst + (size_t)ry0 * ow + x;
+        for (int y = ry0; y <= ry1; ++y, o += ow) {
+            const AxisEntry<T> ey = yt[y];
+            float v = nmean;
+            if (ex.i0 >= 0 && ey.i0 >= 0) {
+                const T *ra = src + (size_t)ey.i0 * prm.fw + ex.i0;
+                const T *rb = ra + prm.fw;
+                const T p00 = __ldg(ra), p01 = __ldg(ra + 1), p10 = __ldg(rb), p11 = __ldg(rb + 1);
+                if constexpr (kU8) {
+                    v = exact_px_u8(p00, p01, p10, p11, ex.td, ey.td, inv_sd, nmean);
+                } else {
+                    const float top = fmaf(p01 - p00, ex.t, p00), bot = fmaf(p11 - p10, ex.t, p10);
+                    v = finish_px(top, bot, ey.t, inv_sd, nmean);
+                }
+            }
+            __stcs(o, v);
+        }
+    }
+}
+
 // One CTA per (crop, channel, slab of output rows).
 //   * coordinate tables (fp64 -> index + weight) for the out_w columns and the slab's rows in smem;
 //   * the valid output rows are processed in bands; for each band the needed source rows, restricted to
@@ -271,6 +301,10 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1)) crop_affine_kernel(cons
     const float zero_out = nmean;
 
     const bool any = vx1 >= vx0 && vy1 >= vy0;
+    if (any && (m.ax < 0.0 || m.ay < 0.0)) {         // mirrored crop: the band staging below assumes a non-decreasing map
+        direct_gather_rows<T>(prm, src, dst, xt, yt, ry0, ry1, inv_sd, nmean);
+        return;
+    }
     // rows with no valid source: constant
     for (int y = ry0 + warp; y <= ry1; y += nthreads / 32) {
         if (any && y >= vy0 && y <= vy1) continue;
@@ -392,13 +426,12 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1)) crop_affine_kernel(cons
 template <typename T>
 __global__ void __launch_bounds__(256) crop_affine_direct_kernel(const CropParams prm) {
     using Entry = AxisEntry<T>;
-    constexpr bool kU8 = std::is_same<T, unsigned char>::value;
     extern __shared__ __align__(128) unsigned char crop_smem[];
     const int ow = prm.ow, oh = prm.oh;
     Entry *xt = reinterpret_cast<Entry *>(crop_smem);
     Entry *yt = xt + ow;
     __shared__ int s_v[4];
-    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int tid = threadIdx.x;
     const int p = blockIdx.x, c = blockIdx.y;
     const float4 box = __ldg(reinterpret_cast<const float4 *>(prm.boxes) + p);
     const AxisMap m = crop_axis_map(box, ow, oh, prm.variant);
@@ -412,26 +445,7 @@ __global__ void __launch_bounds__(256) crop_affine_direct_kernel(const CropParam
     const float mean = c == 0 ? prm.mean[0] : (c == 1 ? prm.mean[1] : prm.mean[2]);
     const float inv_sd = 1.0f / (c == 0 ? prm.stdv[0] : (c == 1 ? prm.stdv[1] : prm.stdv[2]));
     const float nmean = -mean * inv_sd;
-    for (int x = tid; x < ow; x += nthreads) {
-        const Entry ex = xt[x];
-        float *o = dst + x;
-        for (int y = 0; y < oh; ++y, o += ow) {
-            const Entry ey = yt[y];
-            float v = nmean;
-            if (ex.i0 >= 0 && ey.i0 >= 0) {
-                const T *ra = src + (size_t)ey.i0 * prm.fw + ex.i0;
-                const T *rb = ra + prm.fw;
-                const T p00 = __ldg(ra), p01 = __ldg(ra + 1), p10 = __ldg(rb), p11 = __ldg(rb + 1);
-                if constexpr (kU8) {
-                    v = exact_px_u8(p00, p01, p10, p11, ex.td, ey.td, inv_sd, nmean);
-                } else {
-                    const float top = fmaf(p01 - p00, ex.t, p00), bot = fmaf(p11 - p10, ex.t, p10);
-                    v = finish_px(top, bot, ey.t, inv_sd, nmean);
-                }
-            }
-            __stcs(o, v);
-        }
-    }
+    direct_gather_rows<T>(prm, src, dst, xt, yt, 0, oh - 1, inv_sd, nmean);
 }
 
 }  // namespace
@@ -448,11 +462,8 @@ int env_int(const char *name, int dflt, int lo, int hi) {
 
 template <typename T, int C>
 int launch_staged(const CropParams &prm, dim3 grid, size_t smem, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        SPP_CHECK_CUDA(cudaFuncSetAttribute(crop_affine_kernel<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
-    }
+    // per device and per context: set on every launch (about a microsecond; legal during stream capture)
+    SPP_CHECK_CUDA(cudaFuncSetAttribute(crop_affine_kernel<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     crop_affine_kernel<T, C><<<grid, 32 * (prm.ncc * prm.rg + 1), smem, st>>>(prm);
     SPP_CHECK_LAUNCH();
     return SPP_OK;
@@ -488,13 +499,9 @@ int launch_crop(const void *frames, int num_frames, int frame_h, int frame_w, co
     const bool staged = ((size_t)frame_w * sizeof(T) % 16 == 0) && ((reinterpret_cast<uintptr_t>(frames) & 15) == 0) &&
                         ((size_t)prm.stage_bytes / ((size_t)frame_w * sizeof(T)) >= 2) && prm.ncc <= kCropWarps;
     if (!staged) {
-        static bool configured = false;
         const size_t smem = (size_t)(out_w + out_h) * sizeof(AxisEntry<T>);
         SPP_CHECK_ARG(smem <= 160 * 1024, "crop_affine: output size too large");
-        if (!configured) {
-            SPP_CHECK_CUDA(cudaFuncSetAttribute(crop_affine_direct_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            configured = true;
-        }
+        SPP_CHECK_CUDA(cudaFuncSetAttribute(crop_affine_direct_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         int threads = (out_w + 31) / 32 * 32;
         if (threads > 256) threads = 256;
         crop_affine_direct_kernel<T><<<dim3(p, 3), threads, smem, st>>>(prm);

@@ -638,7 +638,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams prm) {
             if (okeys) okeys[r] = -1;
         }
     }
-    if (tid == 0) prm.out_count[b] = raw_count > prm.cap ? -nk : nk;
+    if (tid == 0) prm.out_count[b] = raw_count > prm.cap ? ~nk : nk;        // overflow: -(nk + 1), distinguishable at nk == 0
 }
 
 // cls_levels == nullptr: levels[l] is the concatenated [B, 64+nc, H, W] map; else levels[l] = [B, 64, H, W] box
@@ -703,11 +703,8 @@ Workspace carve(void *ws, int batch, int num_anchors, int nc, int max_candidates
 template <int MODE>
 int launch_nms(const NmsParams &prm, int batch, cudaStream_t st) {
     const size_t smem = (size_t)kSortSmemMax * 8 + (size_t)kBoxSmemMax * 20 + (size_t)kAliveWords * 4 + (size_t)prm.max_det * 4;
-    static bool configured = false;
-    if (!configured) {
-        SPP_CHECK_CUDA(cudaFuncSetAttribute(nms_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        configured = true;
-    }
+    // per device and per context: set on every launch (about a microsecond; legal during stream capture)
+    SPP_CHECK_CUDA(cudaFuncSetAttribute(nms_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     SPP_CHECK_ARG(smem <= 160 * 1024, "nms: max_det %d too large", prm.max_det);
     nms_kernel<MODE><<<batch, kNmsThreads, smem, st>>>(prm);
     SPP_CHECK_LAUNCH();

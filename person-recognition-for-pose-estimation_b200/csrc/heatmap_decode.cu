@@ -478,11 +478,8 @@ __global__ void __launch_bounds__(FLIP ? 256 : 512, 1) heatmap_decode_kernel(con
 
 template <bool FLIP, int RADIUS, bool HFQ = false>
 int launch_decode(const DecodeParams &prm, unsigned grid, size_t smem, cudaStream_t st) {
-    static size_t configured = 0;
-    if (configured < smem) {
-        SPP_CHECK_CUDA(cudaFuncSetAttribute(heatmap_decode_kernel<FLIP, RADIUS, HFQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    // per device and per context: set on every launch (about a microsecond; legal during stream capture)
+    SPP_CHECK_CUDA(cudaFuncSetAttribute(heatmap_decode_kernel<FLIP, RADIUS, HFQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     heatmap_decode_kernel<FLIP, RADIUS, HFQ><<<grid, prm.warps * 32, smem, st>>>(prm);
     SPP_CHECK_LAUNCH();
     return SPP_OK;

@@ -19,6 +19,7 @@
 // every row are re-scored with an exact fp32 dot product in match_finalize_kernel, which also applies
 // the gate and packs the (value, index) key for the multi-GPU top-1 reduction.
 #include "spp_common.cuh"
+#include "peer_exchange.cuh"
 
 #include <cstdlib>
 
@@ -146,11 +147,14 @@ struct GemmParams {
     int m, n;
     int tiles_n, nsplit;   // every M-tile is cut into nsplit chunks of gallery tiles; work item = (M-tile, chunk)
     int items;             // m_tiles * nsplit, distributed round-robin over the persistent CTAs
+    const unsigned *step;  // peer exchange: device step counter, parity selects the probe buffer (tmap_a0 / tmap_a1); NULL: tmap_a0
     Cand *part;            // [m_tiles*BM, nsplit, 2]
+    float *third;          // [m_tiles*BM, nsplit] best bf16 score the top-2 of a (row, chunk) did NOT keep
 };
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
-match_gemm_top2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams prm) {
+match_gemm_top2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
+                       const __grid_constant__ CUtensorMap tmap_b, const GemmParams prm) {
     extern __shared__ unsigned char gemm_smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *smem_a = smem;                                         // [8][128 x 64] bf16, SW128
@@ -186,8 +190,9 @@ match_gemm_top2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    const CUtensorMap *tmap_a = (prm.step && (__ldcg(prm.step) & 1u)) ? &tmap_a1 : &tmap_a0;
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(tmap_a);
         tma_prefetch_desc(&tmap_b);
     }
     tc_fence_before();
@@ -206,7 +211,7 @@ match_gemm_top2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 chunk_range(sp, nt0, ntiles);
                 mbar_wait(a_empty, (it & 1) ^ 1);            // previous item's MMAs are done with the probe tile
                 mbar_arrive_expect_tx(a_full, kKBlocks * kABytes);
-                for (int kb = 0; kb < kKBlocks; ++kb) tma_load_2d(smem_a + (size_t)kb * kABytes, &tmap_a, a_full, kb * BK, mt * BM);
+                for (int kb = 0; kb < kKBlocks; ++kb) tma_load_2d(smem_a + (size_t)kb * kABytes, tmap_a, a_full, kb * BK, mt * BM);
                 for (int t = 0; t < ntiles; ++t) {
                     const int n0 = (nt0 + t) * BN;
                     for (int kb = 0; kb < kKBlocks; ++kb) {
@@ -263,7 +268,7 @@ match_gemm_top2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             const int mt = item / prm.nsplit, sp = item - mt * prm.nsplit;
             int nt0, ntiles;
             chunk_range(sp, nt0, ntiles);
-            float v1 = -INFINITY, v2 = -INFINITY;
+            float v1 = -INFINITY, v2 = -INFINITY, v3 = -INFINITY;     // v3: largest score dropped from the top-2
             int i1 = 0x7fffffff, i2 = 0x7fffffff;
             for (int t = 0; t < ntiles; ++t, ++tcount) {
                 const int acc = tcount & 1;
@@ -286,11 +291,14 @@ match_gemm_top2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                             const float x = v[j];
                             const int n = nb + j;
                             if (n < prm.n) {
-                                if (x > v1) { v2 = v1; i2 = i1; v1 = x; i1 = n; }
-                                else if (x > v2) { v2 = x; i2 = n; }
+                                if (x > v1) { v3 = fmaxf(v3, v2); v2 = v1; i2 = i1; v1 = x; i1 = n; }
+                                else if (x > v2) { v3 = fmaxf(v3, v2); v2 = x; i2 = n; }
+                                else v3 = fmaxf(v3, x);
                             }
                         }
-                    }
+                    } else {
+                        v3 = fmaxf(v3, mx);                 // the whole block is dropped (may include zero-filled rows
+                    }                                       // past the gallery's end: conservative)
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -299,6 +307,7 @@ match_gemm_top2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             Cand *o = prm.part + ((size_t)(mt * BM + row_in_tile) * prm.nsplit + sp) * 2;
             o[0] = Cand{v1, i1};
             o[1] = Cand{v2, i2};
+            prm.third[(size_t)(mt * BM + row_in_tile) * prm.nsplit + sp] = v3;
         }
     }
 
@@ -310,139 +319,394 @@ match_gemm_top2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     }
 }
 
+// chunk sp of an M-tile covers gallery tiles [nt0, nt0 + ntiles) (same split as the GEMM's work items)
+__host__ __device__ __forceinline__ void chunk_tiles(int tiles_n, int nsplit, int sp, int &nt0, int &ntiles) {
+    const int per = tiles_n / nsplit, rem = tiles_n - per * nsplit;
+    nt0 = sp * per + (sp < rem ? sp : rem);
+    ntiles = per + (sp < rem ? 1 : 0);
+}
+
 // CUDA-core fp32 version of the same candidate search — device-side cross-check for the tests
 // (spp_match_top1 never dispatches to it).
 __global__ void __launch_bounds__(128) match_simt_top2_kernel(const float *__restrict__ qn, const __nv_bfloat16 *__restrict__ gal,
-                                                              int m, int n, int nsplit, Cand *part) {
+                                                              int m, int n, int tiles_n, int nsplit, Cand *part, float *third) {
     __shared__ float q[kDim];
     const int row = blockIdx.x, sp = blockIdx.y;
     for (int i = threadIdx.x; i < kDim; i += blockDim.x) q[i] = qn[(size_t)row * kDim + i];
     __syncthreads();
-    const int per = (n + nsplit - 1) / nsplit;
-    const int lo = sp * per, hi = min(n, lo + per);
+    int nt0, ntiles;
+    chunk_tiles(tiles_n, nsplit, sp, nt0, ntiles);
+    const int lo = nt0 * BN, hi = min(n, (nt0 + ntiles) * BN);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float v1 = -INFINITY, v2 = -INFINITY;
+    float v1 = -INFINITY, v2 = -INFINITY, v3 = -INFINITY;
     int i1 = 0x7fffffff, i2 = 0x7fffffff;
     for (int g = lo + warp; g < hi; g += 4) {
         const __nv_bfloat16 *gr = gal + (size_t)g * kDim;
         float s = 0.f;
         for (int i = lane; i < kDim; i += 32) s = fmaf(q[i], __bfloat162float(gr[i]), s);
         s = warp_sum(s);
-        if (s > v1 || (s == v1 && g < i1)) { v2 = v1; i2 = i1; v1 = s; i1 = g; }
-        else if (s > v2 || (s == v2 && g < i2)) { v2 = s; i2 = g; }
+        if (s > v1 || (s == v1 && g < i1)) { v3 = fmaxf(v3, v2); v2 = v1; i2 = i1; v1 = s; i1 = g; }
+        else if (s > v2 || (s == v2 && g < i2)) { v3 = fmaxf(v3, v2); v2 = s; i2 = g; }
+        else v3 = fmaxf(v3, s);
     }
     __shared__ Cand sc[4][2];
-    if (lane == 0) { sc[warp][0] = Cand{v1, i1}; sc[warp][1] = Cand{v2, i2}; }
+    __shared__ float s3[4];
+    if (lane == 0) { sc[warp][0] = Cand{v1, i1}; sc[warp][1] = Cand{v2, i2}; s3[warp] = v3; }
     __syncthreads();
     if (threadIdx.x == 0) {
         Cand b1{-INFINITY, 0x7fffffff}, b2{-INFINITY, 0x7fffffff};
+        float b3 = fmaxf(fmaxf(s3[0], s3[1]), fmaxf(s3[2], s3[3]));
         for (int w = 0; w < 4; ++w)
             for (int k = 0; k < 2; ++k) {
                 const Cand c = sc[w][k];
-                if (c.v > b1.v || (c.v == b1.v && c.i < b1.i)) { b2 = b1; b1 = c; }
-                else if (c.v > b2.v || (c.v == b2.v && c.i < b2.i)) { b2 = c; }
+                if (c.v > b1.v || (c.v == b1.v && c.i < b1.i)) { b3 = fmaxf(b3, b2.v); b2 = b1; b1 = c; }
+                else if (c.v > b2.v || (c.v == b2.v && c.i < b2.i)) { b3 = fmaxf(b3, b2.v); b2 = c; }
+                else b3 = fmaxf(b3, c.v);
             }
         Cand *o = part + ((size_t)row * nsplit + sp) * 2;
         o[0] = b1;
         o[1] = b2;
+        third[(size_t)row * nsplit + sp] = b3;
     }
 }
 
-// Exact fp32 re-score of the surviving candidates, gate, key packing.  One warp per probe.
-// A candidate whose bf16 score is more than kPrune below the row's best bf16 score cannot be the fp32
-// arg-max: the probe is rounded to bf16 (unit roundoff 2^-8), the gallery values are exact, so
-// |s_bf16 - s_fp32| <= 2^-8 * sum|q_i g_i| <= 2^-8 for unit vectors, and kPrune = 0.01 > 2 * 2^-8.
-constexpr float kPrune = 0.01f;
+// ------------------------------------------------------------------------------------------------
+// exact fp32 re-score, gate, key packing
+// ------------------------------------------------------------------------------------------------
+// A gallery row whose candidate-search score is more than `prune` below the row's best candidate-search score cannot be
+// the fp32 arg-max.  Candidate search = bf16 probe x bf16 gallery with fp32 accumulation; re-score = fp32 probe x the
+// re-score gallery (the same bf16 rows, or the caller's fp32 rows).  With R = the largest gallery row norm and unit-norm
+// probes, |s_search - s_rescore| <= u * R (+ u * R when the re-score gallery is fp32, whose rows the bf16 copy rounds),
+// u = 2^-8 the bf16 unit roundoff (Cauchy-Schwarz on sum |q_i g_i|), plus < 1e-4 of fp32 accumulation error.  So
+// prune = 2 * that bound; the host computes it (match_prune_margin).
+//
+// The GEMM epilogue keeps the best TWO scores per (probe, gallery chunk) and the best score it DROPPED (`third`).  When
+// third >= vmax - prune some dropped row of that chunk could still be the fp32 arg-max (three or more near-duplicate
+// enrolments of one person inside one chunk, the crowded top of a 1M-id gallery): the whole chunk is then re-scanned in
+// exact fp32 by all warps of the CTA.  Rare for planted probes; the result is the fp32 arg-max unconditionally.
+struct FinParams {
+    const float *qn;              // [m, 512] normalised probes (peer exchange: parity-0 buffer)
+    size_t qn_parity_stride;      // peer exchange: elements between the two parity buffers
+    const unsigned *step;         // peer exchange: device step counter (parity), else NULL
+    const __nv_bfloat16 *gal;
+    const float *gal_f32;         // optional fp32 rows for the re-score (NULL: the bf16 rows)
+    const Cand *part;
+    const float *third;
+    int m, n, nsplit, tiles_n;
+    float prune, threshold;
+    int id_offset;
+    int *out_id;
+    float *out_sim;
+    unsigned long long *out_key;
+    PeerPtrs peer;                // world > 0: keys go to the owners' exchange buffers instead of out_key
+    size_t off_keys, keys_stride;
+};
 
-__global__ void __launch_bounds__(256) match_finalize_kernel(const float *__restrict__ qn, const __nv_bfloat16 *__restrict__ gal,
-                                                             const Cand *__restrict__ part, int m, int n, int ncand,
-                                                             float threshold, int id_offset, int *out_id, float *out_sim,
-                                                             unsigned long long *out_key) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= m) return;
-    // lane owns 16 contiguous dimensions: the probe is 4 x 128-bit loads, a gallery row 2 x 128-bit loads per lane
-    constexpr int kPer = kDim / 32;                  // 16
-    float q[kPer];
-    {
-        const float4 *qp = reinterpret_cast<const float4 *>(qn + (size_t)row * kDim + lane * kPer);
+constexpr int kFinWarps = 8;
+constexpr int kFinSlots = 4;      // flagged chunks a probe row can hand to the CTA per round
+constexpr int kPer = kDim / 32;   // 16 dimensions per lane
+
+template <bool F32G>
+struct RowFrag {
+    uint4 v[F32G ? 4 : 2];
+};
+template <bool F32G>
+__device__ __forceinline__ RowFrag<F32G> load_frag(const FinParams &p, int g, int lane) {
+    RowFrag<F32G> f;
+    if constexpr (F32G) {
+        const uint4 *r = reinterpret_cast<const uint4 *>(p.gal_f32 + (size_t)g * kDim + lane * kPer);
 #pragma unroll
-        for (int i = 0; i < kPer / 4; ++i) {
-            const float4 v = __ldg(qp + i);
-            q[4 * i] = v.x; q[4 * i + 1] = v.y; q[4 * i + 2] = v.z; q[4 * i + 3] = v.w;
+        for (int i = 0; i < 4; ++i) f.v[i] = __ldg(r + i);
+    } else {
+        const uint4 *r = reinterpret_cast<const uint4 *>(p.gal + (size_t)g * kDim + lane * kPer);
+        f.v[0] = __ldg(r);
+        f.v[1] = __ldg(r + 1);
+    }
+    return f;
+}
+template <bool F32G>
+__device__ __forceinline__ float dot_frag(const float (&q)[kPer], const RowFrag<F32G> &f) {
+    float s = 0.f;
+    if constexpr (F32G) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            s = fmaf(q[4 * i], __uint_as_float(f.v[i].x), s);
+            s = fmaf(q[4 * i + 1], __uint_as_float(f.v[i].y), s);
+            s = fmaf(q[4 * i + 2], __uint_as_float(f.v[i].z), s);
+            s = fmaf(q[4 * i + 3], __uint_as_float(f.v[i].w), s);
         }
-    }
-    const Cand *c = part + (size_t)row * ncand;
-    float vmax = -INFINITY;
-    for (int k = lane; k < ncand; k += 32) {
-        const Cand x = c[k];
-        if (x.i >= 0 && x.i < n) vmax = fmaxf(vmax, x.v);
-    }
-    vmax = warp_max(vmax);
-    float best = -INFINITY;
-    int bidx = 0x7fffffff;
-    auto dot16 = [&](const uint4 &lo, const uint4 &hi) {
-        const unsigned w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-        float s = 0.f;
+    } else {
+        const unsigned w[8] = {f.v[0].x, f.v[0].y, f.v[0].z, f.v[0].w, f.v[1].x, f.v[1].y, f.v[1].z, f.v[1].w};
 #pragma unroll
         for (int i = 0; i < 8; ++i) {                // bf16 -> fp32 is a 16-bit shift
             s = fmaf(q[2 * i], __uint_as_float(w[i] << 16), s);
             s = fmaf(q[2 * i + 1], __uint_as_float(w[i] & 0xffff0000u), s);
         }
-        return s;
-    };
-    for (int k0 = 0; k0 < ncand; k0 += 32) {
-        const int k = k0 + lane;
-        Cand x{-INFINITY, -1};
-        if (k < ncand) x = c[k];
-        const bool need = x.i >= 0 && x.i < n && x.v >= vmax - kPrune;
-        unsigned todo = __ballot_sync(FULL, need);
-        while (todo) {
-            // up to four candidates per round: their rows are all requested before the first dot product
-            int g[4];
-            uint4 lo[4], hi[4];
+    }
+    return s;
+}
+__device__ __forceinline__ void load_probe(const float *qn, int row, int lane, float (&q)[kPer]) {
+    // lane owns 16 contiguous dimensions: the probe is 4 x 128-bit loads, a bf16 gallery row 2 x 128-bit loads per lane
+    const float4 *qp = reinterpret_cast<const float4 *>(qn + (size_t)row * kDim + lane * kPer);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                g[u] = -1;
-                if (todo) {
-                    const int src = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    g[u] = __shfl_sync(FULL, x.i, src);
-                    const uint4 *gr = reinterpret_cast<const uint4 *>(gal + (size_t)g[u] * kDim + lane * kPer);
-                    lo[u] = __ldg(gr);
-                    hi[u] = __ldg(gr + 1);
+    for (int i = 0; i < kPer / 4; ++i) {
+        const float4 v = __ldg(qp + i);
+        q[4 * i] = v.x; q[4 * i + 1] = v.y; q[4 * i + 2] = v.z; q[4 * i + 3] = v.w;
+    }
+}
+
+template <bool F32G>
+__global__ void __launch_bounds__(32 * kFinWarps) match_finalize_kernel(const FinParams prm) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kFinWarps + warp;
+    const bool active = row < prm.m;
+    const int n = prm.n, nsplit = prm.nsplit;
+    unsigned step = 0;
+    const float *qn = prm.qn;
+    if (prm.step) {
+        step = __ldcg(prm.step);
+        qn += (size_t)(step & 1u) * prm.qn_parity_stride;
+    }
+    __shared__ int s_sp[kFinWarps][kFinSlots];
+    __shared__ float s_pv[kFinWarps * kFinSlots][kFinWarps];
+    __shared__ int s_pi[kFinWarps * kFinSlots][kFinWarps];
+
+    float q[kPer];
+    float vmax = -INFINITY, best = -INFINITY;
+    int bidx = 0x7fffffff;
+    if (active) {
+        load_probe(qn, row, lane, q);
+        const int ncand = nsplit * 2;
+        const Cand *c = prm.part + (size_t)row * ncand;
+        for (int k = lane; k < ncand; k += 32) {
+            const Cand x = c[k];
+            if (x.i >= 0 && x.i < n) vmax = fmaxf(vmax, x.v);
+        }
+        vmax = warp_max(vmax);
+        for (int k0 = 0; k0 < ncand; k0 += 32) {
+            const int k = k0 + lane;
+            Cand x{-INFINITY, -1};
+            if (k < ncand) x = c[k];
+            const bool need = x.i >= 0 && x.i < n && x.v >= vmax - prm.prune;
+            unsigned todo = __ballot_sync(FULL, need);
+            while (todo) {
+                // up to four candidates per round: their rows are all requested before the first dot product
+                int g[4];
+                RowFrag<F32G> fr[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    g[u] = -1;
+                    if (todo) {
+                        const int src = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        g[u] = __shfl_sync(FULL, x.i, src);
+                        fr[u] = load_frag<F32G>(prm, g[u], lane);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (g[u] < 0) continue;              // warp-uniform
+                    const float s = warp_sum(dot_frag<F32G>(q, fr[u]));
+                    if (s > best || (s == best && g[u] < bidx)) { best = s; bidx = g[u]; }
                 }
             }
+        }
+    }
+
+    // ---- chunks whose dropped scores reach the prune band: exact fp32 re-scan by the whole CTA ----
+    int sp_next = 0;
+    for (;;) {
+        int found = 0;
+        if (active) {
+            const float *th = prm.third + (size_t)row * nsplit;
+            while (found < kFinSlots && sp_next < nsplit) {
+                const int sp = sp_next + lane;
+                const bool f = sp < nsplit && th[sp] >= vmax - prm.prune;
+                unsigned b = __ballot_sync(FULL, f);
+                int last = -1;
+                while (b && found < kFinSlots) {
+                    last = __ffs(b) - 1;
+                    b &= b - 1;
+                    if (lane == 0) s_sp[warp][found] = sp_next + last;
+                    ++found;
+                }
+                sp_next = b ? sp_next + last + 1 : sp_next + 32;      // slots full: resume right after the last one taken
+            }
+        }
+        if (lane == 0)
+            for (int s = found; s < kFinSlots; ++s) s_sp[warp][s] = -1;
+        if (!__syncthreads_or(found > 0)) break;
+        for (int it = 0; it < kFinWarps * kFinSlots; ++it) {
+            const int sp = s_sp[it / kFinSlots][it % kFinSlots];
+            if (sp < 0) continue;                                   // block-uniform
+            const int orow = blockIdx.x * kFinWarps + it / kFinSlots;
+            int nt0, ntiles;
+            chunk_tiles(prm.tiles_n, nsplit, sp, nt0, ntiles);
+            const int lo = nt0 * BN, hi = min(n, (nt0 + ntiles) * BN);
+            float oq[kPer];
+            load_probe(qn, orow, lane, oq);
+            float pb = -INFINITY;
+            int pi = 0x7fffffff;
+            for (int g0 = lo + warp * 4; g0 < hi; g0 += kFinWarps * 4) {
+                RowFrag<F32G> fr[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (g[u] < 0) continue;              // warp-uniform
-                const float s = warp_sum(dot16(lo[u], hi[u]));
-                if (s > best || (s == best && g[u] < bidx)) { best = s; bidx = g[u]; }
+                for (int u = 0; u < 4; ++u)
+                    if (g0 + u < hi) fr[u] = load_frag<F32G>(prm, g0 + u, lane);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (g0 + u >= hi) continue;
+                    const float s = warp_sum(dot_frag<F32G>(oq, fr[u]));
+                    if (s > pb) { pb = s; pi = g0 + u; }            // ascending ids: the first maximum stays
+                }
+            }
+            if (lane == 0) { s_pv[it][warp] = pb; s_pi[it][warp] = pi; }
+        }
+        __syncthreads();
+        for (int s = 0; s < found; ++s)
+            for (int w = 0; w < kFinWarps; ++w) {
+                const float v = s_pv[warp * kFinSlots + s][w];
+                const int i = s_pi[warp * kFinSlots + s][w];
+                if (v > best || (v == best && i < bidx)) { best = v; bidx = i; }
+            }
+        __syncthreads();                                            // slots are rewritten in the next round
+    }
+
+    if (active && lane == 0) {
+        const bool found = bidx != 0x7fffffff;
+        const int gid = found ? bidx + prm.id_offset : -1;
+        const bool pass = found && !(best < prm.threshold);      // NaN threshold: no gate
+        if (prm.out_id) prm.out_id[row] = pass ? gid : -1;
+        if (prm.out_sim) prm.out_sim[row] = found ? best : -INFINITY;
+        const unsigned long long hi = (unsigned long long)(unsigned)float_to_ordered(found ? best : -INFINITY);
+        const unsigned long long key = (hi << 32) | (unsigned long long)(0xffffffffu - (unsigned)(found ? gid : 0x7fffffff));
+        if (prm.peer.world > 0) {
+            // the key of probe `row` = (owner rank, local row) goes straight into the owner's exchange buffer (P2P store)
+            const int owner = row / prm.peer.m_local, j = row - owner * prm.peer.m_local;
+            unsigned long long *dst = reinterpret_cast<unsigned long long *>(prm.peer.buf[owner] + prm.off_keys + (step & 1u) * prm.keys_stride) +
+                                      (size_t)prm.peer.rank * prm.peer.m_local + j;
+            *dst = key;
+        } else if (prm.out_key) {
+            prm.out_key[row] = key;
+        }
+    }
+    if (prm.peer.world > 0) {
+        // last CTA: every key of this rank has been written -> publish the step number to all owners
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            PeerHeader *h = reinterpret_cast<PeerHeader *>(prm.peer.buf[prm.peer.rank]);
+            if (atomicAdd(&h->key_count, 1u) == gridDim.x - 1) {
+                h->key_count = 0;
+                __threadfence_system();
+                for (int r = 0; r < prm.peer.world; ++r) st_release_sys(peer_key_flag(prm.peer.buf[r], step & 1u, prm.peer.rank), step + 1);
             }
         }
     }
-    if (lane == 0) {
-        const bool found = bidx != 0x7fffffff;
-        const int gid = found ? bidx + id_offset : -1;
-        const bool pass = found && !(best < threshold);      // NaN threshold: no gate
-        if (out_id) out_id[row] = pass ? gid : -1;
-        if (out_sim) out_sim[row] = found ? best : -INFINITY;
-        if (out_key) {
-            const unsigned long long hi = (unsigned long long)(unsigned)float_to_ordered(found ? best : -INFINITY);
-            out_key[row] = (hi << 32) | (unsigned long long)(0xffffffffu - (unsigned)(found ? gid : 0x7fffffff));
-        }
-    }
+}
+
+__device__ __forceinline__ void unpack_key(unsigned long long k, float threshold, int &id, float &sim) {
+    sim = ordered_to_float((int32_t)(unsigned)(k >> 32));
+    const unsigned gid = 0xffffffffu - (unsigned)(k & 0xffffffffu);
+    const bool found = gid != 0x7fffffffu;
+    id = (found && !(sim < threshold)) ? (int)gid : -1;
 }
 
 __global__ void match_unpack_kernel(const unsigned long long *keys, int m, float threshold, int *out_id, float *out_sim) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
-    const unsigned long long k = keys[i];
-    const float sim = ordered_to_float((int32_t)(unsigned)(k >> 32));
-    const unsigned gid = 0xffffffffu - (unsigned)(k & 0xffffffffu);
-    const bool found = gid != 0x7fffffffu;
+    int id;
+    float sim;
+    unpack_key(keys[i], threshold, id, sim);
     if (out_sim) out_sim[i] = sim;
-    if (out_id) out_id[i] = (found && !(sim < threshold)) ? (int)gid : -1;
+    if (out_id) out_id[i] = id;
+}
+
+// ------------------------------------------------------------------------------------------------
+// peer exchange kernels (gallery sharded over the GPUs of one box; peer_exchange.cuh)
+// ------------------------------------------------------------------------------------------------
+// F.normalize of this rank's probes, written as fp32 + bf16 into EVERY rank's exchange buffer (the all-gather, as P2P
+// stores over NVLink), then the step number is published to every peer by the last CTA.
+__global__ void __launch_bounds__(256) peer_normalize_push_kernel(const float *__restrict__ emb, float eps, const PeerPtrs peer,
+                                                                  const PeerLayout lay) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + warp;
+    PeerHeader *h = reinterpret_cast<PeerHeader *>(peer.buf[peer.rank]);
+    const unsigned step = __ldcg(&h->step), parity = step & 1u;
+    if (row < peer.m_local) {
+        const float *xr = emb + (size_t)row * kDim;
+        float v[kDim / 32];
+        float ss = 0.f;
+#pragma unroll
+        for (int k = 0; k < kDim / 32; ++k) {           // same element order as l2_normalize_kernel: bit-identical probes
+            v[k] = xr[lane + 32 * k];
+            ss = fmaf(v[k], v[k], ss);
+        }
+        ss = warp_sum(ss);
+        const float den = fmaxf(sqrtf(ss), eps);
+#pragma unroll
+        for (int k = 0; k < kDim / 32; ++k) v[k] = __fdiv_rn(v[k], den);
+        const size_t grow = (size_t)peer.rank * peer.m_local + row;
+        for (int r = 0; r < peer.world; ++r) {
+            float *df = reinterpret_cast<float *>(peer.buf[r] + lay.off_f32 + parity * lay.f32_stride) + grow * kDim;
+            __nv_bfloat16 *db = reinterpret_cast<__nv_bfloat16 *>(peer.buf[r] + lay.off_bf16 + parity * lay.bf16_stride) + grow * kDim;
+#pragma unroll
+            for (int k = 0; k < kDim / 32; ++k) {
+                df[lane + 32 * k] = v[k];
+                db[lane + 32 * k] = __float2bfloat16_rn(v[k]);
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(&h->push_count, 1u) == gridDim.x - 1) {
+            h->push_count = 0;
+            __threadfence_system();
+            for (int r = 0; r < peer.world; ++r) st_release_sys(peer_probe_flag(peer.buf[r], parity, peer.rank), step + 1);
+        }
+    }
+}
+
+// Wait until the probes of every rank have landed in this rank's buffer.  A kernel of its own: the kernel boundary makes
+// the peers' (generic-proxy) stores visible to the TMA loads of the GEMM that follows.
+__global__ void peer_wait_probes_kernel(const PeerPtrs peer) {
+    unsigned char *own = peer.buf[peer.rank];
+    const unsigned step = __ldcg(&reinterpret_cast<PeerHeader *>(own)->step);
+    if ((int)threadIdx.x < peer.world) peer_wait_flag(peer_probe_flag(own, step & 1u, threadIdx.x), step + 1);
+}
+
+// The top-1 (value, index) reduction: wait for every rank's keys of MY probes, take the integer maximum (higher
+// similarity first, lower id on ties), unpack + gate.  The last CTA advances the step counter.
+__global__ void __launch_bounds__(256) peer_reduce_unpack_kernel(const PeerPtrs peer, const PeerLayout lay, float threshold,
+                                                                 int *out_id, float *out_sim, unsigned long long *out_key) {
+    unsigned char *own = peer.buf[peer.rank];
+    PeerHeader *h = reinterpret_cast<PeerHeader *>(own);
+    const unsigned step = __ldcg(&h->step), parity = step & 1u;
+    if ((int)threadIdx.x < peer.world) peer_wait_flag(peer_key_flag(own, parity, threadIdx.x), step + 1);
+    __syncthreads();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < peer.m_local) {
+        const unsigned long long *keys = reinterpret_cast<const unsigned long long *>(own + lay.off_keys + parity * lay.keys_stride);
+        long long best = (long long)__ldcg(keys + j);
+        for (int r = 1; r < peer.world; ++r) {
+            const long long k = (long long)__ldcg(keys + (size_t)r * peer.m_local + j);
+            best = k > best ? k : best;
+        }
+        int id;
+        float sim;
+        unpack_key((unsigned long long)best, threshold, id, sim);
+        if (out_id) out_id[j] = id;
+        if (out_sim) out_sim[j] = sim;
+        if (out_key) out_key[j] = (unsigned long long)best;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(&h->done_count, 1u) == gridDim.x - 1) {
+            h->done_count = 0;
+            __threadfence();
+            h->step = step + 1;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -488,10 +752,11 @@ int make_tmap(CUtensorMap *map, const void *base, int rows, int box_rows) {
 
 struct MatchPlan {
     int m_tiles, tiles_n, nsplit, sms;
-    size_t off_qn, off_qb, off_part, bytes;
+    size_t off_qn, off_qb, off_part, off_third, bytes;
 };
 
-MatchPlan plan_match(int m, int n) {
+// own_probes: the workspace also holds the normalised probes (fp32 + bf16); false when they live in a peer exchange buffer
+MatchPlan plan_match(int m, int n, bool own_probes = true) {
     MatchPlan p{};
     p.m_tiles = (m + BM - 1) / BM;
     p.tiles_n = (n + BN - 1) / BN;
@@ -504,8 +769,8 @@ MatchPlan plan_match(int m, int n) {
     // branches need from it.  SPP_MATCH_CHUNK_TILES=<t> restores chunks of >= t tiles (profiling knob).
     // Large problems: the grid is one persistent CTA per SM and the chunk count is chosen so that
     // items ~ r * SMs (balanced rounds, <= 8 of them).
-    static const int chunk_tiles = [] { const char *e = getenv("SPP_MATCH_CHUNK_TILES"); const int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();
-    const int want = (p.tiles_n + chunk_tiles - 1) / chunk_tiles > 0 ? (p.tiles_n + chunk_tiles - 1) / chunk_tiles : 1;
+    static const int chunk_tiles_env = [] { const char *e = getenv("SPP_MATCH_CHUNK_TILES"); const int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();
+    const int want = (p.tiles_n + chunk_tiles_env - 1) / chunk_tiles_env > 0 ? (p.tiles_n + chunk_tiles_env - 1) / chunk_tiles_env : 1;
     int ns;
     if ((long long)p.m_tiles * want <= sms) {
         ns = want;
@@ -531,11 +796,51 @@ MatchPlan plan_match(int m, int n) {
     p.nsplit = ns;
     p.sms = sms;
     size_t off = 0;
-    p.off_qn = off;   off += align_up((size_t)m * kDim * 4, 1024);
-    p.off_qb = off;   off += align_up((size_t)m * kDim * 2, 1024);
-    p.off_part = off; off += align_up((size_t)p.m_tiles * BM * ns * 2 * sizeof(Cand), 1024);
+    p.off_qn = off;    off += own_probes ? align_up((size_t)m * kDim * 4, 1024) : 0;
+    p.off_qb = off;    off += own_probes ? align_up((size_t)m * kDim * 2, 1024) : 0;
+    p.off_part = off;  off += align_up((size_t)p.m_tiles * BM * ns * 2 * sizeof(Cand), 1024);
+    p.off_third = off; off += align_up((size_t)p.m_tiles * BM * ns * sizeof(float), 1024);
     p.bytes = off;
     return p;
+}
+
+float match_prune_margin(float max_row_norm, bool f32_rescore) {
+    const float r = max_row_norm > 0.f ? max_row_norm : 1.0f;
+    const float u = 0.00390625f;                         // bf16 unit roundoff 2^-8
+    return 2.0f * ((f32_rescore ? 2.0f : 1.0f) * u * r * 1.02f + 1e-4f);
+}
+
+// candidate search (tcgen05 GEMM or the SIMT cross-check) over `m` normalised probes
+int launch_search(const __nv_bfloat16 *qb0, const __nv_bfloat16 *qb1, const unsigned *step, const float *qn_simt,
+                  const __nv_bfloat16 *gal, int m, int n, const MatchPlan &p, Cand *part, float *third, cudaStream_t st, bool simt) {
+    if (simt) {
+        dim3 grid(m, p.nsplit);
+        match_simt_top2_kernel<<<grid, 128, 0, st>>>(qn_simt, gal, m, n, p.tiles_n, p.nsplit, part, third);
+        SPP_CHECK_LAUNCH();
+        return SPP_OK;
+    }
+    CUtensorMap ta0, ta1, tb;
+    int rc = make_tmap(&ta0, qb0, m, BM);
+    if (rc) return rc;
+    rc = make_tmap(&ta1, qb1 ? qb1 : qb0, m, BM);
+    if (rc) return rc;
+    rc = make_tmap(&tb, gal, n, BN);
+    if (rc) return rc;
+    // per device and per context: set on every launch (about a microsecond; legal during stream capture)
+    SPP_CHECK_CUDA(cudaFuncSetAttribute(match_gemm_top2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+    const int items = p.m_tiles * p.nsplit;
+    GemmParams gp{m, n, p.tiles_n, p.nsplit, items, step, part, third};
+    match_gemm_top2_kernel<<<items < p.sms ? items : p.sms, kGemmThreads, kGemmSmem, st>>>(ta0, ta1, tb, gp);
+    SPP_CHECK_LAUNCH();
+    return SPP_OK;
+}
+
+int launch_finalize(const FinParams &fp, cudaStream_t st) {
+    const int grid = (fp.m + kFinWarps - 1) / kFinWarps;
+    if (fp.gal_f32) match_finalize_kernel<true><<<grid, 32 * kFinWarps, 0, st>>>(fp);
+    else match_finalize_kernel<false><<<grid, 32 * kFinWarps, 0, st>>>(fp);
+    SPP_CHECK_LAUNCH();
+    return SPP_OK;
 }
 
 }  // namespace
@@ -548,7 +853,6 @@ extern "C" int spp_l2_normalize(const float *x, int m, int dim, int mode, float 
     if (m == 0) return SPP_OK;
     SPP_CHECK_ARG(x && m >= 0 && dim > 0, "l2_normalize: bad arguments");
     SPP_CHECK_ARG(mode == 0 || mode == 1, "l2_normalize: mode must be 0 (x/||x||) or 1 (F.normalize)");
-    if (m == 0) return SPP_OK;
     l2_normalize_kernel<<<(m + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, m, dim, mode, eps, out, norm,
                                                                                     reinterpret_cast<__nv_bfloat16 *>(out_bf16));
     SPP_CHECK_LAUNCH();
@@ -570,16 +874,18 @@ extern "C" size_t spp_match_workspace_bytes(int m, int n, int dim) {
     return plan_match(m > 0 ? m : 1, n).bytes;
 }
 
-static int match_common(const float *emb, const uint16_t *gallery, int m, int n, int dim, float threshold, int id_offset,
-                        int *out_id, float *out_sim, unsigned long long *out_key, void *workspace, size_t workspace_bytes,
-                        spp_stream_t stream, bool simt) {
+static int match_common(const float *emb, const uint16_t *gallery, const float *gallery_f32, float max_row_norm, int m, int n, int dim,
+                        float threshold, int id_offset, int *out_id, float *out_sim, unsigned long long *out_key, void *workspace,
+                        size_t workspace_bytes, spp_stream_t stream, bool simt) {
     if (m == 0) return SPP_OK;
     SPP_CHECK_ARG(emb && gallery && workspace, "match_top1: null pointer");
     SPP_CHECK_ARG(dim == kDim, "match_top1: embedding dimension must be %d (got %d)", kDim, dim);
     SPP_CHECK_ARG(m >= 0 && n >= 1, "match_top1: bad m=%d n=%d", m, n);
-    SPP_CHECK_ARG((reinterpret_cast<uintptr_t>(gallery) & 15) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 1023) == 0,
+    SPP_CHECK_ARG(max_row_norm > 0.0f && max_row_norm < 1e4f, "match_top1: max_row_norm must be the largest gallery row norm (got %g)",
+                  (double)max_row_norm);
+    SPP_CHECK_ARG((reinterpret_cast<uintptr_t>(gallery) & 15) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 1023) == 0 &&
+                      (reinterpret_cast<uintptr_t>(gallery_f32) & 15) == 0,
                   "match_top1: gallery must be 16-byte and workspace 1024-byte aligned");
-    if (m == 0) return SPP_OK;
     const MatchPlan p = plan_match(m, n);
     if (workspace_bytes < p.bytes) {
         set_error("match_top1: workspace %zu < required %zu bytes", workspace_bytes, p.bytes);
@@ -590,50 +896,42 @@ static int match_common(const float *emb, const uint16_t *gallery, int m, int n,
     float *qn = reinterpret_cast<float *>(ws + p.off_qn);
     __nv_bfloat16 *qb = reinterpret_cast<__nv_bfloat16 *>(ws + p.off_qb);
     Cand *part = reinterpret_cast<Cand *>(ws + p.off_part);
+    float *third = reinterpret_cast<float *>(ws + p.off_third);
     const __nv_bfloat16 *gal = reinterpret_cast<const __nv_bfloat16 *>(gallery);
 
     l2_normalize_kernel<<<(m + 7) / 8, 256, 0, st>>>(emb, m, kDim, 1, 1e-12f, qn, nullptr, qb);
     SPP_CHECK_LAUNCH();
-
-    if (simt) {
-        dim3 grid(m, p.nsplit);
-        match_simt_top2_kernel<<<grid, 128, 0, st>>>(qn, gal, m, n, p.nsplit, part);
-        SPP_CHECK_LAUNCH();
-    } else {
-        CUtensorMap ta, tb;
-        int rc = make_tmap(&ta, qb, m, BM);
-        if (rc) return rc;
-        rc = make_tmap(&tb, gal, n, BN);
-        if (rc) return rc;
-        static bool configured = false;
-        if (!configured) {
-            SPP_CHECK_CUDA(cudaFuncSetAttribute(match_gemm_top2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
-            configured = true;
-        }
-        const int items = p.m_tiles * p.nsplit;
-        GemmParams gp{m, n, p.tiles_n, p.nsplit, items, part};
-        match_gemm_top2_kernel<<<items < p.sms ? items : p.sms, kGemmThreads, kGemmSmem, st>>>(ta, tb, gp);
-        SPP_CHECK_LAUNCH();
-    }
-    match_finalize_kernel<<<(m + 7) / 8, 256, 0, st>>>(qn, gal, part, m, n, p.nsplit * 2, threshold, id_offset, out_id, out_sim,
-                                                      out_key);
-    SPP_CHECK_LAUNCH();
-    return SPP_OK;
+    int rc = launch_search(qb, nullptr, nullptr, qn, gal, m, n, p, part, third, st, simt);
+    if (rc) return rc;
+    FinParams fp{};
+    fp.qn = qn; fp.gal = gal; fp.gal_f32 = gallery_f32; fp.part = part; fp.third = third;
+    fp.m = m; fp.n = n; fp.nsplit = p.nsplit; fp.tiles_n = p.tiles_n;
+    fp.prune = match_prune_margin(max_row_norm, gallery_f32 != nullptr);
+    fp.threshold = threshold; fp.id_offset = id_offset;
+    fp.out_id = out_id; fp.out_sim = out_sim; fp.out_key = out_key;
+    return launch_finalize(fp, st);
 }
 
 extern "C" int spp_match_top1(const float *emb, const uint16_t *gallery, int m, int n, int dim, float threshold, int id_offset,
                               int *out_id, float *out_sim, unsigned long long *out_key, void *workspace,
                               size_t workspace_bytes, spp_stream_t stream) {
-    return match_common(emb, gallery, m, n, dim, threshold, id_offset, out_id, out_sim, out_key, workspace, workspace_bytes,
-                        stream, false);
+    return match_common(emb, gallery, nullptr, 1.0f, m, n, dim, threshold, id_offset, out_id, out_sim, out_key, workspace,
+                        workspace_bytes, stream, false);
+}
+
+extern "C" int spp_match_top1_ex(const float *emb, const uint16_t *gallery, const float *gallery_f32, float max_row_norm, int m, int n,
+                                 int dim, float threshold, int id_offset, int *out_id, float *out_sim, unsigned long long *out_key,
+                                 void *workspace, size_t workspace_bytes, spp_stream_t stream) {
+    return match_common(emb, gallery, gallery_f32, max_row_norm, m, n, dim, threshold, id_offset, out_id, out_sim, out_key, workspace,
+                        workspace_bytes, stream, false);
 }
 
 // Test hook (declared in spp_internal.h, not part of the drop-in surface): CUDA-core candidate search.
 extern "C" int spp_debug_match_top1_simt(const float *emb, const uint16_t *gallery, int m, int n, int dim, float threshold,
                                          int id_offset, int *out_id, float *out_sim, unsigned long long *out_key,
                                          void *workspace, size_t workspace_bytes, spp_stream_t stream) {
-    return match_common(emb, gallery, m, n, dim, threshold, id_offset, out_id, out_sim, out_key, workspace, workspace_bytes,
-                        stream, true);
+    return match_common(emb, gallery, nullptr, 1.0f, m, n, dim, threshold, id_offset, out_id, out_sim, out_key, workspace,
+                        workspace_bytes, stream, true);
 }
 
 extern "C" int spp_match_unpack_keys(const unsigned long long *keys, int m, float threshold, int *out_id, float *out_sim,
@@ -642,5 +940,85 @@ extern "C" int spp_match_unpack_keys(const unsigned long long *keys, int m, floa
     if (m == 0) return SPP_OK;
     match_unpack_kernel<<<(m + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(keys, m, threshold, out_id, out_sim);
     SPP_CHECK_LAUNCH();
+    return SPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// gallery sharded over the GPUs of one box: peer-memory exchange (include/spp.h, peer_exchange.cuh)
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t spp_peer_buffer_bytes(int world, int m_local, int dim) {
+    if (world < 1 || world > SPP_MAX_PEERS || m_local < 1 || dim != kDim) return 0;
+    return peer_layout(world, m_local).bytes;
+}
+
+extern "C" size_t spp_sharded_match_workspace_bytes(int world, int m_local, int n_shard, int dim) {
+    if (world < 1 || world > SPP_MAX_PEERS || m_local < 1 || n_shard < 1 || dim != kDim) return 0;
+    return plan_match(world * m_local, n_shard, false).bytes;
+}
+
+extern "C" int spp_sharded_match_top1(const spp_peer_group *group, const float *emb, const uint16_t *shard, const float *shard_f32,
+                                      float max_row_norm, int n_shard, int dim, int id_offset, float threshold, int stages, int *out_id,
+                                      float *out_sim, unsigned long long *out_key, void *workspace, size_t workspace_bytes,
+                                      spp_stream_t stream) {
+    SPP_CHECK_ARG(group && emb && shard && workspace, "sharded_match_top1: null pointer");
+    SPP_CHECK_ARG(group->world >= 1 && group->world <= SPP_MAX_PEERS && group->rank >= 0 && group->rank < group->world && group->m_local >= 1,
+                  "sharded_match_top1: bad peer group (world %d rank %d m_local %d)", group->world, group->rank, group->m_local);
+    SPP_CHECK_ARG(dim == kDim && n_shard >= 1, "sharded_match_top1: dim must be %d and the shard non-empty", kDim);
+    SPP_CHECK_ARG(max_row_norm > 0.0f && max_row_norm < 1e4f, "sharded_match_top1: bad max_row_norm");
+    SPP_CHECK_ARG((reinterpret_cast<uintptr_t>(shard) & 15) == 0 && (reinterpret_cast<uintptr_t>(shard_f32) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(workspace) & 1023) == 0,
+                  "sharded_match_top1: shard must be 16-byte and workspace 1024-byte aligned");
+    PeerPtrs peer{};
+    peer.world = group->world; peer.rank = group->rank; peer.m_local = group->m_local;
+    for (int r = 0; r < group->world; ++r) {
+        SPP_CHECK_ARG(group->buffers[r] && (reinterpret_cast<uintptr_t>(group->buffers[r]) & 1023) == 0,
+                      "sharded_match_top1: exchange buffer of rank %d is null or not 1024-byte aligned", r);
+        peer.buf[r] = static_cast<unsigned char *>(group->buffers[r]);
+    }
+    const PeerLayout lay = peer_layout(peer.world, peer.m_local);
+    const int m = peer.world * peer.m_local;
+    const MatchPlan p = plan_match(m, n_shard, false);
+    if (workspace_bytes < p.bytes) {
+        set_error("sharded_match_top1: workspace %zu < required %zu bytes", workspace_bytes, p.bytes);
+        return SPP_ERR_WORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    Cand *part = reinterpret_cast<Cand *>(ws + p.off_part);
+    float *third = reinterpret_cast<float *>(ws + p.off_third);
+    unsigned char *own = peer.buf[peer.rank];
+    const unsigned *step = &reinterpret_cast<const PeerHeader *>(own)->step;
+    const __nv_bfloat16 *gal = reinterpret_cast<const __nv_bfloat16 *>(shard);
+    if (stages & SPP_SHARDED_STAGE_PUSH) {
+        peer_normalize_push_kernel<<<(peer.m_local + 7) / 8, 256, 0, st>>>(emb, 1e-12f, peer, lay);
+        SPP_CHECK_LAUNCH();
+    }
+    if (stages & SPP_SHARDED_STAGE_WAIT) {
+        peer_wait_probes_kernel<<<1, 32, 0, st>>>(peer);
+        SPP_CHECK_LAUNCH();
+    }
+    if (stages & SPP_SHARDED_STAGE_SEARCH) {
+        const __nv_bfloat16 *qb0 = reinterpret_cast<const __nv_bfloat16 *>(own + lay.off_bf16);
+        const __nv_bfloat16 *qb1 = reinterpret_cast<const __nv_bfloat16 *>(own + lay.off_bf16 + lay.bf16_stride);
+        int rc = launch_search(qb0, qb1, step, nullptr, gal, m, n_shard, p, part, third, st, false);
+        if (rc) return rc;
+    }
+    if (stages & SPP_SHARDED_STAGE_FINALIZE) {
+        FinParams fp{};
+        fp.qn = reinterpret_cast<const float *>(own + lay.off_f32);
+        fp.qn_parity_stride = lay.f32_stride / 4;
+        fp.step = step;
+        fp.gal = gal; fp.gal_f32 = shard_f32; fp.part = part; fp.third = third;
+        fp.m = m; fp.n = n_shard; fp.nsplit = p.nsplit; fp.tiles_n = p.tiles_n;
+        fp.prune = match_prune_margin(max_row_norm, shard_f32 != nullptr);
+        fp.threshold = NAN; fp.id_offset = id_offset;           // the gate is applied after the reduction
+        fp.peer = peer; fp.off_keys = lay.off_keys; fp.keys_stride = lay.keys_stride;
+        int rc = launch_finalize(fp, st);
+        if (rc) return rc;
+    }
+    if (stages & SPP_SHARDED_STAGE_REDUCE) {
+        peer_reduce_unpack_kernel<<<(peer.m_local + 255) / 256, 256, 0, st>>>(peer, lay, threshold, out_id, out_sim, out_key);
+        SPP_CHECK_LAUNCH();
+    }
     return SPP_OK;
 }

@@ -69,6 +69,8 @@ class ShardedGalleryMatcher:
     Every rank must bring the same number of probes per step (pad with zeros otherwise).
     """
 
+    capturable = False     # NCCL calls: issued eagerly beside the pipeline's CUDA graph
+
     def __init__(self, local_match: Callable[[torch.Tensor], torch.Tensor], threshold: Optional[float] = None,
                  group: Optional[dist.ProcessGroup] = None,
                  unpack: Callable[[torch.Tensor, Optional[float]], Tuple[torch.Tensor, torch.Tensor]] = unpack_keys):
@@ -103,3 +105,132 @@ def gpu_matcher(gallery_shard_bf16: torch.Tensor, id_offset: int, threshold: Opt
         return ids.long(), sims
 
     return ShardedGalleryMatcher(local, threshold, group, unpack)
+
+
+# ------------------------------------------------------------------------------------------------
+# The same exchange WITHOUT NCCL calls in the step: the match kernels write over NVLink peer memory
+# ------------------------------------------------------------------------------------------------
+
+STAGE_PUSH, STAGE_WAIT, STAGE_SEARCH, STAGE_FINALIZE, STAGE_REDUCE, STAGE_ALL = 1, 2, 4, 8, 16, 31
+
+
+def exchange_handles(handle: bytes, group: Optional[dist.ProcessGroup] = None) -> list:
+    """All ranks' 64-byte IPC handles, in rank order (the only host-side exchange of the peer path; set-up time)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return [handle]
+    out = [None] * world
+    dist.all_gather_object(out, handle, group=group)
+    return out
+
+
+class PeerGroup:
+    """One exchange buffer per rank, all of them mapped into this process (``spp_peer_alloc`` / ``spp_peer_open``,
+    CUDA IPC over NVLink).  One process per GPU; ``m_local`` probes per rank and step."""
+
+    def __init__(self, m_local: int, group: Optional[dist.ProcessGroup] = None,
+                 alloc: Optional[Callable[[int], Tuple[int, bytes]]] = None, open_: Optional[Callable[[bytes], int]] = None):
+        import ctypes
+        from . import _lib
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if self.world > _lib.MAX_PEERS:
+            raise ValueError(f"PeerGroup: at most {_lib.MAX_PEERS} ranks")
+        self.m_local, self.group = int(m_local), group
+        self._alloc, self._open = alloc or _ipc_alloc, open_ or _ipc_open
+        self._injected = alloc is not None
+        nbytes = 1 if self._injected else int(_lib.lib().spp_peer_buffer_bytes(self.world, self.m_local, 512))
+        if nbytes == 0:
+            raise ValueError(f"PeerGroup: unsupported world={self.world} m_local={self.m_local}")
+        self.nbytes = nbytes
+        own, handle = self._alloc(nbytes)
+        self.handles = exchange_handles(handle, group)
+        self.ptrs = [own if r == self.rank else self._open(self.handles[r]) for r in range(self.world)]
+        self._opened = [p for r, p in enumerate(self.ptrs) if r != self.rank]
+        self._own = own
+        self.struct = _lib.PeerGroupStruct(self.world, self.rank, self.m_local, (ctypes.c_void_p * _lib.MAX_PEERS)(*self.ptrs))
+        if self.world > 1:
+            dist.barrier(group)      # every buffer is mapped everywhere before the first kernel touches a peer
+
+    @classmethod
+    def virtual(cls, world: int, m_local: int):
+        """``world`` ranks inside ONE process on the current device (each with its own buffer): the single-GPU tests run
+        the real kernels, flags and waits this way, one stream per virtual rank."""
+        import ctypes
+        from . import _lib
+        nbytes = int(_lib.lib().spp_peer_buffer_bytes(world, m_local, 512))
+        ptrs = [_ipc_alloc(nbytes)[0] for _ in range(world)]
+        out = []
+        for r in range(world):
+            g = cls.__new__(cls)
+            g.world, g.rank, g.m_local, g.group, g.nbytes = world, r, m_local, None, nbytes
+            g.ptrs, g._opened, g._own, g._injected = ptrs, [], ptrs[r], False
+            g.struct = _lib.PeerGroupStruct(world, r, m_local, (ctypes.c_void_p * _lib.MAX_PEERS)(*ptrs))
+            out.append(g)
+        return out
+
+    def close(self) -> None:
+        from . import _lib
+        if self._injected or self._own is None:
+            return
+        if self.world > 1 and dist.is_initialized():
+            dist.barrier(self.group)
+        for p in self._opened:
+            _lib.check(_lib.lib().spp_peer_close(p), "spp_peer_close")
+        _lib.check(_lib.lib().spp_peer_free(self._own), "spp_peer_free")
+        self._own, self._opened = None, []
+
+
+def _ipc_alloc(nbytes: int) -> Tuple[int, bytes]:
+    import ctypes
+    from . import _lib
+    ptr = ctypes.c_void_p()
+    handle = (ctypes.c_ubyte * _lib.IPC_HANDLE_BYTES)()
+    _lib.check(_lib.lib().spp_peer_alloc(nbytes, ctypes.byref(ptr), handle), "spp_peer_alloc")
+    return int(ptr.value), bytes(handle)
+
+
+def _ipc_open(handle: bytes) -> int:
+    import ctypes
+    from . import _lib
+    ptr = ctypes.c_void_p()
+    buf = (ctypes.c_ubyte * _lib.IPC_HANDLE_BYTES).from_buffer_copy(handle)
+    _lib.check(_lib.lib().spp_peer_open(buf, ctypes.byref(ptr)), "spp_peer_open")
+    return int(ptr.value)
+
+
+class PeerShardedMatcher:
+    """Top-1 of this rank's probes over a row-sharded gallery, the exchange done by the kernels themselves
+    (``spp_sharded_match_top1``): probes are normalised and stored into every rank's buffer, every rank scores ALL
+    probes against its shard (tcgen05 GEMM + fp32 re-score), the packed (similarity, id) keys are stored into their
+    owner's buffer, the owner takes the integer maximum.  Five kernels, no NCCL call, CUDA-graph capturable.
+    Every rank must call ``match`` the same number of times."""
+
+    capturable = True
+
+    def __init__(self, peers: PeerGroup, shard_bf16: torch.Tensor, id_offset: int, threshold: Optional[float] = None,
+                 shard_f32: Optional[torch.Tensor] = None, max_row_norm: float = 1.0):
+        from . import _lib, ops
+        self.peers, self.shard, self.shard_f32 = peers, shard_bf16.contiguous(), shard_f32
+        self.id_offset, self.threshold, self.max_row_norm = int(id_offset), threshold, float(max_row_norm)
+        dev = shard_bf16.device
+        nbytes = int(_lib.lib().spp_sharded_match_workspace_bytes(peers.world, peers.m_local, shard_bf16.shape[0], 512))
+        if nbytes == 0:
+            raise ValueError("PeerShardedMatcher: unsupported shape")
+        self._ws, self._ws_bytes = ops.alloc_workspace(dev, nbytes), nbytes
+        self.ids = torch.empty((peers.m_local,), dtype=torch.int32, device=dev)
+        self.sims = torch.empty((peers.m_local,), dtype=torch.float32, device=dev)
+        self.launches = 5
+
+    def match(self, probes: torch.Tensor, stages: int = STAGE_ALL) -> Tuple[torch.Tensor, torch.Tensor]:
+        import ctypes
+        from . import _lib
+        if probes.shape != (self.peers.m_local, 512) or probes.dtype != torch.float32 or not probes.is_contiguous():
+            raise ValueError(f"PeerShardedMatcher.match: probes must be a contiguous fp32 [{self.peers.m_local}, 512] tensor")
+        thr = float("nan") if self.threshold is None else float(self.threshold)
+        p = lambda t: ctypes.c_void_p(0 if t is None else t.data_ptr())
+        _lib.check(_lib.lib().spp_sharded_match_top1(
+            ctypes.byref(self.peers.struct), p(probes), p(self.shard), p(self.shard_f32), self.max_row_norm, self.shard.shape[0], 512,
+            self.id_offset, thr, stages, p(self.ids), p(self.sims), None, p(self._ws), self._ws_bytes,
+            ctypes.c_void_p(torch.cuda.current_stream(probes.device).cuda_stream)), "spp_sharded_match_top1")
+        return self.ids, self.sims

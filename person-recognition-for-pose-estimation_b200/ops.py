@@ -113,38 +113,66 @@ def head_decode(levels: Sequence, strides: Sequence[float] = (8, 16, 32)) -> tor
 
 
 class NmsResult:
-    """Padded, device-resident NMS output: ``dets [B, max_det, 6]``, ``count [B]`` (negative = candidate
-    list overflowed), ``keys [B, max_det]`` (anchor*nc + cls of every kept row, -1 padding)."""
+    """Padded, device-resident NMS output: ``dets [B, max_det, 6]``, ``count [B]`` (negative = the candidate
+    list overflowed ``max_candidates``; kept rows = ``~count``), ``keys [B, max_det]`` (anchor*nc + cls of every kept
+    row, -1 padding)."""
 
     def __init__(self, dets, count, keys):
         self.dets, self.count, self.keys = dets, count, keys
 
+    def kept(self) -> torch.Tensor:
+        """Rows kept per image, overflow flag removed."""
+        return torch.where(self.count < 0, ~self.count, self.count)
+
+    def overflowed(self) -> torch.Tensor:
+        return self.count < 0
+
     def to_list(self) -> List[torch.Tensor]:
         """The reference's return type: a list of ``[n_i, 6]`` tensors (one D2H of the counts)."""
-        counts = self.count.abs().tolist()
+        counts = self.kept().tolist()
         return [self.dets[i, :c] for i, c in enumerate(counts)]
 
     def keys_list(self) -> List[torch.Tensor]:
-        counts = self.count.abs().tolist()
+        counts = self.kept().tolist()
         return [self.keys[i, :c] for i, c in enumerate(counts)]
 
 
 _ws_cache = {}
+_ws_retired = []     # replaced scratch buffers stay referenced: a captured CUDA graph may still hold their address
 
 
-def _workspace(dev: torch.device, nbytes: int, tag: str) -> torch.Tensor:
-    """Grow-only per-(device, stream, tag) scratch buffer, 1 KB aligned (caching allocator gives 512 B)."""
-    key = (dev, torch.cuda.current_stream(dev).cuda_stream, tag)
-    buf = _ws_cache.get(key)
-    if buf is None or buf.numel() < nbytes + 1024:
-        buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
-        _ws_cache[key] = buf
+def alloc_workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
+    """A caller-owned, 1 KB-aligned scratch buffer (pass it as ``workspace=``).  ``SelectivePosePipeline`` owns its
+    workspaces this way, so the addresses baked into its CUDA graph stay valid for the pipeline's life."""
+    buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
     off = (-buf.data_ptr()) % 1024
     return buf[off:off + nbytes]
 
 
+def _workspace(dev: torch.device, nbytes: int, tag: str, given: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``given`` (caller-owned) if passed, else the grow-only per-(device, stream, tag) scratch buffer, 1 KB aligned.
+    A buffer replaced by a larger one is retired, never freed: an earlier graph capture may replay with its address."""
+    if given is not None:
+        if given.dtype != torch.uint8 or not given.is_cuda or given.numel() < nbytes or given.data_ptr() % 1024:
+            raise ValueError(f"workspace must be a 1 KB-aligned CUDA uint8 tensor of at least {nbytes} bytes")
+        return given
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream, tag)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            _ws_retired.append(buf)
+        buf = alloc_workspace(dev, nbytes)
+        _ws_cache[key] = buf
+    return buf[:nbytes]
+
+
+def nms_workspace_bytes(batch: int, num_anchors: int, nc: int, max_candidates: int = 0) -> int:
+    return int(_lib.lib().spp_nms_workspace_bytes(batch, num_anchors, nc, max_candidates))
+
+
 def nms_decoded(pred: torch.Tensor, conf_thres: float = 0.001, iou_thres: float = 0.65, max_det: int = MAX_DET,
-                max_nms: int = MAX_NMS, max_wh: float = MAX_WH, max_candidates: int = 0) -> NmsResult:
+                max_nms: int = MAX_NMS, max_wh: float = MAX_WH, max_candidates: int = 0,
+                workspace: Optional[torch.Tensor] = None) -> NmsResult:
     """``non_max_suppression`` (training/yolopt/util.py:123-169) on a decoded ``[B, 4+nc, A]`` tensor."""
     _need_cuda("nms_decoded", pred)
     pred = _f32c("nms_decoded", pred)
@@ -156,7 +184,7 @@ def nms_decoded(pred: torch.Tensor, conf_thres: float = 0.001, iou_thres: float 
     count = torch.empty((b,), dtype=torch.int32, device=pred.device)
     keys = torch.empty((b, max_det), dtype=torch.int32, device=pred.device)
     nbytes = L.spp_nms_workspace_bytes(b, a, nc, max_candidates)
-    ws = _workspace(pred.device, nbytes, "nms")
+    ws = _workspace(pred.device, nbytes, "nms", workspace)
     _lib.check(L.spp_nms_decoded(_ptr(pred), b, nc, a, conf_thres, iou_thres, max_det, max_nms, max_wh, max_candidates,
                                  _ptr(dets), _ptr(count), _ptr(keys), _ptr(ws), nbytes, _stream(pred)), "spp_nms_decoded")
     return NmsResult(dets, count, keys)
@@ -171,7 +199,7 @@ def set_decode_nms_mode(mode: str) -> str:
 
 def decode_nms(levels: Sequence, strides: Sequence[float] = (8, 16, 32), conf_thres: float = 0.001,
                iou_thres: float = 0.65, max_det: int = MAX_DET, max_nms: int = MAX_NMS, max_wh: float = MAX_WH,
-               max_candidates: int = 0, out: Optional[NmsResult] = None) -> NmsResult:
+               max_candidates: int = 0, out: Optional[NmsResult] = None, workspace: Optional[torch.Tensor] = None) -> NmsResult:
     """Fused ``Head.forward`` (eval) + ``non_max_suppression`` from the raw per-level maps (concatenated, or
     ``(box, cls)`` pairs straight from the head's conv stacks — no ``cat`` copy)."""
     _need_cuda("decode_nms", *_flat_levels(levels))
@@ -183,7 +211,7 @@ def decode_nms(levels: Sequence, strides: Sequence[float] = (8, 16, 32), conf_th
                         torch.empty((b,), dtype=torch.int32, device=dev),
                         torch.empty((b, max_det), dtype=torch.int32, device=dev))
     nbytes = L.spp_nms_workspace_bytes(b, a, nc, max_candidates)
-    ws = _workspace(dev, nbytes, "nms")
+    ws = _workspace(dev, nbytes, "nms", workspace)
     if cptrs is None:
         _lib.check(L.spp_decode_nms(ptrs, hs, ws_, st, n, b, nc, conf_thres, iou_thres, max_det, max_nms, max_wh,
                                     max_candidates, _ptr(out.dets), _ptr(out.count), _ptr(out.keys), _ptr(ws), nbytes,
@@ -224,30 +252,50 @@ def to_bf16(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def match_workspace_bytes(m: int, n: int, d: int = 512) -> int:
+    return int(_lib.lib().spp_match_workspace_bytes(m, n, d))
+
+
 def match_top1(emb: torch.Tensor, gallery_bf16: torch.Tensor, threshold: Optional[float] = None, id_offset: int = 0,
-               want_keys: bool = False, _simt: bool = False):
-    """Cosine top-1 of every probe against a bf16, row-normalised gallery ``[N, 512]``.
+               want_keys: bool = False, _simt: bool = False, gallery_f32: Optional[torch.Tensor] = None,
+               max_row_norm: float = 1.0, workspace: Optional[torch.Tensor] = None, out=None):
+    """Cosine top-1 of every probe against a bf16 gallery ``[N, 512]`` (rows normalised at enrolment).
+    ``gallery_f32``: the fp32 rows the bf16 copy was rounded from — when given, candidates are re-scored against them, so
+    ids and similarities are those of the reference's fp32 ``F.linear(...).max(1)``; ``max_row_norm``: the largest gallery
+    row norm (1 for a normalised gallery).  The id is the exact fp32 arg-max for any gallery content (include/spp.h).
     Returns ``(ids int32 [M], sims fp32 [M])`` (+ packed int64 keys for a cross-shard MAX reduce)."""
-    _need_cuda("match_top1", emb, gallery_bf16)
+    _need_cuda("match_top1", emb, gallery_bf16, gallery_f32)
     emb = _f32c("match_top1", emb)
     if gallery_bf16.dtype != torch.bfloat16 or not gallery_bf16.is_contiguous():
         raise TypeError("match_top1: gallery must be a contiguous bfloat16 [N, 512] tensor (see enrol_gallery)")
     if emb.dim() != 2 or gallery_bf16.dim() != 2 or emb.shape[1] != gallery_bf16.shape[1]:
         raise ValueError(f"match_top1: shape mismatch {tuple(emb.shape)} vs {tuple(gallery_bf16.shape)}")
+    if gallery_f32 is not None:
+        if gallery_f32.dtype != torch.float32 or not gallery_f32.is_contiguous() or gallery_f32.shape != gallery_bf16.shape:
+            raise TypeError("match_top1: gallery_f32 must be a contiguous float32 tensor of the bf16 gallery's shape")
+        if _simt:
+            raise ValueError("match_top1: the SIMT cross-check has no fp32-gallery mode")
     m, d = emb.shape
     n = gallery_bf16.shape[0]
     L = _lib.lib()
-    ids = torch.empty((m,), dtype=torch.int32, device=emb.device)
-    sims = torch.empty((m,), dtype=torch.float32, device=emb.device)
-    keys = torch.empty((m,), dtype=torch.int64, device=emb.device) if want_keys else None
+    if out is None:
+        ids = torch.empty((m,), dtype=torch.int32, device=emb.device)
+        sims = torch.empty((m,), dtype=torch.float32, device=emb.device)
+        keys = torch.empty((m,), dtype=torch.int64, device=emb.device) if want_keys else None
+    else:
+        ids, sims, keys = out
     nbytes = L.spp_match_workspace_bytes(m, n, d)
     if nbytes == 0:
         raise ValueError(f"match_top1: unsupported shape M={m} N={n} D={d} (D must be 512, N >= 1)")
-    ws = _workspace(emb.device, nbytes, "match")
-    fn = L.spp_debug_match_top1_simt if _simt else L.spp_match_top1
+    ws = _workspace(emb.device, nbytes, "match", workspace)
     thr = float("nan") if threshold is None else float(threshold)
-    _lib.check(fn(_ptr(emb), _ptr(gallery_bf16), m, n, d, thr, id_offset, _ptr(ids), _ptr(sims), _ptr(keys), _ptr(ws),
-                  nbytes, _stream(emb)), "spp_match_top1")
+    if _simt:
+        _lib.check(L.spp_debug_match_top1_simt(_ptr(emb), _ptr(gallery_bf16), m, n, d, thr, id_offset, _ptr(ids), _ptr(sims),
+                                               _ptr(keys), _ptr(ws), nbytes, _stream(emb)), "spp_debug_match_top1_simt")
+    else:
+        _lib.check(L.spp_match_top1_ex(_ptr(emb), _ptr(gallery_bf16), _ptr(gallery_f32), float(max_row_norm), m, n, d, thr,
+                                       id_offset, _ptr(ids), _ptr(sims), _ptr(keys), _ptr(ws), nbytes, _stream(emb)),
+                   "spp_match_top1")
     return (ids, sims, keys) if want_keys else (ids, sims)
 
 

@@ -78,11 +78,13 @@ class SelectivePosePipeline:
     def __init__(self, inputs: StepInputs, gallery_bf16: torch.Tensor, device: torch.device, threshold: float = 0.4,
                  conf_thres: float = 0.001, iou_thres: float = 0.65, decode_mode: str = "dark", use_graph: bool = True,
                  id_offset: int = 0, concurrent: bool = True, matcher=None, capture_collectives: bool = False,
-                 select_on_device: bool = False):
+                 select_on_device: bool = False, gallery_f32: Optional[torch.Tensor] = None, max_row_norm: float = 1.0):
         self.device = device
         self.threshold, self.conf, self.iou, self.mode = threshold, conf_thres, iou_thres, decode_mode
         self.id_offset = id_offset
         self.gallery = gallery_bf16.to(device).contiguous()
+        self.gallery_f32 = None if gallery_f32 is None else gallery_f32.to(device).float().contiguous()
+        self.max_row_norm = float(max_row_norm)
         self.inp = StepInputs.from_tensors({k: v.to(device).contiguous() for k, v in inputs.tensors().items()})
         self.out: Dict[str, torch.Tensor] = {}
         self.graph: Optional[torch.cuda.CUDAGraph] = None
@@ -104,13 +106,25 @@ class SelectivePosePipeline:
         # The NCCL collectives run eagerly on a high-priority side stream beside the graph.
         # capture_collectives=True would capture them into the graph instead — NOT the default: on B200 /
         # NCCL 2.28.9 / torch 2.11 a multi-branch capture containing the two collectives hung at replay.
+        # A dist.PeerShardedMatcher (capturable = True) has no NCCL call at all: its five kernels exchange probes and
+        # keys over NVLink peer memory and are captured like every other kernel of the step.
         self.matcher = matcher
-        self.capture_collectives = capture_collectives and use_graph
-        self._eager_match = matcher is not None and not self.capture_collectives
+        self.capture_collectives = (capture_collectives or getattr(matcher, "capturable", False)) and use_graph
+        self._eager_match = matcher is not None and not (self.capture_collectives or getattr(matcher, "capturable", False))
+        # The pipeline owns its scratch buffers: their addresses are baked into the captured graph, so they must live
+        # exactly as long as the pipeline does (ops' shared grow-only cache may replace its buffers at any later call).
+        b_, a_ = self.inp.face_levels[0].shape[0], sum(l.shape[2] * l.shape[3] for l in self.inp.face_levels)
+        nc_ = self.inp.face_levels[0].shape[1] - 64
+        self._ws_face = ops.alloc_workspace(device, ops.nms_workspace_bytes(b_, a_, nc_))
+        ncp_ = self.inp.person_levels[0].shape[1] - 64
+        ap_ = sum(l.shape[2] * l.shape[3] for l in self.inp.person_levels)
+        self._ws_person = ops.alloc_workspace(device, ops.nms_workspace_bytes(self.inp.person_levels[0].shape[0], ap_, ncp_))
+        self._ws_match = (ops.alloc_workspace(device, ops.match_workspace_bytes(self.inp.embeddings.shape[0], self.gallery.shape[0]))
+                          if matcher is None else None)
         self._match_stream = torch.cuda.Stream(device, priority=-1) if self._eager_match else None
         self._side = [torch.cuda.Stream(device) for _ in range(3)]
         with torch.cuda.stream(self._stream):
-            if matcher is not None:
+            if self._eager_match:
                 self.out["ids"], self.out["sims"] = matcher.match(self.inp.embeddings)
             self._enqueue()                       # warm-up: sizes workspaces, sets kernel attributes
             self._enqueue()
@@ -136,24 +150,31 @@ class SelectivePosePipeline:
         sides = self._side if self.concurrent else [main, main, main]
         n = 0
         with torch.cuda.stream(sides[0]):
-            face = ops.decode_nms(i.face_levels, conf_thres=self.conf, iou_thres=self.iou, out=self.out.get("_face"))
+            face = ops.decode_nms(i.face_levels, conf_thres=self.conf, iou_thres=self.iou, out=self.out.get("_face"),
+                                  workspace=self._ws_face)
         with torch.cuda.stream(sides[1]):
-            person = ops.decode_nms(i.person_levels, conf_thres=self.conf, iou_thres=self.iou, out=self.out.get("_person"))
+            person = ops.decode_nms(i.person_levels, conf_thres=self.conf, iou_thres=self.iou, out=self.out.get("_person"),
+                                    workspace=self._ws_person)
         # candidate scan + candidate decode + NMS kernel per head (the count memset is not a kernel); one fused kernel
         # per head after ops.set_decode_nms_mode("fused")
         n += 2 * (1 if _lib.lib().spp_decode_nms_mode(-1) == 1 else 3)
         if self.matcher is None:
             with torch.cuda.stream(sides[2]):
-                ids, sims, keys = ops.match_top1(i.embeddings, self.gallery, self.threshold, self.id_offset, want_keys=True)
+                ids, sims, keys = ops.match_top1(i.embeddings, self.gallery, self.threshold, self.id_offset, want_keys=True,
+                                                 gallery_f32=self.gallery_f32, max_row_norm=self.max_row_norm,
+                                                 workspace=self._ws_match,
+                                                 out=(self.out["ids"], self.out["sims"], self.out["keys"]) if "keys" in self.out and self.out["keys"] is not None else None)
             n += 3          # normalise, tcgen05 GEMM + top-2, fp32 re-score
         elif self._eager_match:
             ids, sims, keys = self.out.get("ids"), self.out.get("sims"), None
             n += 4          # (eager, in step()) normalise, GEMM + top-2, re-score, key unpack
         else:
             with torch.cuda.stream(sides[2]):
-                ids, sims = self.matcher.match(i.embeddings)      # all_gather -> local top-1 -> all_reduce(MAX) -> unpack
+                # peer matcher: push probes -> wait -> local top-1 -> push keys -> reduce (5 kernels, no NCCL);
+                # NCCL matcher (capture_collectives): all_gather -> local top-1 -> all_reduce(MAX) -> unpack
+                ids, sims = self.matcher.match(i.embeddings)
             keys = None
-            n += 4
+            n += getattr(self.matcher, "launches", 4)
         boxes, frame_idx = i.boxes, i.frame_idx
         if self.select_on_device:
             if self.concurrent:              # the selection needs both detection chains and the match

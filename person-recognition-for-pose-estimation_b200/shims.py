@@ -78,22 +78,35 @@ class Gallery:
     ``F.normalize(kernel)`` of training/lightning/face_recognition/module.py:137 (wrong axis).
     Enrolment is off the hot path."""
 
-    def __init__(self, rows_bf16: torch.Tensor, id_offset: int = 0):
+    def __init__(self, rows_bf16: torch.Tensor, id_offset: int = 0, rows_f32: Optional[torch.Tensor] = None,
+                 max_row_norm: Optional[float] = None):
         if rows_bf16.dtype != torch.bfloat16 or rows_bf16.dim() != 2:
             raise TypeError("Gallery: expected a bfloat16 [N, 512] tensor")
         self.rows = rows_bf16.contiguous()
         self.id_offset = int(id_offset)
+        # fp32 rows the bf16 copy was rounded from (optional): candidates are re-scored against them, so ids and
+        # similarities are the reference's fp32 ones; without them they are exact for the bf16 gallery.
+        self.rows_f32 = None if rows_f32 is None else rows_f32.float().contiguous()
+        # Largest row norm: scales the band of bf16 scores that get the exact re-score (1 for normalised rows; the
+        # quirk-Q3 enrolment does NOT give unit rows).  Measured once here — enrolment is off the hot path.
+        if max_row_norm is None:
+            src = self.rows_f32 if self.rows_f32 is not None else self.rows.float()
+            max_row_norm = float(src.norm(dim=1).max()) if src.shape[0] else 1.0
+            if self.rows_f32 is not None and self.rows.shape[0]:
+                max_row_norm = max(max_row_norm, float(self.rows.float().norm(dim=1).max()))
+        self.max_row_norm = float(max(max_row_norm, 1e-6))
 
     @classmethod
-    def from_kernel(cls, kernel: torch.Tensor, quirk_q3: bool = False) -> "Gallery":
+    def from_kernel(cls, kernel: torch.Tensor, quirk_q3: bool = False, keep_f32: bool = False) -> "Gallery":
         kn = torch.nn.functional.normalize(kernel) if quirk_q3 else kernel / torch.norm(kernel, 2, 0, True)
-        return cls(ops.to_bf16(kn.t().contiguous()))
+        rows = kn.t().contiguous()
+        return cls(ops.to_bf16(rows), rows_f32=rows if keep_f32 else None)
 
     @classmethod
-    def from_rows(cls, rows: torch.Tensor, normalize: bool = True, id_offset: int = 0) -> "Gallery":
+    def from_rows(cls, rows: torch.Tensor, normalize: bool = True, id_offset: int = 0, keep_f32: bool = False) -> "Gallery":
         if normalize:
             rows = ops.l2_normalize(rows, mode="normalize")[0]
-        return cls(ops.to_bf16(rows), id_offset)
+        return cls(ops.to_bf16(rows), id_offset, rows_f32=rows if keep_f32 else None)
 
     def __len__(self) -> int:
         return self.rows.shape[0]
@@ -106,7 +119,8 @@ class Gallery:
         self.rows.cpu().view(torch.int16).numpy().tofile(path)
         with open(path + ".json", "w") as f:
             json.dump({"ids": int(self.rows.shape[0]), "dim": int(self.rows.shape[1]), "dtype": "bfloat16",
-                       "id_offset": self.id_offset, "layout": "row-major, rows unit-norm"}, f)
+                       "id_offset": self.id_offset, "max_row_norm": self.max_row_norm,
+                       "layout": "row-major, rows normalised at enrolment"}, f)
 
     @classmethod
     def load(cls, path: str, device, world: int = 1, rank: int = 0) -> "Gallery":
@@ -119,12 +133,13 @@ class Gallery:
         lo, hi = shard_bounds(meta["ids"], world, rank)
         mm = np.memmap(path, dtype=np.int16, mode="r", shape=(meta["ids"], meta["dim"]))
         rows = torch.from_numpy(np.array(mm[lo:hi])).view(torch.bfloat16).to(device)
-        return cls(rows, id_offset=meta.get("id_offset", 0) + lo)
+        return cls(rows, id_offset=meta.get("id_offset", 0) + lo, max_row_norm=meta.get("max_row_norm"))
 
     def match(self, embeddings: torch.Tensor, threshold: Optional[float] = None):
         """``pred = (F.linear(F.normalize(emb), G) * s).max(1)[1]`` (face_recognition/module.py:136-145) plus the
         optional similarity gate; returns ``(ids int64 [M], sims fp32 [M])``, ``ids == -1`` where gated."""
-        ids, sims = ops.match_top1(embeddings, self.rows, threshold, self.id_offset)
+        ids, sims = ops.match_top1(embeddings, self.rows, threshold, self.id_offset, gallery_f32=self.rows_f32,
+                                   max_row_norm=self.max_row_norm)
         return ids.long(), sims
 
 
@@ -245,16 +260,28 @@ COCO_SIGMAS = (.026, .025, .025, .035, .035, .079, .079, .072, .072, .062, .062,
 
 def coco_keypoint_results(pred_coords: torch.Tensor, pred_scores: torch.Tensor, boxes: torch.Tensor, areas: torch.Tensor,
                           masks: torch.Tensor, is_crowd: torch.Tensor, image_ids: Sequence[int],
-                          keypoint_thresh: float = 0.3) -> list:
+                          keypoint_thresh: float = 0.3, seen_image_ids: Optional[set] = None) -> list:
     """The reference builds its COCO predictions with a triple Python loop and ``.item()`` per value
     (module.py:505-560).  Same rows, one kernel: ``pred_coords [B,K,2]`` normalised, ``pred_scores [B,K]``,
     ``boxes [B,N,4]`` xyxy, ``areas [B,N]``, ``masks / is_crowd [B,N]`` bool.  As in the reference, every
     instance ``n < masks[b].sum()`` of image ``b`` that is not a crowd gets image ``b``'s keypoints scaled
-    into its own box; ``bbox`` is the xyxy box as the reference emits it.  One D2H of the packed rows."""
+    into its own box; ``bbox`` is the xyxy box as the reference emits it.  One D2H of the packed rows.
+    ``seen_image_ids`` is the reference's ``self._eval_cache['image_ids']`` (module.py:509-513): an image whose id is
+    already in the set is skipped, every processed id is added — pass the same set for every batch of a validation
+    run (``None``: de-duplicate within this call only)."""
     dev = pred_coords.device
     m = masks.to("cpu").bool()
     crowd = is_crowd.to("cpu").bool()
-    pairs = [(b, n) for b in range(len(image_ids)) for n in range(int(m[b].sum())) if not bool(crowd[b, n])]
+    seen = seen_image_ids if seen_image_ids is not None else set()
+    fresh = []
+    for b in range(len(image_ids)):
+        iid = image_ids[b]
+        iid = iid.item() if hasattr(iid, "item") else iid
+        if iid in seen:
+            continue
+        seen.add(iid)
+        fresh.append(b)
+    pairs = [(b, n) for b in fresh for n in range(int(m[b].sum())) if not bool(crowd[b, n])]
     if not pairs:
         return []
     bi = torch.tensor([b for b, _ in pairs], device=dev)

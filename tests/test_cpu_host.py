@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(spp):
     for name in sorted(declared):
         assert hasattr(lib, name), f"libspp.so does not export {name}"
     assert declared == set(spp._lib.SIGNATURES), "ctypes table and headers disagree"
-    assert lib.spp_abi_version() == 1
+    assert lib.spp_abi_version() == 2
 
 
 def test_no_cpu_fallback(spp):
@@ -101,6 +101,47 @@ def test_sharded_gallery_top1_gloo_world2():
         out = mgr.dict()
         mp.spawn(_worker, args=(world, port, 301, 12, out), nprocs=world, join=True)
         assert dict(out) == {0: True, 1: True}
+
+
+def _peer_worker(rank, world, port, out):
+    import importlib
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = importlib.import_module("person-recognition-for-pose-estimation_b200.dist")
+    opened = []
+
+    def alloc(nbytes):                       # stand-ins for spp_peer_alloc / spp_peer_open (those need a GPU)
+        return 0x1000 * (rank + 1), bytes([rank]) * 64
+
+    def open_(handle):
+        opened.append(handle[0])
+        return 0x1000 * (handle[0] + 1) + 1
+    g = d.PeerGroup(24, alloc=alloc, open_=open_)
+    want = [0x1000 * (r + 1) + (0 if r == rank else 1) for r in range(world)]
+    out[rank] = bool(g.world == world and g.rank == rank and g.ptrs == want and sorted(opened) == [r for r in range(world) if r != rank]
+                     and [g.struct.buffers[r] for r in range(world)] == want and g.struct.m_local == 24
+                     and g.handles == [bytes([r]) * 64 for r in range(world)])
+    g.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_peer_group_handle_exchange_gloo_world2():
+    """Host side of the peer-memory exchange: every rank publishes its IPC handle, opens every other rank's, and the
+    rank-ordered pointer table handed to the kernels (spp_peer_group) has its own buffer at its own rank."""
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_peer_worker, args=(world, port, out), nprocs=world, join=True)
+        assert dict(out) == {0: True, 1: True}
+
+
+def test_peer_buffer_layout_is_pure_host_arithmetic(spp):
+    L = spp._lib.lib()
+    b = L.spp_peer_buffer_bytes(8, 640, 512)
+    assert b >= 2 * 8 * 640 * 512 * 6 + 2 * 8 * 640 * 8 and b % 1024 == 0
+    assert L.spp_peer_buffer_bytes(17, 640, 512) == 0 and L.spp_peer_buffer_bytes(8, 640, 256) == 0
+    assert L.spp_sharded_match_workspace_bytes(8, 640, 125000, 512) > 0
 
 
 def test_synthetic_inputs_are_deterministic(synth):
