@@ -169,6 +169,46 @@ def roi_bytes(boxes, frame_h, frame_w, out_h=256, out_w=192):
     return float(((x1 - x0 + 1) * (y1 - y0 + 1)).sum()) * 3 * 4
 
 
+def shared_config(args, wl, world: int, shard: bool, collective: str) -> dict:
+    """The `config` object both arms print (same keys, same values: the driver compares them)."""
+    return {
+        "workload": f"{args.workload}: {wl['desc']}",
+        "frames_per_step": wl["batch"], "crops_per_step": wl["batch"] * wl["per_frame"], "gallery_ids": wl["gallery"],
+        "frames_dtype": args.frames, "decode_mode": args.decode_mode, "n_gpus": world,
+    }
+
+
+def bind_to_gpu_numa(local_rank: int) -> dict:
+    """Pin this process (and hence the pinned buffers it first-touches and its copy-issuing thread) to the CPUs of the
+    GPU's NUMA node.  Plumbing for the end-to-end region only; a no-op when the box exposes a single node."""
+    info = {"numa_node": None, "cpus": None, "bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        info["numa_node"] = node
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        info["numa_nodes_on_box"] = len(nodes)
+        if node >= 0 and len(nodes) > 1:
+            with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+                cpus = set()
+                for part in f.read().strip().split(","):
+                    a, _, b = part.partition("-")
+                    cpus.update(range(int(a), int(b or a) + 1))
+            os.sched_setaffinity(0, cpus)
+            info.update(cpus=len(cpus), bound=True)
+    except Exception as e:      # no sysfs entry / no permission: leave the affinity alone
+        info["error"] = type(e).__name__
+    return info
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -186,9 +226,15 @@ def main():
                     help="crop list = persons containing a matched face (ops.associate on the NMS output) instead of the synthetic boxes")
     ap.add_argument("--gallery-ids", type=int, default=0, help="override the workload's gallery size")
     ap.add_argument("--shard-gallery", default="auto", choices=["auto", "yes", "no"],
-                    help="N>1: shard the gallery by rows (NCCL top-1 reduce) or replicate it; auto = shard above 100k ids")
-    ap.add_argument("--capture-collectives", action="store_true", help="N>1: capture the NCCL calls into the CUDA graph (hung in testing)")
+                    help="N>1: shard the gallery by rows or replicate it; auto = shard above 100k ids")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="sharded gallery: exchange by the match kernels over NVLink peer memory (captured in the graph), or NCCL "
+                         "all_gather + all_reduce(MAX) issued eagerly beside the graph")
+    ap.add_argument("--capture-collectives", action="store_true", help="--collective nccl: capture the NCCL calls into the CUDA graph (hung in testing)")
     ap.add_argument("--serial", action="store_true", help="run the four chains back to back instead of on forked streams")
+    ap.add_argument("--no-cfg3", action="store_true", help="skip the cfg3 record (1M-id gallery, sharded at N>1)")
+    ap.add_argument("--cfg3-ids", type=int, default=1_000_000)
+    ap.add_argument("--copy-streams", type=int, default=2, help="streams the per-step H2D copies of the e2e region are spread over")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "spp" else args.warmup
 
@@ -219,6 +265,7 @@ def main():
         return
 
     assert torch.cuda.is_available(), "bench.py (impl spp) needs a CUDA device: there is no CPU fallback"
+    numa = bind_to_gpu_numa(local_rank)          # before any pinned allocation (first touch decides the node)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -226,31 +273,6 @@ def main():
         opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)    # NCCL kernels must not queue behind the crop
         dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     peaks = load_peaks()
-
-    # ---- inputs (per-rank shard: every rank owns `batch` frames; weak scaling) ------------------
-    inp = pipeline.synthetic_inputs(wl["batch"], wl["height"], wl["width"], wl["per_frame"], wl["joints"], seed=rank)
-    # One gallery for the whole job (same seed on every rank); with N > 1 it is sharded by rows.  Every rank's
-    # probes are planted from the full gallery.
-    ms = spp.synth.make_match_set(world * wl["batch"] * wl["per_frame"], wl["gallery"], seed=1000)
-    m_local = wl["batch"] * wl["per_frame"]
-    inp.embeddings = ms.embeddings[rank * m_local:(rank + 1) * m_local].contiguous()
-    if args.frames == "u8":
-        inp.frames = (inp.frames * 255.0).round().clamp(0, 255).to(torch.uint8)
-    gallery_bf16 = ms.gallery.to(torch.bfloat16)
-    shard_lo, shard_hi = spp.dist.shard_bounds(wl["gallery"], world, rank)
-    matcher = None
-    # Placement policy (SURVEY.md 8e): a gallery of <= 100k ids (<= 102 MB bf16) is replicated on every GPU and
-    # the step has no collective at all; larger galleries are sharded by rows and reduced over NCCL.
-    shard = world > 1 and (args.shard_gallery == "yes" or (args.shard_gallery == "auto" and wl["gallery"] > 100_000))
-    if shard:          # this rank holds ids [shard_lo, shard_hi); NCCL top-1 (value,index) reduce
-        matcher = spp.dist.gpu_matcher(gallery_bf16[shard_lo:shard_hi].to(dev).contiguous(), shard_lo, 0.4)
-    pipe = pipeline.SelectivePosePipeline(inp, gallery_bf16, dev, decode_mode=args.decode_mode, use_graph=not args.no_graph,
-                                          concurrent=not args.serial, matcher=matcher,
-                                          capture_collectives=args.capture_collectives, select_on_device=args.select_on_device)
-    pipe.bind_host(inp)
-    B, P, K, M = wl["batch"], wl["batch"] * wl["per_frame"], wl["joints"], wl["batch"] * wl["per_frame"]
-    A = sum(l.shape[2] * l.shape[3] for l in inp.face_levels)
-    nc = inp.face_levels[0].shape[1] - 64
 
     def barrier():
         if world > 1:
@@ -265,6 +287,37 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t.item())
         return ms_val
+
+    # ---- inputs (per-rank shard: every rank owns `batch` frames; weak scaling) ------------------
+    inp = pipeline.synthetic_inputs(wl["batch"], wl["height"], wl["width"], wl["per_frame"], wl["joints"], seed=rank)
+    # One gallery for the whole job (same seed on every rank); with N > 1 it is sharded by rows.  Every rank's
+    # probes are planted from the full gallery.
+    ms = spp.synth.make_match_set(world * wl["batch"] * wl["per_frame"], wl["gallery"], seed=1000)
+    m_local = wl["batch"] * wl["per_frame"]
+    inp.embeddings = ms.embeddings[rank * m_local:(rank + 1) * m_local].contiguous()
+    if args.frames == "u8":
+        inp.frames = (inp.frames * 255.0).round().clamp(0, 255).to(torch.uint8)
+    gallery_bf16 = ms.gallery.to(torch.bfloat16)
+    shard_lo, shard_hi = spp.dist.shard_bounds(wl["gallery"], world, rank)
+    matcher, peers = None, None
+    # Placement policy (SURVEY.md 8e): a gallery of <= 100k ids (<= 102 MB bf16) is replicated on every GPU and
+    # the step has no collective at all; larger galleries are sharded by rows (cfg3 record below).
+    shard = world > 1 and (args.shard_gallery == "yes" or (args.shard_gallery == "auto" and wl["gallery"] > 100_000))
+    if shard:          # this rank holds ids [shard_lo, shard_hi)
+        shard_rows = gallery_bf16[shard_lo:shard_hi].to(dev).contiguous()
+        if args.collective == "peer":
+            peers = spp.dist.PeerGroup(m_local)
+            matcher = spp.dist.PeerShardedMatcher(peers, shard_rows, shard_lo, 0.4)
+        else:
+            matcher = spp.dist.gpu_matcher(shard_rows, shard_lo, 0.4)
+    barrier()          # ranks enter the first exchange step together (a peer wait is bounded at 60 s)
+    pipe = pipeline.SelectivePosePipeline(inp, gallery_bf16, dev, decode_mode=args.decode_mode, use_graph=not args.no_graph,
+                                          concurrent=not args.serial, matcher=matcher,
+                                          capture_collectives=args.capture_collectives, select_on_device=args.select_on_device)
+    pipe.bind_host(inp, args.copy_streams)
+    B, P, K, M = wl["batch"], wl["batch"] * wl["per_frame"], wl["joints"], wl["batch"] * wl["per_frame"]
+    A = sum(l.shape[2] * l.shape[3] for l in inp.face_levels)
+    nc = inp.face_levels[0].shape[1] - 64
 
     sampler = ClockSampler(local_rank)
     st = pipe.stream
@@ -285,58 +338,61 @@ def main():
     frames_per_s = world * B * args.steps / (dev_ms / 1e3)
 
     # ---- (2) end to end from pinned host buffers ---------------------------------------------------
-    e2e_steps = max(3, min(args.steps, 20))
-    for _ in range(2):
-        pipe.run_host()
-    barrier()
-    with sampler:
-        e0.record(st)
-        for _ in range(e2e_steps):
-            pipe.run_host()
-        e1.record(st)
+    def time_e2e(p, n_steps):
+        for _ in range(2):
+            p.run_host()
         barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with sampler:
+            a0.record(p.stream)
+            for _ in range(n_steps):
+                p.run_host()
+            a1.record(p.stream)
+            barrier()
+        return max_over_ranks(a0.elapsed_time(a1))
+
+    e2e_steps = max(3, min(args.steps, 20))
+    e2e_ms = time_e2e(pipe, e2e_steps)
     e2e_fps = world * B * e2e_steps / (e2e_ms / 1e3)
 
     # ---- (2b) the same end-to-end pass with uint8 frames (what a video decoder delivers, and what HF's default
-    #      do_rescale=True path expects): 4x fewer frame bytes over PCIe.  Reported beside the fp32 headline. -----
+    #      do_rescale=True path expects): 4x fewer frame bytes over PCIe.  Reported beside the fp32 headline at every N;
+    #      `bench.py --impl reference --frames u8` is the same-config CPU arm. -----
     e2e_u8 = None
-    if world == 1 and args.frames == "f32" and not args.select_on_device and args.workload == "cfg2":
+    if args.frames == "f32" and not args.select_on_device and args.workload == "cfg2" and not shard:
         import copy
         inp8 = copy.copy(inp)
         inp8.frames = (inp.frames * 255.0).round().clamp(0, 255).to(torch.uint8)
         pipe8 = pipeline.SelectivePosePipeline(inp8, gallery_bf16, dev, decode_mode=args.decode_mode, use_graph=not args.no_graph,
                                                concurrent=not args.serial)
-        pipe8.bind_host(inp8)
-        for _ in range(2):
-            pipe8.run_host()
-        pipe8.stream.synchronize()
+        pipe8.bind_host(inp8, args.copy_streams)
         n8 = max(3, min(args.steps, 10))
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record(pipe8.stream)
-        for _ in range(n8):
-            pipe8.run_host()
-        a1.record(pipe8.stream)
-        pipe8.stream.synchronize()
-        ms8 = a0.elapsed_time(a1) / n8
-        e2e_u8 = {"value": round(B / (ms8 / 1e3), 1), "unit": "frames/s", "frames_dtype": "u8", "h2d_bytes_per_step": pipe8.h2d_bytes,
-                  "d2h_bytes_per_step": pipe8.d2h_bytes, "ms_per_step": round(ms8, 3), "steps": n8}
+        ms8 = time_e2e(pipe8, n8) / n8
+        e2e_u8 = {"value": round(world * B / (ms8 / 1e3), 1), "unit": "frames/s", "frames_dtype": "u8", "h2d_bytes_per_step": pipe8.h2d_bytes,
+                  "d2h_bytes_per_step": pipe8.d2h_bytes, "ms_per_step": round(ms8, 3), "steps": n8,
+                  "h2d_gbs_per_gpu": round(pipe8.h2d_bytes / (ms8 * 1e6), 2)}
         del pipe8, inp8
         torch.cuda.empty_cache()
 
     # ---- (3) per-kernel durations (eager launches, CUDA events around each op on its stream) ------
     ops = spp.ops
     i = pipe.inp
+    u8_kw = ({"mean": [m * 255.0 for m in (0.485, 0.456, 0.406)], "std": [v * 255.0 for v in (0.229, 0.224, 0.225)]}
+             if args.frames == "u8" else {})
     stages = {
         "decode_nms_face": lambda: ops.decode_nms(i.face_levels, out=pipe.out["_face"]),
         "decode_nms_person": lambda: ops.decode_nms(i.person_levels, out=pipe.out["_person"]),
         "match_top1": lambda: ops.match_top1(i.embeddings, pipe.gallery, 0.4),
-        "crop_affine": lambda: ops.crop_affine(i.frames, i.boxes, i.frame_idx, out=pipe.out["pixel_values"],
-                                               **({"mean": [m * 255.0 for m in (0.485, 0.456, 0.406)],
-                                                   "std": [v * 255.0 for v in (0.229, 0.224, 0.225)]} if args.frames == "u8" else {})),
+        "crop_affine": lambda: ops.crop_affine(i.frames, i.boxes, i.frame_idx, out=pipe.out["pixel_values"], **u8_kw),
         "heatmap_decode": lambda: ops.heatmap_decode(i.heatmaps, i.flipped, i.perm, i.boxes, args.decode_mode, 11,
                                                      out=(pipe.out["keypoints"], pipe.out["scores"], pipe.out["argmax"])),
     }
+    if args.decode_mode == "dark":
+        # HF's float32 flat-index behaviour (reference quirk Q6) — the mode that reproduces ONE HF call on all 640 crops
+        # literally, which is what the CPU arm below times.  Not the default; timed beside it.
+        q_out = tuple(torch.empty_like(pipe.out[k]) for k in ("keypoints", "scores", "argmax"))
+        stages["heatmap_decode_hf_f32_index"] = lambda: ops.heatmap_decode(i.heatmaps, i.flipped, i.perm, i.boxes, "dark", 11,
+                                                                           flags=ops.FLAG_HF_F32_INDEX, out=q_out)
     # ONE captured graph holding, per stage, [L2 flush, event, stage, event]: kernel-to-kernel hand-over
     # inside a graph is ~1 us, so the events bracket device time, not host launch latency.  The flush is a
     # READ of a 256 MB buffer (2x the L2): it evicts the previous stage's lines without leaving dirty
@@ -353,7 +409,7 @@ def main():
     # back to back between the two events — every launch misses L2 anyway, and the event / launch overhead
     # (~3 us, comparable to 5 % of a 50 us kernel) is amortised; the small-input stages get one launch after
     # the flush so that they are timed cold.
-    inner = {k: (4 if k in ("heatmap_decode", "crop_affine") else 1) for k in stages}
+    inner = {k: (4 if k.startswith(("heatmap_decode", "crop_affine")) else 1) for k in stages}
     tg = torch.cuda.CUDAGraph()
     with torch.cuda.graph(tg, stream=st):
         for k, fn in stages.items():
@@ -371,82 +427,259 @@ def main():
             for k in stages:
                 samples[k].append(ev[k][0].elapsed_time(ev[k][1]) / inner[k])
     kern_us = {k: 1e3 * statistics.median(v) for k, v in samples.items()}
+    del filler
+
+    traffic_all = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic_all = json.load(f).get(args.workload, {})
+    traffic_note = "static: dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/ncu_traffic.json), not measured in this run"
 
     hm_bytes = P * (K * 64 * 48 * 4 * (2 if i.flipped is not None else 1) + K * 16)
-    n_cand = float(pipe.out["_face"].kept().sum())   # kept rows; candidates are a small multiple
     det_full_bytes = B * ((64 + nc) * A * 4 + 300 * 6 * 4 + 4)
     crop_bytes = P * 3 * 256 * 192 * 4 + roi_bytes(inp.boxes, wl["height"], wl["width"]) * (0.25 if args.frames == "u8" else 1.0)
     match_flops = 2.0 * M * wl["gallery"] * 512
     kernels = {
         "heatmap_decode": dict(bound="hbm", us=kern_us["heatmap_decode"], bytes=hm_bytes),
         "crop_affine": dict(bound="hbm", us=kern_us["crop_affine"], bytes=crop_bytes),
-        "decode_nms_face": dict(bound="hbm", us=kern_us["decode_nms_face"], bytes=det_full_bytes,
-                                note="bytes = SURVEY 8(d) figure (all 64+nc planes); the fused kernel only reads the class "
-                                     "planes plus the DFL planes of candidate anchors, so achieved can exceed peak"),
-        "decode_nms_person": dict(bound="hbm", us=kern_us["decode_nms_person"], bytes=det_full_bytes),
+        # decode+NMS reads the class planes of every anchor and the 64 DFL planes of candidate anchors only: a
+        # latency-bound chain of three small launches, not an HBM stream.  `survey_bytes` (SURVEY 8d: every plane of the
+        # head, what the reference's Head.forward reads) is given for scale only — no fraction of peak is derived from it.
+        "decode_nms_face": dict(bound="latency", us=kern_us["decode_nms_face"], survey_bytes=det_full_bytes),
+        "decode_nms_person": dict(bound="latency", us=kern_us["decode_nms_person"], survey_bytes=det_full_bytes),
         "match_top1": dict(bound="tensor", us=kern_us["match_top1"], flops=match_flops),
     }
     for k, d in kernels.items():
+        tr = traffic_all.get(k)
         if d["bound"] == "hbm":
             d["achieved"] = d["bytes"] / (d["us"] * 1e-6) / 1e9
             d["peak"], d["unit"] = peaks["hbm"], "GB/s"
-        else:
+            d["frac"] = d["achieved"] / d["peak"]
+            if tr:
+                d["traffic"] = tr
+                d["frac_dram"] = tr / (d["us"] * 1e-6) / 1e9 / peaks["hbm"]
+        elif d["bound"] == "tensor":
             d["achieved"] = d["flops"] / (d["us"] * 1e-6) / 1e12
             d["peak"], d["unit"] = peaks["bf16"], "TFLOP/s"
-        d["frac"] = d["achieved"] / d["peak"]
-    dominant = max(kernels, key=lambda k: kernels[k]["us"])
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            traffic = json.load(f).get(args.workload, {}).get(dominant)
+            d["frac"] = d["achieved"] / d["peak"]
+        else:
+            if tr:
+                d["bytes_read_actual"] = tr
+                d["achieved"] = tr / (d["us"] * 1e-6) / 1e9
+                d["peak"], d["unit"] = peaks["hbm"], "GB/s"
+                d["frac"] = d["achieved"] / d["peak"]
+            d["note"] = "latency-bound (3 launches, one CTA per frame in the NMS); frac = actual DRAM bytes / time / peak, from the static ncu capture"
+    dominant = max((k for k in kernels if kernels[k]["bound"] != "latency"), key=lambda k: kernels[k]["us"])
     dk = kernels[dominant]
     roofline = dict(kernel=dominant, bound=dk["bound"], achieved=round(dk["achieved"], 1), peak=dk["peak"], unit=dk["unit"],
-                    frac=round(dk["frac"], 4), traffic=traffic, peak_source=peaks["source"],
+                    frac=round(dk["frac"], 4), traffic=dk.get("traffic"), frac_dram=round(dk["frac_dram"], 4) if "frac_dram" in dk else None,
+                    traffic_source=traffic_note, peak_source=peaks["source"],
                     launch_us=round(dk["us"], 2), algorithmic=dk.get("bytes", dk.get("flops")),
                     step_share=round(dk["us"] / sum(v["us"] for v in kernels.values()), 3))
+    step_floor = None
+    if traffic_all:
+        tot = sum(traffic_all.get(k, 0) for k in kernels)
+        step_floor = {"dram_bytes_per_step": tot, "floor_us": round(tot / peaks["hbm"] / 1e3, 1),
+                      "frac_of_floor": round(tot / peaks["hbm"] / 1e3 / (ms_per_step * 1e3), 3), "source": traffic_note}
+
+    # ---- (3b) cfg3: 1M-id gallery, local at N=1, row-sharded at N>1 (north-star config 3) --------------
+    cfg3 = None
+    if not args.no_cfg3 and args.workload == "cfg2" and not args.select_on_device:
+        cfg3 = run_cfg3(args, spp, pipeline, pipe, dev, rank, world, B, wl["per_frame"], barrier, max_over_ranks, peaks)
 
     # ---- (4) CPU baseline on this host (rank 0, N=1 only) ------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n, times = time_cpu_reference(inp, ms.gallery, B, wl["per_frame"], args.cpu_budget)
         cpu = dict(value=round(n / statistics.median(times), 3), unit="frames/s", cores=os.cpu_count(), kind="port",
-                   sample=f"{n} of {B} frames of {args.workload} ({n * wl['per_frame']} crops), 1 timed pass: torch CPU head decode + "
-                          "torchvision nms x2 heads, F.normalize/F.linear/max, HF VitPoseImageProcessor.preprocess, "
-                          "flip-average + HF post_process_pose_estimation",
+                   sample=f"{n} of {B} frames of {args.workload} ({n * wl['per_frame']} crops), 1 timed pass. " + CPU_ARM_TEXT,
                    seconds=round(statistics.median(times), 3))
 
     if rank == 0:
+        cfg = shared_config(args, wl, world, shard, args.collective)
         line = {
             "metric": "frames/sec post-backbone selective-pose pipeline (batch 64, 1/2/4/8 B200)",
             "value": round(frames_per_s, 1), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {wl['desc']}", "frames_per_gpu": B, "crops_per_gpu": P,
-                       "frames_dtype": args.frames,
-                       "arithmetic": "fp32 throughout; gallery match = bf16 tcgen05 candidates re-scored in exact fp32",
-                       "decode_mode": args.decode_mode, "parallelism": f"dp{world}: frames/crops/heatmaps sharded with no collective" + (
-                           f"; the {wl['gallery']}-id gallery sharded by rows ({wl['gallery'] // world} per GPU), probes all-gathered, NCCL all_reduce(MAX) "
-                           "of packed (sim,id) keys" if shard else (f"; the {wl['gallery']}-id gallery replicated per GPU (policy: shard above 100k ids)" if world > 1 else "")),
-                       "l2": "step region: inputs (1.6 GB per step) are larger than the 126 MB L2, no flush; "
-                             "per-kernel region: a 256 MB read before each stage evicts L2 (cold, clean); heatmap decode and crop "
-                             "(inputs > 2x L2) are the mean of 4 back-to-back launches after the flush",
-                       "cuda_graph": not args.no_graph, "crop_boxes": "selected on the device from the detections" if args.select_on_device else "synthetic input boxes",
-                       "streams": "serial" if args.serial else "4 forked chains (crop->heatmap | det face | det person | match)"},
+            "config": cfg,
+            "impl_detail": {
+                "frames_per_gpu": B, "crops_per_gpu": P,
+                "arithmetic": "fp32 throughout; gallery match = bf16 tcgen05 candidate search, every candidate inside the bf16 error band "
+                              "re-scored in exact fp32 (the id is the fp32 arg-max for any gallery content)",
+                "decode_quirk": "intended" if args.decode_mode == "dark" else None,
+                "decode_quirk_note": "DARK taps at their true positions (= HF called on <= 299 crops at a time). The CPU arm calls HF once on all "
+                                     "crops, which from crop 299 on reads its taps through a rounded float32 index (reference quirk Q6); "
+                                     "kernels.heatmap_decode_hf_f32_index times the mode that reproduces that literally",
+                "parallelism": f"dp{world}: frames/crops/heatmaps sharded with no collective" + (
+                    f"; the {wl['gallery']}-id gallery sharded by rows ({wl['gallery'] // world} per GPU), exchange = {args.collective}"
+                    if shard else (f"; the {wl['gallery']}-id gallery replicated per GPU (policy: shard above 100k ids; the sharded case is the cfg3 record)" if world > 1 else "")),
+                "l2": "step region: inputs (1.6 GB per step) are larger than the 126 MB L2, no flush; "
+                      "per-kernel region: a 256 MB read before each stage evicts L2 (cold, clean); heatmap decode and crop "
+                      "(inputs > 2x L2) are the mean of 4 back-to-back launches after the flush",
+                "cuda_graph": not args.no_graph, "crop_boxes": "selected on the device from the detections" if args.select_on_device else "synthetic input boxes",
+                "streams": "serial" if args.serial else "4 forked chains (crop->heatmap | det face | det person | match)",
+                "host_numa": numa,
+            },
             "crops_per_s": round(world * P * args.steps / (dev_ms / 1e3), 1),
             "e2e": {"value": round(e2e_fps, 1), "unit": "frames/s", "h2d_bytes_per_step": pipe.h2d_bytes,
-                    "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": round(e2e_ms / e2e_steps, 3), "steps": e2e_steps},
+                    "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": round(e2e_ms / e2e_steps, 3), "steps": e2e_steps,
+                    "h2d_gbs_per_gpu": round(pipe.h2d_bytes / (e2e_ms / e2e_steps * 1e6), 2), "copy_streams": pipe.copy_streams},
             "e2e_u8_frames": e2e_u8,
             "gpu_launches": pipe.launches_per_step * args.steps,
             "roofline": roofline,
+            "step_dram_floor": step_floor,
             "kernels": {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in d.items()} for k, d in kernels.items()},
+            "cfg3": cfg3,
             "cpu_baseline": cpu,
             "clocks": sampler.summary(),
         }
+        if "heatmap_decode_hf_f32_index" in kern_us:
+            line["kernels"]["heatmap_decode_hf_f32_index"] = {"us": round(kern_us["heatmap_decode_hf_f32_index"], 3),
+                                                              "note": "SPP_DECODE_FLAG_HF_F32_INDEX: literal HF float32 tap index (quirk Q6)"}
         emit(line)
+    if peers is not None:
+        peers.close()
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+CPU_ARM_TEXT = ("Detection decode + NMS and the match are the ORACLE PORT of the reference (oracle.det.head_decode = nn.py:255-270 in torch, "
+                "oracle.det.non_max_suppression = util.py:123-169 with the real torchvision.ops.nms, oracle.match.match_top1 = "
+                "F.normalize / F.linear / max as face_recognition/module.py:136-145) because /root/reference does not exist on the GPU box; "
+                "crop and DARK decode (~95 % of the time) are the REAL HF VitPoseImageProcessor.preprocess / post_process_pose_estimation calls. "
+                "All host threads.")
+
+
+def make_gallery_on_device(n: int, dev, seed: int = 4242, chunk: int = 131072):
+    """[n, 512] unit rows, generated on the GPU in fixed chunks so that every rank of a job builds the same matrix."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    out = torch.empty((n, 512), dtype=torch.bfloat16, device=dev)
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        x = torch.randn((hi - lo, 512), generator=g, device=dev)
+        out[lo:hi] = (x / x.norm(dim=1, keepdim=True)).to(torch.bfloat16)
+    return out
+
+
+def run_cfg3(args, spp, pipeline, pipe2, dev, rank, world, B, per_frame, barrier, max_over_ranks, peaks):
+    """North-star config 3 at this N: the cfg2 step per GPU (64 frames) against a 1M-id gallery — held locally at N=1,
+    row-sharded over the ranks at N>1 with the exchange done by the match kernels over NVLink peer memory (or NCCL with
+    --collective nccl).  Reports the whole step and the three phases of the match; at N>1 rank 0 also runs the replicated
+    match on the full gallery and compares ids and similarities bit for bit."""
+    import copy
+    d = spp.dist
+    n_ids, m_local = args.cfg3_ids, B * per_frame
+    full = make_gallery_on_device(n_ids, dev)                       # 1 GB bf16; every rank builds the same rows
+    g = torch.Generator(device=dev).manual_seed(977 + rank)
+    ids = torch.randint(0, n_ids, (m_local,), generator=g, device=dev)
+    unknown = torch.rand(m_local, generator=g, device=dev) < 0.1
+    noise = torch.randn((m_local, 512), generator=g, device=dev) / 512 ** 0.5
+    probes = torch.where(unknown[:, None], torch.randn((m_local, 512), generator=g, device=dev), full[ids].float() + 0.3 * noise)
+    probes = (probes / probes.norm(dim=1, keepdim=True) * (5.0 + 25.0 * torch.rand((m_local, 1), generator=g, device=dev))).contiguous()
+    lo, hi = d.shard_bounds(n_ids, world, rank)
+    inp3 = copy.copy(pipe2.inp)                                     # same device-resident frames / head maps / heatmaps
+    inp3.embeddings = probes
+    matcher = peers = None
+    if world > 1:
+        shard_rows = full[lo:hi].contiguous()
+        if args.collective == "peer":
+            peers = d.PeerGroup(m_local)
+            matcher = d.PeerShardedMatcher(peers, shard_rows, lo, 0.4)
+        else:
+            matcher = d.gpu_matcher(shard_rows, lo, 0.4)
+        if rank != 0:
+            del full
+            full = None
+            torch.cuda.empty_cache()
+    barrier()
+    pipe3 = pipeline.SelectivePosePipeline(inp3, full if world == 1 else torch.empty((1, 512), dtype=torch.bfloat16), dev,
+                                           decode_mode=args.decode_mode, use_graph=not args.no_graph, concurrent=not args.serial,
+                                           matcher=matcher, capture_collectives=args.capture_collectives)
+    st = pipe3.stream
+    steps = max(5, min(args.steps, 20))
+    for _ in range(3):
+        pipe3.step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(steps):
+        pipe3.step()
+    e1.record(st)
+    barrier()
+    step_ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    ids_step, sims_step = pipe3.out["ids"].clone(), pipe3.out["sims"].clone()
+
+    # phases of the match alone (eager launches on one stream, events between the phases, ranks aligned by a barrier)
+    reps = 5
+    ph = {"allgather_us": [], "match_us": [], "allreduce_us": []}
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    for _ in range(reps + 1):
+        barrier()
+        with torch.cuda.stream(st):
+            if world == 1:
+                evs[0].record(st); evs[1].record(st)
+                spp.ops.match_top1(probes, full, 0.4)
+                evs[2].record(st); evs[3].record(st)
+            elif args.collective == "peer":
+                evs[0].record(st)
+                matcher.match(probes, d.STAGE_PUSH | d.STAGE_WAIT)
+                evs[1].record(st)
+                matcher.match(probes, d.STAGE_SEARCH)
+                evs[2].record(st)
+                matcher.match(probes, d.STAGE_FINALIZE | d.STAGE_REDUCE)
+                evs[3].record(st)
+            else:
+                import torch.distributed as dist
+                evs[0].record(st)
+                gath = torch.empty((world * m_local, 512), dtype=probes.dtype, device=dev)
+                dist.all_gather_into_tensor(gath, probes)
+                evs[1].record(st)
+                keys = matcher.local_match(gath)
+                evs[2].record(st)
+                dist.all_reduce(keys, op=dist.ReduceOp.MAX)
+                spp.ops.match_unpack_keys(keys[rank * m_local:(rank + 1) * m_local].contiguous(), 0.4)
+                evs[3].record(st)
+        st.synchronize()
+        ph["allgather_us"].append(1e3 * evs[0].elapsed_time(evs[1]))
+        ph["match_us"].append(1e3 * evs[1].elapsed_time(evs[2]))
+        ph["allreduce_us"].append(1e3 * evs[2].elapsed_time(evs[3]))
+    phase = {k: max_over_ranks(statistics.median(v[1:])) for k, v in ph.items()}
+
+    equal = None
+    if world > 1:
+        ok = torch.ones(1, device=dev)
+        if rank == 0:       # replicated run on rank 0: its own probes against the whole gallery
+            ref_ids, ref_sims = spp.ops.match_top1(probes, full, 0.4)
+            ok[0] = float(torch.equal(ref_ids, ids_step) and torch.equal(ref_sims, sims_step))
+        import torch.distributed as dist
+        dist.broadcast(ok, 0)
+        equal = bool(ok.item() > 0)
+    planted_ok = bool((torch.where(unknown, torch.full_like(ids, -1), ids).int() == ids_step)[~unknown].all().item())
+    flops = 2.0 * (world * m_local) * (hi - lo) * 512
+    rec = {
+        "workload": f"cfg3: {world * B} frames over {world} GPU(s) ({B} per GPU), {n_ids}-id bf16 gallery " +
+                    ("held locally" if world == 1 else f"sharded by rows ({hi - lo} ids per GPU), every rank scores all {world * m_local} probes against its shard"),
+        "exchange": "none (N=1)" if world == 1 else ("peer: probes and (sim,id) keys written by the match kernels into the peers' buffers over NVLink, 5 kernels captured in the step's CUDA graph, no NCCL call"
+                                                       if args.collective == "peer" else "nccl: all_gather_into_tensor + all_reduce(MAX) on packed keys, eager beside the graph"),
+        "ms_per_step": round(step_ms, 4), "frames_per_s": round(world * B / (step_ms / 1e3), 1), "steps": steps,
+        "match_us": round(phase["match_us"], 1), "allgather_us": round(phase["allgather_us"], 1), "allreduce_us": round(phase["allreduce_us"], 1),
+        "phase_note": "match alone, eager, after a barrier: allgather = normalise + push + wait for all ranks' probes; match = tcgen05 GEMM + top-2 "
+                      "over the local shard; allreduce = fp32 re-score + key push + wait + max + unpack (N=1: the whole local op is match_us)",
+        "match_tflops_per_gpu": round(flops / (phase["match_us"] * 1e-6) / 1e12, 1) if phase["match_us"] > 0 else None,
+        "match_frac_bf16_peak": round(flops / (phase["match_us"] * 1e-6) / 1e12 / peaks["bf16"], 3) if phase["match_us"] > 0 else None,
+        "sharded_ids_equal": equal, "planted_ids_recovered": planted_ok,
+        "limiter": max((("match GEMM", phase["match_us"]), ("probe exchange", phase["allgather_us"]), ("re-score + key reduce", phase["allreduce_us"])),
+                       key=lambda kv: kv[1])[0] + f" ({max(phase.values()):.0f} us of the {1e3 * step_ms:.0f} us step)",
+    }
+    del pipe3
+    if peers is not None:
+        barrier()
+        peers.close()
+    torch.cuda.empty_cache()
+    return rec
 
 
 def run_reference(args, wl, rank, world, pipeline, emit):
@@ -470,12 +703,11 @@ def run_reference(args, wl, rank, world, pipeline, emit):
         "value": round(fps, 3), "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": round(1e3 * total / len(times), 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {wl['desc']}", "frames_per_step": n, "crops_per_step": n * wl["per_frame"],
-                   "frames_dtype": args.frames,
-                   "decode_mode": "dark"},
+        "config": shared_config(args, wl, world, False, "none"),
+        "impl_detail": {"frames_timed_per_step": n, "crops_timed_per_step": n * wl["per_frame"]},
         "cpu_baseline": {"value": round(fps, 3), "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                          "sample": f"each step = the first {n} of {wl['batch']} frames of {args.workload} "
-                                   f"({n * wl['per_frame']} crops) through the reference's CPU calls"},
+                                   f"({n * wl['per_frame']} crops) through the reference's CPU calls. " + CPU_ARM_TEXT},
         "e2e": {"value": round(fps, 3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

@@ -242,20 +242,39 @@ class SelectivePosePipeline:
     # ---- host-fed pass --------------------------------------------------------------------------
     RESULT_KEYS = ("face_dets", "face_count", "person_dets", "person_count", "ids", "sims", "keypoints", "scores")
 
-    def bind_host(self, host_inputs: StepInputs) -> None:
-        """Pin the host-side inputs and allocate pinned result buffers."""
+    def bind_host(self, host_inputs: StepInputs, copy_streams: int = 2) -> None:
+        """Pin the host-side inputs and allocate pinned result buffers.  The H2D copies of a step are spread over
+        ``copy_streams`` streams (largest tensors first, balanced by bytes): one stream already saturates a PCIe link on
+        large copies, the second one hides the issue gaps between the dozen small tensors."""
         self._host_in = {k: (v if v.is_pinned() else v.contiguous().pin_memory()) for k, v in host_inputs.tensors().items()}
         self._host_out = {k: torch.empty(self.out[k].shape, dtype=self.out[k].dtype).pin_memory() for k in self.RESULT_KEYS}
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in self._host_in.values())
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in self._host_out.values())
+        self.copy_streams = max(1, int(copy_streams))
+        self._copy = [torch.cuda.Stream(self.device) for _ in range(self.copy_streams)]
+        load = [0] * self.copy_streams
+        self._copy_plan = [[] for _ in range(self.copy_streams)]
+        for k, t in sorted(self._host_in.items(), key=lambda kv: -kv[1].numel() * kv[1].element_size()):
+            j = load.index(min(load))
+            self._copy_plan[j].append(k)
+            load[j] += t.numel() * t.element_size()
 
     def run_host(self) -> Dict[str, torch.Tensor]:
         """H2D of every input from pinned memory, one pass, D2H of the compact results (async on the
         pipeline stream; call ``stream.synchronize()`` to wait)."""
         dst = self.inp.tensors()
-        with torch.cuda.stream(self._stream):
-            for k, src in self._host_in.items():
-                dst[k].copy_(src, non_blocking=True)
+        main = self._stream
+        ready = torch.cuda.Event()
+        ready.record(main)                       # the previous step's kernels have read the device inputs
+        for cs, names in zip(self._copy, self._copy_plan):
+            cs.wait_event(ready)
+            with torch.cuda.stream(cs):
+                for k in names:
+                    dst[k].copy_(self._host_in[k], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(cs)
+            main.wait_event(done)
+        with torch.cuda.stream(main):
             self._launch()
             for k, buf in self._host_out.items():
                 buf.copy_(self.out[k], non_blocking=True)
