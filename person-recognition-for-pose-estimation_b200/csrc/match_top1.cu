@@ -123,8 +123,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
     return d;
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+// tcgen05.ld 32 lanes x 32 columns: thread = accumulator row, registers = 32 consecutive columns.  Issue and wait are
+// separate so that the load of the next column block overlaps the arithmetic on the current one; the wait names the
+// registers as in/out operands, which keeps every use of them behind it.
+#define SPP_R32(r) \
+    r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8], r[9], r[10], r[11], r[12], r[13], r[14], r[15], r[16], r[17], r[18], \
+        r[19], r[20], r[21], r[22], r[23], r[24], r[25], r[26], r[27], r[28], r[29], r[30], r[31]
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -135,10 +140,30 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+
+// ---- candidate keys ---------------------------------------------------------------------------------------------
+// The epilogue ranks scores through 32-bit keys: the fp32 bits of (score + off) — positive, hence ordered as integers —
+// with the low 8 mantissa bits replaced by (255 - column inside the 256-wide gallery tile).  Inserting a key into a
+// sorted (best, second, dropped-max) triple is four integer min / max operations, branch-free, and the winner's column
+// travels inside the key.  Cost: scores are resolved to 2^-14 (off + score < 4), which the re-score band absorbs.
+__device__ __forceinline__ void key_insert(uint32_t k, uint32_t &k1, uint32_t &k2, uint32_t &k3) {
+    k3 = max(k3, min(k, k2));
+    const uint32_t t = max(k, k2);
+    k2 = min(t, k1);
+    k1 = max(k, k1);
+}
+__device__ __forceinline__ float key_score_lo(uint32_t k, float off) { return k ? __uint_as_float(k & 0xffffff00u) - off : -INFINITY; }
+__device__ __forceinline__ float key_score_hi(uint32_t k, float off) { return k ? __uint_as_float(k | 0xffu) - off : -INFINITY; }
 
 // ------------------------------------------------------------------------------------------------
 // GEMM + fused row top-2
@@ -148,8 +173,10 @@ struct GemmParams {
     int tiles_n, nsplit;   // every M-tile is cut into nsplit chunks of gallery tiles; work item = (M-tile, chunk)
     int items;             // m_tiles * nsplit, distributed round-robin over the persistent CTAs
     const unsigned *step;  // peer exchange: device step counter, parity selects the probe buffer (tmap_a0 / tmap_a1); NULL: tmap_a0
-    Cand *part;            // [m_tiles*BM, nsplit, 2]
-    float *third;          // [m_tiles*BM, nsplit] best bf16 score the top-2 of a (row, chunk) did NOT keep
+    Cand *part;            // [m_tiles*BM, nsplit, 2]  best two (score, id) of every (probe row, chunk)
+    float *dropped;        // [tiles_n, m_tiles*BM]    per (gallery tile, probe row): upper bound of the scores of that tile's
+                           //                          rows that are NOT one of the chunk's best two
+    float key_off;         // score -> key offset (> the largest |score|)
 };
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -260,54 +287,82 @@ match_gemm_top2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid
             }
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> running top-2 per probe row =====
+        // ===== epilogue: TMEM -> registers -> per probe row: best two of the chunk + per-tile dropped maximum =====
         const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
         const int row_in_tile = quarter * 32 + lane;
+        const float off = prm.key_off;
+        const int m_pad = ((prm.m + BM - 1) / BM) * BM;
         uint32_t tcount = 0;
         for (int item = blockIdx.x; item < prm.items; item += gridDim.x) {
             const int mt = item / prm.nsplit, sp = item - mt * prm.nsplit;
             int nt0, ntiles;
             chunk_range(sp, nt0, ntiles);
-            float v1 = -INFINITY, v2 = -INFINITY, v3 = -INFINITY;     // v3: largest score dropped from the top-2
-            int i1 = 0x7fffffff, i2 = 0x7fffffff;
+            uint32_t K1 = 0, K2 = 0;                     // running best two keys of the chunk and the tiles they came from
+            int T1 = 0, T2 = 0;
+            float *drow = prm.dropped + (size_t)(mt * BM + row_in_tile);
             for (int t = 0; t < ntiles; ++t, ++tcount) {
                 const int acc = tcount & 1;
                 const uint32_t acc_phase = (tcount >> 1) & 1;
                 mbar_wait(&t_full[acc], acc_phase);
                 tc_fence_after();
-                const int n0 = (nt0 + t) * BN;
+                const int tile = nt0 + t, n0 = tile * BN;
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
-                    float v[32];
-                    tmem_ld32(taddr + c * 32, v);
-                    float mx = v[0];
+                const bool partial = n0 + BN > prm.n;    // last tile: rows past the gallery's end are zero-filled, not candidates
+                uint32_t L1 = 0, L2 = 0, L3 = 0;         // tile-local best, second, dropped maximum (keys)
+                // One 32-column block.  Skipped whole when even its maximum cannot enter the top two (the usual case after
+                // the first tiles); otherwise 32 branch-free insertions.  Dropped scores only ever raise L3.
+                auto block = [&](const uint32_t (&r)[32], int c) {
+                    float mx = __uint_as_float(r[0]);
 #pragma unroll
-                    for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
-                    if (mx > v2) {                          // rare after the first tiles
-                        const int nb = n0 + c * 32;
+                    for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+                    const uint32_t kmx = __float_as_uint(mx + off) | 0xffu;          // >= every key of the block
+                    if (partial || kmx > max(K2, L2)) {
+                        const uint32_t cb = 255u - (uint32_t)(c * 32);               // low five bits all ones: cb - j == cb ^ j
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const float x = v[j];
-                            const int n = nb + j;
-                            if (n < prm.n) {
-                                if (x > v1) { v3 = fmaxf(v3, v2); v2 = v1; i2 = i1; v1 = x; i1 = n; }
-                                else if (x > v2) { v3 = fmaxf(v3, v2); v2 = x; i2 = n; }
-                                else v3 = fmaxf(v3, x);
-                            }
+                            uint32_t k = (__float_as_uint(__uint_as_float(r[j]) + off) & 0xffffff00u) | (cb ^ (uint32_t)j);
+                            if (partial && n0 + c * 32 + j >= prm.n) k = 0;
+                            key_insert(k, L1, L2, L3);
                         }
                     } else {
-                        v3 = fmaxf(v3, mx);                 // the whole block is dropped (may include zero-filled rows
-                    }                                       // past the gallery's end: conservative)
+                        L3 = max(L3, kmx);
+                    }
+                };
+                uint32_t ra[32], rb[32];
+                tmem_ld32_issue(taddr, ra);
+                tmem_ld32_wait(ra);
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; c += 2) {
+                    tmem_ld32_issue(taddr + (c + 1) * 32, rb);
+                    block(ra, c);
+                    tmem_ld32_wait(rb);
+                    if (c + 2 < BN / 32) tmem_ld32_issue(taddr + (c + 2) * 32, ra);
+                    block(rb, c + 1);
+                    if (c + 2 < BN / 32) tmem_ld32_wait(ra);
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&t_empty[acc]);
+                // merge the tile's best two into the chunk's; whatever falls out is recorded against ITS tile
+                uint32_t D = L3;
+                auto drop = [&](uint32_t k, int tl) {
+                    if (!k) return;
+                    if (tl == tile) { D = max(D, k); return; }
+                    float *p = drow + (size_t)tl * m_pad;                       // an earlier tile of this chunk: this thread wrote it
+                    *p = fmaxf(*p, key_score_hi(k, off));
+                };
+                auto offer = [&](uint32_t k) {
+                    if (k > K1) { drop(K2, T2); K2 = K1; T2 = T1; K1 = k; T1 = tile; }
+                    else if (k > K2) { drop(K2, T2); K2 = k; T2 = tile; }
+                    else D = max(D, k);
+                };
+                offer(L1);
+                offer(L2);
+                drow[(size_t)tile * m_pad] = key_score_hi(D, off);
             }
             Cand *o = prm.part + ((size_t)(mt * BM + row_in_tile) * prm.nsplit + sp) * 2;
-            o[0] = Cand{v1, i1};
-            o[1] = Cand{v2, i2};
-            prm.third[(size_t)(mt * BM + row_in_tile) * prm.nsplit + sp] = v3;
+            o[0] = Cand{key_score_lo(K1, off), K1 ? T1 * BN + 255 - (int)(K1 & 0xffu) : 0x7fffffff};
+            o[1] = Cand{key_score_lo(K2, off), K2 ? T2 * BN + 255 - (int)(K2 & 0xffu) : 0x7fffffff};
         }
     }
 
@@ -327,9 +382,10 @@ __host__ __device__ __forceinline__ void chunk_tiles(int tiles_n, int nsplit, in
 }
 
 // CUDA-core fp32 version of the same candidate search — device-side cross-check for the tests
-// (spp_match_top1 never dispatches to it).
+// (spp_match_top1 never dispatches to it).  One CTA per (probe row, chunk); pass 1 finds the chunk's best two, pass 2
+// the per-tile maximum over all other rows (the `dropped` table).
 __global__ void __launch_bounds__(128) match_simt_top2_kernel(const float *__restrict__ qn, const __nv_bfloat16 *__restrict__ gal,
-                                                              int m, int n, int tiles_n, int nsplit, Cand *part, float *third) {
+                                                              int m, int n, int tiles_n, int nsplit, int m_pad, Cand *part, float *dropped) {
     __shared__ float q[kDim];
     const int row = blockIdx.x, sp = blockIdx.y;
     for (int i = threadIdx.x; i < kDim; i += blockDim.x) q[i] = qn[(size_t)row * kDim + i];
@@ -338,35 +394,45 @@ __global__ void __launch_bounds__(128) match_simt_top2_kernel(const float *__res
     chunk_tiles(tiles_n, nsplit, sp, nt0, ntiles);
     const int lo = nt0 * BN, hi = min(n, (nt0 + ntiles) * BN);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float v1 = -INFINITY, v2 = -INFINITY, v3 = -INFINITY;
-    int i1 = 0x7fffffff, i2 = 0x7fffffff;
-    for (int g = lo + warp; g < hi; g += 4) {
+    auto score = [&](int g) {
         const __nv_bfloat16 *gr = gal + (size_t)g * kDim;
         float s = 0.f;
         for (int i = lane; i < kDim; i += 32) s = fmaf(q[i], __bfloat162float(gr[i]), s);
-        s = warp_sum(s);
-        if (s > v1 || (s == v1 && g < i1)) { v3 = fmaxf(v3, v2); v2 = v1; i2 = i1; v1 = s; i1 = g; }
-        else if (s > v2 || (s == v2 && g < i2)) { v3 = fmaxf(v3, v2); v2 = s; i2 = g; }
-        else v3 = fmaxf(v3, s);
+        return warp_sum(s);
+    };
+    float v1 = -INFINITY, v2 = -INFINITY;
+    int i1 = 0x7fffffff, i2 = 0x7fffffff;
+    for (int g = lo + warp; g < hi; g += 4) {
+        const float s = score(g);
+        if (s > v1 || (s == v1 && g < i1)) { v2 = v1; i2 = i1; v1 = s; i1 = g; }
+        else if (s > v2 || (s == v2 && g < i2)) { v2 = s; i2 = g; }
     }
     __shared__ Cand sc[4][2];
-    __shared__ float s3[4];
-    if (lane == 0) { sc[warp][0] = Cand{v1, i1}; sc[warp][1] = Cand{v2, i2}; s3[warp] = v3; }
+    __shared__ Cand top[2];
+    if (lane == 0) { sc[warp][0] = Cand{v1, i1}; sc[warp][1] = Cand{v2, i2}; }
     __syncthreads();
     if (threadIdx.x == 0) {
         Cand b1{-INFINITY, 0x7fffffff}, b2{-INFINITY, 0x7fffffff};
-        float b3 = fmaxf(fmaxf(s3[0], s3[1]), fmaxf(s3[2], s3[3]));
         for (int w = 0; w < 4; ++w)
             for (int k = 0; k < 2; ++k) {
                 const Cand c = sc[w][k];
-                if (c.v > b1.v || (c.v == b1.v && c.i < b1.i)) { b3 = fmaxf(b3, b2.v); b2 = b1; b1 = c; }
-                else if (c.v > b2.v || (c.v == b2.v && c.i < b2.i)) { b3 = fmaxf(b3, b2.v); b2 = c; }
-                else b3 = fmaxf(b3, c.v);
+                if (c.v > b1.v || (c.v == b1.v && c.i < b1.i)) { b2 = b1; b1 = c; }
+                else if (c.v > b2.v || (c.v == b2.v && c.i < b2.i)) { b2 = c; }
             }
         Cand *o = part + ((size_t)row * nsplit + sp) * 2;
         o[0] = b1;
         o[1] = b2;
-        third[(size_t)row * nsplit + sp] = b3;
+        top[0] = b1;
+        top[1] = b2;
+    }
+    __syncthreads();
+    const int k1 = top[0].i, k2 = top[1].i;
+    for (int t = warp; t < ntiles; t += 4) {                     // a warp per tile
+        const int t_lo = (nt0 + t) * BN, t_hi = min(n, t_lo + BN);
+        float d = -INFINITY;
+        for (int g = t_lo; g < t_hi; ++g)
+            if (g != k1 && g != k2) d = fmaxf(d, score(g));
+        if (lane == 0) dropped[(size_t)(nt0 + t) * m_pad + row] = d;
     }
 }
 
@@ -377,13 +443,14 @@ __global__ void __launch_bounds__(128) match_simt_top2_kernel(const float *__res
 // the fp32 arg-max.  Candidate search = bf16 probe x bf16 gallery with fp32 accumulation; re-score = fp32 probe x the
 // re-score gallery (the same bf16 rows, or the caller's fp32 rows).  With R = the largest gallery row norm and unit-norm
 // probes, |s_search - s_rescore| <= u * R (+ u * R when the re-score gallery is fp32, whose rows the bf16 copy rounds),
-// u = 2^-8 the bf16 unit roundoff (Cauchy-Schwarz on sum |q_i g_i|), plus < 1e-4 of fp32 accumulation error.  So
-// prune = 2 * that bound; the host computes it (match_prune_margin).
+// u = 2^-8 the bf16 unit roundoff (Cauchy-Schwarz on sum |q_i g_i|), plus the key quantisation and < 1e-4 of fp32
+// accumulation error.  prune = 2 * that bound; the host computes it (match_prune_margin).
 //
-// The GEMM epilogue keeps the best TWO scores per (probe, gallery chunk) and the best score it DROPPED (`third`).  When
-// third >= vmax - prune some dropped row of that chunk could still be the fp32 arg-max (three or more near-duplicate
-// enrolments of one person inside one chunk, the crowded top of a 1M-id gallery): the whole chunk is then re-scanned in
-// exact fp32 by all warps of the CTA.  Rare for planted probes; the result is the fp32 arg-max unconditionally.
+// The GEMM epilogue keeps the best TWO rows per (probe, gallery chunk) and, per (probe, 256-row gallery tile), an upper
+// bound of the scores of all OTHER rows of that tile (`dropped`).  A tile whose bound reaches vmax - prune may hide the
+// fp32 arg-max (three or more near-duplicate enrolments of one person, the crowded top of a 1M-id gallery): its 256 rows
+// are then re-scored in exact fp32 by all warps of the CTA.  Rare on realistic data — and the returned id is the fp32
+// arg-max unconditionally.
 struct FinParams {
     const float *qn;              // [m, 512] normalised probes (peer exchange: parity-0 buffer)
     size_t qn_parity_stride;      // peer exchange: elements between the two parity buffers
@@ -391,8 +458,8 @@ struct FinParams {
     const __nv_bfloat16 *gal;
     const float *gal_f32;         // optional fp32 rows for the re-score (NULL: the bf16 rows)
     const Cand *part;
-    const float *third;
-    int m, n, nsplit, tiles_n;
+    const float *dropped;         // [tiles_n, m_pad]
+    int m, n, nsplit, tiles_n, m_pad;
     float prune, threshold;
     int id_offset;
     int *out_id;
@@ -402,8 +469,9 @@ struct FinParams {
     size_t off_keys, keys_stride;
 };
 
-constexpr int kFinWarps = 8;
-constexpr int kFinSlots = 4;      // flagged chunks a probe row can hand to the CTA per round
+constexpr int kFinWarps = 8;      // probe rows per CTA (m_pad is a multiple of 128, so a CTA's 8 rows share a 32-byte sector of `dropped`)
+constexpr int kFinScan = 4;       // gallery tiles per thread and scan round (independent loads in flight)
+constexpr int kFinQueue = 32 * kFinWarps * kFinWarps * kFinScan;   // worst case of one scan round: every (tile, row) pair hits
 constexpr int kPer = kDim / 32;   // 16 dimensions per lane
 
 template <bool F32G>
@@ -458,7 +526,7 @@ __device__ __forceinline__ void load_probe(const float *qn, int row, int lane, f
 template <bool F32G>
 __global__ void __launch_bounds__(32 * kFinWarps) match_finalize_kernel(const FinParams prm) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * kFinWarps + warp;
+    const int row0 = blockIdx.x * kFinWarps, row = row0 + warp;
     const bool active = row < prm.m;
     const int n = prm.n, nsplit = prm.nsplit;
     unsigned step = 0;
@@ -467,9 +535,28 @@ __global__ void __launch_bounds__(32 * kFinWarps) match_finalize_kernel(const Fi
         step = __ldcg(prm.step);
         qn += (size_t)(step & 1u) * prm.qn_parity_stride;
     }
-    __shared__ int s_sp[kFinWarps][kFinSlots];
-    __shared__ float s_pv[kFinWarps * kFinSlots][kFinWarps];
-    __shared__ int s_pi[kFinWarps * kFinSlots][kFinWarps];
+    __shared__ float s_thr[kFinWarps];
+    __shared__ int s_q[kFinQueue];
+    __shared__ int s_nq;
+    __shared__ float s_pv[kFinWarps];
+    __shared__ int s_pi[kFinWarps];
+
+    // first round of the `dropped` scan (below): thread = gallery tile, one 32-byte sector holds the bounds of this CTA's
+    // 8 probe rows.  Requested here so that the loads are in flight during the candidate re-score.
+    constexpr int kRound = 32 * kFinWarps * kFinScan;
+    float4 da[kFinScan], db[kFinScan];
+    auto load_bounds = [&](int t0) {
+#pragma unroll
+        for (int u = 0; u < kFinScan; ++u) {
+            const int tile = t0 + u * 32 * kFinWarps + (int)threadIdx.x;
+            if (tile < prm.tiles_n) {
+                const float4 *d = reinterpret_cast<const float4 *>(prm.dropped + (size_t)tile * prm.m_pad + row0);
+                da[u] = __ldg(d);
+                db[u] = __ldg(d + 1);
+            }
+        }
+    };
+    load_bounds(0);
 
     float q[kPer];
     float vmax = -INFINITY, best = -INFINITY;
@@ -513,62 +600,59 @@ __global__ void __launch_bounds__(32 * kFinWarps) match_finalize_kernel(const Fi
         }
     }
 
-    // ---- chunks whose dropped scores reach the prune band: exact fp32 re-scan by the whole CTA ----
-    int sp_next = 0;
-    for (;;) {
-        int found = 0;
-        if (active) {
-            const float *th = prm.third + (size_t)row * nsplit;
-            while (found < kFinSlots && sp_next < nsplit) {
-                const int sp = sp_next + lane;
-                const bool f = sp < nsplit && th[sp] >= vmax - prm.prune;
-                unsigned b = __ballot_sync(FULL, f);
-                int last = -1;
-                while (b && found < kFinSlots) {
-                    last = __ffs(b) - 1;
-                    b &= b - 1;
-                    if (lane == 0) s_sp[warp][found] = sp_next + last;
-                    ++found;
-                }
-                sp_next = b ? sp_next + last + 1 : sp_next + 32;      // slots full: resume right after the last one taken
-            }
-        }
-        if (lane == 0)
-            for (int s = found; s < kFinSlots; ++s) s_sp[warp][s] = -1;
-        if (!__syncthreads_or(found > 0)) break;
-        for (int it = 0; it < kFinWarps * kFinSlots; ++it) {
-            const int sp = s_sp[it / kFinSlots][it % kFinSlots];
-            if (sp < 0) continue;                                   // block-uniform
-            const int orow = blockIdx.x * kFinWarps + it / kFinSlots;
-            int nt0, ntiles;
-            chunk_tiles(prm.tiles_n, nsplit, sp, nt0, ntiles);
-            const int lo = nt0 * BN, hi = min(n, (nt0 + ntiles) * BN);
-            float oq[kPer];
-            load_probe(qn, orow, lane, oq);
-            float pb = -INFINITY;
-            int pi = 0x7fffffff;
-            for (int g0 = lo + warp * 4; g0 < hi; g0 += kFinWarps * 4) {
-                RowFrag<F32G> fr[4];
+    // ---- tiles whose dropped rows reach the re-score band: exact fp32 re-scan of the tile by the whole CTA ----
+    if (lane == 0) s_thr[warp] = active ? vmax - prm.prune : INFINITY;
+    if (threadIdx.x == 0) s_nq = 0;
+    __syncthreads();
+    constexpr int kInFlight = F32G ? 4 : 8;
+    for (int t0 = 0; t0 < prm.tiles_n; t0 += kRound) {
+        if (t0) load_bounds(t0);
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (g0 + u < hi) fr[u] = load_frag<F32G>(prm, g0 + u, lane);
+        for (int u = 0; u < kFinScan; ++u) {
+            const int tile = t0 + u * 32 * kFinWarps + (int)threadIdx.x;
+            if (tile < prm.tiles_n) {
+                const float bound[kFinWarps] = {da[u].x, da[u].y, da[u].z, da[u].w, db[u].x, db[u].y, db[u].z, db[u].w};
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (g0 + u >= hi) continue;
-                    const float s = warp_sum(dot_frag<F32G>(oq, fr[u]));
-                    if (s > pb) { pb = s; pi = g0 + u; }            // ascending ids: the first maximum stays
-                }
+                for (int r = 0; r < kFinWarps; ++r)
+                    if (row0 + r < prm.m && bound[r] >= s_thr[r]) s_q[atomicAdd(&s_nq, 1)] = (r << 24) | tile;
             }
-            if (lane == 0) { s_pv[it][warp] = pb; s_pi[it][warp] = pi; }
         }
         __syncthreads();
-        for (int s = 0; s < found; ++s)
-            for (int w = 0; w < kFinWarps; ++w) {
-                const float v = s_pv[warp * kFinSlots + s][w];
-                const int i = s_pi[warp * kFinSlots + s][w];
-                if (v > best || (v == best && i < bidx)) { best = v; bidx = i; }
+        const int nq = s_nq;
+        for (int qi = 0; qi < nq; ++qi) {
+            const int e = s_q[qi];
+            const int owner = e >> 24, tl = e & 0xffffff;
+            float oq[kPer];
+            load_probe(qn, row0 + owner, lane, oq);
+            const int lo = tl * BN + warp * (BN / kFinWarps), hi = min(n, lo + BN / kFinWarps);
+            float pb = -INFINITY;
+            int pi = 0x7fffffff;
+            for (int g0 = lo; g0 < hi; g0 += kInFlight) {
+                RowFrag<F32G> fr[kInFlight];
+#pragma unroll
+                for (int u = 0; u < kInFlight; ++u)
+                    if (g0 + u < hi) fr[u] = load_frag<F32G>(prm, g0 + u, lane);
+#pragma unroll
+                for (int u = 0; u < kInFlight; ++u) {
+                    if (g0 + u >= hi) continue;
+                    const float sc = warp_sum(dot_frag<F32G>(oq, fr[u]));
+                    if (sc > pb) { pb = sc; pi = g0 + u; }          // ascending ids: the first maximum stays
+                }
             }
-        __syncthreads();                                            // slots are rewritten in the next round
+            if (lane == 0) { s_pv[warp] = pb; s_pi[warp] = pi; }
+            __syncthreads();
+            if (warp == owner) {
+#pragma unroll
+                for (int w = 0; w < kFinWarps; ++w) {
+                    const float v = s_pv[w];
+                    const int i = s_pi[w];
+                    if (v > best || (v == best && i < bidx)) { best = v; bidx = i; }
+                }
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) s_nq = 0;
+        __syncthreads();
     }
 
     if (active && lane == 0) {
@@ -751,8 +835,8 @@ int make_tmap(CUtensorMap *map, const void *base, int rows, int box_rows) {
 }
 
 struct MatchPlan {
-    int m_tiles, tiles_n, nsplit, sms;
-    size_t off_qn, off_qb, off_part, off_third, bytes;
+    int m_tiles, tiles_n, nsplit, sms, m_pad;
+    size_t off_qn, off_qb, off_part, off_drop, bytes;
 };
 
 // own_probes: the workspace also holds the normalised probes (fp32 + bf16); false when they live in a peer exchange buffer
@@ -798,24 +882,33 @@ MatchPlan plan_match(int m, int n, bool own_probes = true) {
     size_t off = 0;
     p.off_qn = off;    off += own_probes ? align_up((size_t)m * kDim * 4, 1024) : 0;
     p.off_qb = off;    off += own_probes ? align_up((size_t)m * kDim * 2, 1024) : 0;
-    p.off_part = off;  off += align_up((size_t)p.m_tiles * BM * ns * 2 * sizeof(Cand), 1024);
-    p.off_third = off; off += align_up((size_t)p.m_tiles * BM * ns * sizeof(float), 1024);
+    p.m_pad = p.m_tiles * BM;
+    p.off_part = off;  off += align_up((size_t)p.m_pad * ns * 2 * sizeof(Cand), 1024);
+    p.off_drop = off;  off += align_up((size_t)p.m_pad * p.tiles_n * sizeof(float), 1024);
     p.bytes = off;
     return p;
 }
 
+// score -> key offset: keys are the fp32 bits of (score + off), which must stay positive; |score| <= R * 1.01
+float match_key_offset(float max_row_norm) { return (max_row_norm > 0.f ? max_row_norm : 1.0f) * 1.01f + 1.0f; }
+
 float match_prune_margin(float max_row_norm, bool f32_rescore) {
     const float r = max_row_norm > 0.f ? max_row_norm : 1.0f;
     const float u = 0.00390625f;                         // bf16 unit roundoff 2^-8
-    return 2.0f * ((f32_rescore ? 2.0f : 1.0f) * u * r * 1.02f + 1e-4f);
+    // key quantisation: the low 8 mantissa bits of (score + off) < 2 * off are dropped
+    int e = 0;
+    std::frexp(2.0f * match_key_offset(r), &e);          // 2 * off = f * 2^e, f in [0.5, 1)
+    const float quant = std::ldexp(1.0f, e - 1 - 15);
+    return 2.0f * ((f32_rescore ? 2.0f : 1.0f) * u * r * 1.02f + quant + 1e-4f);
 }
 
 // candidate search (tcgen05 GEMM or the SIMT cross-check) over `m` normalised probes
 int launch_search(const __nv_bfloat16 *qb0, const __nv_bfloat16 *qb1, const unsigned *step, const float *qn_simt,
-                  const __nv_bfloat16 *gal, int m, int n, const MatchPlan &p, Cand *part, float *third, cudaStream_t st, bool simt) {
+                  const __nv_bfloat16 *gal, int m, int n, float max_row_norm, const MatchPlan &p, Cand *part, float *dropped,
+                  cudaStream_t st, bool simt) {
     if (simt) {
         dim3 grid(m, p.nsplit);
-        match_simt_top2_kernel<<<grid, 128, 0, st>>>(qn_simt, gal, m, n, p.tiles_n, p.nsplit, part, third);
+        match_simt_top2_kernel<<<grid, 128, 0, st>>>(qn_simt, gal, m, n, p.tiles_n, p.nsplit, p.m_pad, part, dropped);
         SPP_CHECK_LAUNCH();
         return SPP_OK;
     }
@@ -829,7 +922,7 @@ int launch_search(const __nv_bfloat16 *qb0, const __nv_bfloat16 *qb1, const unsi
     // per device and per context: set on every launch (about a microsecond; legal during stream capture)
     SPP_CHECK_CUDA(cudaFuncSetAttribute(match_gemm_top2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
     const int items = p.m_tiles * p.nsplit;
-    GemmParams gp{m, n, p.tiles_n, p.nsplit, items, step, part, third};
+    GemmParams gp{m, n, p.tiles_n, p.nsplit, items, step, part, dropped, match_key_offset(max_row_norm)};
     match_gemm_top2_kernel<<<items < p.sms ? items : p.sms, kGemmThreads, kGemmSmem, st>>>(ta0, ta1, tb, gp);
     SPP_CHECK_LAUNCH();
     return SPP_OK;
@@ -896,16 +989,16 @@ static int match_common(const float *emb, const uint16_t *gallery, const float *
     float *qn = reinterpret_cast<float *>(ws + p.off_qn);
     __nv_bfloat16 *qb = reinterpret_cast<__nv_bfloat16 *>(ws + p.off_qb);
     Cand *part = reinterpret_cast<Cand *>(ws + p.off_part);
-    float *third = reinterpret_cast<float *>(ws + p.off_third);
+    float *dropped = reinterpret_cast<float *>(ws + p.off_drop);
     const __nv_bfloat16 *gal = reinterpret_cast<const __nv_bfloat16 *>(gallery);
 
     l2_normalize_kernel<<<(m + 7) / 8, 256, 0, st>>>(emb, m, kDim, 1, 1e-12f, qn, nullptr, qb);
     SPP_CHECK_LAUNCH();
-    int rc = launch_search(qb, nullptr, nullptr, qn, gal, m, n, p, part, third, st, simt);
+    int rc = launch_search(qb, nullptr, nullptr, qn, gal, m, n, max_row_norm, p, part, dropped, st, simt);
     if (rc) return rc;
     FinParams fp{};
-    fp.qn = qn; fp.gal = gal; fp.gal_f32 = gallery_f32; fp.part = part; fp.third = third;
-    fp.m = m; fp.n = n; fp.nsplit = p.nsplit; fp.tiles_n = p.tiles_n;
+    fp.qn = qn; fp.gal = gal; fp.gal_f32 = gallery_f32; fp.part = part; fp.dropped = dropped;
+    fp.m = m; fp.n = n; fp.nsplit = p.nsplit; fp.tiles_n = p.tiles_n; fp.m_pad = p.m_pad;
     fp.prune = match_prune_margin(max_row_norm, gallery_f32 != nullptr);
     fp.threshold = threshold; fp.id_offset = id_offset;
     fp.out_id = out_id; fp.out_sim = out_sim; fp.out_key = out_key;
@@ -985,7 +1078,7 @@ extern "C" int spp_sharded_match_top1(const spp_peer_group *group, const float *
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     Cand *part = reinterpret_cast<Cand *>(ws + p.off_part);
-    float *third = reinterpret_cast<float *>(ws + p.off_third);
+    float *dropped = reinterpret_cast<float *>(ws + p.off_drop);
     unsigned char *own = peer.buf[peer.rank];
     const unsigned *step = &reinterpret_cast<const PeerHeader *>(own)->step;
     const __nv_bfloat16 *gal = reinterpret_cast<const __nv_bfloat16 *>(shard);
@@ -1000,7 +1093,7 @@ extern "C" int spp_sharded_match_top1(const spp_peer_group *group, const float *
     if (stages & SPP_SHARDED_STAGE_SEARCH) {
         const __nv_bfloat16 *qb0 = reinterpret_cast<const __nv_bfloat16 *>(own + lay.off_bf16);
         const __nv_bfloat16 *qb1 = reinterpret_cast<const __nv_bfloat16 *>(own + lay.off_bf16 + lay.bf16_stride);
-        int rc = launch_search(qb0, qb1, step, nullptr, gal, m, n_shard, p, part, third, st, false);
+        int rc = launch_search(qb0, qb1, step, nullptr, gal, m, n_shard, max_row_norm, p, part, dropped, st, false);
         if (rc) return rc;
     }
     if (stages & SPP_SHARDED_STAGE_FINALIZE) {
@@ -1008,8 +1101,8 @@ extern "C" int spp_sharded_match_top1(const spp_peer_group *group, const float *
         fp.qn = reinterpret_cast<const float *>(own + lay.off_f32);
         fp.qn_parity_stride = lay.f32_stride / 4;
         fp.step = step;
-        fp.gal = gal; fp.gal_f32 = shard_f32; fp.part = part; fp.third = third;
-        fp.m = m; fp.n = n_shard; fp.nsplit = p.nsplit; fp.tiles_n = p.tiles_n;
+        fp.gal = gal; fp.gal_f32 = shard_f32; fp.part = part; fp.dropped = dropped;
+        fp.m = m; fp.n = n_shard; fp.nsplit = p.nsplit; fp.tiles_n = p.tiles_n; fp.m_pad = p.m_pad;
         fp.prune = match_prune_margin(max_row_norm, shard_f32 != nullptr);
         fp.threshold = NAN; fp.id_offset = id_offset;           // the gate is applied after the reduction
         fp.peer = peer; fp.off_keys = lay.off_keys; fp.keys_stride = lay.keys_stride;
