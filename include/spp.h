@@ -276,6 +276,15 @@ int spp_heatmap_decode(const float *hm, const float *hm_flipped, const int *perm
                        const float *boxes, int mode, int flags, int kernel, int crop_h, int crop_w,
                        float *keypoints, float *scores, int *argmax, spp_stream_t stream);
 
+/* The same decode on bf16 heatmaps (a ViTPose decoder that emits bf16 halves the bytes of this HBM-bound
+ * pass — HF modeling_vitpose.py:120-145 is where the heatmaps are produced).  Elements are widened to fp32 on load (exact)
+ * and every operation after that is the fp32 kernel's: results equal spp_heatmap_decode applied to the widened maps, bit
+ * for bit.  Against the reference run on the ORIGINAL fp32 maps the bf16 rounding itself moves ~1.5 % of the arg-max
+ * indices and keypoints by up to 0.1 px (tools/study_bf16_heatmaps.py), so fp32 stays the default input. */
+int spp_heatmap_decode_bf16(const uint16_t *hm, const uint16_t *hm_flipped, const int *perm, int p, int k, int h, int w,
+                            const float *boxes, int mode, int flags, int kernel, int crop_h, int crop_w,
+                            float *keypoints, float *scores, int *argmax, spp_stream_t stream);
+
 /* ------------------------------------------------------------------ pose results ------------- */
 
 /* Replaces the result loop of PoseEstimationModule.validation_step, training/lightning/pose_estimation/

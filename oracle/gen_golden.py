@@ -86,6 +86,47 @@ def gen_det():
         print("det", tag, [d.shape[0] for d in dets])
 
 
+def gen_ref_head():
+    """the reference's REAL ``Head`` module (its conv stacks, BatchNorm statistics, DFL) — state_dict,
+    input features, the per-level ``cat(box(x), cls(x))`` maps, the eval output (nn.py:255-270) and the NMS rows
+    (util.py:123-169).  The GPU test loads the state_dict into oracle/refhead.RefShapedHead and runs
+    ``spp.head_eval_forward`` / ``spp.detect`` on it."""
+    sys.path.insert(0, os.path.join(REF, "training"))
+    from yolopt.nets.nn import Head
+    import yolopt.util as yutil
+    from oracle import det as odet
+
+    yutil.time = lambda: 0.0
+    filters, nc = (16, 32, 64), 2
+    for seed in range(20, 60):
+        torch.manual_seed(seed)
+        head = Head(nc=nc, filters=filters)
+        head.stride = torch.tensor([8.0, 16.0, 32.0])
+        for mod in head.modules():                      # non-trivial BatchNorm statistics and affine parameters
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.normal_(0.0, 0.3)
+                mod.running_var.uniform_(0.5, 1.5)
+                mod.weight.data.uniform_(0.7, 1.3)
+                mod.bias.data.normal_(0.0, 0.2)
+        head.eval()
+        feats = [torch.randn(2, f, 256 // s, 320 // s) * 1.5 for f, s in zip(filters, (8, 16, 32))]
+        with torch.no_grad():
+            cat = [torch.cat((b(x), c(x)), 1) for b, c, x in zip(head.box, head.cls, feats)]      # nn.py:257
+            decoded = head([f.clone() for f in feats])
+        conf = 0.5                                      # random-init class logits sit around 0: about half of the anchors pass
+        dets = yutil.non_max_suppression(decoded, conf, 0.65)
+        if sum(odet.near_threshold_pairs(d, 0.65) for d in dets) == 0 and all(20 <= d.shape[0] for d in dets):
+            break
+    else:
+        raise RuntimeError("no seed without borderline IoU pairs")
+    sd = {"sd." + k: v.numpy() for k, v in head.state_dict().items()}
+    np.savez_compressed(os.path.join(OUT, "ref_head.npz"), nc=np.int64(nc), filters=np.array(filters), conf=np.float32(conf),
+                        iou=np.float32(0.65), f0=feats[0].numpy(), f1=feats[1].numpy(), f2=feats[2].numpy(),
+                        l0=cat[0].numpy(), l1=cat[1].numpy(), l2=cat[2].numpy(), decoded=decoded.numpy(),
+                        n=np.array([d.shape[0] for d in dets]), dets=np.concatenate([d.numpy() for d in dets], 0), **sd)
+    print("ref_head seed", seed, [d.shape[0] for d in dets], "state_dict tensors", len(sd))
+
+
 def gen_match():
     sys.path.insert(0, os.path.join(REF, "libs"))
     import net_adaface
@@ -252,7 +293,13 @@ def gen_pose_results():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    only = sys.argv[1:]               # e.g. `python oracle/gen_golden.py ref_head` regenerates one fixture
+    if only:
+        for name in only:
+            globals()["gen_" + name]()
+        sys.exit(0)
     gen_det()
+    gen_ref_head()
     gen_match()
     gen_pose_live()
     gen_pose_hf()

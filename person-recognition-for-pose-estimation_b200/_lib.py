@@ -63,6 +63,8 @@ SIGNATURES = {
                                    c_int, _P, _P]),
     "spp_heatmap_decode": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P,
                                    _P, _P]),
+    "spp_heatmap_decode_bf16": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P,
+                                        _P, _P]),
     "spp_pose_results": (c_int, [_P, _P, _P, c_int, c_int, c_float, _P, _P, _P]),
     "spp_pose_oks": (c_int, [_P, c_int, _P, _P, _P, _P, c_int, c_int, _P, _P]),
     # test hook (include/spp_internal.h)

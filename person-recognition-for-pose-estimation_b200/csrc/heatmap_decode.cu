@@ -22,7 +22,9 @@
 //     Newton step in fp64.  All of it lives in registers + 64 floats of per-warp scratch.
 #include "spp_common.cuh"
 
+#include <cuda_bf16.h>
 #include <cfloat>
+#include <type_traits>
 #include <cstdlib>
 #include <climits>
 #include <cmath>
@@ -36,8 +38,8 @@ constexpr int kModeCopyOnly = 99;   // undocumented: stream the maps through the
 constexpr int kScratch = 64 + 368;  // floats per warp: 3*(2r+3) <= 57 filter rows, then the (2r+3)^2 <= 361 window
 
 struct DecodeParams {
-    const float *hm;
-    const float *hmf;
+    const void *hm;    // [P, K, H, W] fp32 or bf16 (template parameter T of the kernel)
+    const void *hmf;
     const int *perm;
     const float *boxes;
     float *kpts;
@@ -58,15 +60,25 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
 }
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+// element load / 4-element load widened to fp32 (bf16 -> fp32 is exact)
+__device__ __forceinline__ float ld1(const float *p) { return *p; }
+__device__ __forceinline__ float ld1(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
+__device__ __forceinline__ float4 ld4(const float *base, int q4) { return reinterpret_cast<const float4 *>(base)[q4]; }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16 *base, int q4) {
+    const uint2 w = reinterpret_cast<const uint2 *>(base)[q4];
+    return make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xffff0000u), __uint_as_float(w.y << 16),
+                       __uint_as_float(w.y & 0xffff0000u));
+}
+
 // One (possibly flip-averaged) heatmap; A/B may point to shared or global memory.
-template <bool FLIP>
+template <bool FLIP, typename T>
 struct MapView {
-    const float *A;
-    const float *B;  // raw map of the mirrored crop, channel already pair-swapped
+    const T *A;
+    const T *B;  // raw map of the mirrored crop, channel already pair-swapped
     int W;
     __device__ __forceinline__ float at(int r, int c) const {
-        float a = A[r * W + c];
-        if (FLIP) a = (a + B[r * W + (W - 1 - c)]) * 0.5f;
+        float a = ld1(A + r * W + c);
+        if (FLIP) a = (a + ld1(B + r * W + (W - 1 - c))) * 0.5f;
         return a;
     }
 };
@@ -103,8 +115,8 @@ __device__ __forceinline__ float clip_log(float v) {
 }
 
 // log(clip(blur(map)))[y, x] for ONE position, whole warp cooperating (rare path: score <= 0 quirk).
-template <bool FLIP>
-__device__ float warp_blurred_log_single(const MapView<FLIP> &mv, int H, int y, int x, const double *gw, int radius,
+template <bool FLIP, typename T>
+__device__ float warp_blurred_log_single(const MapView<FLIP, T> &mv, int H, int y, int x, const double *gw, int radius,
                                          float *scratch, int lane) {
     const int n = 2 * radius + 1;
     __syncwarp();
@@ -121,8 +133,8 @@ __device__ float warp_blurred_log_single(const MapView<FLIP> &mv, int H, int y, 
 // Quirk Q6 helper: log(clip(blur(.))) at flat position t of HF's flattened, edge-padded batch ([P*K, H+2, W+2]); the
 // staged map (A, B in shared memory) is used when t falls into map q, global memory otherwise.  Deliberately not inlined:
 // seven call sites, opt-in path.
-template <bool FLIP>
-__device__ __noinline__ float hf_tap_value(const DecodeParams prm, const float *A, const float *B, long long q, long long t,
+template <bool FLIP, typename T>
+__device__ __noinline__ float hf_tap_value(const DecodeParams prm, const T *A, const T *B, long long q, long long t,
                                            float *scratch, int lane) {
     const int H = prm.H, W = prm.W, K = prm.K;
     const long long total = (long long)prm.P * K, stride = (long long)(W + 2) * (H + 2);
@@ -133,12 +145,12 @@ __device__ __noinline__ float hf_tap_value(const DecodeParams prm, const float *
     const int r = (int)(t - qt * stride);
     const int py = r / (W + 2), px = r - py * (W + 2);
     const int ty = clampi(py - 1, 0, H - 1), tx = clampi(px - 1, 0, W - 1);
-    MapView<FLIP> mv{A, B, W};
+    MapView<FLIP, T> mv{A, B, W};
     if (qt != q) {
         const long long pt = qt / K;
         const int kt = (int)(qt - pt * K);
-        mv.A = prm.hm + qt * map_elems;
-        if (FLIP) mv.B = prm.hmf + (pt * K + (prm.perm ? __ldg(prm.perm + kt) : kt)) * map_elems;
+        mv.A = static_cast<const T *>(prm.hm) + qt * map_elems;
+        if (FLIP) mv.B = static_cast<const T *>(prm.hmf) + (pt * K + (prm.perm ? __ldg(prm.perm + kt) : kt)) * map_elems;
     }
     return warp_blurred_log_single(mv, H, ty, tx, prm.gw, prm.radius, scratch, lane);
 }
@@ -153,17 +165,19 @@ struct Best {
     }
 };
 
-template <bool FLIP, int RADIUS, bool HFQ>
+template <bool FLIP, int RADIUS, bool HFQ, typename T>
 __global__ void __launch_bounds__(FLIP ? 256 : 512, 1) heatmap_decode_kernel(const DecodeParams prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int H = prm.H, W = prm.W, K = prm.K;
     const int map_elems = H * W;
-    const uint32_t map_bytes = (uint32_t)map_elems * 4u;
+    const uint32_t map_bytes = (uint32_t)map_elems * (uint32_t)sizeof(T);
+    const T *hm = static_cast<const T *>(prm.hm);
+    const T *hmf = static_cast<const T *>(prm.hmf);
     constexpr int NB = FLIP ? 2 : 1;
     const int stages = prm.stages, warps = prm.warps;
 
-    float *wbase = reinterpret_cast<float *>(smem_raw) + (size_t)warp * stages * NB * map_elems;
+    T *wbase = reinterpret_cast<T *>(smem_raw) + (size_t)warp * stages * NB * map_elems;
     unsigned char *after = smem_raw + (size_t)warps * stages * NB * map_bytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(after) + warp * stages;
     float *scratch = reinterpret_cast<float *>(after + (size_t)warps * stages * 8) + warp * kScratch;
@@ -182,13 +196,13 @@ __global__ void __launch_bounds__(FLIP ? 256 : 512, 1) heatmap_decode_kernel(con
 
     auto issue = [&](long long q, int s) {  // lane 0 only
         mbar_arrive_expect_tx(&bars[s], NB * map_bytes);
-        float *dst = wbase + (size_t)s * NB * map_elems;
-        bulk_g2s(dst, prm.hm + q * map_elems, map_bytes, &bars[s]);
+        T *dst = wbase + (size_t)s * NB * map_elems;
+        bulk_g2s(dst, hm + q * map_elems, map_bytes, &bars[s]);
         if (FLIP) {
             const long long p = q / K;
             const int k = (int)(q - p * K);
             const int kk = prm.perm ? __ldg(prm.perm + k) : k;
-            bulk_g2s(dst + map_elems, prm.hmf + (p * K + kk) * map_elems, map_bytes, &bars[s]);
+            bulk_g2s(dst + map_elems, hmf + (p * K + kk) * map_elems, map_bytes, &bars[s]);
         }
     };
 
@@ -216,21 +230,19 @@ __global__ void __launch_bounds__(FLIP ? 256 : 512, 1) heatmap_decode_kernel(con
             __syncwarp();
             const long long qn = q + (long long)stages * nwarps;
             if (lane == 0 && qn < total) issue(qn, s);
-            if (lane == 0) prm.scores[q] = wbase[(size_t)s * NB * map_elems];
+            if (lane == 0) prm.scores[q] = ld1(wbase + (size_t)s * NB * map_elems);
             continue;
         }
-        const float *A = wbase + (size_t)s * NB * map_elems;
-        const float *B = A + map_elems;
-        const float4 *A4 = reinterpret_cast<const float4 *>(A);
-        const float4 *B4 = reinterpret_cast<const float4 *>(B);
+        const T *A = wbase + (size_t)s * NB * map_elems;
+        const T *B = A + map_elems;
 
         // One float4 of 2 x the flip-average (or of the map itself): element e of quad q4 is flat index
         // 4*q4 + e.  The * 0.5 is an exact power-of-two scaling, so the arg-max can be taken on the sums.
         auto quad = [&](int q4) -> float4 {
-            float4 v = A4[q4];
+            float4 v = ld4(A, q4);
             if (FLIP) {
                 const int r = (int)(((unsigned)q4 * magic) >> 16);
-                const float4 m = B4[2 * r * W4 + W4 - 1 - q4];     // same row, mirrored quad, reversed lanes
+                const float4 m = ld4(B, 2 * r * W4 + W4 - 1 - q4);     // same row, mirrored quad, reversed lanes
                 v.x += m.w;
                 v.y += m.z;
                 v.z += m.y;
@@ -268,7 +280,7 @@ __global__ void __launch_bounds__(FLIP ? 256 : 512, 1) heatmap_decode_kernel(con
         if (FLIP) best *= 0.5f;
         const int ax = bidx % W, ay = bidx / W;
         const long long p = q / K;
-        MapView<FLIP> mv{A, B, W};
+        MapView<FLIP, T> mv{A, B, W};
 
         // ---- phase 2: everything that still needs the staged map ---------------------------------------
         const bool valid = best > 0.0f;
@@ -290,7 +302,7 @@ __global__ void __launch_bounds__(FLIP ? 256 : 512, 1) heatmap_decode_kernel(con
             const long long idx = (long long)(float)((double)c32 + (double)(stride * q));
             const int offs[7] = {0, 1, W + 2, W + 3, -(W + 3), -1, -(W + 2)};
 #pragma unroll
-            for (int t7 = 0; t7 < 7; ++t7) hfL[t7] = hf_tap_value<FLIP>(prm, A, B, q, idx + offs[t7], scratch, lane);
+            for (int t7 = 0; t7 < 7; ++t7) hfL[t7] = hf_tap_value<FLIP, T>(prm, A, B, q, idx + offs[t7], scratch, lane);
         } else if (prm.mode == SPP_DECODE_DARK) {
             if (valid) {
                 // (2r+3)^2 window of the averaged map, 'reflect'-indexed like scipy's line extension
@@ -305,8 +317,8 @@ __global__ void __launch_bounds__(FLIP ? 256 : 512, 1) heatmap_decode_kernel(con
                 const long long qp = (q + total - 1) % total;
                 const long long pp = qp / K;
                 const int kp = (int)(qp - pp * K);
-                MapView<FLIP> prev{prm.hm + qp * map_elems, nullptr, W};
-                if (FLIP) prev.B = prm.hmf + (pp * K + (prm.perm ? __ldg(prm.perm + kp) : kp)) * map_elems;
+                MapView<FLIP, T> prev{hm + qp * map_elems, nullptr, W};
+                if (FLIP) prev.B = hmf + (pp * K + (prm.perm ? __ldg(prm.perm + kp) : kp)) * map_elems;
                 c00 = warp_blurred_log_single(mv, H, 0, 0, gw, radius, scratch, lane);
                 cbr = warp_blurred_log_single(prev, H, H - 1, W - 1, gw, radius, scratch, lane);
                 cbl = warp_blurred_log_single(prev, H, H - 1, 0, gw, radius, scratch, lane);
@@ -476,11 +488,11 @@ __global__ void __launch_bounds__(FLIP ? 256 : 512, 1) heatmap_decode_kernel(con
     }
 }
 
-template <bool FLIP, int RADIUS, bool HFQ = false>
+template <typename T, bool FLIP, int RADIUS, bool HFQ = false>
 int launch_decode(const DecodeParams &prm, unsigned grid, size_t smem, cudaStream_t st) {
     // per device and per context: set on every launch (about a microsecond; legal during stream capture)
-    SPP_CHECK_CUDA(cudaFuncSetAttribute(heatmap_decode_kernel<FLIP, RADIUS, HFQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    heatmap_decode_kernel<FLIP, RADIUS, HFQ><<<grid, prm.warps * 32, smem, st>>>(prm);
+    SPP_CHECK_CUDA(cudaFuncSetAttribute(heatmap_decode_kernel<FLIP, RADIUS, HFQ, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    heatmap_decode_kernel<FLIP, RADIUS, HFQ, T><<<grid, prm.warps * 32, smem, st>>>(prm);
     SPP_CHECK_LAUNCH();
     return SPP_OK;
 }
@@ -489,13 +501,16 @@ int launch_decode(const DecodeParams &prm, unsigned grid, size_t smem, cudaStrea
 
 }  // namespace spp
 
-extern "C" int spp_heatmap_decode(const float *hm, const float *hm_flipped, const int *perm, int p, int k, int h, int w,
-                                  const float *boxes, int mode, int flags, int kernel, int crop_h, int crop_w,
-                                  float *keypoints, float *scores, int *argmax, spp_stream_t stream) {
-    using namespace spp;
+namespace spp {
+namespace {
+template <typename T>
+int heatmap_decode_impl(const T *hm, const T *hm_flipped, const int *perm, int p, int k, int h, int w,
+                        const float *boxes, int mode, int flags, int kernel, int crop_h, int crop_w,
+                        float *keypoints, float *scores, int *argmax, spp_stream_t stream) {
     SPP_CHECK_ARG(p >= 0 && k > 0 && h > 0 && w > 0, "heatmap_decode: bad shape p=%d k=%d h=%d w=%d", p, k, h, w);
     SPP_CHECK_ARG(p == 0 || (hm && keypoints && scores), "heatmap_decode: hm, keypoints and scores must be non-null");
     SPP_CHECK_ARG(w % 4 == 0, "heatmap_decode: heatmap width must be a multiple of 4 (got %d)", w);
+    SPP_CHECK_ARG(((size_t)h * w * sizeof(T)) % 16 == 0, "heatmap_decode: a %dx%d map of %zu-byte elements is not a multiple of 16 bytes", h, w, sizeof(T));
     SPP_CHECK_ARG((mode >= SPP_DECODE_DARK && mode <= SPP_DECODE_QUARTER) || mode == kModeCopyOnly, "heatmap_decode: unknown mode %d", mode);
     SPP_CHECK_ARG(kernel >= 3 && kernel <= 2 * kMaxRadius + 1 && (kernel & 1), "heatmap_decode: kernel must be odd in 3..%d (got %d)",
                   2 * kMaxRadius + 1, kernel);
@@ -521,7 +536,7 @@ extern "C" int spp_heatmap_decode(const float *hm, const float *hm_flipped, cons
 
     SPP_CHECK_ARG(h >= prm.radius + 2 && w >= prm.radius + 2, "heatmap_decode: map %dx%d too small for kernel %d", h, w, kernel);
     const bool flip = hm_flipped != nullptr;
-    const size_t stage_bytes = (size_t)(flip ? 2 : 1) * h * w * 4;
+    const size_t stage_bytes = (size_t)(flip ? 2 : 1) * h * w * sizeof(T);
     const size_t budget = 200 * 1024;
     const int slots = (int)(budget / stage_bytes);
     SPP_CHECK_ARG(slots >= 1, "heatmap_decode: a %dx%d map does not fit the shared-memory pipeline", h, w);
@@ -560,8 +575,24 @@ extern "C" int spp_heatmap_decode(const float *hm, const float *hm_flipped, cons
 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (mode == SPP_DECODE_DARK && (flags & SPP_DECODE_FLAG_HF_F32_INDEX))      // quirk Q6: run-time radius, own instantiation
-        return flip ? launch_decode<true, 0, true>(prm, (unsigned)grid, smem, st) : launch_decode<false, 0, true>(prm, (unsigned)grid, smem, st);
-    if (flip) return prm.radius == 5 ? launch_decode<true, 5>(prm, (unsigned)grid, smem, st) : launch_decode<true, 0>(prm, (unsigned)grid, smem, st);
-    return prm.radius == 5 ? launch_decode<false, 5>(prm, (unsigned)grid, smem, st) : launch_decode<false, 0>(prm, (unsigned)grid, smem, st);
+        return flip ? launch_decode<T, true, 0, true>(prm, (unsigned)grid, smem, st) : launch_decode<T, false, 0, true>(prm, (unsigned)grid, smem, st);
+    if (flip) return prm.radius == 5 ? launch_decode<T, true, 5>(prm, (unsigned)grid, smem, st) : launch_decode<T, true, 0>(prm, (unsigned)grid, smem, st);
+    return prm.radius == 5 ? launch_decode<T, false, 5>(prm, (unsigned)grid, smem, st) : launch_decode<T, false, 0>(prm, (unsigned)grid, smem, st);
+}
+}  // namespace
+}  // namespace spp
+
+extern "C" int spp_heatmap_decode(const float *hm, const float *hm_flipped, const int *perm, int p, int k, int h, int w,
+                                  const float *boxes, int mode, int flags, int kernel, int crop_h, int crop_w,
+                                  float *keypoints, float *scores, int *argmax, spp_stream_t stream) {
+    return spp::heatmap_decode_impl<float>(hm, hm_flipped, perm, p, k, h, w, boxes, mode, flags, kernel, crop_h, crop_w, keypoints, scores,
+                                           argmax, stream);
+}
+
+extern "C" int spp_heatmap_decode_bf16(const uint16_t *hm, const uint16_t *hm_flipped, const int *perm, int p, int k, int h, int w,
+                                       const float *boxes, int mode, int flags, int kernel, int crop_h, int crop_w,
+                                       float *keypoints, float *scores, int *argmax, spp_stream_t stream) {
+    return spp::heatmap_decode_impl<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16 *>(hm), reinterpret_cast<const __nv_bfloat16 *>(hm_flipped),
+                                                   perm, p, k, h, w, boxes, mode, flags, kernel, crop_h, crop_w, keypoints, scores, argmax, stream);
 }
 

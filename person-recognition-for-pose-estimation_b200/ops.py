@@ -383,13 +383,20 @@ def heatmap_decode(hm: torch.Tensor, hm_flipped: Optional[torch.Tensor] = None, 
                    boxes: Optional[torch.Tensor] = None, mode: str = "dark", kernel: int = 11, flags: int = 0,
                    crop_hw: Tuple[int, int] = (256, 192), out=None):
     """One pass over the heatmaps: flip-average (optional), arg-max, refinement, back-projection.
+    ``hm`` / ``hm_flipped``: fp32, or bf16 (half the HBM bytes; widened to fp32 on load, then the same arithmetic).
     Returns ``(keypoints [P,K,2] fp32, scores [P,K] fp32, argmax [P,K] int32)``."""
     _need_cuda("heatmap_decode", hm, hm_flipped, perm, boxes)
-    hm = _f32c("heatmap_decode", hm)
+    bf16 = hm.dtype == torch.bfloat16
+    if bf16:
+        hm = hm if hm.is_contiguous() else hm.contiguous()
+    else:
+        hm = _f32c("heatmap_decode", hm)
     if hm.dim() != 4:
         raise ValueError(f"heatmap_decode: expected [P, K, H, W], got {tuple(hm.shape)}")
     if hm_flipped is not None:
-        hm_flipped = _f32c("heatmap_decode flipped", hm_flipped)
+        if hm_flipped.dtype != hm.dtype:
+            raise TypeError("heatmap_decode: heatmaps and flipped heatmaps must have the same dtype")
+        hm_flipped = hm_flipped.contiguous() if bf16 else _f32c("heatmap_decode flipped", hm_flipped)
         if hm_flipped.shape != hm.shape:
             raise ValueError("heatmap_decode: flipped heatmaps must have the same shape")
     p, k, h, w = hm.shape
@@ -408,9 +415,9 @@ def heatmap_decode(hm: torch.Tensor, hm_flipped: Optional[torch.Tensor] = None, 
         am = torch.empty((p, k), dtype=torch.int32, device=hm.device)
     else:
         kp, sc, am = out
-    _lib.check(_lib.lib().spp_heatmap_decode(_ptr(hm), _ptr(hm_flipped), _ptr(perm), p, k, h, w, _ptr(boxes),
-                                             DECODE_MODES[mode], flags, kernel, crop_hw[0], crop_hw[1], _ptr(kp), _ptr(sc),
-                                             _ptr(am), _stream(hm)), "spp_heatmap_decode")
+    fn = _lib.lib().spp_heatmap_decode_bf16 if bf16 else _lib.lib().spp_heatmap_decode
+    _lib.check(fn(_ptr(hm), _ptr(hm_flipped), _ptr(perm), p, k, h, w, _ptr(boxes), DECODE_MODES[mode], flags, kernel, crop_hw[0],
+                  crop_hw[1], _ptr(kp), _ptr(sc), _ptr(am), _stream(hm)), "spp_heatmap_decode")
     return kp, sc, am
 
 

@@ -731,6 +731,37 @@ def test_heatmap_other_shapes(spp, synth, dev, k, h, w):
     _close(s_.cpu().numpy(), s_o.numpy(), what="softargmax scores")
 
 
+@pytest.mark.parametrize("mode", ["dark", "softargmax", "quarter"])
+@pytest.mark.parametrize("flip", [False, True])
+def test_heatmap_bf16_maps(spp, synth, dev, mode, flip):
+    """bf16 heatmaps: (a) identical, bit for bit, to the fp32 kernel on the widened maps; (b) against the
+    ORACLE on the widened maps: arg-max / scores bit-exact, keypoints within 1e-3; (c) against the fp32 originals the
+    rounding itself costs what tools/study_bf16_heatmaps.py measured (a few arg-max indices, <= ~0.1 px) — bounded here."""
+    hs = synth.make_heatmaps(24, 17, seed=41, negative_frac=0.05)
+    cs = synth.make_crop_set(2, 480, 640, per_frame=12, seed=3)
+    hb, fb = hs.heatmaps.to(torch.bfloat16), hs.flipped.to(torch.bfloat16)
+    boxes = cs.boxes.to(dev) if mode != "softargmax" else None
+    args16 = (hb.to(dev), fb.to(dev) if flip else None, hs.perm.to(dev) if flip else None, boxes, mode, 11)
+    args32 = (hb.float().to(dev), fb.float().to(dev) if flip else None, hs.perm.to(dev) if flip else None, boxes, mode, 11)
+    kp16, sc16, am16 = spp.heatmap_decode(*args16)
+    kp32, sc32, am32 = spp.heatmap_decode(*args32)
+    assert torch.equal(am16, am32) and torch.equal(sc16, sc32) and torch.equal(kp16, kp32)
+    if mode == "dark":
+        avg = opose.flip_average(hb.float(), fb.float(), hs.perm) if flip else hb.float()
+        kp_o, sc_o, idx_o = opose.hf_dark_decode(avg.numpy(), cs.boxes.tolist())
+        np.testing.assert_array_equal(am16.cpu().numpy(), idx_o)
+        np.testing.assert_array_equal(sc16.cpu().numpy(), sc_o)
+        _close(kp16.cpu().numpy()[sc_o > 0], kp_o[sc_o > 0], what="DARK keypoints, bf16 maps vs oracle on the widened maps")
+        # (c) vs the fp32 originals
+        avg0 = opose.flip_average(hs.heatmaps, hs.flipped, hs.perm) if flip else hs.heatmaps
+        kp0, sc0, idx0 = opose.hf_dark_decode(avg0.numpy(), cs.boxes.tolist())
+        same = idx0 == idx_o
+        assert same.mean() > 0.9
+        good = same & (sc0 > 0)
+        assert np.abs(kp16.cpu().numpy()[good] - kp0[good]).max() < 2.0        # image pixels; 0.1 heatmap px * ~4x crop scale
+        np.testing.assert_allclose(sc16.cpu().numpy(), sc0, atol=5e-3)
+
+
 def test_heatmap_ties_and_constant_maps(spp, dev):
     hm = torch.zeros(2, 3, 64, 48)
     hm[0, 0, 10, 5] = hm[0, 0, 10, 6] = hm[0, 0, 40, 1] = 2.0          # three equal maxima: the first one wins
@@ -920,6 +951,43 @@ def test_head_eval_forward_with_torch_convs(spp, dev):
         cat = [torch.cat((b(x), c(x)), 1) for b, c, x in zip(head.box, head.cls, feats)]
     ref = odet.head_decode([l.cpu() for l in cat])
     _close(out.cpu().numpy(), ref.numpy(), atol=1e-4, what="head_eval_forward")
+
+
+def test_reference_head_module_drop_in(spp, golden, dev):
+    """The reference's REAL detection head (state_dict saved from training/yolopt/nets/nn.py ``Head`` by
+    oracle/gen_golden.py) loaded into a same-layout module: ``spp.head_eval_forward(head, feats)`` replaces
+    ``head(feats)`` in eval mode (nn.py:255-270), ``spp.detect`` replaces ``non_max_suppression(head(feats))``."""
+    from oracle.refhead import RefShapedHead
+    g = golden("ref_head.npz")
+    head = RefShapedHead(int(g["nc"]), tuple(int(x) for x in g["filters"]))
+    head.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}, strict=True)
+    head = head.to(dev).eval()
+    head.stride = head.stride.to(dev)
+    feats = [torch.from_numpy(g[k]).to(dev) for k in ("f0", "f1", "f2")]
+    conf, iou = float(g["conf"]), float(g["iou"])
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False          # the fixture is fp32 CPU convolution; TF32 would cost 1e-3 on the logits
+    try:
+        with torch.no_grad():
+            out = spp.head_eval_forward(head, feats)
+            pairs = spp.head_conv_outputs(head, feats)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    assert out.shape == g["decoded"].shape
+    _close(out.cpu().numpy(), g["decoded"], atol=2e-3, what="head_eval_forward on the reference head vs the reference's eval output")
+    for (bx, cl), k in zip(pairs, ("l0", "l1", "l2")):
+        _close(torch.cat((bx, cl), 1).cpu().numpy(), g[k], rtol=1e-4, atol=1e-4, what="conv stacks of the loaded head")
+    # post-processing on the reference's own conv outputs: same rows as the reference's non_max_suppression(head(x))
+    lv = [torch.from_numpy(g[k]).to(dev) for k in ("l0", "l1", "l2")]
+    dets = spp.detect(lv, conf, iou)
+    assert [d.shape[0] for d in dets] == g["n"].tolist()
+    _close(torch.cat(dets).cpu().numpy(), g["dets"], atol=1e-3, what="detect() rows vs the reference's NMS rows")
+    assert np.array_equal(torch.cat(dets).cpu().numpy()[:, 5], g["dets"][:, 5])
+    dets2 = spp.non_max_suppression(torch.from_numpy(g["decoded"]).to(dev), conf, iou)
+    np.testing.assert_array_equal(torch.cat(dets2).cpu().numpy(), g["dets"])          # from the decoded tensor: bit-exact
+    # end to end through the module on the GPU (cuDNN convolutions): same number of detections per image up to score ties
+    dets3 = spp.detect(pairs, conf, iou)
+    assert all(abs(d.shape[0] - n) <= max(3, n // 20) for d, n in zip(dets3, g["n"].tolist()))
 
 
 @pytest.mark.parametrize("tag", ["nc1", "nc3"])

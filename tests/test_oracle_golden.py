@@ -28,6 +28,27 @@ def test_head_decode_and_nms_match_reference(golden, tag):
         np.testing.assert_array_equal(torch.cat(dets).numpy(), g["dets"])
 
 
+def test_reference_head_module_fixture(golden):
+    """The fixture of the reference's REAL ``Head`` (conv stacks + BatchNorm + DFL, nn.py:228-270): the layout restatement
+    loads its state_dict strictly and reproduces its conv outputs; the oracle's decode and NMS reproduce its eval output
+    and the reference's NMS rows bit for bit."""
+    from oracle.refhead import RefShapedHead
+    g = golden("ref_head.npz")
+    head = RefShapedHead(int(g["nc"]), tuple(int(x) for x in g["filters"]))
+    head.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}, strict=True)
+    head.eval()
+    feats = [torch.from_numpy(g[k]) for k in ("f0", "f1", "f2")]
+    with torch.no_grad():
+        cat = [torch.cat((b(x), c(x)), 1) for b, c, x in zip(head.box, head.cls, feats)]
+    for c, k in zip(cat, ("l0", "l1", "l2")):
+        np.testing.assert_array_equal(c.numpy(), g[k])
+    dec = odet.head_decode(cat)
+    np.testing.assert_array_equal(dec.numpy(), g["decoded"])
+    dets = odet.non_max_suppression(dec, float(g["conf"]), float(g["iou"]))
+    assert [d.shape[0] for d in dets] == g["n"].tolist() and min(g["n"]) >= 20
+    np.testing.assert_array_equal(torch.cat(dets).numpy(), g["dets"])
+
+
 def test_nms_restatement_matches_torchvision():
     import torchvision
     gen = torch.Generator().manual_seed(0)
