@@ -234,6 +234,10 @@ def main():
     ap.add_argument("--serial", action="store_true", help="run the four chains back to back instead of on forked streams")
     ap.add_argument("--no-cfg3", action="store_true", help="skip the cfg3 record (1M-id gallery, sharded at N>1)")
     ap.add_argument("--cfg3-ids", type=int, default=1_000_000)
+    ap.add_argument("--det-max-candidates", type=int, default=-1,
+                    help="bound on NMS candidates per image (<= 512 selects the small-footprint NMS kernel); -1 = 512 for cfg1/cfg2, unbounded else")
+    ap.add_argument("--match-sms", type=int, default=-1, help="SMs reserved for the match GEMM beside the heatmap decode; -1 = 24 for cfg2, 0 = no split")
+    ap.add_argument("--crop-first", action="store_true", help="round-1 order: crop then heatmap decode on the main stream")
     ap.add_argument("--copy-streams", type=int, default=2, help="streams the per-step H2D copies of the e2e region are spread over")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "spp" else args.warmup
@@ -259,6 +263,12 @@ def main():
         wl["desc"] += f" [gallery overridden to {args.gallery_ids} ids]"
     spp = importlib.import_module(PKG)
     pipeline = importlib.import_module(PKG + ".pipeline")
+    if args.det_max_candidates < 0:
+        args.det_max_candidates = 512 if args.workload in ("cfg1", "cfg2") else 0
+    if args.match_sms < 0:
+        args.match_sms = 24 if args.workload == "cfg2" else 0
+    pipe_kw = dict(decode_mode=args.decode_mode, use_graph=not args.no_graph, concurrent=not args.serial,
+                   det_max_candidates=args.det_max_candidates, match_sms=args.match_sms, heatmap_first=not args.crop_first)
 
     if args.impl == "reference":
         run_reference(args, wl, rank, world, pipeline, emit)
@@ -311,9 +321,8 @@ def main():
         else:
             matcher = spp.dist.gpu_matcher(shard_rows, shard_lo, 0.4)
     barrier()          # ranks enter the first exchange step together (a peer wait is bounded at 60 s)
-    pipe = pipeline.SelectivePosePipeline(inp, gallery_bf16, dev, decode_mode=args.decode_mode, use_graph=not args.no_graph,
-                                          concurrent=not args.serial, matcher=matcher,
-                                          capture_collectives=args.capture_collectives, select_on_device=args.select_on_device)
+    pipe = pipeline.SelectivePosePipeline(inp, gallery_bf16, dev, matcher=matcher, capture_collectives=args.capture_collectives,
+                                          select_on_device=args.select_on_device, **pipe_kw)
     pipe.bind_host(inp, args.copy_streams)
     B, P, K, M = wl["batch"], wl["batch"] * wl["per_frame"], wl["joints"], wl["batch"] * wl["per_frame"]
     A = sum(l.shape[2] * l.shape[3] for l in inp.face_levels)
@@ -336,6 +345,8 @@ def main():
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
     ms_per_step = dev_ms / args.steps
     frames_per_s = world * B * args.steps / (dev_ms / 1e3)
+    det_overflow = bool(pipe.out["_face"].overflowed().any().item() or pipe.out["_person"].overflowed().any().item())
+    assert not det_overflow, "a frame has more NMS candidates than --det-max-candidates: results would be truncated"
 
     # ---- (2) end to end from pinned host buffers ---------------------------------------------------
     def time_e2e(p, n_steps):
@@ -363,8 +374,7 @@ def main():
         import copy
         inp8 = copy.copy(inp)
         inp8.frames = (inp.frames * 255.0).round().clamp(0, 255).to(torch.uint8)
-        pipe8 = pipeline.SelectivePosePipeline(inp8, gallery_bf16, dev, decode_mode=args.decode_mode, use_graph=not args.no_graph,
-                                               concurrent=not args.serial)
+        pipe8 = pipeline.SelectivePosePipeline(inp8, gallery_bf16, dev, **pipe_kw)
         pipe8.bind_host(inp8, args.copy_streams)
         n8 = max(3, min(args.steps, 10))
         ms8 = time_e2e(pipe8, n8) / n8
@@ -486,7 +496,7 @@ def main():
     # ---- (3b) cfg3: 1M-id gallery, local at N=1, row-sharded at N>1 (north-star config 3) --------------
     cfg3 = None
     if not args.no_cfg3 and args.workload == "cfg2" and not args.select_on_device:
-        cfg3 = run_cfg3(args, spp, pipeline, pipe, dev, rank, world, B, wl["per_frame"], barrier, max_over_ranks, peaks)
+        cfg3 = run_cfg3(args, spp, pipeline, pipe, dev, rank, world, B, wl["per_frame"], barrier, max_over_ranks, peaks, pipe_kw)
 
     # ---- (4) CPU baseline on this host (rank 0, N=1 only) ------------------------------------------
     cpu = None
@@ -519,7 +529,11 @@ def main():
                       "per-kernel region: a 256 MB read before each stage evicts L2 (cold, clean); heatmap decode and crop "
                       "(inputs > 2x L2) are the mean of 4 back-to-back launches after the flush",
                 "cuda_graph": not args.no_graph, "crop_boxes": "selected on the device from the detections" if args.select_on_device else "synthetic input boxes",
-                "streams": "serial" if args.serial else "4 forked chains (crop->heatmap | det face | det person | match)",
+                "streams": "serial" if args.serial else ("4 forked chains (" + ("crop -> heatmap decode" if args.crop_first else "heatmap decode -> crop") +
+                                                           " | det face | det person | match)"),
+                "det_max_candidates": args.det_max_candidates or "unbounded",
+                "det_overflow": det_overflow,
+                "sm_split": (f"match GEMM on {args.match_sms} SMs beside the heatmap decode on the others" if args.match_sms else "none"),
                 "host_numa": numa,
             },
             "crops_per_s": round(world * P * args.steps / (dev_ms / 1e3), 1),
@@ -564,7 +578,7 @@ def make_gallery_on_device(n: int, dev, seed: int = 4242, chunk: int = 131072):
     return out
 
 
-def run_cfg3(args, spp, pipeline, pipe2, dev, rank, world, B, per_frame, barrier, max_over_ranks, peaks):
+def run_cfg3(args, spp, pipeline, pipe2, dev, rank, world, B, per_frame, barrier, max_over_ranks, peaks, pipe_kw):
     """North-star config 3 at this N: the cfg2 step per GPU (64 frames) against a 1M-id gallery — held locally at N=1,
     row-sharded over the ranks at N>1 with the exchange done by the match kernels over NVLink peer memory (or NCCL with
     --collective nccl).  Reports the whole step and the three phases of the match; at N>1 rank 0 also runs the replicated
@@ -595,9 +609,10 @@ def run_cfg3(args, spp, pipeline, pipe2, dev, rank, world, B, per_frame, barrier
             full = None
             torch.cuda.empty_cache()
     barrier()
+    kw3 = dict(pipe_kw)
+    kw3["match_sms"] = 0            # a 1M-id match is the step's longest kernel: it gets the whole machine
     pipe3 = pipeline.SelectivePosePipeline(inp3, full if world == 1 else torch.empty((1, 512), dtype=torch.bfloat16), dev,
-                                           decode_mode=args.decode_mode, use_graph=not args.no_graph, concurrent=not args.serial,
-                                           matcher=matcher, capture_collectives=args.capture_collectives)
+                                           matcher=matcher, capture_collectives=args.capture_collectives, **kw3)
     st = pipe3.stream
     steps = max(5, min(args.steps, 20))
     for _ in range(3):

@@ -39,6 +39,14 @@ const char *spp_last_error(void);
 /* Number of SMs of the current device (grid sizing is a multiple of it); <0 on error. */
 int spp_device_sm_count(void);
 
+/* Process-wide CTA budgets for the two kernels that otherwise take every SM (one persistent CTA per SM): a caller that
+ * runs them side by side (the pipeline: heatmap decode on 148 - R SMs, match GEMM on R) sets both before it captures its
+ * CUDA graph.  max_ctas = 0 removes the limit, < 0 only queries; returns the previous value (or -1 for a bad `which`).
+ * spp_match_workspace_bytes depends on the match limit: query it after setting the limit. */
+#define SPP_LIMIT_HEATMAP_CTAS 0
+#define SPP_LIMIT_MATCH_CTAS 1
+int spp_set_launch_limit(int which, int max_ctas);
+
 /* ------------------------------------------------------------------ detection head + NMS ----- */
 
 /* Replaces Head.forward, eval branch — training/yolopt/nets/nn.py:255-270 (after the per-level conv
@@ -53,7 +61,9 @@ int spp_head_decode(const float *const *levels, const int *level_h, const int *l
  * candidate list: min(num_anchors * nc, max_candidates) candidates are kept per image (pass <= 0 for
  * "all of them").  Results are exact whenever the number of candidates of every image fits; beyond
  * that the surplus (arbitrary) candidates are dropped and out_count[b] is returned as ~kept = -(kept + 1).  With
- * nc == 1 and max_candidates <= 0 this cannot happen. */
+ * nc == 1 and max_candidates <= 0 this cannot happen.  A bound of <= 512 also selects the small-footprint NMS kernel
+ * (512 threads, ~15 KB of shared memory instead of 1 024 threads / 112 KB): same results, but its CTAs fit beside the
+ * resident CTAs of the bandwidth-bound kernels, so a caller that knows its scene density gets the overlap. */
 size_t spp_nms_workspace_bytes(int batch, int num_anchors, int nc, int max_candidates);
 
 /* Replaces non_max_suppression(outputs, conf, iou) — training/yolopt/util.py:123-169, without its

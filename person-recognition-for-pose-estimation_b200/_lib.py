@@ -30,6 +30,7 @@ SIGNATURES = {
     "spp_abi_version": (c_int, []),
     "spp_last_error": (c_char_p, []),
     "spp_device_sm_count": (c_int, []),
+    "spp_set_launch_limit": (c_int, [c_int, c_int]),
     "spp_head_decode": (c_int, [POINTER(_P), POINTER(c_int), POINTER(c_int), POINTER(c_float), c_int, c_int, c_int, _P, _P]),
     "spp_head_decode_split": (c_int, [POINTER(_P), POINTER(_P), POINTER(c_int), POINTER(c_int), POINTER(c_float), c_int, c_int, c_int,
                                       _P, _P]),

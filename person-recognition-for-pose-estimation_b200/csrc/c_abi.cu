@@ -1,6 +1,7 @@
 // C-ABI plumbing shared by all entry points: thread-local error string, device queries.
 #include "spp_common.cuh"
 
+#include <atomic>
 #include <cstring>
 
 namespace spp {
@@ -32,6 +33,17 @@ int sm_count() {
 }
 
 }  // namespace spp
+
+namespace spp {
+static std::atomic<int> g_limits[2] = {{0}, {0}};
+int launch_limit(int which) { return (which >= 0 && which < 2) ? g_limits[which].load(std::memory_order_relaxed) : 0; }
+}  // namespace spp
+
+extern "C" int spp_set_launch_limit(int which, int max_ctas) {
+    if (which < 0 || which >= 2) return -1;
+    if (max_ctas < 0) return spp::g_limits[which].load();
+    return spp::g_limits[which].exchange(max_ctas);
+}
 
 extern "C" int spp_abi_version(void) { return 2; }
 extern "C" const char *spp_last_error(void) { return spp::g_error; }

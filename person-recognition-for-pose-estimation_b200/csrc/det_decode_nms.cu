@@ -361,11 +361,12 @@ __device__ void bitonic_sort(unsigned long long *d, int npad) {
     }
 }
 
-// Bitonic sort of up to kNmsThreads keys, one per thread: compare-exchange partners closer than 32 are
+// Bitonic sort of up to NT keys, one per thread: compare-exchange partners closer than 32 are
 // reached with warp shuffles (no barrier, no shared memory), the 10 longer strides go through `xch`.
+template <int NT>
 __device__ unsigned long long block_bitonic_reg(unsigned long long key, unsigned long long *xch) {
     const int tid = threadIdx.x;
-    for (int k = 2; k <= kNmsThreads; k <<= 1) {
+    for (int k = 2; k <= NT; k <<= 1) {
         const bool up = (tid & k) == 0;
         for (int j = k >> 1; j > 0; j >>= 1) {
             unsigned long long other;
@@ -399,9 +400,21 @@ __device__ unsigned long long block_bitonic_reg(unsigned long long key, unsigned
 //   MODE 2: FUSED — step 0 of the CTA is the candidate scan over its image's class planes and the DFL decode of
 //           the candidates (half-warp per candidate, two in flight per half-warp): one launch per head instead
 //           of three, and one CTA per image instead of two full-machine latency-bound launches in front of it.
-template <int MODE>
-__global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams prm) {
+//   CFG: launch configuration.  NmsBig (1 024 threads, 112 KB of shared memory) handles any candidate count;
+//   NmsSmall (512 threads, ~15 KB) is chosen by the host when the caller bounds the candidate list to <= 512 per image
+//   (max_candidates): same code, same results, but a CTA that fits beside the resident CTAs of the bandwidth-bound
+//   kernels (heatmap decode: 206 KB of shared memory per SM), so the detection chain overlaps them instead of queueing.
+struct NmsBig {
+    static constexpr int kThreads = kNmsThreads, kSortMax = kSortSmemMax, kBoxMax = kBoxSmemMax, kWords = kAliveWords;
+};
+struct NmsSmall {
+    static constexpr int kThreads = 512, kSortMax = 512, kBoxMax = 512, kWords = 16;
+};
+
+template <int MODE, typename CFG>
+__global__ void __launch_bounds__(CFG::kThreads) nms_kernel(const NmsParams prm) {
     constexpr bool RAW = MODE != 0;
+    constexpr int kNmsThreads = CFG::kThreads, kSortSmemMax = CFG::kSortMax, kBoxSmemMax = CFG::kBoxMax, kAliveWords = CFG::kWords;
     extern __shared__ __align__(16) unsigned char nms_smem[];
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -470,7 +483,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams prm) {
     int n = raw_count < prm.cap ? raw_count : prm.cap;
     unsigned long long *keys;
     if (n <= kNmsThreads) {
-        const unsigned long long mine = block_bitonic_reg(tid < n ? gkeys[tid] : ~0ull, reinterpret_cast<unsigned long long *>(sbox));
+        const unsigned long long mine = block_bitonic_reg<kNmsThreads>(tid < n ? gkeys[tid] : ~0ull, reinterpret_cast<unsigned long long *>(sbox));
         skeys[tid] = mine;
         __syncthreads();
         keys = skeys;
@@ -700,15 +713,23 @@ Workspace carve(void *ws, int batch, int num_anchors, int nc, int max_candidates
     return w;
 }
 
-template <int MODE>
-int launch_nms(const NmsParams &prm, int batch, cudaStream_t st) {
-    const size_t smem = (size_t)kSortSmemMax * 8 + (size_t)kBoxSmemMax * 20 + (size_t)kAliveWords * 4 + (size_t)prm.max_det * 4;
+template <int MODE, typename CFG>
+int launch_nms_cfg(const NmsParams &prm, int batch, cudaStream_t st) {
+    const size_t smem = (size_t)CFG::kSortMax * 8 + (size_t)CFG::kBoxMax * 20 + (size_t)CFG::kWords * 4 + (size_t)prm.max_det * 4;
     // per device and per context: set on every launch (about a microsecond; legal during stream capture)
-    SPP_CHECK_CUDA(cudaFuncSetAttribute(nms_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    SPP_CHECK_CUDA(cudaFuncSetAttribute(nms_kernel<MODE, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     SPP_CHECK_ARG(smem <= 160 * 1024, "nms: max_det %d too large", prm.max_det);
-    nms_kernel<MODE><<<batch, kNmsThreads, smem, st>>>(prm);
+    nms_kernel<MODE, CFG><<<batch, CFG::kThreads, smem, st>>>(prm);
     SPP_CHECK_LAUNCH();
     return SPP_OK;
+}
+
+template <int MODE>
+int launch_nms(const NmsParams &prm, int batch, cudaStream_t st) {
+    // a caller-bounded candidate list of <= 512 per image: the small-footprint configuration
+    if (prm.cap <= NmsSmall::kSortMax && prm.max_det <= 1024)
+        return launch_nms_cfg<MODE, NmsSmall>(prm, batch, st);
+    return launch_nms_cfg<MODE, NmsBig>(prm, batch, st);
 }
 
 int check_nms_args(int batch, int nc, float iou, int max_det, int max_nms, const float *out_dets, const int *out_count,

@@ -572,6 +572,10 @@ int heatmap_decode_impl(const T *hm, const T *hm_flipped, const int *perm, int p
     if (sms <= 0) return SPP_ERR_CUDA;
     long long grid = (total + warps - 1) / warps;
     if (grid > sms) grid = sms;
+    {   // spp_set_launch_limit(SPP_LIMIT_HEATMAP_CTAS): leave SMs free for a kernel that needs whole SMs beside this one
+        const int lim = launch_limit(0);
+        if (lim > 0 && grid > lim) grid = lim;
+    }
 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (mode == SPP_DECODE_DARK && (flags & SPP_DECODE_FLAG_HF_F32_INDEX))      // quirk Q6: run-time radius, own instantiation

@@ -846,6 +846,10 @@ MatchPlan plan_match(int m, int n, bool own_probes = true) {
     p.tiles_n = (n + BN - 1) / BN;
     int sms = sm_count();
     if (sms <= 0) sms = 148;
+    {   // spp_set_launch_limit(SPP_LIMIT_MATCH_CTAS): run the GEMM on a few SMs beside a kernel that holds the others
+        const int lim = launch_limit(1);
+        if (lim > 0 && sms > lim) sms = lim;
+    }
     // Work items = (M-tile, chunk of gallery tiles).  Small problems (fewer items than SMs even at one gallery
     // tile per item): one item per CTA and as many CTAs as there are SMs — every CTA pays a 128 KB probe-tile
     // load, but the kernel is over in ~1/6 of the time 8-tile chunks take (cfg2: 145 CTAs x 1-2 tiles instead of

@@ -78,10 +78,20 @@ class SelectivePosePipeline:
     def __init__(self, inputs: StepInputs, gallery_bf16: torch.Tensor, device: torch.device, threshold: float = 0.4,
                  conf_thres: float = 0.001, iou_thres: float = 0.65, decode_mode: str = "dark", use_graph: bool = True,
                  id_offset: int = 0, concurrent: bool = True, matcher=None, capture_collectives: bool = False,
-                 select_on_device: bool = False, gallery_f32: Optional[torch.Tensor] = None, max_row_norm: float = 1.0):
+                 select_on_device: bool = False, gallery_f32: Optional[torch.Tensor] = None, max_row_norm: float = 1.0,
+                 det_max_candidates: int = 0, match_sms: int = 0, heatmap_first: bool = True):
         self.device = device
         self.threshold, self.conf, self.iou, self.mode = threshold, conf_thres, iou_thres, decode_mode
         self.id_offset = id_offset
+        # det_max_candidates: bound on the candidates per image handed to the NMS (ops.decode_nms max_candidates).  <= 512
+        # selects the small-footprint NMS kernel, whose CTAs fit beside the heatmap decode's, so the detection chains run
+        # under it; an image with more candidates is flagged (NmsResult.overflowed()).  0 = every anchor may be one.
+        # match_sms: SMs given to the match GEMM (it needs whole SMs); the heatmap decode runs on the others at the same
+        # time.  0 = no split (each kernel takes the whole machine in turn).
+        # heatmap_first: heatmap decode, then crop on the main stream (they are independent inputs of a step); the
+        # latency-bound chains overlap the heatmap decode, whose CTAs leave registers and 20 KB of shared memory free.
+        self.det_max_candidates, self.match_sms = int(det_max_candidates), int(match_sms)
+        self.heatmap_first = heatmap_first and not select_on_device
         self.gallery = gallery_bf16.to(device).contiguous()
         self.gallery_f32 = None if gallery_f32 is None else gallery_f32.to(device).float().contiguous()
         self.max_row_norm = float(max_row_norm)
@@ -115,15 +125,17 @@ class SelectivePosePipeline:
         # exactly as long as the pipeline does (ops' shared grow-only cache may replace its buffers at any later call).
         b_, a_ = self.inp.face_levels[0].shape[0], sum(l.shape[2] * l.shape[3] for l in self.inp.face_levels)
         nc_ = self.inp.face_levels[0].shape[1] - 64
-        self._ws_face = ops.alloc_workspace(device, ops.nms_workspace_bytes(b_, a_, nc_))
+        self._ws_face = ops.alloc_workspace(device, ops.nms_workspace_bytes(b_, a_, nc_, self.det_max_candidates))
         ncp_ = self.inp.person_levels[0].shape[1] - 64
         ap_ = sum(l.shape[2] * l.shape[3] for l in self.inp.person_levels)
-        self._ws_person = ops.alloc_workspace(device, ops.nms_workspace_bytes(self.inp.person_levels[0].shape[0], ap_, ncp_))
-        self._ws_match = (ops.alloc_workspace(device, ops.match_workspace_bytes(self.inp.embeddings.shape[0], self.gallery.shape[0]))
-                          if matcher is None else None)
+        self._ws_person = ops.alloc_workspace(device, ops.nms_workspace_bytes(self.inp.person_levels[0].shape[0], ap_, ncp_,
+                                                                              self.det_max_candidates))
+        with self._limits():
+            self._ws_match = (ops.alloc_workspace(device, ops.match_workspace_bytes(self.inp.embeddings.shape[0], self.gallery.shape[0]))
+                              if matcher is None else None)
         self._match_stream = torch.cuda.Stream(device, priority=-1) if self._eager_match else None
         self._side = [torch.cuda.Stream(device) for _ in range(3)]
-        with torch.cuda.stream(self._stream):
+        with torch.cuda.stream(self._stream), self._limits():
             if self._eager_match:
                 self.out["ids"], self.out["sims"] = matcher.match(self.inp.embeddings)
             self._enqueue()                       # warm-up: sizes workspaces, sets kernel attributes
@@ -131,9 +143,29 @@ class SelectivePosePipeline:
         self._stream.synchronize()
         if use_graph:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=self._stream):
+            with self._limits(), torch.cuda.graph(g, stream=self._stream):
                 self._enqueue()
             self.graph = g
+
+    def _limits(self):
+        """CTA budgets of the two whole-machine kernels while this pipeline enqueues (or captures) its step."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            L = _lib.lib()
+            if self.match_sms <= 0:
+                yield
+                return
+            sms = L.spp_device_sm_count()
+            prev_h = L.spp_set_launch_limit(0, max(1, sms - self.match_sms))
+            prev_m = L.spp_set_launch_limit(1, self.match_sms)
+            try:
+                yield
+            finally:
+                L.spp_set_launch_limit(0, prev_h)
+                L.spp_set_launch_limit(1, prev_m)
+        return ctx()
 
     def _enqueue(self) -> None:
         """Enqueue one pass.  Four independent chains run on forked streams and join at the end (inside a
@@ -149,12 +181,18 @@ class SelectivePosePipeline:
                 s.wait_event(fork)
         sides = self._side if self.concurrent else [main, main, main]
         n = 0
+        flags = (ops.FLAG_SCALE_SCORE | ops.FLAG_BACKPROJECT) if self.mode == "softargmax" else 0
+        kp = None
+        if self.heatmap_first:
+            kp = ops.heatmap_decode(i.heatmaps, i.flipped, i.perm, i.boxes, self.mode, 11, flags,
+                                    out=(self.out["keypoints"], self.out["scores"], self.out["argmax"]) if "keypoints" in self.out else None)
+            n += 1
         with torch.cuda.stream(sides[0]):
             face = ops.decode_nms(i.face_levels, conf_thres=self.conf, iou_thres=self.iou, out=self.out.get("_face"),
-                                  workspace=self._ws_face)
+                                  workspace=self._ws_face, max_candidates=self.det_max_candidates)
         with torch.cuda.stream(sides[1]):
             person = ops.decode_nms(i.person_levels, conf_thres=self.conf, iou_thres=self.iou, out=self.out.get("_person"),
-                                    workspace=self._ws_person)
+                                    workspace=self._ws_person, max_candidates=self.det_max_candidates)
         # candidate scan + candidate decode + NMS kernel per head (the count memset is not a kernel); one fused kernel
         # per head after ops.set_decode_nms_mode("fused")
         n += 2 * (1 if _lib.lib().spp_decode_nms_mode(-1) == 1 else 3)
@@ -194,10 +232,10 @@ class SelectivePosePipeline:
         else:
             pix = ops.crop_affine(i.frames, boxes, frame_idx, out=self.out.get("pixel_values"))
         n += 1
-        flags = (ops.FLAG_SCALE_SCORE | ops.FLAG_BACKPROJECT) if self.mode == "softargmax" else 0
-        kp = ops.heatmap_decode(i.heatmaps, i.flipped, i.perm, boxes, self.mode, 11, flags,
-                                out=(self.out["keypoints"], self.out["scores"], self.out["argmax"]) if "keypoints" in self.out else None)
-        n += 1
+        if kp is None:
+            kp = ops.heatmap_decode(i.heatmaps, i.flipped, i.perm, boxes, self.mode, 11, flags,
+                                    out=(self.out["keypoints"], self.out["scores"], self.out["argmax"]) if "keypoints" in self.out else None)
+            n += 1
         if self.concurrent:
             for s in self._side:
                 join = torch.cuda.Event()
@@ -222,7 +260,8 @@ class SelectivePosePipeline:
         if self.graph is not None:
             self.graph.replay()
         else:
-            self._enqueue()
+            with self._limits():
+                self._enqueue()
         if self._eager_match:
             # gallery-sharded match: all_gather -> local top-1 -> all_reduce(MAX).  Enqueued AFTER the graph
             # launch so the host issues these eager calls while the device is busy with the graph; on the
