@@ -236,7 +236,7 @@ def main():
     ap.add_argument("--cfg3-ids", type=int, default=1_000_000)
     ap.add_argument("--det-max-candidates", type=int, default=-1,
                     help="bound on NMS candidates per image (<= 512 selects the small-footprint NMS kernel); -1 = 512 for cfg1/cfg2, unbounded else")
-    ap.add_argument("--match-sms", type=int, default=-1, help="SMs reserved for the match GEMM beside the heatmap decode; -1 = 24 for cfg2, 0 = no split")
+    ap.add_argument("--match-sms", type=int, default=0, help="SMs reserved for the match GEMM beside the heatmap decode; 0 = no split (measured best)")
     ap.add_argument("--crop-first", action="store_true", help="round-1 order: crop then heatmap decode on the main stream")
     ap.add_argument("--copy-streams", type=int, default=2, help="streams the per-step H2D copies of the e2e region are spread over")
     args = ap.parse_args()
@@ -265,8 +265,6 @@ def main():
     pipeline = importlib.import_module(PKG + ".pipeline")
     if args.det_max_candidates < 0:
         args.det_max_candidates = 512 if args.workload in ("cfg1", "cfg2") else 0
-    if args.match_sms < 0:
-        args.match_sms = 24 if args.workload == "cfg2" else 0
     pipe_kw = dict(decode_mode=args.decode_mode, use_graph=not args.no_graph, concurrent=not args.serial,
                    det_max_candidates=args.det_max_candidates, match_sms=args.match_sms, heatmap_first=not args.crop_first)
 

@@ -83,7 +83,7 @@ __device__ __forceinline__ AxisMap crop_axis_map(const float4 box, int ow, int o
 template <typename T>
 struct AxisEntry;
 template <>
-struct AxisEntry<float> {
+struct __align__(8) AxisEntry<float> {      // one 8-byte shared-memory load per entry
     int i0;
     float t;
     __device__ __forceinline__ void set(int i, double w) { i0 = i; t = (float)w; }
@@ -256,7 +256,8 @@ __device__ __forceinline__ void direct_gather_rows(const CropParams &prm, const 
 // fp64 tables + first band), hence 2 stages of 20 KB (fp32) / 12 KB (uint8) -> 5-7 CTAs per SM.
 // Needs 16-byte aligned source rows (bulk TMA) and room for 2 source rows of the widest window in a band
 // buffer; anything else goes to crop_affine_direct_kernel.
-template <typename T, int C>
+// FULL: out_w is a multiple of the 32*C columns a warp covers, so no per-pixel column bound is needed.
+template <typename T, int C, bool FULL>
 __global__ void __launch_bounds__(32 * (kCropWarps + 1)) crop_affine_kernel(const CropParams prm) {
     using Entry = AxisEntry<T>;
     constexpr bool kU8 = std::is_same<T, unsigned char>::value;
@@ -356,16 +357,17 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1)) crop_affine_kernel(cons
     const int cc = warp % ncc, grp = warp / ncc;
     uint32_t coff[C];
     float wx[C];
-    bool live[C];
+    float isd[C];                       // 1/std of a live column, 0 of a dead one: (finite sample) * 0 + nmean = the constant
     const int xbase = cc * 32 * C + lane;
     const int safe_col = xt[vx0].i0;
 #pragma unroll
     for (int j = 0; j < C; ++j) {
         const int x = xbase + 32 * j;
         const Entry ex = xt[x < ow ? x : ow - 1];
-        live[j] = ex.i0 >= 0;
-        coff[j] = (uint32_t)(((live[j] ? ex.i0 : safe_col) - cx0) * (int)sizeof(T));   // dead columns read a staged address
+        const bool live = ex.i0 >= 0;
+        coff[j] = (uint32_t)(((live ? ex.i0 : safe_col) - cx0) * (int)sizeof(T));   // dead columns read a staged address
         wx[j] = ex.t;
+        isd[j] = live ? inv_sd : 0.0f;
     }
 
     const uint32_t smem_base = smem_u32(crop_smem);
@@ -404,16 +406,16 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1)) crop_affine_kernel(cons
             for (int j = 0; j < C; ++j) {
                 float v;
                 if constexpr (kU8) {
-                    if (!fast_px_u8(top[j], bot[j], ey.t, inv_sd, nmean, v)) {
+                    if (!fast_px_u8(top[j], bot[j], ey.t, isd[j], nmean, v)) {
                         const int x = xbase + 32 * j;
                         const uint32_t a0 = ra + coff[j], a1 = rb + coff[j];
                         v = exact_px_u8(lds_u8(a0), lds_u8(a0 + 1), lds_u8(a1), lds_u8(a1 + 1), xt[x < ow ? x : ow - 1].td, ey.td,
-                                        inv_sd, nmean);
+                                        isd[j], nmean);
                     }
                 } else {
-                    v = finish_px(top[j], bot[j], ey.t, inv_sd, nmean);
+                    v = finish_px(top[j], bot[j], ey.t, isd[j], nmean);
                 }
-                if (xbase + 32 * j < ow) __stcs(o + 32 * j, live[j] ? v : zero_out);
+                if (FULL || xbase + 32 * j < ow) __stcs(o + 32 * j, v);
             }
         }
         __syncwarp();
@@ -460,13 +462,18 @@ int env_int(const char *name, int dflt, int lo, int hi) {
     return (v < lo || v > hi) ? dflt : v;
 }
 
-template <typename T, int C>
-int launch_staged(const CropParams &prm, dim3 grid, size_t smem, cudaStream_t st) {
+template <typename T, int C, bool FULL>
+int launch_staged_full(const CropParams &prm, dim3 grid, size_t smem, cudaStream_t st) {
     // per device and per context: set on every launch (about a microsecond; legal during stream capture)
-    SPP_CHECK_CUDA(cudaFuncSetAttribute(crop_affine_kernel<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    crop_affine_kernel<T, C><<<grid, 32 * (prm.ncc * prm.rg + 1), smem, st>>>(prm);
+    SPP_CHECK_CUDA(cudaFuncSetAttribute(crop_affine_kernel<T, C, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    crop_affine_kernel<T, C, FULL><<<grid, 32 * (prm.ncc * prm.rg + 1), smem, st>>>(prm);
     SPP_CHECK_LAUNCH();
     return SPP_OK;
+}
+
+template <typename T, int C>
+int launch_staged(const CropParams &prm, dim3 grid, size_t smem, cudaStream_t st) {
+    return prm.ow % (32 * C) == 0 ? launch_staged_full<T, C, true>(prm, grid, smem, st) : launch_staged_full<T, C, false>(prm, grid, smem, st);
 }
 
 template <typename T>

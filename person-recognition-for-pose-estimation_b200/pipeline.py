@@ -79,7 +79,7 @@ class SelectivePosePipeline:
                  conf_thres: float = 0.001, iou_thres: float = 0.65, decode_mode: str = "dark", use_graph: bool = True,
                  id_offset: int = 0, concurrent: bool = True, matcher=None, capture_collectives: bool = False,
                  select_on_device: bool = False, gallery_f32: Optional[torch.Tensor] = None, max_row_norm: float = 1.0,
-                 det_max_candidates: int = 0, match_sms: int = 0, heatmap_first: bool = True):
+                 det_max_candidates: int = 0, match_sms: int = 0, heatmap_first: bool = True, det_fused: Optional[bool] = None):
         self.device = device
         self.threshold, self.conf, self.iou, self.mode = threshold, conf_thres, iou_thres, decode_mode
         self.id_offset = id_offset
@@ -90,7 +90,11 @@ class SelectivePosePipeline:
         # time.  0 = no split (each kernel takes the whole machine in turn).
         # heatmap_first: heatmap decode, then crop on the main stream (they are independent inputs of a step); the
         # latency-bound chains overlap the heatmap decode, whose CTAs leave registers and 20 KB of shared memory free.
+        # det_fused: one kernel per head (a CTA per image: scan, candidate decode, sort, NMS) instead of three launches.
+        # Default: fused exactly when the small-footprint configuration applies — 128 small CTAs then run under the heatmap
+        # decode with no launch gaps and no waves; the three-launch form is faster when the chain has the machine to itself.
         self.det_max_candidates, self.match_sms = int(det_max_candidates), int(match_sms)
+        self.det_fused = (0 < self.det_max_candidates <= 512) if det_fused is None else bool(det_fused)
         self.heatmap_first = heatmap_first and not select_on_device
         self.gallery = gallery_bf16.to(device).contiguous()
         self.gallery_f32 = None if gallery_f32 is None else gallery_f32.to(device).float().contiguous()
@@ -154,17 +158,19 @@ class SelectivePosePipeline:
         @contextlib.contextmanager
         def ctx():
             L = _lib.lib()
-            if self.match_sms <= 0:
-                yield
-                return
-            sms = L.spp_device_sm_count()
-            prev_h = L.spp_set_launch_limit(0, max(1, sms - self.match_sms))
-            prev_m = L.spp_set_launch_limit(1, self.match_sms)
+            prev_mode = L.spp_decode_nms_mode(1 if self.det_fused else 0)
+            prev_h = prev_m = None
+            if self.match_sms > 0:
+                sms = L.spp_device_sm_count()
+                prev_h = L.spp_set_launch_limit(0, max(1, sms - self.match_sms))
+                prev_m = L.spp_set_launch_limit(1, self.match_sms)
             try:
                 yield
             finally:
-                L.spp_set_launch_limit(0, prev_h)
-                L.spp_set_launch_limit(1, prev_m)
+                L.spp_decode_nms_mode(prev_mode)
+                if prev_h is not None:
+                    L.spp_set_launch_limit(0, prev_h)
+                    L.spp_set_launch_limit(1, prev_m)
         return ctx()
 
     def _enqueue(self) -> None:
