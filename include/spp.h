@@ -319,6 +319,36 @@ int spp_pose_results(const float *keypoints, const float *scores, const float *b
 int spp_pose_oks(const float *pred, int pred_stride, const float *gt, const float *gt_boxes_xywh, const float *gt_area,
                  const float *sigmas, int p, int k, float *out_oks, spp_stream_t stream);
 
+/* ------------------------------------------------------------------ detection evaluation ----- */
+
+/* Replaces compute_metric(output, target, iou_v) — training/yolopt/util.py:99-120 — for a whole batch: which detections are
+ * true positives at each IoU threshold (the rows the reference's test loop collects, training/yolopt/main.py:210-229).
+ *   dets          DEVICE [batch, det_cap, 6] rows of spp_nms_decoded / spp_decode_nms;  det_count DEVICE [batch] int32
+ *   targets       DEVICE [batch, target_cap, 5] fp32 (cls, x1, y1, x2, y2) in the detections' pixel frame, zero padded
+ *   target_count  DEVICE [batch] int32
+ *   iou_v         HOST   [n_iou] fp32 thresholds (the reference: linspace(0.5, 0.95, 10)); n_iou <= 16
+ *   correct       DEVICE [batch, det_cap, n_iou] uint8 (0 / 1); rows >= det_count[b] are 0
+ * IoU = inter / (area_label + area_det - inter + 1e-7) in fp32, operations in the reference's order: bit-exact. */
+int spp_det_match_targets(const float *dets, const int *det_count, int det_cap, const float *targets, const int *target_count,
+                          int target_cap, const float *iou_v, int n_iou, int batch, unsigned char *correct, spp_stream_t stream);
+
+size_t spp_det_ap_workspace_bytes(int n, int n_iou, int nc_max);
+
+/* Replaces compute_ap(tp, conf, output, target) — training/yolopt/util.py:225-300 (plots excluded; `smooth` :172-177).
+ *   tp          DEVICE [n, n_iou] uint8   true-positive matrix of all detections of the evaluation set
+ *   conf        DEVICE [n] fp32;  pred_cls DEVICE [n] fp32 (class ids as the detection rows carry them)
+ *   target_cls  DEVICE [nt] fp32 class id of every label;  classes are integers in [0, nc_max)
+ *   eps         the reference's 1e-16
+ *   out_classes      DEVICE [nc_max] int32   numpy.unique(target) (ascending; -1 padding);  out_num_classes DEVICE [1]
+ *   out_ap           DEVICE [nc_max, n_iou] fp64   AP per (class, threshold), rows in out_classes order
+ *   out_class_stats  DEVICE [nc_max, 4] fp64       tp, fp, precision, recall at the max-F1 confidence
+ *   out_summary      DEVICE [6] fp64               m_pre, m_rec, map50, mean_ap, max-F1 index (0..999), number of classes
+ * fp64 throughout, numpy's summation orders and numpy.interp's branches reproduced (see det_metrics.cu). */
+int spp_det_average_precision(const unsigned char *tp, const float *conf, const float *pred_cls, int n, const float *target_cls,
+                              int nt, int n_iou, int nc_max, double eps, int *out_classes, int *out_num_classes, double *out_ap,
+                              double *out_class_stats, double *out_summary, void *workspace, size_t workspace_bytes,
+                              spp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

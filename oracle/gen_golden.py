@@ -127,6 +127,74 @@ def gen_ref_head():
     print("ref_head seed", seed, [d.shape[0] for d in dets], "state_dict tensors", len(sd))
 
 
+def make_eval_set(batch=8, seed=0, nc=3, max_targets=14, det_cap=300):
+    """Synthetic evaluation batch: per image a few labelled boxes, detections = jittered copies of them (true positives of
+    varying IoU, duplicates, wrong classes) + background boxes; rows conf-descending like NMS output; tie-free scores."""
+    g = torch.Generator().manual_seed(seed)
+    dets = torch.zeros(batch, det_cap, 6)
+    dcount = torch.zeros(batch, dtype=torch.int32)
+    targets = torch.zeros(batch, max_targets, 5)
+    tcount = torch.zeros(batch, dtype=torch.int32)
+    for b in range(batch):
+        m = int(torch.randint(0 if b == 3 else 2, max_targets + 1, (1,), generator=g))
+        xy = torch.rand(m, 2, generator=g) * 500
+        wh = torch.rand(m, 2, generator=g) * 150 + 20
+        cls = torch.randint(0, nc, (m,), generator=g).float()
+        targets[b, :m] = torch.cat([cls[:, None], xy, xy + wh], 1)
+        tcount[b] = m
+        rows = []
+        for t in range(m):
+            for _ in range(int(torch.randint(0, 5, (1,), generator=g))):
+                jit = (torch.rand(4, generator=g) - 0.5) * wh[t].repeat(2) * float(torch.rand(1, generator=g)) * 0.6
+                c = cls[t] if float(torch.rand(1, generator=g)) < 0.85 else float((int(cls[t]) + 1) % nc)
+                rows.append(torch.cat([torch.cat([xy[t], xy[t] + wh[t]]) + jit, torch.rand(1, generator=g) * 0.9 + 0.05,
+                                       torch.tensor([float(c)])]))
+        for _ in range(int(torch.randint(0, 12, (1,), generator=g))):
+            p = torch.rand(2, generator=g) * 600
+            rows.append(torch.cat([p, p + torch.rand(2, generator=g) * 120 + 10, torch.rand(1, generator=g) * 0.6 + 0.01,
+                                   torch.randint(0, nc + 1, (1,), generator=g).float()]))      # class nc never appears in the labels
+        if b == 5:
+            rows = []                                                                           # labels but no detections
+        if rows:
+            r = torch.stack(rows)
+            r = r[torch.argsort(r[:, 4], descending=True)][:det_cap]
+            dets[b, :r.shape[0]] = r
+            dcount[b] = r.shape[0]
+    return dets, dcount, targets, tcount
+
+
+def gen_det_metrics():
+    """the reference's own ``compute_metric`` (util.py:99-120) per image and ``compute_ap`` (util.py:225-300)
+    over the whole set, driven exactly as training/yolopt/main.py:210-234 drives them."""
+    import warnings
+    sys.path.insert(0, os.path.join(REF, "training"))
+    import yolopt.util as yutil
+    dets, dcount, targets, tcount = make_eval_set()
+    iou_v = torch.linspace(0.5, 0.95, 10)                                    # main.py:193
+    correct = np.zeros((dets.shape[0], dets.shape[1], 10), dtype=bool)
+    metrics = []
+    for b in range(dets.shape[0]):
+        n, m = int(dcount[b]), int(tcount[b])
+        output, cls = dets[b, :n], targets[b, :m, 0:1]
+        metric = torch.zeros(n, 10, dtype=torch.bool)
+        if n == 0:
+            if m:
+                metrics.append((metric, *torch.zeros((2, 0)), cls.squeeze(-1)))
+            continue
+        if m:
+            metric = yutil.compute_metric(output[:, :6], targets[b, :m], iou_v)
+        correct[b, :n] = metric.numpy()
+        metrics.append((metric, output[:, 4], output[:, 5], cls.squeeze(-1)))
+    cat = [torch.cat(x, dim=0).cpu().numpy() for x in zip(*metrics)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                                       # numpy.trapz deprecation
+        tp, fp, m_pre, m_rec, map50, mean_ap = yutil.compute_ap(*cat)
+    np.savez_compressed(os.path.join(OUT, "det_metrics.npz"), dets=dets.numpy(), dcount=dcount.numpy(), targets=targets.numpy(),
+                        tcount=tcount.numpy(), iou_v=iou_v.numpy(), correct=correct, cat_tp=cat[0], cat_conf=cat[1], cat_cls=cat[2],
+                        cat_target_cls=cat[3], tp=tp, fp=fp, summary=np.array([m_pre, m_rec, map50, mean_ap]))
+    print("det_metrics", correct.sum(), tp, fp, m_pre, m_rec, map50, mean_ap)
+
+
 def gen_match():
     sys.path.insert(0, os.path.join(REF, "libs"))
     import net_adaface
@@ -300,6 +368,7 @@ if __name__ == "__main__":
         sys.exit(0)
     gen_det()
     gen_ref_head()
+    gen_det_metrics()
     gen_match()
     gen_pose_live()
     gen_pose_hf()

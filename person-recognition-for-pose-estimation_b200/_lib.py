@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes
 import os
 import subprocess
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_size_t, c_ubyte, c_uint16, c_ulonglong, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_size_t, c_ubyte, c_uint16, c_ulonglong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libspp.so")
@@ -68,6 +68,9 @@ SIGNATURES = {
                                         _P, _P]),
     "spp_pose_results": (c_int, [_P, _P, _P, c_int, c_int, c_float, _P, _P, _P]),
     "spp_pose_oks": (c_int, [_P, c_int, _P, _P, _P, _P, c_int, c_int, _P, _P]),
+    "spp_det_match_targets": (c_int, [_P, _P, c_int, _P, _P, c_int, POINTER(c_float), c_int, c_int, _P, _P]),
+    "spp_det_ap_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "spp_det_average_precision": (c_int, [_P, _P, _P, c_int, _P, c_int, c_int, c_int, c_double, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     # test hook (include/spp_internal.h)
     "spp_debug_match_top1_simt": (c_int, [_P, _P, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, c_size_t, _P]),
 }

@@ -463,3 +463,57 @@ def pose_oks(pred: torch.Tensor, gt: torch.Tensor, gt_area: torch.Tensor, sigmas
     _lib.check(_lib.lib().spp_pose_oks(_ptr(pred), int(pred.shape[2]), _ptr(gt), _ptr(gt_boxes_xywh), _ptr(gt_area), _ptr(sigmas), p, k,
                                        _ptr(out), _stream(out)), "spp_pose_oks")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# detection evaluation: compute_metric / compute_ap of training/yolopt/util.py
+# ------------------------------------------------------------------------------------------------
+
+def det_match_targets(dets: torch.Tensor, det_count: torch.Tensor, targets: torch.Tensor, target_count: torch.Tensor,
+                      iou_v: Sequence[float]) -> torch.Tensor:
+    """``compute_metric`` (util.py:99-120) for a batch: ``dets [B, cap, 6]`` + ``det_count [B]`` (an ``NmsResult``),
+    ``targets [B, tcap, 5]`` (cls, x1, y1, x2, y2) + ``target_count [B]`` -> ``correct [B, cap, len(iou_v)]`` bool."""
+    _need_cuda("det_match_targets", dets, det_count, targets, target_count)
+    dets, targets = _f32c("det_match_targets dets", dets), _f32c("det_match_targets targets", targets)
+    if dets.dim() != 3 or dets.shape[2] != 6 or targets.dim() != 3 or targets.shape[2] != 5 or targets.shape[0] != dets.shape[0]:
+        raise ValueError("det_match_targets: dets must be [B, cap, 6] and targets [B, tcap, 5]")
+    b, cap, tcap = dets.shape[0], dets.shape[1], targets.shape[1]
+    t = len(iou_v)
+    correct = torch.zeros((b, cap, t), dtype=torch.uint8, device=dets.device)
+    if b == 0 or cap == 0:
+        return correct.bool()
+    if tcap == 0:
+        return correct.bool()
+    iv = (ctypes.c_float * t)(*[float(v) for v in iou_v])
+    _lib.check(_lib.lib().spp_det_match_targets(_ptr(dets), _ptr(det_count.to(torch.int32).contiguous()), cap, _ptr(targets),
+                                                _ptr(target_count.to(torch.int32).contiguous()), tcap, iv, t, b, _ptr(correct),
+                                                _stream(dets)), "spp_det_match_targets")
+    return correct.bool()
+
+
+def det_average_precision(tp: torch.Tensor, conf: torch.Tensor, pred_cls: torch.Tensor, target_cls: torch.Tensor,
+                          nc_max: int = 128, eps: float = 1e-16):
+    """``compute_ap`` (util.py:225-300) on the device.  Returns a dict: ``classes [nc]`` int32, ``ap [nc, T]`` fp64,
+    ``tp / fp / p / r [nc]`` fp64 at the max-F1 confidence, and the scalars ``m_pre, m_rec, map50, mean_ap, index``."""
+    _need_cuda("det_average_precision", tp, conf, pred_cls, target_cls)
+    n, t = int(tp.shape[0]), int(tp.shape[1])
+    tp8 = tp.to(torch.uint8).contiguous()
+    conf, pred_cls, target_cls = _f32c("conf", conf.float()), _f32c("pred_cls", pred_cls.float()), _f32c("target_cls", target_cls.float())
+    dev = tp.device
+    L = _lib.lib()
+    nbytes = L.spp_det_ap_workspace_bytes(n, t, nc_max)
+    if nbytes == 0:
+        raise ValueError("det_average_precision: unsupported sizes")
+    ws = _workspace(dev, nbytes, "det_ap")
+    classes = torch.empty((nc_max,), dtype=torch.int32, device=dev)
+    num = torch.zeros((1,), dtype=torch.int32, device=dev)
+    ap = torch.empty((nc_max, t), dtype=torch.float64, device=dev)
+    stats = torch.empty((nc_max, 4), dtype=torch.float64, device=dev)
+    summary = torch.empty((6,), dtype=torch.float64, device=dev)
+    _lib.check(L.spp_det_average_precision(_ptr(tp8), _ptr(conf), _ptr(pred_cls), n, _ptr(target_cls), int(target_cls.numel()), t, nc_max,
+                                           float(eps), _ptr(classes), _ptr(num), _ptr(ap), _ptr(stats), _ptr(summary), _ptr(ws), nbytes,
+                                           _stream(tp8)), "spp_det_average_precision")
+    nc = int(num.item())
+    s = summary.tolist()
+    return dict(classes=classes[:nc], ap=ap[:nc], tp=stats[:nc, 0], fp=stats[:nc, 1], p=stats[:nc, 2], r=stats[:nc, 3],
+                m_pre=s[0], m_rec=s[1], map50=s[2], mean_ap=s[3], index=int(s[4]))

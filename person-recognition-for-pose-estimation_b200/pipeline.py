@@ -189,16 +189,19 @@ class SelectivePosePipeline:
         n = 0
         flags = (ops.FLAG_SCALE_SCORE | ops.FLAG_BACKPROJECT) if self.mode == "softargmax" else 0
         kp = None
-        if self.heatmap_first:
-            kp = ops.heatmap_decode(i.heatmaps, i.flipped, i.perm, i.boxes, self.mode, 11, flags,
-                                    out=(self.out["keypoints"], self.out["scores"], self.out["argmax"]) if "keypoints" in self.out else None)
-            n += 1
+        # Enqueue (= graph launch) order matters for who gets SM slots first: the two detection chains go first (one small
+        # CTA per image lands on its own SM), then the heatmap decode, whose persistent CTAs co-reside with them, then the
+        # match chain — its GEMM needs whole SMs and must not sit in front of the detection kernels in a hardware queue.
         with torch.cuda.stream(sides[0]):
             face = ops.decode_nms(i.face_levels, conf_thres=self.conf, iou_thres=self.iou, out=self.out.get("_face"),
                                   workspace=self._ws_face, max_candidates=self.det_max_candidates)
         with torch.cuda.stream(sides[1]):
             person = ops.decode_nms(i.person_levels, conf_thres=self.conf, iou_thres=self.iou, out=self.out.get("_person"),
                                     workspace=self._ws_person, max_candidates=self.det_max_candidates)
+        if self.heatmap_first:
+            kp = ops.heatmap_decode(i.heatmaps, i.flipped, i.perm, i.boxes, self.mode, 11, flags,
+                                    out=(self.out["keypoints"], self.out["scores"], self.out["argmax"]) if "keypoints" in self.out else None)
+            n += 1
         # candidate scan + candidate decode + NMS kernel per head (the count memset is not a kernel); one fused kernel
         # per head after ops.set_decode_nms_mode("fused")
         n += 2 * (1 if _lib.lib().spp_decode_nms_mode(-1) == 1 else 3)

@@ -298,3 +298,26 @@ def coco_keypoint_results(pred_coords: torch.Tensor, pred_scores: torch.Tensor, 
                     "keypoints": [v if i < 2 else int(v) for xyv in kp for i, v in enumerate(xyv)],
                     "score": float(inst[r]), "bbox": [float(v) for v in sel_boxes[r]], "area": float(areas[b, n])})
     return out
+
+
+# ---- training/yolopt/util.py:99 / :225 (evaluation: true-positive matrix and AP summary) ------------------------------
+def compute_metric(output: torch.Tensor, target: torch.Tensor, iou_v: torch.Tensor) -> torch.Tensor:
+    """``compute_metric(output, target, iou_v)`` — training/yolopt/util.py:99-120: ``output [n, 6]`` detections of one
+    image, ``target [m, 5]`` (cls, x1, y1, x2, y2), ``iou_v [T]`` -> ``correct [n, T]`` bool."""
+    n, m = output.shape[0], target.shape[0]
+    if n == 0 or m == 0:
+        return torch.zeros((n, iou_v.shape[0]), dtype=torch.bool, device=output.device)
+    cnt = torch.tensor([n], dtype=torch.int32, device=output.device)
+    tcn = torch.tensor([m], dtype=torch.int32, device=output.device)
+    return ops.det_match_targets(output[None, :, :6].contiguous(), cnt, target[None].contiguous(), tcn, iou_v.tolist())[0]
+
+
+def compute_ap(tp, conf, output, target, plot: bool = False, names=(), eps: float = 1e-16):
+    """``compute_ap(tp, conf, output, target)`` — training/yolopt/util.py:225-300 without the plots; tensors (CUDA) or
+    numpy arrays as the reference passes them.  Returns ``(tp, fp, m_pre, m_rec, map50, mean_ap)`` (numpy / floats)."""
+    if plot:
+        raise NotImplementedError("compute_ap: the PR / F1 plots of the reference are not reproduced")
+    dev = tp.device if isinstance(tp, torch.Tensor) and tp.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    as_t = lambda x: (x if isinstance(x, torch.Tensor) else torch.as_tensor(x)).to(dev)
+    res = ops.det_average_precision(as_t(tp), as_t(conf), as_t(output), as_t(target), eps=eps)
+    return res["tp"].cpu().numpy(), res["fp"].cpu().numpy(), res["m_pre"], res["m_rec"], res["map50"], res["mean_ap"]

@@ -914,6 +914,59 @@ def test_pose_results_and_oks_vs_oracle(spp, dev):
 
 
 # ------------------------------------------------------------------------------------------------
+# detection evaluation on the device (8f-3): compute_metric / compute_ap
+# ------------------------------------------------------------------------------------------------
+
+def test_det_metrics_vs_reference_fixture(spp, golden, dev):
+    """True-positive matrix bit-exact and AP summary to 1e-12 against the reference's own compute_metric / compute_ap
+    (tests/golden/det_metrics.npz), driven as training/yolopt/main.py:210-234 drives them."""
+    g = golden("det_metrics.npz")
+    dets, dcount = torch.from_numpy(g["dets"]).to(dev), torch.from_numpy(g["dcount"]).to(dev)
+    targets, tcount = torch.from_numpy(g["targets"]).to(dev), torch.from_numpy(g["tcount"]).to(dev)
+    iou_v = torch.from_numpy(g["iou_v"])
+    correct = spp.det_match_targets(dets, dcount, targets, tcount, iou_v.tolist())
+    np.testing.assert_array_equal(correct.cpu().numpy(), g["correct"])
+    # the reference's single-image signature
+    for b in (0, 1, 3, 5):
+        n, m = int(g["dcount"][b]), int(g["tcount"][b])
+        c = spp.compute_metric(dets[b, :n], targets[b, :m], iou_v.to(dev))
+        np.testing.assert_array_equal(c.cpu().numpy(), g["correct"][b, :n])
+    res = spp.det_average_precision(torch.from_numpy(g["cat_tp"]).to(dev), torch.from_numpy(g["cat_conf"]).to(dev),
+                                    torch.from_numpy(g["cat_cls"]).to(dev), torch.from_numpy(g["cat_target_cls"]).to(dev))
+    np.testing.assert_array_equal(res["tp"].cpu().numpy(), g["tp"])
+    np.testing.assert_array_equal(res["fp"].cpu().numpy(), g["fp"])
+    got = np.array([res["m_pre"], res["m_rec"], res["map50"], res["mean_ap"]])
+    np.testing.assert_allclose(got, g["summary"], rtol=1e-12, atol=0)
+    tp, fp, m_pre, m_rec, map50, mean_ap = spp.compute_ap(g["cat_tp"], g["cat_conf"], g["cat_cls"], g["cat_target_cls"])
+    np.testing.assert_allclose([m_pre, m_rec, map50, mean_ap], g["summary"], rtol=1e-12)
+
+
+def test_det_metrics_vs_oracle_larger(spp, dev):
+    """More detections than one sort block (2 048) and 7 classes, two of them without any detection: per-class AP matrix,
+    curves' operating point and summary against the numpy restatement."""
+    from oracle import detmetrics as dm
+    g = torch.Generator().manual_seed(3)
+    n, nt, nc = 9000, 700, 7
+    conf = torch.rand(n, generator=g) * 0.98 + 0.01
+    cls = torch.randint(0, 5, (n,), generator=g).float()                 # classes 5, 6 have labels but no detections
+    tcls = torch.randint(0, nc, (nt,), generator=g).float()
+    tp = (torch.rand(n, 10, generator=g) < (conf[:, None] * torch.linspace(0.9, 0.2, 10)[None])).cummin(1).values   # nested in the threshold
+    want = dm.compute_ap(tp.numpy(), conf.numpy(), cls.numpy(), tcls.numpy())
+    res = spp.det_average_precision(tp.to(dev), conf.to(dev), cls.to(dev), tcls.to(dev), nc_max=16)
+    ex = want[6]
+    np.testing.assert_array_equal(res["classes"].cpu().numpy(), ex["classes"].astype(np.int32))
+    np.testing.assert_allclose(res["ap"].cpu().numpy(), ex["ap"], rtol=1e-12, atol=1e-15)
+    assert res["index"] == ex["index"]
+    np.testing.assert_array_equal(res["tp"].cpu().numpy(), want[0])
+    np.testing.assert_array_equal(res["fp"].cpu().numpy(), want[1])
+    np.testing.assert_allclose([res["m_pre"], res["m_rec"], res["map50"], res["mean_ap"]], list(want[2:6]), rtol=1e-12)
+    # no detections at all: every AP is zero
+    z = spp.det_average_precision(torch.zeros(0, 10, dtype=torch.bool, device=dev), torch.zeros(0, device=dev), torch.zeros(0, device=dev),
+                                  tcls.to(dev), nc_max=16)
+    assert float(z["ap"].abs().sum()) == 0.0 and z["classes"].numel() == nc
+
+
+# ------------------------------------------------------------------------------------------------
 # detection head consumed before the per-level cat (8f-1)
 # ------------------------------------------------------------------------------------------------
 

@@ -49,6 +49,21 @@ def test_reference_head_module_fixture(golden):
     np.testing.assert_array_equal(torch.cat(dets).numpy(), g["dets"])
 
 
+def test_det_metrics_oracle_matches_reference(golden):
+    """compute_metric / compute_ap restatement (oracle/detmetrics.py) against the reference's own outputs."""
+    from oracle import detmetrics as dm
+    g = golden("det_metrics.npz")
+    for b in range(g["dets"].shape[0]):
+        n, m = int(g["dcount"][b]), int(g["tcount"][b])
+        c = dm.compute_metric(g["dets"][b, :n], g["targets"][b, :m], g["iou_v"])
+        np.testing.assert_array_equal(c, g["correct"][b, :n])
+    assert g["correct"].sum() > 100
+    tp, fp, m_pre, m_rec, map50, mean_ap, _ = dm.compute_ap(g["cat_tp"], g["cat_conf"], g["cat_cls"], g["cat_target_cls"])
+    np.testing.assert_array_equal(tp, g["tp"])
+    np.testing.assert_array_equal(fp, g["fp"])
+    np.testing.assert_array_equal(np.array([m_pre, m_rec, map50, mean_ap]), g["summary"])
+
+
 def test_nms_restatement_matches_torchvision():
     import torchvision
     gen = torch.Generator().manual_seed(0)
