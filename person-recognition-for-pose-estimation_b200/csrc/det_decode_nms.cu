@@ -405,10 +405,10 @@ __device__ unsigned long long block_bitonic_reg(unsigned long long key, unsigned
 //   (max_candidates): same code, same results, but a CTA that fits beside the resident CTAs of the bandwidth-bound
 //   kernels (heatmap decode: 206 KB of shared memory per SM), so the detection chain overlaps them instead of queueing.
 struct NmsBig {
-    static constexpr int kThreads = kNmsThreads, kSortMax = kSortSmemMax, kBoxMax = kBoxSmemMax, kWords = kAliveWords;
+    static constexpr int kThreads = kNmsThreads, kSortMax = kSortSmemMax, kBoxMax = kBoxSmemMax, kWords = kAliveWords, kGroup = 4;
 };
 struct NmsSmall {
-    static constexpr int kThreads = 512, kSortMax = 512, kBoxMax = 512, kWords = 16;
+    static constexpr int kThreads = 512, kSortMax = 512, kBoxMax = 512, kWords = 16, kGroup = 1;
 };
 
 template <int MODE, typename CFG>
@@ -540,90 +540,118 @@ __global__ void __launch_bounds__(CFG::kThreads) nms_kernel(const NmsParams prm)
 
     const float thr = prm.iou;
     const int max_det = prm.max_det;
-    // Greedy suppression, one 32-candidate bitmask word at a time (three block barriers per word instead of one per kept box):
-    //   (r) every warp computes, for two alive candidates l of the word, the row "which lanes of this word does l
-    //       suppress" (IoU > thr, one ballot) into shared memory — the geometry is independent of who survives;
-    //   (a) warp 0 resolves the word in sorted order with bit operations only: the first alive lane is kept and its
-    //       row cleared from the word; it publishes the kept lanes;
+    // Greedy suppression, one GROUP of G 32-candidate bitmask words at a time (three block barriers per 32*G candidates):
+    //   (r) every warp computes, for the alive candidates c of the group it owns, the row "which candidates of this group
+    //       after c does c suppress" (IoU > thr, one ballot per word) into shared memory — geometry, independent of who
+    //       survives;
+    //   (a) warp 0 resolves the group in sorted order with bit operations only: the first alive candidate is kept and its
+    //       row cleared from the group's alive bits; it publishes the kept bits;
     //   (b) every warp applies those kept boxes to the later words it owns, four boxes in flight (intersections first,
     //       the IEEE division only when some alive lane intersects one of them).
-    // A candidate is kept iff no earlier KEPT candidate suppresses it: identical to the serial loop of torchvision's CPU nms.
+    // A candidate is kept iff no earlier KEPT candidate suppresses it: identical to the serial loop of torchvision's CPU
+    // nms.  G = 4 (crowd scenes: ~2 000 candidates, the barrier chain per word was the cost) or 1 (small configuration).
+    constexpr int G = CFG::kGroup;
     int nk = 0;
-    __shared__ unsigned s_rows[32];
-    __shared__ unsigned s_keptmask;
-    for (int w = 0; w < nwords && nk < max_det; ++w) {
-        const unsigned word_w = alive[w];                // final: every earlier word has been applied
-        if (word_w == 0u) continue;                      // uniform: every thread reads the same word
-        {   // (r)
-            const int j = w * 32 + lane;
-            float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
-            float aj = 0.f;
-            const bool mine = (word_w >> lane) & 1u;
-            if (mine) get_box(j, bj, aj);
+    __shared__ unsigned s_rows[32 * G][G];
+    __shared__ unsigned s_kept[G];
+    for (int w0 = 0; w0 < nwords && nk < max_det; w0 += G) {
+        unsigned aw[G];
+        unsigned any_alive = 0u;
 #pragma unroll
-            for (int u = 0; u < 32 / NW; ++u) {
-                const int l = warp + u * NW;
-                if ((word_w >> l) & 1u) {                // warp-uniform
-                    float4 bl;
-                    float al;
-                    get_box(w * 32 + l, bl, al);
-                    const unsigned row = suppress_ballot(bl, al, bj, aj, mine && lane > l, thr);
-                    if (lane == 0) s_rows[l] = row;
-                }
+        for (int q = 0; q < G; ++q) {
+            aw[q] = w0 + q < nwords ? alive[w0 + q] : 0u;       // final: every earlier group has been applied
+            any_alive |= aw[q];
+        }
+        if (any_alive == 0u) continue;                          // uniform: every thread reads the same words
+        // (r)
+        for (int c = warp; c < 32 * G; c += NW) {
+            const int cq = c >> 5, cl = c & 31;
+            if (!((aw[cq] >> cl) & 1u)) continue;               // warp-uniform
+            float4 bl;
+            float al;
+            get_box((w0 + cq) * 32 + cl, bl, al);
+#pragma unroll
+            for (int q = 0; q < G; ++q) {
+                if (q < cq) continue;
+                const bool mine = (aw[q] >> lane) & 1u;
+                float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
+                float aj = 0.f;
+                if (mine) get_box((w0 + q) * 32 + lane, bj, aj);
+                const unsigned row = suppress_ballot(bl, al, bj, aj, mine && (q > cq || lane > cl), thr);
+                if (lane == 0) s_rows[c][q] = row;
             }
         }
         __syncthreads();
         if (warp == 0) {   // (a)
-            unsigned word = word_w, kept = 0u;
+            unsigned kw[G];
+#pragma unroll
+            for (int q = 0; q < G; ++q) kw[q] = 0u;
             int cnt = nk;
-            while (word && cnt < max_det) {
-                const int l = __ffs(word) - 1;
-                kept |= 1u << l;
-                if (lane == 0) kept_idx[cnt] = w * 32 + l;
-                ++cnt;
-                word &= ~(1u << l) & ~s_rows[l];
+#pragma unroll
+            for (int q = 0; q < G; ++q) {
+                unsigned word = aw[q];
+                while (word && cnt < max_det) {
+                    const int l = __ffs(word) - 1;
+                    kw[q] |= 1u << l;
+                    if (lane == 0) kept_idx[cnt] = (w0 + q) * 32 + l;
+                    ++cnt;
+                    word &= ~(1u << l) & ~s_rows[q * 32 + l][q];
+#pragma unroll
+                    for (int q2 = 0; q2 < G; ++q2)
+                        if (q2 > q) aw[q2] &= ~s_rows[q * 32 + l][q2];
+                }
             }
             if (lane == 0) {
-                s_keptmask = kept;
-                alive[w] = 0u;
+#pragma unroll
+                for (int q = 0; q < G; ++q) {
+                    s_kept[q] = kw[q];
+                    if (w0 + q < nwords) alive[w0 + q] = 0u;
+                }
             }
         }
         __syncthreads();
-        const unsigned kept = s_keptmask;
-        nk += __popc(kept);
+        unsigned kw[G];
+#pragma unroll
+        for (int q = 0; q < G; ++q) {
+            kw[q] = s_kept[q];
+            nk += __popc(kw[q]);
+        }
         if (nk < max_det) {   // (b)
-            for (int wi = w + 1 + warp; wi < nwords; wi += NW) {
+            for (int wi = w0 + G + warp; wi < nwords; wi += NW) {
                 unsigned word = alive[wi];
                 if (!word) continue;
                 const int j = wi * 32 + lane;
                 float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
                 float aj = 0.f;
                 if ((word >> lane) & 1u) get_box(j, bj, aj);
-                unsigned km = kept;
-                while (km && word) {
-                    // up to four kept boxes in flight: straight-line intersections, one vote, then (rarely) the divisions
-                    float4 bl[4];
-                    float al[4], inter[4];
-                    bool touch[4];
-                    bool any_touch = false;
-                    const bool alive_lane = (word >> lane) & 1u;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int l = km ? __ffs(km) - 1 : -1;
-                        km &= km - 1;                    // 0 stays 0
-                        touch[u] = false;
-                        if (l >= 0) {                    // warp-uniform
-                            get_box(w * 32 + l, bl[u], al[u]);
-                            inter[u] = box_inter(bl[u], bj);
-                            touch[u] = alive_lane && (inter[u] > 0.0f || thr < 0.0f);
+                for (int q = 0; q < G; ++q) {
+                    unsigned km = kw[q];
+                    while (km && word) {
+                        // up to four kept boxes in flight: straight-line intersections, one vote, then (rarely) the divisions
+                        float4 bl[4];
+                        float al[4], inter[4];
+                        bool touch[4];
+                        bool any_touch = false;
+                        const bool alive_lane = (word >> lane) & 1u;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int l = km ? __ffs(km) - 1 : -1;
+                            km &= km - 1;                    // 0 stays 0
+                            touch[u] = false;
+                            if (l >= 0) {                    // warp-uniform
+                                get_box((w0 + q) * 32 + l, bl[u], al[u]);
+                                inter[u] = box_inter(bl[u], bj);
+                                touch[u] = alive_lane && (inter[u] > 0.0f || thr < 0.0f);
+                            }
+                            any_touch |= touch[u];
                         }
-                        any_touch |= touch[u];
-                    }
-                    if (__any_sync(FULL, any_touch)) {
-                        unsigned m = 0u;
+                        if (__any_sync(FULL, any_touch)) {
+                            unsigned m = 0u;
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) m |= __ballot_sync(FULL, ratio_gt(inter[u], al[u], aj, thr, touch[u]));
-                        word &= ~m;
+                            for (int u = 0; u < 4; ++u) m |= __ballot_sync(FULL, ratio_gt(inter[u], al[u], aj, thr, touch[u]));
+                            word &= ~m;
+                        }
                     }
                 }
                 if (lane == 0) alive[wi] = word;
