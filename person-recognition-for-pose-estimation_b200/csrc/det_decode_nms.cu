@@ -325,14 +325,22 @@ __device__ __forceinline__ float box_inter(const float4 &a, const float4 &b) {
     const float h = fmaxf(0.0f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
     return __fmul_rn(w, h);
 }
-// inter / (area_a + area_b - inter) > thr with IEEE division, exactly as torchvision's CPU loop evaluates it.
-// `live` = this lane's result is used.  Lanes whose result is discarded divide 1 by 4 instead: the division's range check
-// (FCHK) sends a ZERO numerator — every lane that does not intersect the box — to the out-of-line slow path, and one such
-// lane drags the whole warp through it (measured: ~1 500 cycles per batch of four boxes instead of ~300).
+// inter / (area_a + area_b - inter) > thr, with the result of the IEEE division torchvision's CPU loop performs — but the
+// division itself is only executed when the ratio lies within 2^-20 (relative) of the threshold:
+//   u = (area_a + area_b) - inter exactly as the reference forms it, t = thr * u (one rounding, 2^-24).
+//   inter > t * (1 + 2^-20)  =>  inter / u > thr * (1 + 2^-21)  =>  RN(inter / u) > thr;   symmetric for "<".
+// Valid for u > 0 and thr > 0; anything else (empty or degenerate boxes: u <= 0, NaN) takes the division.  The division
+// (a ~20-instruction sequence with a range check) was the bulk of the apply phase at crowd density, where most kept boxes
+// intersect some lane of every later word.
 __device__ __forceinline__ bool ratio_gt(float inter, float area_a, float area_b, float thr, bool live) {
-    const float num = live ? inter : 1.0f;
-    const float den = live ? __fsub_rn(__fadd_rn(area_a, area_b), inter) : 4.0f;
-    return live && __fdiv_rn(num, den) > thr;
+    const float u = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+    const float t = __fmul_rn(thr, u);
+    const bool fast = live && u > 0.0f && thr > 0.0f;
+    const bool surely = fast && inter > __fmul_rn(t, 1.00000095367431640625f);         // 1 + 2^-20
+    const bool surely_not = fast && inter < __fmul_rn(t, 0.99999904632568359375f);     // 1 - 2^-20
+    bool r = surely;
+    if (live && !surely && !surely_not) r = __fdiv_rn(inter, u) > thr;                 // rare: the exact IEEE quotient decides
+    return r;
 }
 // Warp-level "which alive lanes does box `a` suppress": the division is skipped when no alive lane intersects the box at
 // all (an empty intersection gives IoU 0, or NaN for two empty boxes — never > thr for thr >= 0)
@@ -385,6 +393,53 @@ __device__ unsigned long long block_bitonic_reg(unsigned long long key, unsigned
         }
     }
     return key;
+}
+
+// Bitonic sort of NT * E keys, E consecutive keys per thread: compare-exchange distances below E stay in registers,
+// distances up to 16 threads go through warp shuffles, only the longer ones (15 of the 78 steps at 4 096 keys) through
+// `xch` (NT * E keys, conflict-free [e][thread] layout) with two block barriers each.
+template <int NT, int E>
+__device__ void block_bitonic_multi(unsigned long long (&key)[E], unsigned long long *xch) {
+    const int tid = threadIdx.x;
+    auto cmpx = [](unsigned long long &a, unsigned long long &b, bool up) {      // a at the lower index
+        const unsigned long long lo = a < b ? a : b, hi = a < b ? b : a;
+        a = up ? lo : hi;
+        b = up ? hi : lo;
+    };
+    for (int K = 2; K <= NT * E; K <<= 1) {
+        for (int J = K >> 1; J > 0; J >>= 1) {
+            if (J < E) {                                       // compile-time register indices only (no local memory)
+#pragma unroll
+                for (int JJ = 1; JJ < E; JJ <<= 1) {
+                    if (JJ != J) continue;
+#pragma unroll
+                    for (int e = 0; e < E; ++e)
+                        if ((e & JJ) == 0) cmpx(key[e], key[e | JJ], ((tid * E + e) & K) == 0);
+                }
+            } else {
+                const int dt = J / E;                          // partner thread distance
+                unsigned long long other[E];
+                if (dt < 32) {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) other[e] = __shfl_xor_sync(FULL, key[e], dt);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) xch[e * NT + tid] = key[e];
+                    __syncthreads();
+#pragma unroll
+                    for (int e = 0; e < E; ++e) other[e] = xch[e * NT + (tid ^ dt)];
+                    __syncthreads();
+                }
+                const bool lower = (tid & dt) == 0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const bool up = ((tid * E + e) & K) == 0;
+                    const bool take_min = lower == up;
+                    key[e] = take_min ? (key[e] < other[e] ? key[e] : other[e]) : (key[e] > other[e] ? key[e] : other[e]);
+                }
+            }
+        }
+    }
 }
 
 // One CTA per image.
@@ -480,6 +535,13 @@ __global__ void __launch_bounds__(CFG::kThreads) nms_kernel(const NmsParams prm)
     } else {
         raw_count = prm.counts[b];
     }
+#ifdef SPP_NMS_PROF
+    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long pc = clock64();
+#define SPP_PROF_MARK(i) do { const long long now_ = clock64(); pt[i] += now_ - pc; pc = now_; } while (0)
+#else
+#define SPP_PROF_MARK(i) do { } while (0)
+#endif
     int n = raw_count < prm.cap ? raw_count : prm.cap;
     unsigned long long *keys;
     if (n <= kNmsThreads) {
@@ -490,17 +552,33 @@ __global__ void __launch_bounds__(CFG::kThreads) nms_kernel(const NmsParams prm)
     } else {
         int npad = 1;
         while (npad < n) npad <<= 1;
-        const bool in_smem = npad <= kSortSmemMax;
-        keys = in_smem ? skeys : gkeys;
-        if (in_smem) {
-            for (int i = tid; i < npad; i += kNmsThreads) skeys[i] = i < n ? gkeys[i] : ~0ull;
-        } else {
-            for (int i = n + tid; i < npad; i += kNmsThreads) gkeys[i] = ~0ull;
+        if (npad <= 4 * kNmsThreads && 4 * kNmsThreads <= kSortSmemMax) {
+            // up to 4 096 candidates (crowd scenes): four keys per thread, sorted in registers / shuffles
+            unsigned long long k4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) k4[e] = tid * 4 + e < n ? gkeys[tid * 4 + e] : ~0ull;
+            block_bitonic_multi<kNmsThreads, 4>(k4, skeys);
+            __syncthreads();
+#pragma unroll
+            for (int e = 0; e < 4; ++e) skeys[tid * 4 + e] = k4[e];
+            __syncthreads();
+            keys = skeys;
+            npad = 0;                                       // sorted: skip the generic path below
         }
-        __syncthreads();
-        bitonic_sort(keys, npad);
+        const bool in_smem = npad <= kSortSmemMax;
+        if (npad) {
+            keys = in_smem ? skeys : gkeys;
+            if (in_smem) {
+                for (int i = tid; i < npad; i += kNmsThreads) skeys[i] = i < n ? gkeys[i] : ~0ull;
+            } else {
+                for (int i = n + tid; i < npad; i += kNmsThreads) gkeys[i] = ~0ull;
+            }
+            __syncthreads();
+            bitonic_sort(keys, npad);
+        }
     }
     if (n > prm.max_nms) n = prm.max_nms;                                   // util.py:157 [:max_nms]
+    SPP_PROF_MARK(0);      // sort
 
     // un-offset box of sorted candidate j
     auto raw_box = [&](unsigned cand, int &cls) -> float4 {
@@ -538,6 +616,7 @@ __global__ void __launch_bounds__(CFG::kThreads) nms_kernel(const NmsParams prm)
     for (int w = tid; w < nwords; w += kNmsThreads) alive[w] = (w * 32 + 32 <= n) ? 0xffffffffu : ((1u << (n - w * 32)) - 1u);
     __syncthreads();
 
+    SPP_PROF_MARK(1);      // staging
     const float thr = prm.iou;
     const int max_det = prm.max_det;
     // Greedy suppression, one GROUP of G 32-candidate bitmask words at a time (three block barriers per 32*G candidates):
@@ -553,7 +632,9 @@ __global__ void __launch_bounds__(CFG::kThreads) nms_kernel(const NmsParams prm)
     constexpr int G = CFG::kGroup;
     int nk = 0;
     __shared__ unsigned s_rows[32 * G][G];
-    __shared__ unsigned s_kept[G];
+    __shared__ float4 s_kb[32 * G];          // boxes kept in the current round (class-offset) and their areas: what (b) applies
+    __shared__ float s_ka[32 * G];
+    __shared__ int s_nkr;
     for (int w0 = 0; w0 < nwords && nk < max_det; w0 += G) {
         unsigned aw[G];
         unsigned any_alive = 0u;
@@ -563,7 +644,15 @@ __global__ void __launch_bounds__(CFG::kThreads) nms_kernel(const NmsParams prm)
             any_alive |= aw[q];
         }
         if (any_alive == 0u) continue;                          // uniform: every thread reads the same words
-        // (r)
+        // (r)  this lane's own candidate of each word of the group, loaded once per round
+        float4 bjq[G];
+        float ajq[G];
+#pragma unroll
+        for (int q = 0; q < G; ++q) {
+            bjq[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            ajq[q] = 0.f;
+            if ((aw[q] >> lane) & 1u) get_box((w0 + q) * 32 + lane, bjq[q], ajq[q]);
+        }
         for (int c = warp; c < 32 * G; c += NW) {
             const int cq = c >> 5, cl = c & 31;
             if (!((aw[cq] >> cl) & 1u)) continue;               // warp-uniform
@@ -574,25 +663,19 @@ __global__ void __launch_bounds__(CFG::kThreads) nms_kernel(const NmsParams prm)
             for (int q = 0; q < G; ++q) {
                 if (q < cq) continue;
                 const bool mine = (aw[q] >> lane) & 1u;
-                float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
-                float aj = 0.f;
-                if (mine) get_box((w0 + q) * 32 + lane, bj, aj);
-                const unsigned row = suppress_ballot(bl, al, bj, aj, mine && (q > cq || lane > cl), thr);
+                const unsigned row = suppress_ballot(bl, al, bjq[q], ajq[q], mine && (q > cq || lane > cl), thr);
                 if (lane == 0) s_rows[c][q] = row;
             }
         }
         __syncthreads();
+        SPP_PROF_MARK(2);  // (r) + barrier
         if (warp == 0) {   // (a)
-            unsigned kw[G];
-#pragma unroll
-            for (int q = 0; q < G; ++q) kw[q] = 0u;
             int cnt = nk;
 #pragma unroll
             for (int q = 0; q < G; ++q) {
                 unsigned word = aw[q];
                 while (word && cnt < max_det) {
                     const int l = __ffs(word) - 1;
-                    kw[q] |= 1u << l;
                     if (lane == 0) kept_idx[cnt] = (w0 + q) * 32 + l;
                     ++cnt;
                     word &= ~(1u << l) & ~s_rows[q * 32 + l][q];
@@ -601,21 +684,25 @@ __global__ void __launch_bounds__(CFG::kThreads) nms_kernel(const NmsParams prm)
                         if (q2 > q) aw[q2] &= ~s_rows[q * 32 + l][q2];
                 }
             }
+            __syncwarp();
+            for (int i = lane; i < cnt - nk; i += 32) {          // stage this round's kept boxes for the apply phase
+                float4 kb;
+                float ka;
+                get_box(kept_idx[nk + i], kb, ka);
+                s_kb[i] = kb;
+                s_ka[i] = ka;
+            }
             if (lane == 0) {
+                s_nkr = cnt - nk;
 #pragma unroll
-                for (int q = 0; q < G; ++q) {
-                    s_kept[q] = kw[q];
+                for (int q = 0; q < G; ++q)
                     if (w0 + q < nwords) alive[w0 + q] = 0u;
-                }
             }
         }
         __syncthreads();
-        unsigned kw[G];
-#pragma unroll
-        for (int q = 0; q < G; ++q) {
-            kw[q] = s_kept[q];
-            nk += __popc(kw[q]);
-        }
+        SPP_PROF_MARK(3);  // (a) + barrier
+        const int nkr = s_nkr;
+        nk += nkr;
         if (nk < max_det) {   // (b)
             for (int wi = w0 + G + warp; wi < nwords; wi += NW) {
                 unsigned word = alive[wi];
@@ -623,43 +710,33 @@ __global__ void __launch_bounds__(CFG::kThreads) nms_kernel(const NmsParams prm)
                 const int j = wi * 32 + lane;
                 float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
                 float aj = 0.f;
-                if ((word >> lane) & 1u) get_box(j, bj, aj);
+                const bool alive_lane = (word >> lane) & 1u;
+                if (alive_lane) get_box(j, bj, aj);
+                bool sup = false;
+                for (int i0 = 0; i0 < nkr; i0 += 4) {
+                    // four kept boxes in flight: straight-line intersections; the (banded) IoU test only for touching lanes
 #pragma unroll
-                for (int q = 0; q < G; ++q) {
-                    unsigned km = kw[q];
-                    while (km && word) {
-                        // up to four kept boxes in flight: straight-line intersections, one vote, then (rarely) the divisions
-                        float4 bl[4];
-                        float al[4], inter[4];
-                        bool touch[4];
-                        bool any_touch = false;
-                        const bool alive_lane = (word >> lane) & 1u;
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int l = km ? __ffs(km) - 1 : -1;
-                            km &= km - 1;                    // 0 stays 0
-                            touch[u] = false;
-                            if (l >= 0) {                    // warp-uniform
-                                get_box((w0 + q) * 32 + l, bl[u], al[u]);
-                                inter[u] = box_inter(bl[u], bj);
-                                touch[u] = alive_lane && (inter[u] > 0.0f || thr < 0.0f);
-                            }
-                            any_touch |= touch[u];
-                        }
-                        if (__any_sync(FULL, any_touch)) {
-                            unsigned m = 0u;
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) m |= __ballot_sync(FULL, ratio_gt(inter[u], al[u], aj, thr, touch[u]));
-                            word &= ~m;
+                    for (int u = 0; u < 4; ++u) {
+                        if (i0 + u < nkr) {                  // warp-uniform
+                            const float4 bl = s_kb[i0 + u];
+                            const float inter = box_inter(bl, bj);
+                            const bool touch = alive_lane && (inter > 0.0f || thr < 0.0f);
+                            sup |= ratio_gt(inter, s_ka[i0 + u], aj, thr, touch);
                         }
                     }
                 }
+                word &= ~__ballot_sync(FULL, sup);               // all of them are KEPT boxes: any one suppresses the lane
                 if (lane == 0) alive[wi] = word;
             }
         }
+        SPP_PROF_MARK(4);  // (b) own work
         __syncthreads();
+        SPP_PROF_MARK(5);  // (b) waiting for the slowest warp
     }
     __syncthreads();
+#ifdef SPP_NMS_PROF
+    if (b == 0 && (tid == 0 || tid == 32 * 17)) printf("nms prof tid %d n %d nk %d: sort %lld staging %lld r %lld a %lld b %lld bwait %lld cycles\n", tid, n, nk, pt[0], pt[1], pt[2], pt[3], pt[4], pt[5]);
+#endif
 
     // emit the kept rows (un-offset box, score, class) in parallel
     float *dets = prm.out_dets + (size_t)b * max_det * 6;
