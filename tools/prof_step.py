@@ -19,7 +19,9 @@ dev = torch.device("cuda:0")
 inp = pipeline.synthetic_inputs(b, h, w, pf, k, seed=0)
 ms = spp.synth.make_match_set(b * pf, n, seed=1000)
 inp.embeddings = ms.embeddings
-pipe = pipeline.SelectivePosePipeline(inp, ms.gallery.to(torch.bfloat16), dev, use_graph=False)   # 2 warm-up passes inside
+# the kernels bench.py's default graph holds (fused small-footprint detection kernels, heatmap decode first), launched eagerly
+pipe = pipeline.SelectivePosePipeline(inp, ms.gallery.to(torch.bfloat16), dev, use_graph=False, concurrent=False,
+                                      det_max_candidates=int(os.environ.get("SPP_PROF_MAXCAND", "512")))   # 2 warm-up passes inside
 for _ in range(steps):
     pipe.step()
 pipe.stream.synchronize()
