@@ -636,6 +636,21 @@ def test_pipeline_graph_vs_eager_and_device_selection(spp, synth, dev):
     host = a.bind_host(inp) or a.run_host()
     a.stream.synchronize()
     assert torch.equal(host["keypoints"], a.out["keypoints"].cpu()) and torch.equal(host["ids"], a.out["ids"].cpu())
+    # bench.py's configuration: bounded candidate list -> fused small-footprint detection kernels, heatmap decode first,
+    # match GEMM on reserved SMs; and the round-1 order.  Same tensors, bit for bit.
+    for kw in (dict(det_max_candidates=512), dict(det_max_candidates=512, match_sms=24), dict(det_max_candidates=512, det_fused=False),
+               dict(heatmap_first=False)):
+        v = pipeline.SelectivePosePipeline(inp, gal, dev, use_graph=True, concurrent=True, **kw)
+        for _ in range(2):
+            v.step()
+        v.stream.synchronize()
+        assert not bool(v.out["_face"].overflowed().any())
+        for k in ("face_dets", "face_count", "person_dets", "person_count", "ids", "sims", "pixel_values", "keypoints", "scores", "argmax"):
+            assert torch.equal(v.out[k], e.out[k]), (kw, k)
+    # a bound that is too small is flagged, not silently truncated
+    t = pipeline.SelectivePosePipeline(inp, gal, dev, use_graph=False, det_max_candidates=8)
+    t.step(); t.stream.synchronize()
+    assert bool(t.out["_face"].overflowed().any()) and bool((t.out["_face"].kept() <= 8).all())
     # crop boxes selected on the device
     s = pipeline.SelectivePosePipeline(inp, gal, dev, use_graph=True, select_on_device=True)
     s.step(); s.stream.synchronize()
@@ -1082,6 +1097,7 @@ def test_cfg2_full_size_against_cpu_reference_calls(spp, synth, dev):
     pipe.stream.synchronize()
     ref = bench.cpu_reference_step(inp, ms.gallery, b, pf)
     # detections: same number of rows per frame, same rows (boxes / scores within 1e-3, conf-descending order)
+    skipped = {}
     for name in ("face", "person"):
         rows = pipe.out["_" + name].to_list()
         checked = 0
@@ -1091,7 +1107,11 @@ def test_cfg2_full_size_against_cpu_reference_calls(spp, synth, dev):
             checked += 1
             assert got.shape == want.shape, name
             _close(got.cpu().numpy(), want.numpy(), atol=1e-3, what=f"{name} detections")
+        skipped[name] = b - checked
         assert checked >= 0.9 * b, f"{name}: only {checked} of {b} frames free of borderline IoU pairs"
+    # how many frames the raw-path comparison skipped (an IoU within 1e-6 of the threshold somewhere in
+    # the frame); shown with `pytest -rP`, recorded in DESIGN.md section 4
+    print(f"cfg2 raw-path detection parity: frames skipped for a borderline IoU pair: face {skipped['face']} / {b}, person {skipped['person']} / {b}")
     # identities: exact wherever the fp32 top-2 gap and the gate margin are not degenerate
     gap = omatch.top2_gap(ms.embeddings, ms.gallery.to(torch.bfloat16).float())
     ref_ids, ref_sims = omatch.match_top1(ms.embeddings, ms.gallery.to(torch.bfloat16).float(), threshold=0.4)
