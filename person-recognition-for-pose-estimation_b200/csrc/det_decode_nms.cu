@@ -316,6 +316,7 @@ struct NmsParams {
     int nc, A, cap, cap_pad;
     float iou, max_wh;
     int max_det, max_nms;
+    int compact_pct;            // compaction when the alive share of the not-yet-visited candidates drops to this percentage
     float *out_dets;
     int *out_count, *out_keys;
 };
@@ -461,9 +462,11 @@ __device__ void block_bitonic_multi(unsigned long long (&key)[E], unsigned long 
 //   kernels (heatmap decode: 206 KB of shared memory per SM), so the detection chain overlaps them instead of queueing.
 struct NmsBig {
     static constexpr int kThreads = kNmsThreads, kSortMax = kSortSmemMax, kBoxMax = kBoxSmemMax, kWords = kAliveWords, kGroup = 4;
+    static constexpr bool kCompact = true;
 };
 struct NmsSmall {
     static constexpr int kThreads = 512, kSortMax = 512, kBoxMax = 512, kWords = 16, kGroup = 1;
+    static constexpr bool kCompact = false;
 };
 
 template <int MODE, typename CFG>
@@ -480,6 +483,7 @@ __global__ void __launch_bounds__(CFG::kThreads) nms_kernel(const NmsParams prm)
     float *sarea = reinterpret_cast<float *>(sbox + kBoxSmemMax);                              // [kBoxSmemMax]
     unsigned *alive = reinterpret_cast<unsigned *>(sarea + kBoxSmemMax);                       // [kAliveWords]
     int *kept_idx = reinterpret_cast<int *>(alive + kAliveWords);                              // [max_det]
+    int *sorig = kept_idx + prm.max_det;                                                       // [kBoxSmemMax] (compaction only)
 
     unsigned long long *gkeys = prm.keys + (size_t)b * prm.cap_pad;
     int raw_count;
@@ -605,7 +609,7 @@ __global__ void __launch_bounds__(CFG::kThreads) nms_kernel(const NmsParams prm)
         }
     };
 
-    const int nwords = (n + 31) >> 5;
+    int nwords = (n + 31) >> 5;
     for (int j = tid; j < n && j < kBoxSmemMax; j += kNmsThreads) {
         float4 ob;
         float ar;
@@ -634,14 +638,26 @@ __global__ void __launch_bounds__(CFG::kThreads) nms_kernel(const NmsParams prm)
     __shared__ unsigned s_rows[32 * G][G];
     __shared__ float4 s_kb[32 * G];          // boxes kept in the current round (class-offset) and their areas: what (b) applies
     __shared__ float s_ka[32 * G];
+    __shared__ int s_kpos[32 * G];
     __shared__ int s_nkr;
+    // Compaction (crowd scenes): once more than half of the not-yet-visited candidates are dead, the alive ones are moved
+    // (order preserved) to the front of the shared-memory box table and the loop restarts on the dense list: the apply
+    // phase and the row phase cost per WORD, dead lanes included.  `sorig` maps a position back to the sorted index the
+    // emit phase needs.
+    __shared__ int s_alive;                  // alive candidates in words not yet visited
+    __shared__ int s_pref[kAliveWords > 256 ? 256 : kAliveWords];
+    bool compacted = false;
+    if (tid == 0) s_alive = n;
+    __syncthreads();
     for (int w0 = 0; w0 < nwords && nk < max_det; w0 += G) {
         unsigned aw[G];
         unsigned any_alive = 0u;
+        int group_alive = 0;
 #pragma unroll
         for (int q = 0; q < G; ++q) {
             aw[q] = w0 + q < nwords ? alive[w0 + q] : 0u;       // final: every earlier group has been applied
             any_alive |= aw[q];
+            group_alive += __popc(aw[q]);
         }
         if (any_alive == 0u) continue;                          // uniform: every thread reads the same words
         // (r)  this lane's own candidate of each word of the group, loaded once per round
@@ -676,7 +692,11 @@ __global__ void __launch_bounds__(CFG::kThreads) nms_kernel(const NmsParams prm)
                 unsigned word = aw[q];
                 while (word && cnt < max_det) {
                     const int l = __ffs(word) - 1;
-                    if (lane == 0) kept_idx[cnt] = (w0 + q) * 32 + l;
+                    if (lane == 0) {
+                        const int pos = (w0 + q) * 32 + l;
+                        s_kpos[cnt - nk] = pos;
+                        kept_idx[cnt] = compacted ? sorig[pos] : pos;
+                    }
                     ++cnt;
                     word &= ~(1u << l) & ~s_rows[q * 32 + l][q];
 #pragma unroll
@@ -688,12 +708,13 @@ __global__ void __launch_bounds__(CFG::kThreads) nms_kernel(const NmsParams prm)
             for (int i = lane; i < cnt - nk; i += 32) {          // stage this round's kept boxes for the apply phase
                 float4 kb;
                 float ka;
-                get_box(kept_idx[nk + i], kb, ka);
+                get_box(s_kpos[i], kb, ka);
                 s_kb[i] = kb;
                 s_ka[i] = ka;
             }
             if (lane == 0) {
                 s_nkr = cnt - nk;
+                s_alive -= group_alive;                          // the whole group is now decided
 #pragma unroll
                 for (int q = 0; q < G; ++q)
                     if (w0 + q < nwords) alive[w0 + q] = 0u;
@@ -725,13 +746,68 @@ __global__ void __launch_bounds__(CFG::kThreads) nms_kernel(const NmsParams prm)
                         }
                     }
                 }
-                word &= ~__ballot_sync(FULL, sup);               // all of them are KEPT boxes: any one suppresses the lane
-                if (lane == 0) alive[wi] = word;
+                const unsigned gone = word & __ballot_sync(FULL, sup);   // all of them are KEPT boxes: any one suppresses the lane
+                word &= ~gone;
+                if (lane == 0) {
+                    alive[wi] = word;
+                    if (CFG::kCompact && gone) atomicSub(&s_alive, __popc(gone));
+                }
             }
         }
         SPP_PROF_MARK(4);  // (b) own work
         __syncthreads();
         SPP_PROF_MARK(5);  // (b) waiting for the slowest warp
+        if (CFG::kCompact) {
+            const int first = w0 + G;                            // first word not yet visited
+            const int span = n - first * 32, left = s_alive;     // candidates / alive candidates from there on
+            if (nk < max_det && span >= 256 && left * 100 <= span * prm.compact_pct && left <= kBoxSmemMax && nwords - first <= 256) {
+                // exclusive prefix of the alive counts of the remaining words (warp 0, up to 8 words per lane)
+                if (warp == 0) {
+                    int run = 0;
+                    for (int base = first; base < nwords; base += 32) {
+                        const int w = base + lane;
+                        const int c = w < nwords ? __popc(alive[w]) : 0;
+                        int inc = c;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int t = __shfl_up_sync(FULL, inc, o);
+                            if (lane >= o) inc += t;
+                        }
+                        if (w < nwords) s_pref[w - first] = run + inc - c;
+                        run += __shfl_sync(FULL, inc, 31);
+                    }
+                }
+                __syncthreads();
+                // move the alive candidates to the front, a chunk of kNmsThreads old positions at a time (new <= old)
+                for (int base = first * 32; base < n; base += kNmsThreads) {
+                    const int j = base + tid;
+                    float4 ob = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float ar = 0.f;
+                    int np = -1, og = 0;
+                    if (j < n) {
+                        const unsigned wd = alive[j >> 5];
+                        if ((wd >> (j & 31)) & 1u) {
+                            np = s_pref[(j >> 5) - first] + __popc(wd & ((1u << (j & 31)) - 1u));
+                            get_box(j, ob, ar);
+                            og = compacted ? sorig[j] : j;
+                        }
+                    }
+                    __syncthreads();
+                    if (np >= 0) {
+                        sbox[np] = ob;
+                        sarea[np] = ar;
+                        sorig[np] = og;
+                    }
+                    __syncthreads();
+                }
+                n = left;
+                nwords = (n + 31) >> 5;
+                for (int w = tid; w < nwords; w += kNmsThreads) alive[w] = (w * 32 + 32 <= n) ? 0xffffffffu : ((1u << (n - w * 32)) - 1u);
+                compacted = true;
+                w0 = -G;                                         // restart on the dense list
+                __syncthreads();
+            }
+        }
     }
     __syncthreads();
 #ifdef SPP_NMS_PROF
@@ -820,7 +896,8 @@ Workspace carve(void *ws, int batch, int num_anchors, int nc, int max_candidates
 
 template <int MODE, typename CFG>
 int launch_nms_cfg(const NmsParams &prm, int batch, cudaStream_t st) {
-    const size_t smem = (size_t)CFG::kSortMax * 8 + (size_t)CFG::kBoxMax * 20 + (size_t)CFG::kWords * 4 + (size_t)prm.max_det * 4;
+    const size_t smem = (size_t)CFG::kSortMax * 8 + (size_t)CFG::kBoxMax * 20 + (size_t)CFG::kWords * 4 + (size_t)prm.max_det * 4 +
+                        (CFG::kCompact ? (size_t)CFG::kBoxMax * 4 : 0);
     // per device and per context: set on every launch (about a microsecond; legal during stream capture)
     SPP_CHECK_CUDA(cudaFuncSetAttribute(nms_kernel<MODE, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     SPP_CHECK_ARG(smem <= 160 * 1024, "nms: max_det %d too large", prm.max_det);
@@ -830,7 +907,10 @@ int launch_nms_cfg(const NmsParams &prm, int batch, cudaStream_t st) {
 }
 
 template <int MODE>
-int launch_nms(const NmsParams &prm, int batch, cudaStream_t st) {
+int launch_nms(const NmsParams &prm_in, int batch, cudaStream_t st) {
+    NmsParams prm = prm_in;
+    static const int compact_pct = [] { const char *e = getenv("SPP_NMS_COMPACT_PCT"); const int v = e ? atoi(e) : 50; return v < 0 ? 0 : (v > 100 ? 100 : v); }();
+    prm.compact_pct = compact_pct;
     // a caller-bounded candidate list of <= 512 per image: the small-footprint configuration
     if (prm.cap <= NmsSmall::kSortMax && prm.max_det <= 1024)
         return launch_nms_cfg<MODE, NmsSmall>(prm, batch, st);
