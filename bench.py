@@ -607,8 +607,11 @@ def run_cfg3(args, spp, pipeline, pipe2, dev, rank, world, B, per_frame, barrier
             full = None
             torch.cuda.empty_cache()
     barrier()
+    # A 1M-id match is the step's longest kernel (one persistent CTA per SM, 225 KB of shared memory: nothing co-resides), so
+    # here the step is a sum of whole-machine kernels and the chains should be SHORT rather than small: three-launch
+    # detection chains on the whole machine, crop -> heatmap decode on the main stream, no SM split.
     kw3 = dict(pipe_kw)
-    kw3["match_sms"] = 0            # a 1M-id match is the step's longest kernel: it gets the whole machine
+    kw3.update(match_sms=0, det_max_candidates=0, det_fused=False, heatmap_first=False)
     pipe3 = pipeline.SelectivePosePipeline(inp3, full if world == 1 else torch.empty((1, 512), dtype=torch.bfloat16), dev,
                                            matcher=matcher, capture_collectives=args.capture_collectives, **kw3)
     st = pipe3.stream

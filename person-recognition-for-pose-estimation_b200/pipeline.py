@@ -79,7 +79,8 @@ class SelectivePosePipeline:
                  conf_thres: float = 0.001, iou_thres: float = 0.65, decode_mode: str = "dark", use_graph: bool = True,
                  id_offset: int = 0, concurrent: bool = True, matcher=None, capture_collectives: bool = False,
                  select_on_device: bool = False, gallery_f32: Optional[torch.Tensor] = None, max_row_norm: float = 1.0,
-                 det_max_candidates: int = 0, match_sms: int = 0, heatmap_first: bool = True, det_fused: Optional[bool] = None):
+                 det_max_candidates: int = 0, match_sms: int = 0, heatmap_first: bool = True, det_fused: Optional[bool] = None,
+                 det_after_heatmap: int = 0):
         self.device = device
         self.threshold, self.conf, self.iou, self.mode = threshold, conf_thres, iou_thres, decode_mode
         self.id_offset = id_offset
@@ -96,6 +97,8 @@ class SelectivePosePipeline:
         self.det_max_candidates, self.match_sms = int(det_max_candidates), int(match_sms)
         self.det_fused = (0 < self.det_max_candidates <= 512) if det_fused is None else bool(det_fused)
         self.heatmap_first = heatmap_first and not select_on_device
+        # experiment knob: number of detection chains (0, 1, 2) that wait for the heatmap decode and run under the crop instead
+        self.det_after_heatmap = int(det_after_heatmap) if self.heatmap_first else 0
         self.gallery = gallery_bf16.to(device).contiguous()
         self.gallery_f32 = None if gallery_f32 is None else gallery_f32.to(device).float().contiguous()
         self.max_row_norm = float(max_row_norm)
@@ -192,16 +195,27 @@ class SelectivePosePipeline:
         # Enqueue (= graph launch) order matters for who gets SM slots first: the two detection chains go first (one small
         # CTA per image lands on its own SM), then the heatmap decode, whose persistent CTAs co-reside with them, then the
         # match chain — its GEMM needs whole SMs and must not sit in front of the detection kernels in a hardware queue.
-        with torch.cuda.stream(sides[0]):
-            face = ops.decode_nms(i.face_levels, conf_thres=self.conf, iou_thres=self.iou, out=self.out.get("_face"),
-                                  workspace=self._ws_face, max_candidates=self.det_max_candidates)
-        with torch.cuda.stream(sides[1]):
-            person = ops.decode_nms(i.person_levels, conf_thres=self.conf, iou_thres=self.iou, out=self.out.get("_person"),
-                                    workspace=self._ws_person, max_candidates=self.det_max_candidates)
+        def det(which, stream):
+            lv, key, ws = ((i.face_levels, "_face", self._ws_face) if which == 0 else (i.person_levels, "_person", self._ws_person))
+            with torch.cuda.stream(stream):
+                return ops.decode_nms(lv, conf_thres=self.conf, iou_thres=self.iou, out=self.out.get(key), workspace=ws,
+                                      max_candidates=self.det_max_candidates)
+        late = self.det_after_heatmap if self.concurrent else 0
+        face = det(0, sides[0]) if late < 2 else None
+        person = det(1, sides[1]) if late < 1 else None
         if self.heatmap_first:
             kp = ops.heatmap_decode(i.heatmaps, i.flipped, i.perm, i.boxes, self.mode, 11, flags,
                                     out=(self.out["keypoints"], self.out["scores"], self.out["argmax"]) if "keypoints" in self.out else None)
             n += 1
+        if late:
+            done = torch.cuda.Event()
+            done.record(main)
+            if person is None:
+                sides[1].wait_event(done)
+                person = det(1, sides[1])
+            if face is None:
+                sides[0].wait_event(done)
+                face = det(0, sides[0])
         # candidate scan + candidate decode + NMS kernel per head (the count memset is not a kernel); one fused kernel
         # per head after ops.set_decode_nms_mode("fused")
         n += 2 * (1 if _lib.lib().spp_decode_nms_mode(-1) == 1 else 3)
