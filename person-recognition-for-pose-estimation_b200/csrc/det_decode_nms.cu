@@ -231,22 +231,32 @@ __global__ void __launch_bounds__(256) cand_scan_kernel(const Levels lv, int nc,
 // use the full mask with xor offsets < 16).  Lane `sub` owns DFL bin `sub` of all four sides (4 loads in flight
 // per lane, 64 per candidate); softmax max / sum and the expectation are 16-lane xor-shuffle reductions.
 // The xyxy box is written to img_boxes[anchor] by lane 0 of the half-warp.
-__device__ __forceinline__ void decode_candidate(const Levels &lv, int b, int anchor, bool valid, int sub, float4 *img_boxes) {
+struct DflLoad {
+    float v[4];          // this lane's DFL bin of the four sides
+    int i, w;            // anchor index inside its level, level width
+    float stride;
+};
+__device__ __forceinline__ DflLoad dfl_load(const Levels &lv, int b, int anchor, int sub) {
+    DflLoad d;
     const LevelRef lr = find_level(lv, anchor);
     const float *basep = lr.box + (size_t)b * lr.bs_box + lr.i;
-    float v[4];
 #pragma unroll
-    for (int sd = 0; sd < 4; ++sd) v[sd] = __ldg(basep + (size_t)(sd * kDfl + sub) * lr.hw);
+    for (int sd = 0; sd < 4; ++sd) d.v[sd] = __ldg(basep + (size_t)(sd * kDfl + sub) * lr.hw);
+    d.i = lr.i; d.w = lr.w; d.stride = lr.stride;
+    return d;
+}
+__device__ __forceinline__ void dfl_finish(const DflLoad &ld, int anchor, bool valid, int sub, float4 *img_boxes) {
+    const DflLoad &lr = ld;
     float m[4], sum[4], d[4];
 #pragma unroll
-    for (int sd = 0; sd < 4; ++sd) m[sd] = v[sd];
+    for (int sd = 0; sd < 4; ++sd) m[sd] = ld.v[sd];
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1)
 #pragma unroll
         for (int sd = 0; sd < 4; ++sd) m[sd] = fmaxf(m[sd], __shfl_xor_sync(FULL, m[sd], o));
 #pragma unroll
     for (int sd = 0; sd < 4; ++sd) {
-        sum[sd] = __expf(v[sd] - m[sd]);
+        sum[sd] = __expf(ld.v[sd] - m[sd]);
         d[sd] = (float)sub * sum[sd];
     }
 #pragma unroll
@@ -270,6 +280,10 @@ __device__ __forceinline__ void decode_candidate(const Levels &lv, int b, int an
         r.w = __fmul_rn(__fsub_rn(y2, y1), lr.stride);
         img_boxes[anchor] = wh2xy(r);
     }
+}
+__device__ __forceinline__ void decode_candidate(const Levels &lv, int b, int anchor, bool valid, int sub, float4 *img_boxes) {
+    const DflLoad ld = dfl_load(lv, b, anchor, sub);
+    dfl_finish(ld, anchor, valid, sub, img_boxes);
 }
 
 // Box decode for the candidates only: one half-warp per (image, candidate).  Lane j of the half-warp
@@ -463,14 +477,16 @@ __device__ void block_bitonic_multi(unsigned long long (&key)[E], unsigned long 
 struct NmsBig {
     static constexpr int kThreads = kNmsThreads, kSortMax = kSortSmemMax, kBoxMax = kBoxSmemMax, kWords = kAliveWords, kGroup = 4;
     static constexpr bool kCompact = true;
+    static constexpr int kMaxRegs = 64;
 };
 struct NmsSmall {
     static constexpr int kThreads = 512, kSortMax = 512, kBoxMax = 512, kWords = 16, kGroup = 1;
     static constexpr bool kCompact = false;
+    static constexpr int kMaxRegs = 48;       // 512 x 48 registers + the heatmap decode's 256 x 160 = one SM's register file
 };
 
 template <int MODE, typename CFG>
-__global__ void __launch_bounds__(CFG::kThreads) nms_kernel(const NmsParams prm) {
+__global__ void __launch_bounds__(CFG::kThreads) __maxnreg__(CFG::kMaxRegs) nms_kernel(const NmsParams prm) {
     constexpr bool RAW = MODE != 0;
     constexpr int kNmsThreads = CFG::kThreads, kSortSmemMax = CFG::kSortMax, kBoxSmemMax = CFG::kBoxMax, kAliveWords = CFG::kWords;
     extern __shared__ __align__(16) unsigned char nms_smem[];
@@ -487,18 +503,27 @@ __global__ void __launch_bounds__(CFG::kThreads) nms_kernel(const NmsParams prm)
 
     unsigned long long *gkeys = prm.keys + (size_t)b * prm.cap_pad;
     int raw_count;
+#ifdef SPP_NMS_PROF
+    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long pc = clock64();
+#define SPP_PROF_MARK(i) do { const long long now_ = clock64(); pt[i] += now_ - pc; pc = now_; } while (0)
+#else
+#define SPP_PROF_MARK(i) do { } while (0)
+#endif
     if (MODE == 2) {
         __shared__ int s_count;
         if (tid == 0) s_count = 0;
         __syncthreads();
         const Levels &lv = prm.lv;
         const int nc = prm.nc;
-        // ---- candidate scan: 4 anchors per thread in flight, class planes read as coalesced lines ----
+        // ---- candidate scan: U anchors per thread in flight (the CTA is alone with its image: DRAM latency is paid once per
+        //      U loads), class planes read as coalesced lines ----
+        constexpr int U = 4;              // 8 / 16 in flight measured no faster (49 vs 48 us alone) and cost registers
         for (int j = 0; j < nc; ++j) {
-            for (int a0 = 0; a0 < lv.A; a0 += 4 * kNmsThreads) {
-                float x[4];
+            for (int a0 = 0; a0 < lv.A; a0 += U * kNmsThreads) {
+                float x[U];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < U; ++u) {
                     const int a = a0 + u * kNmsThreads + tid;
                     x[u] = -INFINITY;
                     if (a < lv.A) {
@@ -507,7 +532,7 @@ __global__ void __launch_bounds__(CFG::kThreads) nms_kernel(const NmsParams prm)
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < U; ++u) {
                     const int a = a0 + u * kNmsThreads + tid;
                     float sc = 0.f;
                     bool c = false;
@@ -521,31 +546,34 @@ __global__ void __launch_bounds__(CFG::kThreads) nms_kernel(const NmsParams prm)
         }
         __syncthreads();
         raw_count = s_count;
+        SPP_PROF_MARK(6);  // fused: candidate scan
         // ---- DFL decode of the candidates into this image's box table ----
         const int nd = raw_count < prm.cap ? raw_count : prm.cap;
         const int sub = lane & 15, half = tid >> 4;
         constexpr int NH = kNmsThreads / 16;
         float4 *img_boxes = prm.boxes + (size_t)b * lv.A;
-        for (int base = 0; base < nd; base += 2 * NH) {
+        constexpr int DU = 2;                            // candidates per half-warp in flight: keys first, then the DFL loads (4 measured no faster)
+        for (int base = 0; base < nd; base += DU * NH) {
+            int anchor[DU];
+            bool valid[DU];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < DU; ++u) {
                 const int t = base + u * NH + half;
-                const bool valid = t < nd;
-                const unsigned cand = valid ? (unsigned)(gkeys[t] & 0xffffffffu) : 0u;
-                decode_candidate(lv, b, (int)(cand / (unsigned)nc), valid, sub, img_boxes);
+                valid[u] = t < nd;
+                const unsigned cand = valid[u] ? (unsigned)(gkeys[t] & 0xffffffffu) : 0u;
+                anchor[u] = (int)(cand / (unsigned)nc);
             }
+            DflLoad ld[DU];
+#pragma unroll
+            for (int u = 0; u < DU; ++u) ld[u] = dfl_load(lv, b, anchor[u], sub);
+#pragma unroll
+            for (int u = 0; u < DU; ++u) dfl_finish(ld[u], anchor[u], valid[u], sub, img_boxes);
         }
         __syncthreads();                                 // keys and boxes written above are read below
+        SPP_PROF_MARK(7);  // fused: candidate decode
     } else {
         raw_count = prm.counts[b];
     }
-#ifdef SPP_NMS_PROF
-    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long pc = clock64();
-#define SPP_PROF_MARK(i) do { const long long now_ = clock64(); pt[i] += now_ - pc; pc = now_; } while (0)
-#else
-#define SPP_PROF_MARK(i) do { } while (0)
-#endif
     int n = raw_count < prm.cap ? raw_count : prm.cap;
     unsigned long long *keys;
     if (n <= kNmsThreads) {
@@ -811,7 +839,7 @@ __global__ void __launch_bounds__(CFG::kThreads) nms_kernel(const NmsParams prm)
     }
     __syncthreads();
 #ifdef SPP_NMS_PROF
-    if (b == 0 && (tid == 0 || tid == 32 * 17)) printf("nms prof tid %d n %d nk %d: sort %lld staging %lld r %lld a %lld b %lld bwait %lld cycles\n", tid, n, nk, pt[0], pt[1], pt[2], pt[3], pt[4], pt[5]);
+    if (b == 0 && (tid == 0 || tid == 32 * 17)) printf("nms prof tid %d n %d nk %d: scan %lld decode %lld sort %lld staging %lld r %lld a %lld b %lld bwait %lld cycles\n", tid, n, nk, pt[6], pt[7], pt[0], pt[1], pt[2], pt[3], pt[4], pt[5]);
 #endif
 
     // emit the kept rows (un-offset box, score, class) in parallel

@@ -51,4 +51,5 @@ elif what == "det":
     pf = int(sys.argv[2]) if len(sys.argv) > 2 else 10
     hm = spp.synth.make_head_maps_fast(64, 736, 1280, n_obj=pf, nc=1, seed=0)
     lv = [l.to(dev) for l in hm.levels]
-    run(lambda: spp.decode_nms(lv))
+    mc = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    run(lambda: spp.decode_nms(lv, max_candidates=mc))
