@@ -482,7 +482,7 @@ struct NmsBig {
 struct NmsSmall {
     static constexpr int kThreads = 512, kSortMax = 512, kBoxMax = 512, kWords = 16, kGroup = 1;
     static constexpr bool kCompact = false;
-    static constexpr int kMaxRegs = 48;       // 512 x 48 registers + the heatmap decode's 256 x 160 = one SM's register file
+    static constexpr int kMaxRegs = 40;       // 512 x 40 registers fit beside the heatmap decode (256 x 160) in one SM register file
 };
 
 template <int MODE, typename CFG>
