@@ -516,31 +516,33 @@ __global__ void __launch_bounds__(CFG::kThreads) __maxnreg__(CFG::kMaxRegs) nms_
         __syncthreads();
         const Levels &lv = prm.lv;
         const int nc = prm.nc;
-        // ---- candidate scan: U anchors per thread in flight (the CTA is alone with its image: DRAM latency is paid once per
-        //      U loads), class planes read as coalesced lines ----
-        constexpr int U = 4;              // 8 / 16 in flight measured no faster (49 vs 48 us alone) and cost registers
+        // ---- candidate scan, level by level (plain pointer arithmetic per anchor instead of a level search), U anchors per
+        //      thread in flight, class planes read as coalesced lines ----
+        constexpr int U = 8;
         for (int j = 0; j < nc; ++j) {
-            for (int a0 = 0; a0 < lv.A; a0 += U * kNmsThreads) {
-                float x[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int a = a0 + u * kNmsThreads + tid;
-                    x[u] = -INFINITY;
-                    if (a < lv.A) {
-                        const LevelRef lr = find_level(lv, a);
-                        x[u] = __ldg(lr.cls + (size_t)b * lr.bs_cls + (size_t)j * lr.hw + lr.i);
-                    }
-                }
+            for (int l = 0; l < SPP_MAX_LEVELS; ++l) {
+                if (l >= lv.n) continue;
+                const int hw = lv.h[l] * lv.w[l], off = lv.off[l];
+                const float *plane = lv.cls[l] + (size_t)b * lv.bs_cls[l] + (size_t)j * hw;
+                for (int i0 = 0; i0 < hw; i0 += U * kNmsThreads) {
+                    float x[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int a = a0 + u * kNmsThreads + tid;
-                    float sc = 0.f;
-                    bool c = false;
-                    if (x[u] > prm.logit_lo) {          // -inf for anchors past the end
-                        sc = sigmoidf_ref(x[u]);
-                        c = sc > prm.conf;
+                    for (int u = 0; u < U; ++u) {
+                        const int i = i0 + u * kNmsThreads + tid;
+                        x[u] = i < hw ? __ldg(plane + i) : -INFINITY;
                     }
-                    append_candidate(c, make_sort_key(sc, (unsigned)(a * nc + j)), &s_count, gkeys, prm.cap);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int a = off + i0 + u * kNmsThreads + tid;
+                        float sc = 0.f;
+                        bool c = false;
+                        if (x[u] > prm.logit_lo) {          // -inf for anchors past the end of the level
+                            sc = sigmoidf_ref(x[u]);
+                            c = sc > prm.conf;
+                        }
+                        append_candidate(c, make_sort_key(sc, (unsigned)(a * nc + j)), &s_count, gkeys, prm.cap);
+                    }
                 }
             }
         }
@@ -552,7 +554,7 @@ __global__ void __launch_bounds__(CFG::kThreads) __maxnreg__(CFG::kMaxRegs) nms_
         const int sub = lane & 15, half = tid >> 4;
         constexpr int NH = kNmsThreads / 16;
         float4 *img_boxes = prm.boxes + (size_t)b * lv.A;
-        constexpr int DU = 2;                            // candidates per half-warp in flight: keys first, then the DFL loads (4 measured no faster)
+        constexpr int DU = 2;                            // candidates per half-warp in flight (3 / 4 spill at 40 registers and measured slower)
         for (int base = 0; base < nd; base += DU * NH) {
             int anchor[DU];
             bool valid[DU];
