@@ -31,7 +31,8 @@ struct CropParams {
     float *out;
     int num_frames, fh, fw, P, oh, ow, variant;
     int stage_bytes;            // size of one shared-memory band buffer
-    int stages;                 // band buffers per CTA
+    int stages;                 // band buffers per CTA (a power of two)
+    int stages_log2;
     int ncc, rg;                // staged kernel: column chunks (of 32 C columns) x row groups = warps per CTA
     float mean[3], stdv[3];
 };
@@ -277,10 +278,14 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1)) crop_affine_kernel(cons
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
     const int p = blockIdx.x, c = blockIdx.y;
-    const float4 box = __ldg(reinterpret_cast<const float4 *>(prm.boxes) + p);
-    int f = __ldg(prm.frame_idx + p);                 // both loads in flight before the fp64 map is built
-    const AxisMap m = crop_axis_map(box, ow, oh, prm.variant);
-    if (tid == 0) {
+    __shared__ AxisMap s_map;
+    int f = __ldg(prm.frame_idx + p);
+    if (warp == 0) {          // the fp64 map (about ten fp64 divisions) is built by one warp, not by all seven
+        const float4 box = __ldg(reinterpret_cast<const float4 *>(prm.boxes) + p);
+        const AxisMap mm = crop_axis_map(box, ow, oh, prm.variant);
+        if (lane == 0) s_map = mm;
+    }
+    if (tid == 32) {
         s_v[0] = ow; s_v[1] = -1; s_v[2] = oh; s_v[3] = -1;
         for (int i = 0; i < prm.stages; ++i) {
             mbar_init(&full[i], 1);
@@ -290,6 +295,7 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1)) crop_affine_kernel(cons
         fence_proxy_async();
     }
     __syncthreads();
+    const AxisMap m = s_map;
     build_tables<T>(m, prm, xt, yt, ry0, ry1, s_v);
     const int vx0 = s_v[0], vx1 = s_v[1], vy0 = s_v[2], vy1 = s_v[3];
 
@@ -334,11 +340,11 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1)) crop_affine_kernel(cons
 
     // ---- producer warp: bulk-copy the source rows of band b into buffer b % S once its previous tenant
     //      (band b - S) has been released by every consumer warp ---------------------------------------------
-    const int S = prm.stages;
+    const int S = prm.stages, lgS = prm.stages_log2;         // S = 1 << lgS: stage and phase of band b by mask and shift
     if (warp == ncc * rg) {
         for (int b = 0; b < nbands; ++b) {
-            const int s = b % S;
-            if (b >= S) mbar_wait(&empty[s], (uint32_t)((b / S - 1) & 1));
+            const int s = b & (S - 1);
+            if (b >= S) mbar_wait(&empty[s], (uint32_t)(((b >> lgS) - 1) & 1));
             const int r0 = vy0 + b * band;
             const int r1 = (r0 + band - 1) < vy1 ? (r0 + band - 1) : vy1;
             const int sy_lo = yt[r0].i0;
@@ -372,10 +378,10 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1)) crop_affine_kernel(cons
 
     const uint32_t smem_base = smem_u32(crop_smem);
     for (int b = 0; b < nbands; ++b) {
-        const int s = b % S;
+        const int s = b & (S - 1);
         const int r0 = vy0 + b * band;
         const int r1 = (r0 + band - 1) < vy1 ? (r0 + band - 1) : vy1;
-        mbar_wait(&full[s], (uint32_t)((b / S) & 1));
+        mbar_wait(&full[s], (uint32_t)((b >> lgS) & 1));
 
         const int ya = r0 + grp * rpg;
         const int yb = (ya + rpg - 1) < r1 ? (ya + rpg - 1) : r1;
@@ -496,9 +502,10 @@ int launch_crop(const void *frames, int num_frames, int frame_h, int frame_w, co
     static const int stage_kb = env_int("SPP_CROP_STAGE_KB", (sizeof(T) == 1 ? kStageBytesDefaultU8 : kStageBytesDefault) / 1024, 2, 80);
     static const int split_env = env_int("SPP_CROP_SPLIT", 0, 1, 64);
     static const int cols = env_int("SPP_CROP_COLS", 3, 3, 6) == 6 ? 6 : 3;
-    static const int stages = env_int("SPP_CROP_STAGES", 2, 2, 8);
+    static const int stages_log2 = [] { const int v = env_int("SPP_CROP_STAGES", 2, 2, 8); return v >= 8 ? 3 : (v >= 4 ? 2 : 1); }();
     prm.stage_bytes = stage_kb * 1024;
-    prm.stages = stages;
+    prm.stages_log2 = stages_log2;
+    prm.stages = 1 << stages_log2;
     // Bulk-TMA row copies need 16-byte aligned row segments (base and row pitch multiples of 16 bytes), and the widest
     // possible source window (the whole frame width) has to leave room for the 2 source rows of a 1-row band.
     prm.ncc = (out_w + 32 * cols - 1) / (32 * cols);

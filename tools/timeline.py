@@ -15,7 +15,16 @@ spp = importlib.import_module(PKG)
 pipeline = importlib.import_module(PKG + ".pipeline")
 
 dev = torch.device("cuda:0")
+if os.environ.get("SPP_TL_L2GRAN"):      # experiment: cudaLimitMaxL2FetchGranularity (32 / 64 / 128 bytes; default 64)
+    import ctypes
+    rt = ctypes.CDLL("libcudart.so.12")
+    torch.zeros(1, device=dev)
+    print("cudaDeviceSetLimit(L2 fetch granularity) ->", rt.cudaDeviceSetLimit(5, ctypes.c_size_t(int(os.environ["SPP_TL_L2GRAN"]))))
 inp = pipeline.synthetic_inputs(64, 720, 1280, 10, 17, seed=0)
+if os.environ.get("SPP_TL_DET_OBJ"):     # experiment: detection heads with fewer / more planted objects than crops per frame
+    n_obj = int(os.environ["SPP_TL_DET_OBJ"])
+    inp.face_levels = spp.synth.make_head_maps_fast(64, 736, 1280, n_obj=n_obj, nc=1, seed=0).levels
+    inp.person_levels = spp.synth.make_head_maps_fast(64, 736, 1280, n_obj=n_obj, nc=1, seed=1).levels
 ms = spp.synth.make_match_set(640, 10000, seed=1000)
 inp.embeddings = ms.embeddings
 if len(sys.argv) > 1 and sys.argv[1] == "u8":
