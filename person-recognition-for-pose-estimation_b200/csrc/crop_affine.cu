@@ -136,11 +136,13 @@ __device__ __forceinline__ float exact_px_u8(unsigned p00, unsigned p01, unsigne
 // IS scipy's.  Near a tie (2 * kU8Guard of the pixels on noise; every pixel of e.g. an exact 2x upscale)
 // the caller recomputes in fp64.
 constexpr float kU8Guard = 1.0f / 1024.0f;
+// No clamp to 255 on this path: both lerps are convex combinations of values <= 255 with fp32 weights in [0, 1], so
+// v <= 255 + 2^-16 and its nearest integer is at most 255.
 __device__ __forceinline__ bool fast_px_u8(float top, float bot, float wy, float inv_sd, float nmean, float &out) {
     const float v = fmaf(bot - top, wy, top);
     const float r = __fsub_rn(__fadd_rn(v, 8388608.0f), 8388608.0f);
     const float fr = fabsf(v - r);
-    out = fmaf(fminf(r, 255.0f), inv_sd, nmean);
+    out = fmaf(r, inv_sd, nmean);
     return fr < 0.5f - kU8Guard;
 }
 
@@ -155,17 +157,6 @@ __device__ __forceinline__ float lds_px1(uint32_t addr, float) {
     asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(v) : "r"(addr));
     return v;
 }
-// uint8: widened with the 2^23 trick (one logic op + one FADD instead of a quarter-rate I2F)
-__device__ __forceinline__ float lds_px(uint32_t addr, unsigned char) {
-    unsigned v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
-    return __int_as_float(0x4B000000 | (int)v) - 8388608.0f;
-}
-__device__ __forceinline__ float lds_px1(uint32_t addr, unsigned char) {
-    unsigned v;
-    asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(v) : "r"(addr));
-    return __int_as_float(0x4B000000 | (int)v) - 8388608.0f;
-}
 __device__ __forceinline__ unsigned lds_u8(uint32_t addr) {
     unsigned v;
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -173,8 +164,14 @@ __device__ __forceinline__ unsigned lds_u8(uint32_t addr) {
 }
 template <typename T>
 __device__ __forceinline__ float hlerp_s(uint32_t addr, float wx) {
-    const float a = lds_px(addr, T()), b = lds_px1(addr, T());
-    return fmaf(b - a, wx, a);
+    if constexpr (std::is_same<T, unsigned char>::value) {
+        // 2^23 + a and 2^23 + b as floats (one logic op each); their difference is exactly b - a, so only a is de-biased
+        const float A = __int_as_float(0x4B000000 | (int)lds_u8(addr)), B = __int_as_float(0x4B000000 | (int)lds_u8(addr + 1));
+        return fmaf(B - A, wx, A - 8388608.0f);
+    } else {
+        const float a = lds_px(addr, T()), b = lds_px1(addr, T());
+        return fmaf(b - a, wx, a);
+    }
 }
 
 constexpr int kStageBytesDefault = 20 * 1024;   // one source band buffer of a CTA, fp32 frames
@@ -391,37 +388,53 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1)) crop_affine_kernel(cons
         int prev = INT_MIN;
         float *o = dst + (size_t)ya * ow + xbase;
         for (int y = ya; y <= yb; ++y, o += ow) {
-            const Entry ey = yt[y];
-            const uint32_t ra = tile + (uint32_t)(ey.i0 * pitch);
+            // (index, fp32 weight) only: the fp64 weight of a uint8 entry is read on the rare exact path
+            const int2 ey2 = *reinterpret_cast<const int2 *>(&yt[y]);
+            const int ey_i0 = ey2.x;
+            const float ey_t = __int_as_float(ey2.y);
+            const uint32_t ra = tile + (uint32_t)(ey_i0 * pitch);
             const uint32_t rb = ra + (uint32_t)pitch;
-            if (ey.i0 == prev + 1) {
+            if (ey_i0 == prev + 1) {
 #pragma unroll
                 for (int j = 0; j < C; ++j) {
                     top[j] = bot[j];
                     bot[j] = hlerp_s<T>(rb + coff[j], wx[j]);
                 }
-            } else if (ey.i0 != prev) {
+            } else if (ey_i0 != prev) {
 #pragma unroll
                 for (int j = 0; j < C; ++j) {
                     top[j] = hlerp_s<T>(ra + coff[j], wx[j]);
                     bot[j] = hlerp_s<T>(rb + coff[j], wx[j]);
                 }
             }
-            prev = ey.i0;
+            prev = ey_i0;
+            if constexpr (kU8) {
+                float v[C];
+                unsigned bad = 0u;
 #pragma unroll
-            for (int j = 0; j < C; ++j) {
-                float v;
-                if constexpr (kU8) {
-                    if (!fast_px_u8(top[j], bot[j], ey.t, isd[j], nmean, v)) {
-                        const int x = xbase + 32 * j;
-                        const uint32_t a0 = ra + coff[j], a1 = rb + coff[j];
-                        v = exact_px_u8(lds_u8(a0), lds_u8(a0 + 1), lds_u8(a1), lds_u8(a1 + 1), xt[x < ow ? x : ow - 1].td, ey.td,
-                                        isd[j], nmean);
+                for (int j = 0; j < C; ++j)
+                    if (!fast_px_u8(top[j], bot[j], ey_t, isd[j], nmean, v[j])) bad |= 1u << j;
+                if (bad) {                           // near a rounding tie (0.2 % of the pixels on noise): fp64, as scipy computes it
+                    const double wyd = yt[y].td;
+#pragma unroll
+                    for (int j = 0; j < C; ++j) {
+                        if ((bad >> j) & 1u) {
+                            const int x = xbase + 32 * j;
+                            const uint32_t a0 = ra + coff[j], a1 = rb + coff[j];
+                            v[j] = exact_px_u8(lds_u8(a0), lds_u8(a0 + 1), lds_u8(a1), lds_u8(a1 + 1), xt[x < ow ? x : ow - 1].td, wyd,
+                                               isd[j], nmean);
+                        }
                     }
-                } else {
-                    v = finish_px(top[j], bot[j], ey.t, isd[j], nmean);
                 }
-                if (FULL || xbase + 32 * j < ow) __stcs(o + 32 * j, v);
+#pragma unroll
+                for (int j = 0; j < C; ++j)
+                    if (FULL || xbase + 32 * j < ow) __stcs(o + 32 * j, v[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < C; ++j) {
+                    const float v = finish_px(top[j], bot[j], ey_t, isd[j], nmean);
+                    if (FULL || xbase + 32 * j < ow) __stcs(o + 32 * j, v);
+                }
             }
         }
         __syncwarp();
