@@ -252,6 +252,20 @@ int spp_crop_affine_u8(const uint8_t *frames, int num_frames, int frame_h, int f
                        const int *frame_idx, int p, int out_h, int out_w, const float *mean, const float *std,
                        int variant, float *out, spp_stream_t stream);
 
+/* The same two ops through the persistent kernels: a plan kernel computes the fp64 source map, both coordinate tables and the
+ * band layout once per crop into `workspace`, and a resident stream kernel pulls (crop, channel, 64-row slab) items from a
+ * ticket counter in it, fed by bulk-TMA copies of the planned tables (no per-CTA set-up, short drain).  Results are identical
+ * bit for bit.  workspace: DEVICE, 16-byte aligned, spp_crop_workspace_bytes(p, out_h, out_w, frames_u8) bytes, private to
+ * the call until it has finished on `stream`; NULL selects the kernels of spp_crop_affine / spp_crop_affine_u8.
+ * Replaces the same reference code as spp_crop_affine (HF image_processing_vitpose.py:68-172, 386-448). */
+size_t spp_crop_workspace_bytes(int p, int out_h, int out_w, int frames_u8);
+int spp_crop_affine_ws(const float *frames, int num_frames, int frame_h, int frame_w, const float *boxes,
+                       const int *frame_idx, int p, int out_h, int out_w, const float *mean, const float *std,
+                       int variant, float *out, void *workspace, size_t workspace_bytes, spp_stream_t stream);
+int spp_crop_affine_u8_ws(const uint8_t *frames, int num_frames, int frame_h, int frame_w, const float *boxes,
+                          const int *frame_idx, int p, int out_h, int out_w, const float *mean, const float *std,
+                          int variant, float *out, void *workspace, size_t workspace_bytes, spp_stream_t stream);
+
 /* ------------------------------------------------------------------ heatmap decode ----------- */
 
 #define SPP_DECODE_DARK 0        /* HF post_process_pose_estimation: argmax + DARK + UDP back-projection */

@@ -33,6 +33,8 @@ struct CropParams {
     int stage_bytes;            // size of one shared-memory band buffer
     int stages;                 // band buffers per CTA (a power of two)
     int stages_log2;
+    int split;                  // persistent kernels: row slabs per (crop, channel)
+    unsigned char *ws;          // persistent kernels: workspace (ticket counter, planned tables and item descriptors)
     int ncc, rg;                // staged kernel: column chunks (of 32 C columns) x row groups = warps per CTA
     float mean[3], stdv[3];
 };
@@ -212,10 +214,11 @@ __device__ __forceinline__ void build_tables(const AxisMap &m, const CropParams 
 // width AND height gives a negative scale on both axes; HF / scipy then produce the mirrored crop).
 template <typename T>
 __device__ __forceinline__ void direct_gather_rows(const CropParams &prm, const T *src, float *dst, const AxisEntry<T> *xt,
-                                                   const AxisEntry<T> *yt, int ry0, int ry1, float inv_sd, float nmean) {
+                                                   const AxisEntry<T> *yt, int ry0, int ry1, float inv_sd, float nmean, int tid,
+                                                   int nthreads) {
     constexpr bool kU8 = std::is_same<T, unsigned char>::value;
     const int ow = prm.ow;
-    for (int x = threadIdx.x; x < ow; x += blockDim.x) {
+    for (int x = tid; x < ow; x += nthreads) {
         const AxisEntry<T> ex = xt[x];
         float *o = dst + (size_t)ry0 * ow + x;
         for (int y = ry0; y <= ry1; ++y, o += ow) {
@@ -306,7 +309,7 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1)) crop_affine_kernel(cons
 
     const bool any = vx1 >= vx0 && vy1 >= vy0;
     if (any && (m.ax < 0.0 || m.ay < 0.0)) {         // mirrored crop: the band staging below assumes a non-decreasing map
-        direct_gather_rows<T>(prm, src, dst, xt, yt, ry0, ry1, inv_sd, nmean);
+        direct_gather_rows<T>(prm, src, dst, xt, yt, ry0, ry1, inv_sd, nmean, threadIdx.x, blockDim.x);
         return;
     }
     // rows with no valid source: constant
@@ -442,6 +445,314 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1)) crop_affine_kernel(cons
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent variant (spp_crop_affine*_ws, the default of ops.crop_affine): a PLAN kernel + a STREAM kernel.
+//
+// Why.  Per-CTA traces of the one-CTA-per-item kernel above (cfg2, 3 840 CTAs of 12-51 us) show where its time goes beyond
+// the bytes: every CTA spends ~6 us (box -> fp64 map -> tables -> first band over a loaded HBM queue) before its first
+// pixel, with both of its band buffers empty; the last CTA starts at 128 us and the machine drains until 157 us; time vs
+// crop count is 18 us + 145 us per 640 crops.  Shorter items would shrink the drain but multiply the set-up.
+//   * crop_plan_kernel, one CTA per crop: the fp64 map and both coordinate tables ONCE per crop (not once per channel and
+//     slab), plus one 64-byte descriptor per row slab (valid ranges, source window, band layout), into the workspace;
+//   * crop_stream_kernel, resident CTAs pulling (crop, slab, channel) tickets from a counter in the workspace: the set-up of
+//     an item is three bulk-TMA copies (x table, the slab's y entries, descriptor) into the spare half of a double-buffered
+//     table area, issued by the producer warp one item ahead and completing on an mbarrier — no arithmetic, no block
+//     barrier — so the producer goes straight from the last band of item k to the first band of item k + 1 while the
+//     consumers are still on item k, and items can be 64-row slabs (12 per crop).
+// Barriers: full[2] / empty[2] as above, indexed by a band counter that runs across items; ready[2] (tables + descriptor of
+// the item in half h have landed; a transaction barrier) and done[2] (one arrival per consumer warp: half h may be reused).
+// The ticket for item k + 2 is requested while item k + 1 is fetched: a global atomic takes microseconds under a saturated
+// HBM queue and must never sit between two band copies.
+struct __align__(16) CropItem {
+    int kind;                 // kItemStaged / kItemConstant / kItemMirrored / kItemStop
+    int p, f, ry0, ry1;       // crop, frame, output rows [ry0, ry1]
+    int vx0, vy0, vy1;        // first valid column, valid output rows of the slab
+    int cx0, pitch;           // source window start (elements), staged row pitch (bytes)
+    int band, nbands, rpg;    // output rows per band, number of bands, rows per row group
+    int safe_off;             // staged byte offset that dead output columns read
+    int pad[2];
+};
+static_assert(sizeof(CropItem) == 64, "CropItem is copied by bulk TMA");
+enum { kItemStaged = 0, kItemConstant = 1, kItemMirrored = 2, kItemStop = 3 };
+constexpr int kPlanHeader = 256;              // workspace: [header: ticket counter][tables P x (ow + oh)][items P x nslabs]
+constexpr int kPlanMaxSlabs = 32;
+
+template <typename T>
+__global__ void __launch_bounds__(256) crop_plan_kernel(const CropParams prm) {
+    using Entry = AxisEntry<T>;
+    constexpr int kAlign = 16 / (int)sizeof(T);
+    const int ow = prm.ow, oh = prm.oh, p = blockIdx.x, tid = threadIdx.x;
+    const int slab = (oh + prm.split - 1) / prm.split, nslabs = (oh + slab - 1) / slab;
+    Entry *tab = reinterpret_cast<Entry *>(prm.ws + kPlanHeader) + (size_t)p * (ow + oh);
+    CropItem *items = reinterpret_cast<CropItem *>(prm.ws + kPlanHeader + (size_t)prm.P * (ow + oh) * sizeof(Entry)) + (size_t)p * nslabs;
+    __shared__ AxisMap s_map;
+    __shared__ int s_x[2], s_y[kPlanMaxSlabs][2];
+    if (p == 0 && tid == 0) *reinterpret_cast<unsigned int *>(prm.ws) = 0u;          // the stream kernel's ticket counter
+    if (tid < 32) {
+        const float4 box = __ldg(reinterpret_cast<const float4 *>(prm.boxes) + p);
+        const AxisMap mm = crop_axis_map(box, ow, oh, prm.variant);
+        if (tid == 0) { s_map = mm; s_x[0] = INT_MAX; s_x[1] = -1; }
+    } else if (tid - 32 < nslabs) {
+        s_y[tid - 32][0] = INT_MAX; s_y[tid - 32][1] = -1;
+    }
+    __syncthreads();
+    const AxisMap m = s_map;
+    for (int i = tid; i < ow + oh; i += blockDim.x) {
+        if (i < ow) {
+            const Entry e = axis_entry<T>(m.ax * (double)i + m.bx, prm.fw);
+            tab[i] = e;
+            if (e.i0 >= 0) { atomicMin(&s_x[0], i); atomicMax(&s_x[1], i); }
+        } else {
+            const int y = i - ow;
+            const Entry e = axis_entry<T>(m.ay * (double)y + m.by, prm.fh);
+            tab[i] = e;
+            if (e.i0 >= 0) { atomicMin(&s_y[y / slab][0], y); atomicMax(&s_y[y / slab][1], y); }
+        }
+    }
+    __syncthreads();                                   // also orders this CTA's table stores before the reads below
+    if (tid < nslabs) {
+        const int z = tid;
+        int f = __ldg(prm.frame_idx + p);
+        f = f < 0 ? 0 : (f >= prm.num_frames ? prm.num_frames - 1 : f);
+        CropItem it;
+        it.p = p; it.f = f; it.ry0 = z * slab; it.ry1 = (it.ry0 + slab < oh ? it.ry0 + slab : oh) - 1;
+        const int vx0 = s_x[0], vx1 = s_x[1], vy0 = s_y[z][0], vy1 = s_y[z][1];
+        it.vx0 = vx0; it.vy0 = vy0; it.vy1 = vy1;
+        it.cx0 = 0; it.pitch = 0; it.band = 1; it.nbands = 0; it.rpg = 1; it.safe_off = 0; it.pad[0] = it.pad[1] = 0;
+        if (!(vx1 >= vx0 && vy1 >= vy0)) {
+            it.kind = kItemConstant;
+        } else if (m.ax < 0.0 || m.ay < 0.0) {         // mirrored crop: the band staging assumes a non-decreasing source map
+            it.kind = kItemMirrored;
+        } else {
+            it.kind = kItemStaged;
+            const int i_lo = tab[vx0].i0, i_hi = tab[vx1].i0;
+            const int cx0 = i_lo & ~(kAlign - 1);
+            int cx1 = (i_hi + 2 + kAlign - 1) & ~(kAlign - 1);
+            if (cx1 > prm.fw) cx1 = prm.fw;
+            const int pitch = (cx1 - cx0) * (int)sizeof(T);
+            const int rows_cap = prm.stage_bytes / pitch;
+            const int rg = prm.rg, nrows = it.ry1 - it.ry0 + 1;
+            const double per = m.ay > 0.0 ? m.ay : 1.0;
+            const double br = floor((double)(rows_cap - 3) / per) + 1.0;
+            int band = br > (double)nrows ? nrows : (int)br;
+            if (band > rg) band = band / rg * rg;
+            if (band < 1) band = 1;
+            it.cx0 = cx0; it.pitch = pitch; it.band = band;
+            it.nbands = (vy1 - vy0 + band) / band;
+            it.rpg = (band + rg - 1) / rg;
+            it.safe_off = (i_lo - cx0) * (int)sizeof(T);
+        }
+        items[z] = it;
+    }
+}
+
+template <typename T, int C, bool FULL>
+__global__ void __launch_bounds__(32 * (kCropWarps + 1), 5) crop_stream_kernel(const CropParams prm) {
+    using Entry = AxisEntry<T>;
+    constexpr bool kU8 = std::is_same<T, unsigned char>::value;
+    extern __shared__ __align__(128) unsigned char crop_smem[];
+    const int ow = prm.ow, oh = prm.oh, P = prm.P;
+    const int kStageBytes = prm.stage_bytes;
+    const int slab = (oh + prm.split - 1) / prm.split, nslabs = (oh + slab - 1) / slab;
+    const int total = P * 3 * nslabs;
+    const int tab_n = ow + slab;
+    Entry *tab = reinterpret_cast<Entry *>(crop_smem + 2 * (size_t)kStageBytes);        // [2][ow + slab]
+    CropItem *items = reinterpret_cast<CropItem *>(tab + 2 * (size_t)tab_n);            // [2]
+    uint64_t *full = reinterpret_cast<uint64_t *>(items + 2);                           // [2] band landed
+    uint64_t *empty = full + 2;                                                         // [2] band released by the consumers
+    uint64_t *ready = full + 4;                                                         // [2] tables + descriptor landed
+    uint64_t *done = full + 6;                                                          // [2] item finished by the consumers
+    int *s_chan = reinterpret_cast<int *>(full + 8);                                    // [2] channel of the item in each half
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ncc = prm.ncc, rg = prm.rg, nwarps = ncc * rg;                            // consumer warps
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], nwarps);
+            mbar_init(&ready[i], 1);
+            mbar_init(&done[i], nwarps);
+        }
+        mbar_fence_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    // ---- producer warp ---------------------------------------------------------------------------------------------
+    if (warp == nwarps) {
+        unsigned int *tk = reinterpret_cast<unsigned int *>(prm.ws);
+        const Entry *gtab = reinterpret_cast<const Entry *>(prm.ws + kPlanHeader);
+        const CropItem *gitems = reinterpret_cast<const CropItem *>(prm.ws + kPlanHeader + (size_t)P * (ow + oh) * sizeof(Entry));
+        // fetch item t into half h: descriptor + tables by bulk TMA (or the stop mark), completing on ready[h]
+        auto fetch = [&](int t, int h) {
+            if (lane != 0) return;
+            if (t >= total) {
+                items[h].kind = kItemStop;
+                mbar_arrive(&ready[h]);
+                return;
+            }
+            const int pz = t % (P * nslabs), c = t / (P * nslabs);     // tickets: crop fastest, then slab, then channel
+            const int p = pz % P, z = pz / P;
+            const int ry0 = z * slab, nrows = (ry0 + slab < oh ? ry0 + slab : oh) - ry0;
+            s_chan[h] = c;
+            Entry *xt = tab + (size_t)h * tab_n;
+            const uint32_t bx = (uint32_t)(ow * sizeof(Entry)), by = (uint32_t)(nrows * sizeof(Entry));
+            mbar_arrive_expect_tx(&ready[h], bx + by + (uint32_t)sizeof(CropItem));   // release: s_chan
+            bulk_g2s(xt, gtab + (size_t)p * (ow + oh), bx, &ready[h]);
+            bulk_g2s(xt + ow, gtab + (size_t)p * (ow + oh) + ow + ry0, by, &ready[h]);
+            bulk_g2s(&items[h], gitems + (size_t)p * nslabs + z, (uint32_t)sizeof(CropItem), &ready[h]);
+        };
+        fetch((int)blockIdx.x, 0);
+        int t_next = 0;                                    // lane 0: ticket of item k + 1, requested one item early
+        if (lane == 0) t_next = (int)gridDim.x + (int)atomicAdd(tk, 1u);
+        uint32_t gb = 0;                                   // bands issued so far, over all items
+        for (int k = 0;; ++k) {
+            mbar_wait(&ready[k & 1], (uint32_t)((k >> 1) & 1));
+            const CropItem it = items[k & 1];
+            if (it.kind == kItemStop) break;
+            // Item k + 1 goes into the other half as soon as the consumers have left it (item k - 1) — but its three copies and
+            // the ticket request for item k + 2 are issued AFTER item k's first band copy, never in front of it.
+            // (The wait is mbar_wait, i.e. try_wait: polling this barrier with mbarrier.test_wait between the band copies and
+            // fetching on success reproducibly killed the launch with an illegal-instruction error on B200.)
+            bool pending = true;
+            auto next_item = [&]() {
+                if (k >= 1) mbar_wait(&done[(k + 1) & 1], (uint32_t)(((k - 1) >> 1) & 1));
+                fetch(t_next, (k + 1) & 1);
+                if (lane == 0) t_next = (int)gridDim.x + (int)atomicAdd(tk, 1u);
+                pending = false;
+            };
+            if (it.kind == kItemStaged) {
+                const int c = s_chan[k & 1];
+                const T *src = static_cast<const T *>(prm.frames) + ((size_t)it.f * 3 + c) * prm.fh * prm.fw;
+                const Entry *yt = tab + (size_t)(k & 1) * tab_n + ow - it.ry0;
+                for (int b = 0; b < it.nbands; ++b, ++gb) {
+                    const int s = (int)(gb & 1u);
+                    if (gb >= 2u) mbar_wait(&empty[s], ((gb >> 1) - 1u) & 1u);
+                    const int r0 = it.vy0 + b * it.band;
+                    const int r1 = (r0 + it.band - 1) < it.vy1 ? (r0 + it.band - 1) : it.vy1;
+                    const int sy_lo = yt[r0].i0;
+                    const int nrows = yt[r1].i0 + 1 - sy_lo + 1;
+                    unsigned char *buf = crop_smem + (size_t)s * kStageBytes;
+                    if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(nrows * it.pitch));
+                    __syncwarp();
+                    for (int r = lane; r < nrows; r += 32)
+                        bulk_g2s(buf + (size_t)r * it.pitch, src + (size_t)(sy_lo + r) * prm.fw + it.cx0, (uint32_t)it.pitch, &full[s]);
+                    if (pending) next_item();
+                }
+            }
+            if (pending) next_item();
+        }
+        return;
+    }
+
+    // ---- consumer warps --------------------------------------------------------------------------------------------
+    const int cc = warp % ncc, grp = warp / ncc;
+    const int xbase = cc * 32 * C + lane;
+    const uint32_t smem_base = smem_u32(crop_smem);
+    uint32_t gb = 0;
+    for (int k = 0;; ++k) {
+        mbar_wait(&ready[k & 1], (uint32_t)((k >> 1) & 1));
+        const CropItem it = items[k & 1];
+        if (it.kind == kItemStop) break;
+        const Entry *xt = tab + (size_t)(k & 1) * tab_n;
+        const Entry *yt = xt + ow - it.ry0;
+        const int c = s_chan[k & 1];
+        float *dst = prm.out + ((size_t)it.p * 3 + c) * oh * ow;
+        const float mean = c == 0 ? prm.mean[0] : (c == 1 ? prm.mean[1] : prm.mean[2]);
+        const float inv_sd = 1.0f / (c == 0 ? prm.stdv[0] : (c == 1 ? prm.stdv[1] : prm.stdv[2]));
+        const float nmean = -mean * inv_sd;
+        if (it.kind == kItemMirrored) {
+            const T *src = static_cast<const T *>(prm.frames) + ((size_t)it.f * 3 + c) * prm.fh * prm.fw;
+            direct_gather_rows<T>(prm, src, dst, xt, yt, it.ry0, it.ry1, inv_sd, nmean, tid, 32 * nwarps);
+        } else {
+            const bool staged = it.kind == kItemStaged;
+            for (int y = it.ry0 + warp; y <= it.ry1; y += nwarps) {          // rows with no valid source: constant
+                if (staged && y >= it.vy0 && y <= it.vy1) continue;
+                for (int x = lane; x < ow; x += 32) __stcs(dst + (size_t)y * ow + x, nmean);
+            }
+            if (staged) {
+                const int pitch = it.pitch;
+                uint32_t coff[C];
+                float wx[C], isd[C];
+#pragma unroll
+                for (int j = 0; j < C; ++j) {
+                    const int x = xbase + 32 * j;
+                    const int2 e2 = *reinterpret_cast<const int2 *>(&xt[x < ow ? x : ow - 1]);
+                    const bool live = e2.x >= 0;
+                    coff[j] = live ? (uint32_t)((e2.x - it.cx0) * (int)sizeof(T)) : (uint32_t)it.safe_off;
+                    wx[j] = __int_as_float(e2.y);
+                    isd[j] = live ? inv_sd : 0.0f;
+                }
+                for (int b = 0; b < it.nbands; ++b, ++gb) {
+                    const int s = (int)(gb & 1u);
+                    const int r0 = it.vy0 + b * it.band;
+                    const int r1 = (r0 + it.band - 1) < it.vy1 ? (r0 + it.band - 1) : it.vy1;
+                    mbar_wait(&full[s], (gb >> 1) & 1u);
+                    const int ya = r0 + grp * it.rpg;
+                    const int yb = (ya + it.rpg - 1) < r1 ? (ya + it.rpg - 1) : r1;
+                    const uint32_t tile = smem_base + (uint32_t)(s * kStageBytes) - (uint32_t)(yt[r0].i0 * pitch);
+                    float top[C], bot[C];
+                    int prev = INT_MIN;
+                    float *o = dst + (size_t)ya * ow + xbase;
+                    for (int y = ya; y <= yb; ++y, o += ow) {
+                        const int2 ey2 = *reinterpret_cast<const int2 *>(&yt[y]);
+                        const int ey_i0 = ey2.x;
+                        const float ey_t = __int_as_float(ey2.y);
+                        const uint32_t ra = tile + (uint32_t)(ey_i0 * pitch);
+                        const uint32_t rb = ra + (uint32_t)pitch;
+                        if (ey_i0 == prev + 1) {
+#pragma unroll
+                            for (int j = 0; j < C; ++j) {
+                                top[j] = bot[j];
+                                bot[j] = hlerp_s<T>(rb + coff[j], wx[j]);
+                            }
+                        } else if (ey_i0 != prev) {
+#pragma unroll
+                            for (int j = 0; j < C; ++j) {
+                                top[j] = hlerp_s<T>(ra + coff[j], wx[j]);
+                                bot[j] = hlerp_s<T>(rb + coff[j], wx[j]);
+                            }
+                        }
+                        prev = ey_i0;
+                        if constexpr (kU8) {
+                            float v[C];
+                            unsigned bad = 0u;
+#pragma unroll
+                            for (int j = 0; j < C; ++j)
+                                if (!fast_px_u8(top[j], bot[j], ey_t, isd[j], nmean, v[j])) bad |= 1u << j;
+                            if (bad) {
+                                const double wyd = yt[y].td;
+#pragma unroll
+                                for (int j = 0; j < C; ++j) {
+                                    if ((bad >> j) & 1u) {
+                                        const int x = xbase + 32 * j;
+                                        const uint32_t a0 = ra + coff[j], a1 = rb + coff[j];
+                                        v[j] = exact_px_u8(lds_u8(a0), lds_u8(a0 + 1), lds_u8(a1), lds_u8(a1 + 1), xt[x < ow ? x : ow - 1].td,
+                                                           wyd, isd[j], nmean);
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < C; ++j)
+                                if (FULL || xbase + 32 * j < ow) __stcs(o + 32 * j, v[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < C; ++j) {
+                                const float v = finish_px(top[j], bot[j], ey_t, isd[j], nmean);
+                                if (FULL || xbase + 32 * j < ow) __stcs(o + 32 * j, v);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[s]);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&done[k & 1]);            // this warp no longer reads half k & 1
+    }
+}
+
 // Fallback without staging (frame rows not 16-byte aligned, or a source window too wide for a band buffer):
 // the same tables, direct global gathers, one thread per output column.
 template <typename T>
@@ -466,7 +777,7 @@ __global__ void __launch_bounds__(256) crop_affine_direct_kernel(const CropParam
     const float mean = c == 0 ? prm.mean[0] : (c == 1 ? prm.mean[1] : prm.mean[2]);
     const float inv_sd = 1.0f / (c == 0 ? prm.stdv[0] : (c == 1 ? prm.stdv[1] : prm.stdv[2]));
     const float nmean = -mean * inv_sd;
-    direct_gather_rows<T>(prm, src, dst, xt, yt, 0, oh - 1, inv_sd, nmean);
+    direct_gather_rows<T>(prm, src, dst, xt, yt, 0, oh - 1, inv_sd, nmean, threadIdx.x, blockDim.x);
 }
 
 }  // namespace
@@ -490,6 +801,40 @@ int launch_staged_full(const CropParams &prm, dim3 grid, size_t smem, cudaStream
     return SPP_OK;
 }
 
+template <typename T, int C, bool FULL>
+int launch_stream_full(const CropParams &prm, int total, size_t smem, cudaStream_t st) {
+    SPP_CHECK_CUDA(cudaFuncSetAttribute(crop_stream_kernel<T, C, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    int occ = 0;
+    SPP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, crop_stream_kernel<T, C, FULL>, 32 * (kCropWarps + 1), smem));
+    if (occ < 1) occ = 1;
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    const int grid = total < occ * sms ? total : occ * sms;
+    crop_plan_kernel<T><<<prm.P, 256, 0, st>>>(prm);
+    SPP_CHECK_LAUNCH();
+    crop_stream_kernel<T, C, FULL><<<grid, 32 * (kCropWarps + 1), smem, st>>>(prm);
+    SPP_CHECK_LAUNCH();
+    return SPP_OK;
+}
+template <typename T, int C>
+int launch_stream(const CropParams &prm, int total, size_t smem, cudaStream_t st) {
+    return prm.ow % (32 * C) == 0 ? launch_stream_full<T, C, true>(prm, total, smem, st) : launch_stream_full<T, C, false>(prm, total, smem, st);
+}
+
+// Row slabs of the persistent kernel (SPP_CROP_SPLIT overrides), at most kPlanMaxSlabs: 32 output rows for fp32 frames
+// (memory-bound: short items, short drain), 64 for uint8 frames (issue-bound: the per-item work of the consumers counts).
+// Measured at cfg2: fp32 166 / 164 / 156 / 166 us at 3 / 4 / 8 / 16 slabs, uint8 151 / 153 / 163 / 191 us.
+int stream_split(int out_h, int split_env, int rows) {
+    int split = split_env ? split_env : (out_h + rows - 1) / rows;
+    if (split > kPlanMaxSlabs) split = kPlanMaxSlabs;
+    if (split > out_h) split = out_h;
+    return split < 1 ? 1 : split;
+}
+template <typename T>
+size_t stream_workspace_bytes(int p, int out_h, int out_w, int split) {
+    const int slab = (out_h + split - 1) / split, nslabs = (out_h + slab - 1) / slab;
+    return (size_t)kPlanHeader + (size_t)p * (out_w + out_h) * sizeof(AxisEntry<T>) + (size_t)p * nslabs * sizeof(CropItem);
+}
+
 template <typename T, int C>
 int launch_staged(const CropParams &prm, dim3 grid, size_t smem, cudaStream_t st) {
     return prm.ow % (32 * C) == 0 ? launch_staged_full<T, C, true>(prm, grid, smem, st) : launch_staged_full<T, C, false>(prm, grid, smem, st);
@@ -497,7 +842,8 @@ int launch_staged(const CropParams &prm, dim3 grid, size_t smem, cudaStream_t st
 
 template <typename T>
 int launch_crop(const void *frames, int num_frames, int frame_h, int frame_w, const float *boxes, const int *frame_idx, int p,
-                int out_h, int out_w, const float *mean, const float *std, int variant, float *out, spp_stream_t stream) {
+                int out_h, int out_w, const float *mean, const float *std, int variant, float *out, spp_stream_t stream,
+                void *workspace = nullptr, size_t workspace_bytes = 0) {
     if (p == 0) return SPP_OK;
     SPP_CHECK_ARG(frames && boxes && frame_idx && out && mean && std, "crop_affine: null pointer");
     SPP_CHECK_ARG(num_frames > 0 && frame_h >= 2 && frame_w >= 2 && p >= 0, "crop_affine: frames must be at least 2x2");
@@ -535,6 +881,28 @@ int launch_crop(const void *frames, int num_frames, int frame_h, int frame_w, co
         SPP_CHECK_LAUNCH();
         return SPP_OK;
     }
+    // Persistent plan + stream kernels when the caller brings a workspace (spp_crop_affine*_ws).  They need exactly
+    // kCropWarps consumer warps and table slices that bulk TMA can copy (16-byte multiples: even sizes for 8-byte entries).
+    static const int persist = env_int("SPP_CROP_PERSIST", 1, 0, 1);
+    if (workspace && persist && prm.ncc * prm.rg == kCropWarps) {
+        const int psplit = stream_split(out_h, split_env, sizeof(T) == 1 ? 64 : 32);
+        const int pslab = (out_h + psplit - 1) / psplit, nslabs = (out_h + pslab - 1) / pslab;
+        const bool even = sizeof(AxisEntry<T>) % 16 == 0 || (out_w % 2 == 0 && out_h % 2 == 0 && pslab % 2 == 0);
+        if (even && nslabs <= kPlanMaxSlabs) {
+            SPP_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "crop_affine: workspace must be 16-byte aligned");
+            SPP_CHECK_ARG(workspace_bytes >= stream_workspace_bytes<T>(p, out_h, out_w, psplit), "crop_affine: workspace too small (%zu bytes)",
+                          workspace_bytes);
+            prm.split = psplit;
+            prm.ws = static_cast<unsigned char *>(workspace);
+            prm.stages = 2; prm.stages_log2 = 1;
+            const size_t psmem = 2 * (size_t)prm.stage_bytes + 2 * (size_t)(out_w + pslab) * sizeof(AxisEntry<T>) + 2 * sizeof(CropItem) +
+                                 8 * sizeof(uint64_t) + 16;
+            SPP_CHECK_ARG(psmem <= 200 * 1024, "crop_affine: output size too large");
+            const long long total = (long long)p * 3 * nslabs;
+            SPP_CHECK_ARG(total < (1LL << 30), "crop_affine: too many crops");
+            return cols == 3 ? launch_stream<T, 3>(prm, (int)total, psmem, st) : launch_stream<T, 6>(prm, (int)total, psmem, st);
+        }
+    }
     // Slabs of output rows: enough CTAs that the last wave is a small part of the launch, but never slabs shorter
     // than 64 rows (the tables and the first band are per-CTA overhead).
     int split = split_env;
@@ -557,6 +925,27 @@ extern "C" int spp_crop_affine(const float *frames, int num_frames, int frame_h,
                                const int *frame_idx, int p, int out_h, int out_w, const float *mean, const float *std,
                                int variant, float *out, spp_stream_t stream) {
     return spp::launch_crop<float>(frames, num_frames, frame_h, frame_w, boxes, frame_idx, p, out_h, out_w, mean, std, variant, out, stream);
+}
+
+extern "C" size_t spp_crop_workspace_bytes(int p, int out_h, int out_w, int frames_u8) {
+    if (p <= 0 || out_h <= 0 || out_w <= 0) return 0;
+    // sized for the largest slab count the launcher may choose (SPP_CROP_SPLIT is read there)
+    const int split = spp::kPlanMaxSlabs < out_h ? spp::kPlanMaxSlabs : out_h;
+    return frames_u8 ? spp::stream_workspace_bytes<unsigned char>(p, out_h, out_w, split) : spp::stream_workspace_bytes<float>(p, out_h, out_w, split);
+}
+
+extern "C" int spp_crop_affine_ws(const float *frames, int num_frames, int frame_h, int frame_w, const float *boxes,
+                                  const int *frame_idx, int p, int out_h, int out_w, const float *mean, const float *std,
+                                  int variant, float *out, void *workspace, size_t workspace_bytes, spp_stream_t stream) {
+    return spp::launch_crop<float>(frames, num_frames, frame_h, frame_w, boxes, frame_idx, p, out_h, out_w, mean, std, variant, out, stream,
+                                   workspace, workspace_bytes);
+}
+
+extern "C" int spp_crop_affine_u8_ws(const uint8_t *frames, int num_frames, int frame_h, int frame_w, const float *boxes,
+                                     const int *frame_idx, int p, int out_h, int out_w, const float *mean, const float *std,
+                                     int variant, float *out, void *workspace, size_t workspace_bytes, spp_stream_t stream) {
+    return spp::launch_crop<unsigned char>(frames, num_frames, frame_h, frame_w, boxes, frame_idx, p, out_h, out_w, mean, std, variant, out,
+                                           stream, workspace, workspace_bytes);
 }
 
 extern "C" int spp_crop_affine_u8(const uint8_t *frames, int num_frames, int frame_h, int frame_w, const float *boxes,

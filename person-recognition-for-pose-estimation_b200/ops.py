@@ -340,17 +340,19 @@ def associate(face: "NmsResult", face_ids: torch.Tensor, person: "NmsResult", ca
 
 def crop_affine(frames: torch.Tensor, boxes: torch.Tensor, frame_idx: torch.Tensor, out_hw: Tuple[int, int] = (256, 192),
                 mean: Sequence[float] = (0.485, 0.456, 0.406), std: Sequence[float] = (0.229, 0.224, 0.225),
-                variant: str = "hf", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                variant: str = "hf", out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Bilinear affine crop of every box to ``out_hw`` with ``(x - mean) / std`` fused.
     ``frames [B,3,H,W]`` fp32 or uint8 (mean/std are in the frames' units: multiply ImageNet mean/std by 255 for
-    uint8, as HF does when it folds the 1/255 rescale), ``boxes [P,4]`` COCO (x,y,w,h), ``frame_idx [P]`` int32."""
+    uint8, as HF does when it folds the 1/255 rescale), ``boxes [P,4]`` COCO (x,y,w,h), ``frame_idx [P]`` int32.
+    Runs the persistent plan + stream kernels (``spp_crop_affine*_ws``) on ``workspace`` (caller-owned, from
+    :func:`crop_workspace_bytes` / :func:`alloc_workspace`) or on the per-stream scratch buffer."""
     _need_cuda("crop_affine", frames, boxes, frame_idx)
     if frames.dtype == torch.uint8:      # HF semantics for uint8 images: interpolate, round half-up to uint8, then normalise
         frames = frames if frames.is_contiguous() else frames.contiguous()
-        fn = _lib.lib().spp_crop_affine_u8
+        fn = _lib.lib().spp_crop_affine_u8_ws
     else:
         frames = _f32c("crop_affine frames", frames)
-        fn = _lib.lib().spp_crop_affine
+        fn = _lib.lib().spp_crop_affine_ws
     boxes = _f32c("crop_affine boxes", boxes)
     if frames.dim() != 4 or frames.shape[1] != 3:
         raise ValueError(f"crop_affine: frames must be [B, 3, H, W], got {tuple(frames.shape)}")
@@ -364,9 +366,16 @@ def crop_affine(frames: torch.Tensor, boxes: torch.Tensor, frame_idx: torch.Tens
         out = torch.empty((p, 3, oh, ow), dtype=torch.float32, device=frames.device)
     m3 = (ctypes.c_float * 3)(*[float(v) for v in mean])
     s3 = (ctypes.c_float * 3)(*[float(v) for v in std])
+    nbytes = crop_workspace_bytes(p, oh, ow, frames.dtype == torch.uint8)
+    ws = _workspace(frames.device, max(nbytes, 16), "crop", workspace)
     _lib.check(fn(_ptr(frames), frames.shape[0], frames.shape[2], frames.shape[3], _ptr(boxes), _ptr(frame_idx.contiguous()),
-                  p, oh, ow, m3, s3, CROP_VARIANTS[variant], _ptr(out), _stream(out)), "spp_crop_affine")
+                  p, oh, ow, m3, s3, CROP_VARIANTS[variant], _ptr(out), _ptr(ws), ws.numel(), _stream(out)), "spp_crop_affine")
     return out
+
+
+def crop_workspace_bytes(p: int, out_h: int = 256, out_w: int = 192, frames_u8: bool = False) -> int:
+    """Bytes of scratch the persistent crop kernels need for ``p`` crops (planned tables, item descriptors, ticket counter)."""
+    return int(_lib.lib().spp_crop_workspace_bytes(int(p), int(out_h), int(out_w), 1 if frames_u8 else 0))
 
 
 # ------------------------------------------------------------------------------------------------

@@ -140,6 +140,8 @@ class SelectivePosePipeline:
         with self._limits():
             self._ws_match = (ops.alloc_workspace(device, ops.match_workspace_bytes(self.inp.embeddings.shape[0], self.gallery.shape[0]))
                               if matcher is None else None)
+        self._ws_crop = ops.alloc_workspace(device, ops.crop_workspace_bytes(self.inp.boxes.shape[0], 256, 192,
+                                                                             self.inp.frames.dtype == torch.uint8))
         self._match_stream = torch.cuda.Stream(device, priority=-1) if self._eager_match else None
         self._side = [torch.cuda.Stream(device) for _ in range(3)]
         with torch.cuda.stream(self._stream), self._limits():
@@ -251,9 +253,9 @@ class SelectivePosePipeline:
             n += 2
         if i.frames.dtype == torch.uint8:     # HF default for uint8 images: 1/255 rescale folded into mean / std
             mean, std = [m * 255.0 for m in (0.485, 0.456, 0.406)], [s * 255.0 for s in (0.229, 0.224, 0.225)]
-            pix = ops.crop_affine(i.frames, boxes, frame_idx, mean=mean, std=std, out=self.out.get("pixel_values"))
+            pix = ops.crop_affine(i.frames, boxes, frame_idx, mean=mean, std=std, out=self.out.get("pixel_values"), workspace=self._ws_crop)
         else:
-            pix = ops.crop_affine(i.frames, boxes, frame_idx, out=self.out.get("pixel_values"))
+            pix = ops.crop_affine(i.frames, boxes, frame_idx, out=self.out.get("pixel_values"), workspace=self._ws_crop)
         n += 1
         if kp is None:
             kp = ops.heatmap_decode(i.heatmaps, i.flipped, i.perm, boxes, self.mode, 11, flags,

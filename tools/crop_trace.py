@@ -1,0 +1,23 @@
+"""Debug: event trace of one CTA of the persistent crop kernel (needs the trace build of crop_affine.cu)."""
+import importlib, os, sys, torch, numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+spp = importlib.import_module("person-recognition-for-pose-estimation_b200")
+dev = torch.device("cuda:0")
+cs = spp.synth.make_crop_set(64, 720, 1280, per_frame=10, seed=2, smooth=False)
+frames, boxes, idx = cs.frames.to(dev), cs.boxes.to(dev), cs.frame_idx.to(dev)
+out = spp.crop_affine(frames, boxes, idx)
+tr = torch.zeros(1 + 2 * 4000, dtype=torch.int64, device=dev)
+for _ in range(3):
+    spp.crop_affine(frames, boxes, idx, out=out)
+torch.cuda.synchronize()
+os.environ["SPP_CROP_TRACE_PTR"] = str(tr.data_ptr())
+spp.crop_affine(frames, boxes, idx, out=out)
+torch.cuda.synchronize()
+t = tr.cpu().numpy()
+n = int(t[0]); ev = t[1:1 + 2 * min(n, 4000)].reshape(-1, 2)
+ev = ev[np.argsort(ev[:, 1])]
+t0 = ev[0, 1]
+names = {1: "P issue band", 2: "P bands done", 3: "P next item published", 10: "C item start", 11: "C wait full", 12: "C got band", 13: "C item done"}
+for code, ts in ev[:160]:
+    ty, k, b = code >> 48, (code >> 24) & 0xffffff, code & 0xffffff
+    print(f"{(ts - t0) / 1e3:8.2f} us  {names.get(ty, ty):24s} item {k} band/kind {b}")
