@@ -45,6 +45,11 @@ int spp_device_sm_count(void);
  * spp_match_workspace_bytes depends on the match limit: query it after setting the limit. */
 #define SPP_LIMIT_HEATMAP_CTAS 0
 #define SPP_LIMIT_MATCH_CTAS 1
+/* Third budget, a different kind: the persistent crop kernel (spp_crop_affine*_ws / _run) normally fills every CTA slot of the
+ * machine for its whole run, so a small kernel enqueued beside it (the match re-score, a late detection kernel) would wait for
+ * it to end.  SPP_LIMIT_CROP_FREE_CTAS = n launches it with n CTAs fewer: n slots of 224 threads / 12.5 k registers / 45 KB stay
+ * free across the SMs.  The crop is HBM-bound, a few per cent fewer CTAs do not slow it. */
+#define SPP_LIMIT_CROP_FREE_CTAS 2
 int spp_set_launch_limit(int which, int max_ctas);
 
 /* ------------------------------------------------------------------ detection head + NMS ----- */
@@ -265,6 +270,18 @@ int spp_crop_affine_ws(const float *frames, int num_frames, int frame_h, int fra
 int spp_crop_affine_u8_ws(const uint8_t *frames, int num_frames, int frame_h, int frame_w, const float *boxes,
                           const int *frame_idx, int p, int out_h, int out_w, const float *mean, const float *std,
                           int variant, float *out, void *workspace, size_t workspace_bytes, spp_stream_t stream);
+
+/* The two halves of spp_crop_affine*_ws as separate calls, same arguments and workspace: the plan reads only the boxes, so it
+ * can be enqueued early (SelectivePosePipeline runs it beside the heatmap decode); the run must follow ITS plan on the device
+ * (every run consumes the ticket counter its plan reset).  frames_u8 selects the table format of the uint8 kernels. */
+int spp_crop_plan(int frames_u8, int num_frames, int frame_h, int frame_w, const float *boxes, const int *frame_idx, int p,
+                  int out_h, int out_w, int variant, void *workspace, size_t workspace_bytes, spp_stream_t stream);
+int spp_crop_affine_run(const float *frames, int num_frames, int frame_h, int frame_w, const float *boxes,
+                        const int *frame_idx, int p, int out_h, int out_w, const float *mean, const float *std,
+                        int variant, float *out, void *workspace, size_t workspace_bytes, spp_stream_t stream);
+int spp_crop_affine_u8_run(const uint8_t *frames, int num_frames, int frame_h, int frame_w, const float *boxes,
+                           const int *frame_idx, int p, int out_h, int out_w, const float *mean, const float *std,
+                           int variant, float *out, void *workspace, size_t workspace_bytes, spp_stream_t stream);
 
 /* ------------------------------------------------------------------ heatmap decode ----------- */
 

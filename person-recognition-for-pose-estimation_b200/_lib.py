@@ -65,6 +65,11 @@ SIGNATURES = {
     "spp_crop_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "spp_crop_affine_ws": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float),
                                    c_int, _P, _P, c_size_t, _P]),
+    "spp_crop_plan": (c_int, [c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "spp_crop_affine_run": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float),
+                                    c_int, _P, _P, c_size_t, _P]),
+    "spp_crop_affine_u8_run": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float),
+                                       c_int, _P, _P, c_size_t, _P]),
     "spp_crop_affine_u8_ws": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float),
                                       c_int, _P, _P, c_size_t, _P]),
     "spp_heatmap_decode": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P,

@@ -35,12 +35,12 @@ int sm_count() {
 }  // namespace spp
 
 namespace spp {
-static std::atomic<int> g_limits[2] = {{0}, {0}};
-int launch_limit(int which) { return (which >= 0 && which < 2) ? g_limits[which].load(std::memory_order_relaxed) : 0; }
+static std::atomic<int> g_limits[3] = {{0}, {0}, {0}};
+int launch_limit(int which) { return (which >= 0 && which < 3) ? g_limits[which].load(std::memory_order_relaxed) : 0; }
 }  // namespace spp
 
 extern "C" int spp_set_launch_limit(int which, int max_ctas) {
-    if (which < 0 || which >= 2) return -1;
+    if (which < 0 || which >= 3) return -1;
     if (max_ctas < 0) return spp::g_limits[which].load();
     return spp::g_limits[which].exchange(max_ctas);
 }

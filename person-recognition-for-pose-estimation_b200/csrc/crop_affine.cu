@@ -801,23 +801,30 @@ int launch_staged_full(const CropParams &prm, dim3 grid, size_t smem, cudaStream
     return SPP_OK;
 }
 
+enum { kCropPlanAndRun = 0, kCropPlanOnly = 1, kCropRunOnly = 2 };
 template <typename T, int C, bool FULL>
-int launch_stream_full(const CropParams &prm, int total, size_t smem, cudaStream_t st) {
+int launch_stream_full(const CropParams &prm, int total, size_t smem, cudaStream_t st, int mode) {
     SPP_CHECK_CUDA(cudaFuncSetAttribute(crop_stream_kernel<T, C, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int occ = 0;
     SPP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, crop_stream_kernel<T, C, FULL>, 32 * (kCropWarps + 1), smem));
     if (occ < 1) occ = 1;
     const int sms = sm_count() > 0 ? sm_count() : 148;
-    const int grid = total < occ * sms ? total : occ * sms;
-    crop_plan_kernel<T><<<prm.P, 256, 0, st>>>(prm);
-    SPP_CHECK_LAUNCH();
-    crop_stream_kernel<T, C, FULL><<<grid, 32 * (kCropWarps + 1), smem, st>>>(prm);
-    SPP_CHECK_LAUNCH();
+    int slots = occ * sms - launch_limit(2);               // SPP_LIMIT_CROP_FREE_CTAS: slots left to kernels enqueued beside this one
+    if (slots < sms) slots = sms;
+    const int grid = total < slots ? total : slots;
+    if (mode != kCropRunOnly) {
+        crop_plan_kernel<T><<<prm.P, 256, 0, st>>>(prm);
+        SPP_CHECK_LAUNCH();
+    }
+    if (mode != kCropPlanOnly) {
+        crop_stream_kernel<T, C, FULL><<<grid, 32 * (kCropWarps + 1), smem, st>>>(prm);
+        SPP_CHECK_LAUNCH();
+    }
     return SPP_OK;
 }
 template <typename T, int C>
-int launch_stream(const CropParams &prm, int total, size_t smem, cudaStream_t st) {
-    return prm.ow % (32 * C) == 0 ? launch_stream_full<T, C, true>(prm, total, smem, st) : launch_stream_full<T, C, false>(prm, total, smem, st);
+int launch_stream(const CropParams &prm, int total, size_t smem, cudaStream_t st, int mode) {
+    return prm.ow % (32 * C) == 0 ? launch_stream_full<T, C, true>(prm, total, smem, st, mode) : launch_stream_full<T, C, false>(prm, total, smem, st, mode);
 }
 
 // Row slabs of the persistent kernel (SPP_CROP_SPLIT overrides), at most kPlanMaxSlabs: 32 output rows for fp32 frames
@@ -843,9 +850,9 @@ int launch_staged(const CropParams &prm, dim3 grid, size_t smem, cudaStream_t st
 template <typename T>
 int launch_crop(const void *frames, int num_frames, int frame_h, int frame_w, const float *boxes, const int *frame_idx, int p,
                 int out_h, int out_w, const float *mean, const float *std, int variant, float *out, spp_stream_t stream,
-                void *workspace = nullptr, size_t workspace_bytes = 0) {
+                void *workspace = nullptr, size_t workspace_bytes = 0, int mode = kCropPlanAndRun) {
     if (p == 0) return SPP_OK;
-    SPP_CHECK_ARG(frames && boxes && frame_idx && out && mean && std, "crop_affine: null pointer");
+    SPP_CHECK_ARG(boxes && frame_idx && mean && std && (mode == kCropPlanOnly || (frames && out)), "crop_affine: null pointer");
     SPP_CHECK_ARG(num_frames > 0 && frame_h >= 2 && frame_w >= 2 && p >= 0, "crop_affine: frames must be at least 2x2");
     SPP_CHECK_ARG(out_h > 0 && out_w > 0 && out_w <= 2048 && out_h <= 2048, "crop_affine: output size must be within 2048 x 2048");
     SPP_CHECK_ARG(variant == SPP_CROP_HF_UDP || variant == SPP_CROP_GLUONCV, "crop_affine: unknown variant %d", variant);
@@ -872,6 +879,7 @@ int launch_crop(const void *frames, int num_frames, int frame_h, int frame_w, co
     const bool staged = ((size_t)frame_w * sizeof(T) % 16 == 0) && ((reinterpret_cast<uintptr_t>(frames) & 15) == 0) &&
                         ((size_t)prm.stage_bytes / ((size_t)frame_w * sizeof(T)) >= 2) && prm.ncc <= kCropWarps;
     if (!staged) {
+        if (mode == kCropPlanOnly) return SPP_OK;      // nothing to plan: the run call takes the staging-free kernel
         const size_t smem = (size_t)(out_w + out_h) * sizeof(AxisEntry<T>);
         SPP_CHECK_ARG(smem <= 160 * 1024, "crop_affine: output size too large");
         SPP_CHECK_CUDA(cudaFuncSetAttribute(crop_affine_direct_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -883,8 +891,13 @@ int launch_crop(const void *frames, int num_frames, int frame_h, int frame_w, co
     }
     // Persistent plan + stream kernels when the caller brings a workspace (spp_crop_affine*_ws).  They need exactly
     // kCropWarps consumer warps and table slices that bulk TMA can copy (16-byte multiples: even sizes for 8-byte entries).
-    static const int persist = env_int("SPP_CROP_PERSIST", 1, 0, 1);
-    if (workspace && persist && prm.ncc * prm.rg == kCropWarps) {
+    // Chosen for launches of up to ~8 waves of per-item CTAs, where the set-up bubbles and the drain at the end are 10 % of the
+    // time; beyond that the one-CTA-per-item kernel's steady state is faster (measured: 157 vs 161 us at 640 crops, 320 vs 308 at
+    // 1 280, 671 vs 599 at 2 560; SPP_CROP_PERSIST=0 / 2 = never / always).
+    static const int persist = env_int("SPP_CROP_PERSIST", 1, 0, 2);
+    const int sms_ = sm_count() > 0 ? sm_count() : 148;
+    const bool few = (long long)p * 3 * 2 <= 8LL * 5 * sms_;
+    if (workspace && (persist == 2 || (persist == 1 && few)) && prm.ncc * prm.rg == kCropWarps) {
         const int psplit = stream_split(out_h, split_env, sizeof(T) == 1 ? 64 : 32);
         const int pslab = (out_h + psplit - 1) / psplit, nslabs = (out_h + pslab - 1) / pslab;
         const bool even = sizeof(AxisEntry<T>) % 16 == 0 || (out_w % 2 == 0 && out_h % 2 == 0 && pslab % 2 == 0);
@@ -900,9 +913,10 @@ int launch_crop(const void *frames, int num_frames, int frame_h, int frame_w, co
             SPP_CHECK_ARG(psmem <= 200 * 1024, "crop_affine: output size too large");
             const long long total = (long long)p * 3 * nslabs;
             SPP_CHECK_ARG(total < (1LL << 30), "crop_affine: too many crops");
-            return cols == 3 ? launch_stream<T, 3>(prm, (int)total, psmem, st) : launch_stream<T, 6>(prm, (int)total, psmem, st);
+            return cols == 3 ? launch_stream<T, 3>(prm, (int)total, psmem, st, mode) : launch_stream<T, 6>(prm, (int)total, psmem, st, mode);
         }
     }
+    if (mode == kCropPlanOnly) return SPP_OK;          // shapes the persistent kernels do not take: the run call does all the work
     // Slabs of output rows: enough CTAs that the last wave is a small part of the launch, but never slabs shorter
     // than 64 rows (the tables and the first band are per-CTA overhead).
     int split = split_env;
@@ -939,6 +953,32 @@ extern "C" int spp_crop_affine_ws(const float *frames, int num_frames, int frame
                                   int variant, float *out, void *workspace, size_t workspace_bytes, spp_stream_t stream) {
     return spp::launch_crop<float>(frames, num_frames, frame_h, frame_w, boxes, frame_idx, p, out_h, out_w, mean, std, variant, out, stream,
                                    workspace, workspace_bytes);
+}
+
+// Plan and run as two calls (same arguments, same workspace; the run must follow its plan on the device): the plan only
+// reads the boxes, so a caller can enqueue it early — SelectivePosePipeline runs it beside the heatmap decode.
+extern "C" int spp_crop_plan(int frames_u8, int num_frames, int frame_h, int frame_w, const float *boxes, const int *frame_idx, int p,
+                             int out_h, int out_w, int variant, void *workspace, size_t workspace_bytes, spp_stream_t stream) {
+    const float unit[3] = {0.f, 0.f, 0.f}, one[3] = {1.f, 1.f, 1.f};
+    SPP_CHECK_ARG(workspace, "crop_plan: workspace required");
+    return frames_u8 ? spp::launch_crop<unsigned char>(nullptr, num_frames, frame_h, frame_w, boxes, frame_idx, p, out_h, out_w, unit, one, variant,
+                                                       nullptr, stream, workspace, workspace_bytes, spp::kCropPlanOnly)
+                     : spp::launch_crop<float>(nullptr, num_frames, frame_h, frame_w, boxes, frame_idx, p, out_h, out_w, unit, one, variant, nullptr,
+                                               stream, workspace, workspace_bytes, spp::kCropPlanOnly);
+}
+extern "C" int spp_crop_affine_run(const float *frames, int num_frames, int frame_h, int frame_w, const float *boxes,
+                                   const int *frame_idx, int p, int out_h, int out_w, const float *mean, const float *std,
+                                   int variant, float *out, void *workspace, size_t workspace_bytes, spp_stream_t stream) {
+    SPP_CHECK_ARG(workspace, "crop_affine_run: workspace required");
+    return spp::launch_crop<float>(frames, num_frames, frame_h, frame_w, boxes, frame_idx, p, out_h, out_w, mean, std, variant, out, stream,
+                                   workspace, workspace_bytes, spp::kCropRunOnly);
+}
+extern "C" int spp_crop_affine_u8_run(const uint8_t *frames, int num_frames, int frame_h, int frame_w, const float *boxes,
+                                      const int *frame_idx, int p, int out_h, int out_w, const float *mean, const float *std,
+                                      int variant, float *out, void *workspace, size_t workspace_bytes, spp_stream_t stream) {
+    SPP_CHECK_ARG(workspace, "crop_affine_run: workspace required");
+    return spp::launch_crop<unsigned char>(frames, num_frames, frame_h, frame_w, boxes, frame_idx, p, out_h, out_w, mean, std, variant, out,
+                                           stream, workspace, workspace_bytes, spp::kCropRunOnly);
 }
 
 extern "C" int spp_crop_affine_u8_ws(const uint8_t *frames, int num_frames, int frame_h, int frame_w, const float *boxes,

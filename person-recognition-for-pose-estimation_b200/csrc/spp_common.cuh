@@ -33,7 +33,7 @@ void set_error(const char *fmt, ...);
 #define SPP_CHECK_LAUNCH() SPP_CHECK_CUDA(cudaGetLastError())
 
 int sm_count();
-int launch_limit(int which);      // spp_set_launch_limit: 0 = heatmap decode CTAs, 1 = match GEMM CTAs; 0 = no limit
+int launch_limit(int which);      // spp_set_launch_limit: 0 = heatmap decode CTAs, 1 = match GEMM CTAs (0 = no limit), 2 = CTA slots the crop leaves free
 
 #ifdef __CUDACC__
 #define SPP_HD __host__ __device__

@@ -338,21 +338,30 @@ def associate(face: "NmsResult", face_ids: torch.Tensor, person: "NmsResult", ca
 # crop
 # ------------------------------------------------------------------------------------------------
 
+# Test hook: False sends crop_affine through the entry points without a workspace (the one-CTA-per-item kernels).
+CROP_USE_WORKSPACE = True
+
+
 def crop_affine(frames: torch.Tensor, boxes: torch.Tensor, frame_idx: torch.Tensor, out_hw: Tuple[int, int] = (256, 192),
                 mean: Sequence[float] = (0.485, 0.456, 0.406), std: Sequence[float] = (0.229, 0.224, 0.225),
-                variant: str = "hf", out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+                variant: str = "hf", out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None,
+                planned: bool = False) -> torch.Tensor:
     """Bilinear affine crop of every box to ``out_hw`` with ``(x - mean) / std`` fused.
     ``frames [B,3,H,W]`` fp32 or uint8 (mean/std are in the frames' units: multiply ImageNet mean/std by 255 for
     uint8, as HF does when it folds the 1/255 rescale), ``boxes [P,4]`` COCO (x,y,w,h), ``frame_idx [P]`` int32.
     Runs the persistent plan + stream kernels (``spp_crop_affine*_ws``) on ``workspace`` (caller-owned, from
-    :func:`crop_workspace_bytes` / :func:`alloc_workspace`) or on the per-stream scratch buffer."""
+    :func:`crop_workspace_bytes` / :func:`alloc_workspace`) or on the per-stream scratch buffer.  ``planned=True``: the
+    caller has already enqueued :func:`crop_plan` for these boxes on ``workspace`` (ordered before this call), only the
+    stream kernel runs."""
     _need_cuda("crop_affine", frames, boxes, frame_idx)
     if frames.dtype == torch.uint8:      # HF semantics for uint8 images: interpolate, round half-up to uint8, then normalise
         frames = frames if frames.is_contiguous() else frames.contiguous()
-        fn = _lib.lib().spp_crop_affine_u8_ws
+        fn = _lib.lib().spp_crop_affine_u8_run if planned else _lib.lib().spp_crop_affine_u8_ws
     else:
         frames = _f32c("crop_affine frames", frames)
-        fn = _lib.lib().spp_crop_affine_ws
+        fn = _lib.lib().spp_crop_affine_run if planned else _lib.lib().spp_crop_affine_ws
+    if planned and workspace is None:
+        raise ValueError("crop_affine(planned=True) needs the workspace crop_plan wrote")
     boxes = _f32c("crop_affine boxes", boxes)
     if frames.dim() != 4 or frames.shape[1] != 3:
         raise ValueError(f"crop_affine: frames must be [B, 3, H, W], got {tuple(frames.shape)}")
@@ -366,11 +375,30 @@ def crop_affine(frames: torch.Tensor, boxes: torch.Tensor, frame_idx: torch.Tens
         out = torch.empty((p, 3, oh, ow), dtype=torch.float32, device=frames.device)
     m3 = (ctypes.c_float * 3)(*[float(v) for v in mean])
     s3 = (ctypes.c_float * 3)(*[float(v) for v in std])
+    if not CROP_USE_WORKSPACE and not planned:
+        fn = _lib.lib().spp_crop_affine_u8 if frames.dtype == torch.uint8 else _lib.lib().spp_crop_affine
+        _lib.check(fn(_ptr(frames), frames.shape[0], frames.shape[2], frames.shape[3], _ptr(boxes), _ptr(frame_idx.contiguous()),
+                      p, oh, ow, m3, s3, CROP_VARIANTS[variant], _ptr(out), _stream(out)), "spp_crop_affine")
+        return out
     nbytes = crop_workspace_bytes(p, oh, ow, frames.dtype == torch.uint8)
     ws = _workspace(frames.device, max(nbytes, 16), "crop", workspace)
     _lib.check(fn(_ptr(frames), frames.shape[0], frames.shape[2], frames.shape[3], _ptr(boxes), _ptr(frame_idx.contiguous()),
                   p, oh, ow, m3, s3, CROP_VARIANTS[variant], _ptr(out), _ptr(ws), ws.numel(), _stream(out)), "spp_crop_affine")
     return out
+
+
+def crop_plan(boxes: torch.Tensor, frame_idx: torch.Tensor, frames_shape: Sequence[int], frames_u8: bool, workspace: torch.Tensor,
+              out_hw: Tuple[int, int] = (256, 192), variant: str = "hf") -> None:
+    """First half of :func:`crop_affine` on its own: source map, coordinate tables and band layout of every box into
+    ``workspace`` (on the current stream).  Follow with ``crop_affine(..., workspace=workspace, planned=True)``."""
+    _need_cuda("crop_plan", boxes, frame_idx)
+    boxes = _f32c("crop_plan boxes", boxes)
+    if frame_idx.dtype != torch.int32:
+        frame_idx = frame_idx.to(torch.int32)
+    b, _, fh, fw = frames_shape
+    _lib.check(_lib.lib().spp_crop_plan(1 if frames_u8 else 0, int(b), int(fh), int(fw), _ptr(boxes), _ptr(frame_idx.contiguous()),
+                                        boxes.shape[0], out_hw[0], out_hw[1], CROP_VARIANTS[variant], _ptr(workspace), workspace.numel(),
+                                        _stream(boxes)), "spp_crop_plan")
 
 
 def crop_workspace_bytes(p: int, out_h: int = 256, out_w: int = 192, frames_u8: bool = False) -> int:

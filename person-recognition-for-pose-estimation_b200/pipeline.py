@@ -80,7 +80,7 @@ class SelectivePosePipeline:
                  id_offset: int = 0, concurrent: bool = True, matcher=None, capture_collectives: bool = False,
                  select_on_device: bool = False, gallery_f32: Optional[torch.Tensor] = None, max_row_norm: float = 1.0,
                  det_max_candidates: int = 0, match_sms: int = 0, heatmap_first: bool = True, det_fused: Optional[bool] = None,
-                 det_after_heatmap: int = 0):
+                 det_after_heatmap: int = 0, crop_free_ctas: int = 48):
         self.device = device
         self.threshold, self.conf, self.iou, self.mode = threshold, conf_thres, iou_thres, decode_mode
         self.id_offset = id_offset
@@ -99,6 +99,9 @@ class SelectivePosePipeline:
         self.heatmap_first = heatmap_first and not select_on_device
         # experiment knob: number of detection chains (0, 1, 2) that wait for the heatmap decode and run under the crop instead
         self.det_after_heatmap = int(det_after_heatmap) if self.heatmap_first else 0
+        # crop_free_ctas: CTA slots the persistent crop kernel leaves free (SPP_LIMIT_CROP_FREE_CTAS) so that the match re-score,
+        # which becomes ready while the crop holds the machine, runs beside it instead of after it.
+        self.crop_free_ctas = int(crop_free_ctas) if concurrent else 0
         self.gallery = gallery_bf16.to(device).contiguous()
         self.gallery_f32 = None if gallery_f32 is None else gallery_f32.to(device).float().contiguous()
         self.max_row_norm = float(max_row_norm)
@@ -144,6 +147,7 @@ class SelectivePosePipeline:
                                                                              self.inp.frames.dtype == torch.uint8))
         self._match_stream = torch.cuda.Stream(device, priority=-1) if self._eager_match else None
         self._side = [torch.cuda.Stream(device) for _ in range(3)]
+        self._plan_stream = torch.cuda.Stream(device)
         with torch.cuda.stream(self._stream), self._limits():
             if self._eager_match:
                 self.out["ids"], self.out["sims"] = matcher.match(self.inp.embeddings)
@@ -164,6 +168,7 @@ class SelectivePosePipeline:
         def ctx():
             L = _lib.lib()
             prev_mode = L.spp_decode_nms_mode(1 if self.det_fused else 0)
+            prev_c = L.spp_set_launch_limit(2, self.crop_free_ctas)
             prev_h = prev_m = None
             if self.match_sms > 0:
                 sms = L.spp_device_sm_count()
@@ -173,6 +178,7 @@ class SelectivePosePipeline:
                 yield
             finally:
                 L.spp_decode_nms_mode(prev_mode)
+                L.spp_set_launch_limit(2, prev_c)
                 if prev_h is not None:
                     L.spp_set_launch_limit(0, prev_h)
                     L.spp_set_launch_limit(1, prev_m)
@@ -202,6 +208,17 @@ class SelectivePosePipeline:
             with torch.cuda.stream(stream):
                 return ops.decode_nms(lv, conf_thres=self.conf, iou_thres=self.iou, out=self.out.get(key), workspace=ws,
                                       max_candidates=self.det_max_candidates)
+        # The crop's plan kernel (source map, coordinate tables, band layout per box) only reads the boxes: when they are inputs
+        # of the step it runs here, on the match chain's stream, beside the heatmap decode, and the crop itself is only the
+        # stream kernel.
+        crop_planned = self.concurrent and not self.select_on_device
+        if crop_planned:
+            self._plan_stream.wait_event(fork)
+            with torch.cuda.stream(self._plan_stream):
+                ops.crop_plan(i.boxes, i.frame_idx, i.frames.shape, i.frames.dtype == torch.uint8, self._ws_crop)
+                plan_done = torch.cuda.Event()
+                plan_done.record(self._plan_stream)
+            n += 1
         late = self.det_after_heatmap if self.concurrent else 0
         face = det(0, sides[0]) if late < 2 else None
         person = det(1, sides[1]) if late < 1 else None
@@ -253,10 +270,15 @@ class SelectivePosePipeline:
             n += 2
         if i.frames.dtype == torch.uint8:     # HF default for uint8 images: 1/255 rescale folded into mean / std
             mean, std = [m * 255.0 for m in (0.485, 0.456, 0.406)], [s * 255.0 for s in (0.229, 0.224, 0.225)]
-            pix = ops.crop_affine(i.frames, boxes, frame_idx, mean=mean, std=std, out=self.out.get("pixel_values"), workspace=self._ws_crop)
+            if crop_planned:
+                main.wait_event(plan_done)
+            pix = ops.crop_affine(i.frames, boxes, frame_idx, mean=mean, std=std, out=self.out.get("pixel_values"), workspace=self._ws_crop,
+                                  planned=crop_planned)
         else:
-            pix = ops.crop_affine(i.frames, boxes, frame_idx, out=self.out.get("pixel_values"), workspace=self._ws_crop)
-        n += 1
+            if crop_planned:
+                main.wait_event(plan_done)
+            pix = ops.crop_affine(i.frames, boxes, frame_idx, out=self.out.get("pixel_values"), workspace=self._ws_crop, planned=crop_planned)
+        n += 1 if crop_planned else 2          # stream kernel (+ plan kernel when it was not run ahead)
         if kp is None:
             kp = ops.heatmap_decode(i.heatmaps, i.flipped, i.perm, boxes, self.mode, 11, flags,
                                     out=(self.out["keypoints"], self.out["scores"], self.out["argmax"]) if "keypoints" in self.out else None)

@@ -25,6 +25,16 @@ def _close(a, b, rtol=RTOL, atol=0.0, what=""):
     assert not bad.any(), f"{what}: {bad.sum()} / {bad.size} beyond tolerance, max err {err.max():.3e} at {np.argmax(err - tol)}"
 
 
+@pytest.fixture(params=["persistent", "per_item"])
+def crop_path(request, spp):
+    """Both crop implementations: the persistent plan + stream kernels (spp_crop_affine*_ws, the default) and the
+    one-CTA-per-item kernels (spp_crop_affine / _u8, no workspace)."""
+    prev = spp.ops.CROP_USE_WORKSPACE
+    spp.ops.CROP_USE_WORKSPACE = request.param == "persistent"
+    yield request.param
+    spp.ops.CROP_USE_WORKSPACE = prev
+
+
 @pytest.fixture(scope="module")
 def dev():
     assert torch.cuda.is_available(), "these tests need a CUDA device"
@@ -185,7 +195,7 @@ def test_det_edge_cases(spp, synth, dev):
 # crop
 # ------------------------------------------------------------------------------------------------
 
-def test_crop_vs_oracle(spp, synth, dev):
+def test_crop_vs_oracle(spp, synth, dev, crop_path):
     cs = synth.make_crop_set(2, 360, 480, per_frame=6, seed=11)
     ref = ocrop.crop_affine_hf(cs.frames.numpy(), cs.boxes.tolist(), cs.frame_idx.tolist())
     out = spp.crop_affine(cs.frames.to(dev), cs.boxes.to(dev), cs.frame_idx.to(dev))
@@ -196,7 +206,7 @@ def test_crop_vs_oracle(spp, synth, dev):
     assert float(np.abs(out.cpu().numpy() - ref).max()) < 2e-5
 
 
-def test_crop_uint8_vs_oracle(spp, synth, dev):
+def test_crop_uint8_vs_oracle(spp, synth, dev, crop_path):
     cs = synth.make_crop_set(2, 360, 480, per_frame=6, seed=12)
     fr8 = (cs.frames * 255.0).round().clamp(0, 255).to(torch.uint8)
     ref = ocrop.crop_affine_hf(fr8.numpy(), cs.boxes.tolist(), cs.frame_idx.tolist(), rescale_factor=1 / 255)
@@ -540,7 +550,7 @@ def test_nms_candidate_overflow_flag(spp, dev):
     assert len(res.to_list()[1]) == 3
 
 
-def test_crop_mirrored_boxes_vs_hf(spp, dev):
+def test_crop_mirrored_boxes_vs_hf(spp, dev, crop_path):
     """Negative width AND height: HF / scipy produce the mirrored crop (the staged kernel assumed a
     non-decreasing source map).  Compared against the real HF preprocess."""
     from transformers import VitPoseImageProcessor
@@ -1150,7 +1160,7 @@ def test_cfg2_full_size_against_cpu_reference_calls(spp, synth, dev):
     _close(qk.cpu().numpy()[~valid], once_kp[~valid], atol=1e-2, what="score <= 0 joints, quirk mode")
 
 
-def test_crop_uint8_720p_against_hf_preprocess(spp, dev):
+def test_crop_uint8_720p_against_hf_preprocess(spp, dev, crop_path):
     """uint8 1280x720 frames (HF's default do_rescale=True input) through the real HF VitPoseImageProcessor.preprocess:
     every pixel of 160 crops, i.e. every uint8 rounding decision of the fast path / fp64 re-computation split."""
     from transformers import VitPoseImageProcessor
@@ -1165,7 +1175,7 @@ def test_crop_uint8_720p_against_hf_preprocess(spp, dev):
     assert float(diff.max()) < 2e-5, f"{int((diff > 2e-5).sum())} of {diff.numel()} pixels differ (one flipped rounding = 0.017)"
 
 
-def test_crop_extreme_boxes_vs_oracle(spp, dev):
+def test_crop_extreme_boxes_vs_oracle(spp, dev, crop_path):
     """Boxes far from the synthetic distribution: down-scales of 3-7x (one source band per output row, source windows as wide
     as the frame), 20x up-scales (many output rows per source row), boxes mostly or entirely outside the frame."""
     g = torch.Generator().manual_seed(21)
@@ -1189,3 +1199,29 @@ def test_crop_extreme_boxes_vs_oracle(spp, dev):
     refb = ocrop.crop_affine_v2(frames.numpy(), boxes, fidx)
     outb = spp.crop_affine(frames.to(dev), torch.tensor(boxes, device=dev), torch.tensor(fidx, dtype=torch.int32, device=dev), variant="gluoncv")
     assert float(np.abs(outb.cpu().numpy() - refb).max()) < 2e-5
+
+
+@pytest.mark.gpu
+def test_crop_persistent_equals_per_item_and_planned(spp, synth, dev):
+    """The persistent plan + stream kernels, the same as two calls (crop_plan, then crop_affine(planned=True)) and the
+    one-CTA-per-item kernels produce the same bits — fp32 and uint8 frames, boxes partly and wholly outside the frame, a
+    mirrored box, more items than resident CTAs (tickets), an odd crop count."""
+    cs = synth.make_crop_set(24, 360, 640, per_frame=11, seed=5)
+    boxes = cs.boxes.clone()
+    boxes[3] = torch.tensor([-500.0, -500.0, 40.0, 60.0])          # wholly outside: constant crop
+    boxes[7] = torch.tensor([600.0, 300.0, 200.0, 150.0])          # hangs over the corner
+    boxes[9] = torch.tensor([300.0, 200.0, -80.0, -120.0])         # mirrored
+    fr, bx, fi = cs.frames.to(dev), boxes.to(dev), cs.frame_idx.to(dev)
+    fr8 = (cs.frames * 255).round().to(torch.uint8).to(dev)
+    for frames, kw in ((fr, {}), (fr8, {"mean": [123.7, 116.3, 103.5], "std": [58.4, 57.1, 57.4]})):
+        spp.ops.CROP_USE_WORKSPACE = False
+        try:
+            ref = spp.crop_affine(frames, bx, fi, **kw)
+        finally:
+            spp.ops.CROP_USE_WORKSPACE = True
+        got = spp.crop_affine(frames, bx, fi, **kw)
+        assert torch.equal(got, ref)
+        ws = spp.ops.alloc_workspace(dev, spp.crop_workspace_bytes(bx.shape[0], 256, 192, frames.dtype == torch.uint8))
+        spp.ops.crop_plan(bx, fi, frames.shape, frames.dtype == torch.uint8, ws)
+        got2 = spp.crop_affine(frames, bx, fi, workspace=ws, planned=True, **kw)
+        assert torch.equal(got2, ref)

@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 spp = importlib.import_module("person-recognition-for-pose-estimation_b200")
 dev = torch.device("cuda:0")
-cs = spp.synth.make_crop_set(64, 720, 1280, per_frame=10, seed=2, smooth=False)
+cs = spp.synth.make_crop_set(64, 720, 1280, per_frame=int(os.environ.get("MICRO_CROP_PER_FRAME", "10")), seed=2, smooth=False)
 frames, boxes, idx = cs.frames.to(dev), cs.boxes.to(dev), cs.frame_idx.to(dev)
 out = spp.crop_affine(frames, boxes, idx)
 for dtype in ("f32", "u8"):
