@@ -35,6 +35,9 @@ struct CropParams {
     int stages_log2;
     int split;                  // persistent kernels: row slabs per (crop, channel)
     unsigned char *ws;          // persistent kernels: workspace (ticket counter, planned tables and item descriptors)
+#ifdef SPP_CROP_TRACE
+    unsigned long long *trace;  // debug build (make EXTRA=-DSPP_CROP_TRACE): event log of one CTA, see tools/crop_trace.py
+#endif
     int ncc, rg;                // staged kernel: column chunks (of 32 C columns) x row groups = warps per CTA
     float mean[3], stdv[3];
 };
@@ -546,6 +549,24 @@ __global__ void __launch_bounds__(256) crop_plan_kernel(const CropParams prm) {
     }
 }
 
+// Event log of one CTA of the stream kernel (trace builds only): (type, item, band) + %globaltimer per event.
+#ifdef SPP_CROP_TRACE
+__device__ __forceinline__ void crop_trace(const CropParams &prm, int type, int k, int b) {
+    if (prm.trace && blockIdx.x == 7 && (threadIdx.x & 31) == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        const unsigned long long i = atomicAdd(prm.trace, 1ull);
+        if (i < 4000) {
+            prm.trace[1 + 2 * i] = ((unsigned long long)type << 48) | ((unsigned long long)k << 24) | (unsigned)b;
+            prm.trace[2 + 2 * i] = t;
+        }
+    }
+}
+#define SPP_CROP_EVENT(type, k, b) crop_trace(prm, type, k, b)
+#else
+#define SPP_CROP_EVENT(type, k, b) do { } while (0)
+#endif
+
 template <typename T, int C, bool FULL>
 __global__ void __launch_bounds__(32 * (kCropWarps + 1), 5) crop_stream_kernel(const CropParams prm) {
     using Entry = AxisEntry<T>;
@@ -633,6 +654,7 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1), 5) crop_stream_kernel(c
                     const int sy_lo = yt[r0].i0;
                     const int nrows = yt[r1].i0 + 1 - sy_lo + 1;
                     unsigned char *buf = crop_smem + (size_t)s * kStageBytes;
+                    SPP_CROP_EVENT(1, k, b);
                     if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(nrows * it.pitch));
                     __syncwarp();
                     for (int r = lane; r < nrows; r += 32)
@@ -640,6 +662,7 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1), 5) crop_stream_kernel(c
                     if (pending) next_item();
                 }
             }
+            SPP_CROP_EVENT(2, k, 0);
             if (pending) next_item();
         }
         return;
@@ -653,6 +676,7 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1), 5) crop_stream_kernel(c
     for (int k = 0;; ++k) {
         mbar_wait(&ready[k & 1], (uint32_t)((k >> 1) & 1));
         const CropItem it = items[k & 1];
+        if (warp == 0) SPP_CROP_EVENT(10, k, it.kind);
         if (it.kind == kItemStop) break;
         const Entry *xt = tab + (size_t)(k & 1) * tab_n;
         const Entry *yt = xt + ow - it.ry0;
@@ -687,7 +711,9 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1), 5) crop_stream_kernel(c
                     const int s = (int)(gb & 1u);
                     const int r0 = it.vy0 + b * it.band;
                     const int r1 = (r0 + it.band - 1) < it.vy1 ? (r0 + it.band - 1) : it.vy1;
+                    if (warp == 0) SPP_CROP_EVENT(11, k, b);
                     mbar_wait(&full[s], (gb >> 1) & 1u);
+                    if (warp == 0) SPP_CROP_EVENT(12, k, b);
                     const int ya = r0 + grp * it.rpg;
                     const int yb = (ya + it.rpg - 1) < r1 ? (ya + it.rpg - 1) : r1;
                     const uint32_t tile = smem_base + (uint32_t)(s * kStageBytes) - (uint32_t)(yt[r0].i0 * pitch);
@@ -749,6 +775,7 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1), 5) crop_stream_kernel(c
             }
         }
         __syncwarp();
+        if (warp == 0) SPP_CROP_EVENT(13, k, 0);
         if (lane == 0) mbar_arrive(&done[k & 1]);            // this warp no longer reads half k & 1
     }
 }
@@ -907,6 +934,9 @@ int launch_crop(const void *frames, int num_frames, int frame_h, int frame_w, co
                           workspace_bytes);
             prm.split = psplit;
             prm.ws = static_cast<unsigned char *>(workspace);
+#ifdef SPP_CROP_TRACE
+            { const char *e = getenv("SPP_CROP_TRACE_PTR"); prm.trace = e ? reinterpret_cast<unsigned long long *>(strtoull(e, nullptr, 10)) : nullptr; }
+#endif
             prm.stages = 2; prm.stages_log2 = 1;
             const size_t psmem = 2 * (size_t)prm.stage_bytes + 2 * (size_t)(out_w + pslab) * sizeof(AxisEntry<T>) + 2 * sizeof(CropItem) +
                                  8 * sizeof(uint64_t) + 16;
