@@ -271,6 +271,14 @@ int spp_crop_affine_u8_ws(const uint8_t *frames, int num_frames, int frame_h, in
                           const int *frame_idx, int p, int out_h, int out_w, const float *mean, const float *std,
                           int variant, float *out, void *workspace, size_t workspace_bytes, spp_stream_t stream);
 
+/* Every combination in one call: frames fp32 (frames_u8 = 0) or uint8, output fp32 or bf16 (out_bf16 = 1: the fp32 result rounded
+ * to nearest even, `[p, 3, out_h, out_w]` of 2-byte elements — for a pose backbone under bf16 autocast it halves the bytes this
+ * HBM-bound op writes), workspace NULL (one CTA per work item) or from spp_crop_workspace_bytes (persistent kernels), planned = 1
+ * when spp_crop_plan has already run on that workspace for these boxes. */
+int spp_crop_affine_ex(const void *frames, int frames_u8, int num_frames, int frame_h, int frame_w, const float *boxes,
+                       const int *frame_idx, int p, int out_h, int out_w, const float *mean, const float *std, int variant,
+                       void *out, int out_bf16, void *workspace, size_t workspace_bytes, int planned, spp_stream_t stream);
+
 /* The two halves of spp_crop_affine*_ws as separate calls, same arguments and workspace: the plan reads only the boxes, so it
  * can be enqueued early (SelectivePosePipeline runs it beside the heatmap decode); the run must follow ITS plan on the device
  * (every run consumes the ticket counter its plan reset).  frames_u8 selects the table format of the uint8 kernels. */

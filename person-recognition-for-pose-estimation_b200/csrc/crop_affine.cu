@@ -17,6 +17,8 @@
 // HBM-bound: 4 B written per output element + the source ROI read once.
 #include "spp_common.cuh"
 
+#include <cuda_bf16.h>
+
 #include <climits>
 #include <cstdlib>
 #include <type_traits>
@@ -28,7 +30,7 @@ struct CropParams {
     const void *frames;         // [num_frames, 3, fh, fw] fp32 or uint8
     const float *boxes;
     const int *frame_idx;
-    float *out;
+    void *out;                  // [P, 3, oh, ow] fp32 or bf16 (template parameter O of the kernels)
     int num_frames, fh, fw, P, oh, ow, variant;
     int stage_bytes;            // size of one shared-memory band buffer
     int stages;                 // band buffers per CTA (a power of two)
@@ -212,18 +214,25 @@ __device__ __forceinline__ void build_tables(const AxisMap &m, const CropParams 
     __syncthreads();
 }
 
+// Streaming store of one output element: fp32, or rounded to bf16 (round to nearest even — what `.to(torch.bfloat16)` does to
+// the fp32 result; for a backbone that runs under bf16 autocast it halves the bytes this HBM-bound op writes).
+__device__ __forceinline__ void store_px(float *p, float v) { __stcs(p, v); }
+__device__ __forceinline__ void store_px(__nv_bfloat16 *p, float v) {
+    __stcs(reinterpret_cast<unsigned short *>(p), __bfloat16_as_ushort(__float2bfloat16_rn(v)));
+}
+
 // Direct global gathers for output rows [ry0, ry1] of one (crop, channel): no monotonicity assumption on the source
 // map.  Used by the staging-free fallback kernel and, inside the staged kernel, for mirrored crops (a box with negative
 // width AND height gives a negative scale on both axes; HF / scipy then produce the mirrored crop).
-template <typename T>
-__device__ __forceinline__ void direct_gather_rows(const CropParams &prm, const T *src, float *dst, const AxisEntry<T> *xt,
+template <typename T, typename O>
+__device__ __forceinline__ void direct_gather_rows(const CropParams &prm, const T *src, O *dst, const AxisEntry<T> *xt,
                                                    const AxisEntry<T> *yt, int ry0, int ry1, float inv_sd, float nmean, int tid,
                                                    int nthreads) {
     constexpr bool kU8 = std::is_same<T, unsigned char>::value;
     const int ow = prm.ow;
     for (int x = tid; x < ow; x += nthreads) {
         const AxisEntry<T> ex = xt[x];
-        float *o = dst + (size_t)ry0 * ow + x;
+        O *o = dst + (size_t)ry0 * ow + x;
         for (int y = ry0; y <= ry1; ++y, o += ow) {
             const AxisEntry<T> ey = yt[y];
             float v = nmean;
@@ -238,7 +247,7 @@ __device__ __forceinline__ void direct_gather_rows(const CropParams &prm, const 
                     v = finish_px(top, bot, ey.t, inv_sd, nmean);
                 }
             }
-            __stcs(o, v);
+            store_px(o, v);
         }
     }
 }
@@ -261,7 +270,7 @@ __device__ __forceinline__ void direct_gather_rows(const CropParams &prm, const 
 // Needs 16-byte aligned source rows (bulk TMA) and room for 2 source rows of the widest window in a band
 // buffer; anything else goes to crop_affine_direct_kernel.
 // FULL: out_w is a multiple of the 32*C columns a warp covers, so no per-pixel column bound is needed.
-template <typename T, int C, bool FULL>
+template <typename T, typename O, int C, bool FULL>
 __global__ void __launch_bounds__(32 * (kCropWarps + 1)) crop_affine_kernel(const CropParams prm) {
     using Entry = AxisEntry<T>;
     constexpr bool kU8 = std::is_same<T, unsigned char>::value;
@@ -304,7 +313,7 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1)) crop_affine_kernel(cons
 
     f = f < 0 ? 0 : (f >= prm.num_frames ? prm.num_frames - 1 : f);
     const T *src = static_cast<const T *>(prm.frames) + ((size_t)f * 3 + c) * prm.fh * prm.fw;
-    float *dst = prm.out + ((size_t)p * 3 + c) * oh * ow;
+    O *dst = static_cast<O *>(prm.out) + ((size_t)p * 3 + c) * oh * ow;
     const float mean = c == 0 ? prm.mean[0] : (c == 1 ? prm.mean[1] : prm.mean[2]);     // constant-bank selects
     const float inv_sd = 1.0f / (c == 0 ? prm.stdv[0] : (c == 1 ? prm.stdv[1] : prm.stdv[2]));
     const float nmean = -mean * inv_sd;              // out = v * inv_sd + nmean
@@ -312,13 +321,13 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1)) crop_affine_kernel(cons
 
     const bool any = vx1 >= vx0 && vy1 >= vy0;
     if (any && (m.ax < 0.0 || m.ay < 0.0)) {         // mirrored crop: the band staging below assumes a non-decreasing map
-        direct_gather_rows<T>(prm, src, dst, xt, yt, ry0, ry1, inv_sd, nmean, threadIdx.x, blockDim.x);
+        direct_gather_rows<T, O>(prm, src, dst, xt, yt, ry0, ry1, inv_sd, nmean, threadIdx.x, blockDim.x);
         return;
     }
     // rows with no valid source: constant
     for (int y = ry0 + warp; y <= ry1; y += nthreads / 32) {
         if (any && y >= vy0 && y <= vy1) continue;
-        for (int x = lane; x < ow; x += 32) __stcs(dst + (size_t)y * ow + x, zero_out);
+        for (int x = lane; x < ow; x += 32) store_px(dst + (size_t)y * ow + x, zero_out);
     }
     if (!any) return;
 
@@ -392,7 +401,7 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1)) crop_affine_kernel(cons
         const uint32_t tile = smem_base + (uint32_t)(s * kStageBytes) - (uint32_t)(yt[r0].i0 * pitch);
         float top[C], bot[C];
         int prev = INT_MIN;
-        float *o = dst + (size_t)ya * ow + xbase;
+        O *o = dst + (size_t)ya * ow + xbase;
         for (int y = ya; y <= yb; ++y, o += ow) {
             // (index, fp32 weight) only: the fp64 weight of a uint8 entry is read on the rare exact path
             const int2 ey2 = *reinterpret_cast<const int2 *>(&yt[y]);
@@ -434,12 +443,12 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1)) crop_affine_kernel(cons
                 }
 #pragma unroll
                 for (int j = 0; j < C; ++j)
-                    if (FULL || xbase + 32 * j < ow) __stcs(o + 32 * j, v[j]);
+                    if (FULL || xbase + 32 * j < ow) store_px(o + 32 * j, v[j]);
             } else {
 #pragma unroll
                 for (int j = 0; j < C; ++j) {
                     const float v = finish_px(top[j], bot[j], ey_t, isd[j], nmean);
-                    if (FULL || xbase + 32 * j < ow) __stcs(o + 32 * j, v);
+                    if (FULL || xbase + 32 * j < ow) store_px(o + 32 * j, v);
                 }
             }
         }
@@ -567,7 +576,7 @@ __device__ __forceinline__ void crop_trace(const CropParams &prm, int type, int 
 #define SPP_CROP_EVENT(type, k, b) do { } while (0)
 #endif
 
-template <typename T, int C, bool FULL>
+template <typename T, typename O, int C, bool FULL>
 __global__ void __launch_bounds__(32 * (kCropWarps + 1), 5) crop_stream_kernel(const CropParams prm) {
     using Entry = AxisEntry<T>;
     constexpr bool kU8 = std::is_same<T, unsigned char>::value;
@@ -681,18 +690,18 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1), 5) crop_stream_kernel(c
         const Entry *xt = tab + (size_t)(k & 1) * tab_n;
         const Entry *yt = xt + ow - it.ry0;
         const int c = s_chan[k & 1];
-        float *dst = prm.out + ((size_t)it.p * 3 + c) * oh * ow;
+        O *dst = static_cast<O *>(prm.out) + ((size_t)it.p * 3 + c) * oh * ow;
         const float mean = c == 0 ? prm.mean[0] : (c == 1 ? prm.mean[1] : prm.mean[2]);
         const float inv_sd = 1.0f / (c == 0 ? prm.stdv[0] : (c == 1 ? prm.stdv[1] : prm.stdv[2]));
         const float nmean = -mean * inv_sd;
         if (it.kind == kItemMirrored) {
             const T *src = static_cast<const T *>(prm.frames) + ((size_t)it.f * 3 + c) * prm.fh * prm.fw;
-            direct_gather_rows<T>(prm, src, dst, xt, yt, it.ry0, it.ry1, inv_sd, nmean, tid, 32 * nwarps);
+            direct_gather_rows<T, O>(prm, src, dst, xt, yt, it.ry0, it.ry1, inv_sd, nmean, tid, 32 * nwarps);
         } else {
             const bool staged = it.kind == kItemStaged;
             for (int y = it.ry0 + warp; y <= it.ry1; y += nwarps) {          // rows with no valid source: constant
                 if (staged && y >= it.vy0 && y <= it.vy1) continue;
-                for (int x = lane; x < ow; x += 32) __stcs(dst + (size_t)y * ow + x, nmean);
+                for (int x = lane; x < ow; x += 32) store_px(dst + (size_t)y * ow + x, nmean);
             }
             if (staged) {
                 const int pitch = it.pitch;
@@ -719,7 +728,7 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1), 5) crop_stream_kernel(c
                     const uint32_t tile = smem_base + (uint32_t)(s * kStageBytes) - (uint32_t)(yt[r0].i0 * pitch);
                     float top[C], bot[C];
                     int prev = INT_MIN;
-                    float *o = dst + (size_t)ya * ow + xbase;
+                    O *o = dst + (size_t)ya * ow + xbase;
                     for (int y = ya; y <= yb; ++y, o += ow) {
                         const int2 ey2 = *reinterpret_cast<const int2 *>(&yt[y]);
                         const int ey_i0 = ey2.x;
@@ -760,12 +769,12 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1), 5) crop_stream_kernel(c
                             }
 #pragma unroll
                             for (int j = 0; j < C; ++j)
-                                if (FULL || xbase + 32 * j < ow) __stcs(o + 32 * j, v[j]);
+                                if (FULL || xbase + 32 * j < ow) store_px(o + 32 * j, v[j]);
                         } else {
 #pragma unroll
                             for (int j = 0; j < C; ++j) {
                                 const float v = finish_px(top[j], bot[j], ey_t, isd[j], nmean);
-                                if (FULL || xbase + 32 * j < ow) __stcs(o + 32 * j, v);
+                                if (FULL || xbase + 32 * j < ow) store_px(o + 32 * j, v);
                             }
                         }
                     }
@@ -782,7 +791,7 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1), 5) crop_stream_kernel(c
 
 // Fallback without staging (frame rows not 16-byte aligned, or a source window too wide for a band buffer):
 // the same tables, direct global gathers, one thread per output column.
-template <typename T>
+template <typename T, typename O>
 __global__ void __launch_bounds__(256) crop_affine_direct_kernel(const CropParams prm) {
     using Entry = AxisEntry<T>;
     extern __shared__ __align__(128) unsigned char crop_smem[];
@@ -800,11 +809,11 @@ __global__ void __launch_bounds__(256) crop_affine_direct_kernel(const CropParam
     int f = __ldg(prm.frame_idx + p);
     f = f < 0 ? 0 : (f >= prm.num_frames ? prm.num_frames - 1 : f);
     const T *src = static_cast<const T *>(prm.frames) + ((size_t)f * 3 + c) * prm.fh * prm.fw;
-    float *dst = prm.out + ((size_t)p * 3 + c) * oh * ow;
+    O *dst = static_cast<O *>(prm.out) + ((size_t)p * 3 + c) * oh * ow;
     const float mean = c == 0 ? prm.mean[0] : (c == 1 ? prm.mean[1] : prm.mean[2]);
     const float inv_sd = 1.0f / (c == 0 ? prm.stdv[0] : (c == 1 ? prm.stdv[1] : prm.stdv[2]));
     const float nmean = -mean * inv_sd;
-    direct_gather_rows<T>(prm, src, dst, xt, yt, 0, oh - 1, inv_sd, nmean, threadIdx.x, blockDim.x);
+    direct_gather_rows<T, O>(prm, src, dst, xt, yt, 0, oh - 1, inv_sd, nmean, threadIdx.x, blockDim.x);
 }
 
 }  // namespace
@@ -819,21 +828,21 @@ int env_int(const char *name, int dflt, int lo, int hi) {
     return (v < lo || v > hi) ? dflt : v;
 }
 
-template <typename T, int C, bool FULL>
+template <typename T, typename O, int C, bool FULL>
 int launch_staged_full(const CropParams &prm, dim3 grid, size_t smem, cudaStream_t st) {
     // per device and per context: set on every launch (about a microsecond; legal during stream capture)
-    SPP_CHECK_CUDA(cudaFuncSetAttribute(crop_affine_kernel<T, C, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    crop_affine_kernel<T, C, FULL><<<grid, 32 * (prm.ncc * prm.rg + 1), smem, st>>>(prm);
+    SPP_CHECK_CUDA(cudaFuncSetAttribute(crop_affine_kernel<T, O, C, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    crop_affine_kernel<T, O, C, FULL><<<grid, 32 * (prm.ncc * prm.rg + 1), smem, st>>>(prm);
     SPP_CHECK_LAUNCH();
     return SPP_OK;
 }
 
 enum { kCropPlanAndRun = 0, kCropPlanOnly = 1, kCropRunOnly = 2 };
-template <typename T, int C, bool FULL>
+template <typename T, typename O, int C, bool FULL>
 int launch_stream_full(const CropParams &prm, int total, size_t smem, cudaStream_t st, int mode) {
-    SPP_CHECK_CUDA(cudaFuncSetAttribute(crop_stream_kernel<T, C, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SPP_CHECK_CUDA(cudaFuncSetAttribute(crop_stream_kernel<T, O, C, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int occ = 0;
-    SPP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, crop_stream_kernel<T, C, FULL>, 32 * (kCropWarps + 1), smem));
+    SPP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, crop_stream_kernel<T, O, C, FULL>, 32 * (kCropWarps + 1), smem));
     if (occ < 1) occ = 1;
     const int sms = sm_count() > 0 ? sm_count() : 148;
     int slots = occ * sms - launch_limit(2);               // SPP_LIMIT_CROP_FREE_CTAS: slots left to kernels enqueued beside this one
@@ -844,14 +853,14 @@ int launch_stream_full(const CropParams &prm, int total, size_t smem, cudaStream
         SPP_CHECK_LAUNCH();
     }
     if (mode != kCropPlanOnly) {
-        crop_stream_kernel<T, C, FULL><<<grid, 32 * (kCropWarps + 1), smem, st>>>(prm);
+        crop_stream_kernel<T, O, C, FULL><<<grid, 32 * (kCropWarps + 1), smem, st>>>(prm);
         SPP_CHECK_LAUNCH();
     }
     return SPP_OK;
 }
-template <typename T, int C>
+template <typename T, typename O, int C>
 int launch_stream(const CropParams &prm, int total, size_t smem, cudaStream_t st, int mode) {
-    return prm.ow % (32 * C) == 0 ? launch_stream_full<T, C, true>(prm, total, smem, st, mode) : launch_stream_full<T, C, false>(prm, total, smem, st, mode);
+    return prm.ow % (32 * C) == 0 ? launch_stream_full<T, O, C, true>(prm, total, smem, st, mode) : launch_stream_full<T, O, C, false>(prm, total, smem, st, mode);
 }
 
 // Row slabs of the persistent kernel (SPP_CROP_SPLIT overrides), at most kPlanMaxSlabs: 32 output rows for fp32 frames
@@ -869,14 +878,14 @@ size_t stream_workspace_bytes(int p, int out_h, int out_w, int split) {
     return (size_t)kPlanHeader + (size_t)p * (out_w + out_h) * sizeof(AxisEntry<T>) + (size_t)p * nslabs * sizeof(CropItem);
 }
 
-template <typename T, int C>
+template <typename T, typename O, int C>
 int launch_staged(const CropParams &prm, dim3 grid, size_t smem, cudaStream_t st) {
-    return prm.ow % (32 * C) == 0 ? launch_staged_full<T, C, true>(prm, grid, smem, st) : launch_staged_full<T, C, false>(prm, grid, smem, st);
+    return prm.ow % (32 * C) == 0 ? launch_staged_full<T, O, C, true>(prm, grid, smem, st) : launch_staged_full<T, O, C, false>(prm, grid, smem, st);
 }
 
-template <typename T>
+template <typename T, typename O = float>
 int launch_crop(const void *frames, int num_frames, int frame_h, int frame_w, const float *boxes, const int *frame_idx, int p,
-                int out_h, int out_w, const float *mean, const float *std, int variant, float *out, spp_stream_t stream,
+                int out_h, int out_w, const float *mean, const float *std, int variant, void *out, spp_stream_t stream,
                 void *workspace = nullptr, size_t workspace_bytes = 0, int mode = kCropPlanAndRun) {
     if (p == 0) return SPP_OK;
     SPP_CHECK_ARG(boxes && frame_idx && mean && std && (mode == kCropPlanOnly || (frames && out)), "crop_affine: null pointer");
@@ -909,10 +918,10 @@ int launch_crop(const void *frames, int num_frames, int frame_h, int frame_w, co
         if (mode == kCropPlanOnly) return SPP_OK;      // nothing to plan: the run call takes the staging-free kernel
         const size_t smem = (size_t)(out_w + out_h) * sizeof(AxisEntry<T>);
         SPP_CHECK_ARG(smem <= 160 * 1024, "crop_affine: output size too large");
-        SPP_CHECK_CUDA(cudaFuncSetAttribute(crop_affine_direct_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        SPP_CHECK_CUDA(cudaFuncSetAttribute(crop_affine_direct_kernel<T, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         int threads = (out_w + 31) / 32 * 32;
         if (threads > 256) threads = 256;
-        crop_affine_direct_kernel<T><<<dim3(p, 3), threads, smem, st>>>(prm);
+        crop_affine_direct_kernel<T, O><<<dim3(p, 3), threads, smem, st>>>(prm);
         SPP_CHECK_LAUNCH();
         return SPP_OK;
     }
@@ -943,7 +952,7 @@ int launch_crop(const void *frames, int num_frames, int frame_h, int frame_w, co
             SPP_CHECK_ARG(psmem <= 200 * 1024, "crop_affine: output size too large");
             const long long total = (long long)p * 3 * nslabs;
             SPP_CHECK_ARG(total < (1LL << 30), "crop_affine: too many crops");
-            return cols == 3 ? launch_stream<T, 3>(prm, (int)total, psmem, st, mode) : launch_stream<T, 6>(prm, (int)total, psmem, st, mode);
+            return cols == 3 ? launch_stream<T, O, 3>(prm, (int)total, psmem, st, mode) : launch_stream<T, O, 6>(prm, (int)total, psmem, st, mode);
         }
     }
     if (mode == kCropPlanOnly) return SPP_OK;          // shapes the persistent kernels do not take: the run call does all the work
@@ -960,7 +969,7 @@ int launch_crop(const void *frames, int num_frames, int frame_h, int frame_w, co
     const size_t smem = (size_t)prm.stages * prm.stage_bytes + (size_t)(out_w + slab) * sizeof(AxisEntry<T>) + 16 * (size_t)prm.stages;
     SPP_CHECK_ARG(smem <= 200 * 1024, "crop_affine: output size too large");
     dim3 grid(p, 3, split);
-    return cols == 3 ? launch_staged<T, 3>(prm, grid, smem, st) : launch_staged<T, 6>(prm, grid, smem, st);
+    return cols == 3 ? launch_staged<T, O, 3>(prm, grid, smem, st) : launch_staged<T, O, 6>(prm, grid, smem, st);
 }
 }  // namespace
 }  // namespace spp
@@ -969,6 +978,23 @@ extern "C" int spp_crop_affine(const float *frames, int num_frames, int frame_h,
                                const int *frame_idx, int p, int out_h, int out_w, const float *mean, const float *std,
                                int variant, float *out, spp_stream_t stream) {
     return spp::launch_crop<float>(frames, num_frames, frame_h, frame_w, boxes, frame_idx, p, out_h, out_w, mean, std, variant, out, stream);
+}
+
+// Everything in one call: frames fp32 or uint8, output fp32 or bf16, with or without a workspace, planned ahead or not.
+extern "C" int spp_crop_affine_ex(const void *frames, int frames_u8, int num_frames, int frame_h, int frame_w, const float *boxes,
+                                  const int *frame_idx, int p, int out_h, int out_w, const float *mean, const float *std, int variant,
+                                  void *out, int out_bf16, void *workspace, size_t workspace_bytes, int planned, spp_stream_t stream) {
+    SPP_CHECK_ARG(!planned || workspace, "crop_affine_ex: planned = 1 needs the workspace spp_crop_plan wrote");
+    const int mode = planned ? spp::kCropRunOnly : spp::kCropPlanAndRun;
+    if (frames_u8)
+        return out_bf16 ? spp::launch_crop<unsigned char, __nv_bfloat16>(frames, num_frames, frame_h, frame_w, boxes, frame_idx, p, out_h, out_w, mean,
+                                                                        std, variant, out, stream, workspace, workspace_bytes, mode)
+                        : spp::launch_crop<unsigned char, float>(frames, num_frames, frame_h, frame_w, boxes, frame_idx, p, out_h, out_w, mean, std,
+                                                                 variant, out, stream, workspace, workspace_bytes, mode);
+    return out_bf16 ? spp::launch_crop<float, __nv_bfloat16>(frames, num_frames, frame_h, frame_w, boxes, frame_idx, p, out_h, out_w, mean, std, variant,
+                                                            out, stream, workspace, workspace_bytes, mode)
+                    : spp::launch_crop<float, float>(frames, num_frames, frame_h, frame_w, boxes, frame_idx, p, out_h, out_w, mean, std, variant, out,
+                                                     stream, workspace, workspace_bytes, mode);
 }
 
 extern "C" size_t spp_crop_workspace_bytes(int p, int out_h, int out_w, int frames_u8) {

@@ -338,28 +338,27 @@ def associate(face: "NmsResult", face_ids: torch.Tensor, person: "NmsResult", ca
 # crop
 # ------------------------------------------------------------------------------------------------
 
-# Test hook: False sends crop_affine through the entry points without a workspace (the one-CTA-per-item kernels).
+# Test hook: False sends crop_affine through the one-CTA-per-item kernels (no workspace).
 CROP_USE_WORKSPACE = True
 
 
 def crop_affine(frames: torch.Tensor, boxes: torch.Tensor, frame_idx: torch.Tensor, out_hw: Tuple[int, int] = (256, 192),
                 mean: Sequence[float] = (0.485, 0.456, 0.406), std: Sequence[float] = (0.229, 0.224, 0.225),
                 variant: str = "hf", out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None,
-                planned: bool = False) -> torch.Tensor:
+                planned: bool = False, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """Bilinear affine crop of every box to ``out_hw`` with ``(x - mean) / std`` fused.
     ``frames [B,3,H,W]`` fp32 or uint8 (mean/std are in the frames' units: multiply ImageNet mean/std by 255 for
     uint8, as HF does when it folds the 1/255 rescale), ``boxes [P,4]`` COCO (x,y,w,h), ``frame_idx [P]`` int32.
-    Runs the persistent plan + stream kernels (``spp_crop_affine*_ws``) on ``workspace`` (caller-owned, from
-    :func:`crop_workspace_bytes` / :func:`alloc_workspace`) or on the per-stream scratch buffer.  ``planned=True``: the
-    caller has already enqueued :func:`crop_plan` for these boxes on ``workspace`` (ordered before this call), only the
-    stream kernel runs."""
+    Runs the persistent plan + stream kernels on ``workspace`` (caller-owned, from :func:`crop_workspace_bytes` /
+    :func:`alloc_workspace`) or on the per-stream scratch buffer.  ``planned=True``: the caller has already enqueued
+    :func:`crop_plan` for these boxes on ``workspace`` (ordered before this call), only the stream kernel runs.
+    ``out_dtype=torch.bfloat16``: the same fp32 arithmetic, the result rounded to bf16 on the store (an option for a pose
+    backbone under bf16 autocast; the reference's processor returns fp32, which stays the default)."""
     _need_cuda("crop_affine", frames, boxes, frame_idx)
-    if frames.dtype == torch.uint8:      # HF semantics for uint8 images: interpolate, round half-up to uint8, then normalise
-        frames = frames if frames.is_contiguous() else frames.contiguous()
-        fn = _lib.lib().spp_crop_affine_u8_run if planned else _lib.lib().spp_crop_affine_u8_ws
-    else:
-        frames = _f32c("crop_affine frames", frames)
-        fn = _lib.lib().spp_crop_affine_run if planned else _lib.lib().spp_crop_affine_ws
+    u8 = frames.dtype == torch.uint8     # HF semantics for uint8 images: interpolate, round half-up to uint8, then normalise
+    frames = (frames if frames.is_contiguous() else frames.contiguous()) if u8 else _f32c("crop_affine frames", frames)
+    if out_dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("crop_affine: out_dtype must be torch.float32 or torch.bfloat16")
     if planned and workspace is None:
         raise ValueError("crop_affine(planned=True) needs the workspace crop_plan wrote")
     boxes = _f32c("crop_affine boxes", boxes)
@@ -372,18 +371,18 @@ def crop_affine(frames: torch.Tensor, boxes: torch.Tensor, frame_idx: torch.Tens
     p = boxes.shape[0]
     oh, ow = out_hw
     if out is None:
-        out = torch.empty((p, 3, oh, ow), dtype=torch.float32, device=frames.device)
+        out = torch.empty((p, 3, oh, ow), dtype=out_dtype, device=frames.device)
+    elif out.dtype != out_dtype or tuple(out.shape) != (p, 3, oh, ow) or not out.is_contiguous():
+        raise ValueError(f"crop_affine: out must be a contiguous {out_dtype} tensor of shape {(p, 3, oh, ow)}")
     m3 = (ctypes.c_float * 3)(*[float(v) for v in mean])
     s3 = (ctypes.c_float * 3)(*[float(v) for v in std])
-    if not CROP_USE_WORKSPACE and not planned:
-        fn = _lib.lib().spp_crop_affine_u8 if frames.dtype == torch.uint8 else _lib.lib().spp_crop_affine
-        _lib.check(fn(_ptr(frames), frames.shape[0], frames.shape[2], frames.shape[3], _ptr(boxes), _ptr(frame_idx.contiguous()),
-                      p, oh, ow, m3, s3, CROP_VARIANTS[variant], _ptr(out), _stream(out)), "spp_crop_affine")
-        return out
-    nbytes = crop_workspace_bytes(p, oh, ow, frames.dtype == torch.uint8)
-    ws = _workspace(frames.device, max(nbytes, 16), "crop", workspace)
-    _lib.check(fn(_ptr(frames), frames.shape[0], frames.shape[2], frames.shape[3], _ptr(boxes), _ptr(frame_idx.contiguous()),
-                  p, oh, ow, m3, s3, CROP_VARIANTS[variant], _ptr(out), _ptr(ws), ws.numel(), _stream(out)), "spp_crop_affine")
+    ws = None
+    if CROP_USE_WORKSPACE or planned:
+        ws = _workspace(frames.device, max(crop_workspace_bytes(p, oh, ow, u8), 16), "crop", workspace)
+    _lib.check(_lib.lib().spp_crop_affine_ex(_ptr(frames), 1 if u8 else 0, frames.shape[0], frames.shape[2], frames.shape[3], _ptr(boxes),
+                                             _ptr(frame_idx.contiguous()), p, oh, ow, m3, s3, CROP_VARIANTS[variant], _ptr(out),
+                                             1 if out_dtype == torch.bfloat16 else 0, _ptr(ws), 0 if ws is None else ws.numel(),
+                                             1 if planned else 0, _stream(out)), "spp_crop_affine_ex")
     return out
 
 

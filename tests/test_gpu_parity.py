@@ -1225,3 +1225,29 @@ def test_crop_persistent_equals_per_item_and_planned(spp, synth, dev):
         spp.ops.crop_plan(bx, fi, frames.shape, frames.dtype == torch.uint8, ws)
         got2 = spp.crop_affine(frames, bx, fi, workspace=ws, planned=True, **kw)
         assert torch.equal(got2, ref)
+        # bf16 output = the fp32 result rounded to nearest even, on both implementations
+        gotb = spp.crop_affine(frames, bx, fi, out_dtype=torch.bfloat16, **kw)
+        assert gotb.dtype == torch.bfloat16 and torch.equal(gotb, ref.to(torch.bfloat16))
+        spp.ops.CROP_USE_WORKSPACE = False
+        try:
+            gotb2 = spp.crop_affine(frames, bx, fi, out_dtype=torch.bfloat16, **kw)
+        finally:
+            spp.ops.CROP_USE_WORKSPACE = True
+        assert torch.equal(gotb2, gotb)
+        # the fixed-signature entry points of include/spp.h (fp32 output) through ctypes
+        import ctypes
+        L = spp._lib.lib()
+        u8 = frames.dtype == torch.uint8
+        m3 = (ctypes.c_float * 3)(*[float(v) for v in kw.get("mean", (0.485, 0.456, 0.406))])
+        s3 = (ctypes.c_float * 3)(*[float(v) for v in kw.get("std", (0.229, 0.224, 0.225))])
+        st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        vp = lambda t: ctypes.c_void_p(t.data_ptr())
+        head = (vp(frames), frames.shape[0], frames.shape[2], frames.shape[3], vp(bx), vp(fi), bx.shape[0], 256, 192, m3, s3, 0)
+        for name, tail in (("spp_crop_affine", ()), ("spp_crop_affine_ws", (vp(ws), ws.numel())), ("spp_crop_affine_run", (vp(ws), ws.numel()))):
+            fn = getattr(L, name.replace("affine", "affine_u8") if u8 else name)
+            o = torch.full_like(ref, float("nan"))
+            if name.endswith("_run"):
+                assert L.spp_crop_plan(1 if u8 else 0, frames.shape[0], frames.shape[2], frames.shape[3], vp(bx), vp(fi), bx.shape[0], 256, 192, 0,
+                                       vp(ws), ws.numel(), st) == 0
+            assert fn(*head, vp(o), *tail, st) == 0, spp._lib.lib().spp_last_error()
+            assert torch.equal(o, ref), name
