@@ -9,12 +9,19 @@
 //              get_affine_transform + warpAffine; exact bilinear here, no 1/32-px quantisation)
 //
 // The warp has no rotation, so source coordinates are separable: x_s depends only on the output
-// column, y_s only on the output row.  One CTA per (crop, channel, slab of output rows) computes both
-// coordinate tables ONCE in fp64 (the oracle inverts the fp32 matrix in fp64 and samples in fp64; an fp32
-// coordinate at x ~ 1000 px would already be off by 6e-5 px) and keeps (index, weight) pairs in shared
-// memory.  A producer warp streams the needed source rows into shared-memory band buffers with bulk TMA
-// (full / empty mbarriers, no block barrier in the main loop); six consumer warps sample them in fp32.
-// HBM-bound: 4 B written per output element + the source ROI read once.
+// column, y_s only on the output row.  Both coordinate tables are computed in fp64 (the oracle inverts the
+// fp32 matrix in fp64 and samples in fp64; an fp32 coordinate at x ~ 1000 px would already be off by 6e-5 px)
+// and kept as (index, weight) pairs in shared memory.  A producer warp streams the needed source rows into
+// shared-memory band buffers with bulk TMA (full / empty mbarriers, no block barrier in the main loop); six
+// consumer warps sample them in fp32.  HBM-bound: 4 B (2 B with bf16 output) written per output element + the
+// source ROI read once.
+//
+// Two implementations of the same work item (crop, channel, slab of output rows), bit-identical results:
+//   crop_affine_kernel    one CTA per item, tables built by the CTA itself (no workspace; spp_crop_affine[_u8]);
+//   crop_plan_kernel + crop_stream_kernel    tables planned once per crop into a workspace, resident CTAs pulling
+//                         items from a ticket counter and fetching their tables by bulk TMA (spp_crop_affine*_ws /
+//                         _run / _ex with a workspace; chosen up to ~8 waves of items, see launch_crop).
+//   crop_affine_direct_kernel    staging-free fallback (unaligned frame rows, windows too wide for a band buffer).
 #include "spp_common.cuh"
 
 #include <cuda_bf16.h>
