@@ -1251,3 +1251,28 @@ def test_crop_persistent_equals_per_item_and_planned(spp, synth, dev):
                                        vp(ws), ws.numel(), st) == 0
             assert fn(*head, vp(o), *tail, st) == 0, spp._lib.lib().spp_last_error()
             assert torch.equal(o, ref), name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("out_hw", [(128, 96), (384, 288), (64, 48), (100, 75), (256, 200), (96, 640), (33, 17)])
+def test_crop_output_sizes_vs_oracle(spp, synth, dev, crop_path, out_hw):
+    """Output sizes other than ViTPose-B's 256x192 (the HF processor's `size` is configurable): one / three column chunks per
+    warp row, widths that are not a multiple of the 96 columns a warp covers, odd sizes (8-byte table entries cannot be copied
+    by bulk TMA: the persistent path hands over to the per-item kernel), a width beyond six column chunks (staging-free
+    kernel) — fp32 and uint8 frames, on a frame whose rows are 16-byte aligned and on one whose rows are not."""
+    from oracle import crop as ocrop
+    for fw in (320, 322):
+        cs = synth.make_crop_set(3, 200, fw, per_frame=4, seed=11 + fw)
+        boxes = cs.boxes.clone()
+        boxes[1] = torch.tensor([-30.0, 150.0, 120.0, 90.0])       # hangs over two edges
+        want = ocrop.crop_affine_hf(cs.frames.numpy(), boxes.tolist(), cs.frame_idx.tolist(), out_hw=out_hw)
+        got = spp.crop_affine(cs.frames.to(dev), boxes.to(dev), cs.frame_idx.to(dev), out_hw=out_hw)
+        assert tuple(got.shape) == (boxes.shape[0], 3) + tuple(out_hw)
+        assert float(np.abs(got.cpu().numpy() - want).max()) < 2e-5, (out_hw, fw)
+        fr8 = (cs.frames * 255).round().to(torch.uint8)
+        m = np.array([0.485, 0.456, 0.406], np.float32) * 255
+        sd = np.array([0.229, 0.224, 0.225], np.float32) * 255
+        want8 = ocrop.crop_affine_hf(fr8.numpy(), boxes.tolist(), cs.frame_idx.tolist(), out_hw=out_hw, mean=m, std=sd)
+        got8 = spp.crop_affine(fr8.to(dev), boxes.to(dev), cs.frame_idx.to(dev), out_hw=out_hw, mean=m.tolist(), std=sd.tolist())
+        d8 = np.abs(got8.cpu().numpy() - want8)
+        assert float(d8.max()) < 2e-5, (out_hw, fw, float(d8.max()))      # a flipped uint8 rounding would show up as ~0.017
