@@ -63,6 +63,7 @@ SIGNATURES = {
     "spp_crop_affine_u8": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float),
                                    c_int, _P, _P]),
     "spp_crop_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "spp_crop_policy": (c_int, [c_int]),
     "spp_crop_affine_ws": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float),
                                    c_int, _P, _P, c_size_t, _P]),
     "spp_crop_affine_ex": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float), c_int,

@@ -26,6 +26,7 @@
 
 #include <cuda_bf16.h>
 
+#include <atomic>
 #include <climits>
 #include <cstdlib>
 #include <type_traits>
@@ -473,7 +474,7 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1)) crop_affine_kernel(cons
 // crop count is 18 us + 145 us per 640 crops.  Shorter items would shrink the drain but multiply the set-up.
 //   * crop_plan_kernel, one CTA per crop: the fp64 map and both coordinate tables ONCE per crop (not once per channel and
 //     slab), plus one 64-byte descriptor per row slab (valid ranges, source window, band layout), into the workspace;
-//   * crop_stream_kernel, resident CTAs pulling (crop, slab, channel) tickets from a counter in the workspace: the set-up of
+//   * crop_stream_kernel, resident CTAs pulling (slab, crop, channel) tickets from a counter in the workspace: the set-up of
 //     an item is three bulk-TMA copies (x table, the slab's y entries, descriptor) into the spare half of a double-buffered
 //     table area, issued by the producer warp one item ahead and completing on an mbarrier — no arithmetic, no block
 //     barrier — so the producer goes straight from the last band of item k to the first band of item k + 1 while the
@@ -628,8 +629,11 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1), 5) crop_stream_kernel(c
                 mbar_arrive(&ready[h]);
                 return;
             }
-            const int pz = t % (P * nslabs), c = t / (P * nslabs);     // tickets: crop fastest, then slab, then channel
-            const int p = pz % P, z = pz / P;
+            // Tickets: slab fastest, then crop, then channel — the slabs of a crop and the crops of a frame are in flight at
+            // the same time, so the source rows that overlapping boxes share are read from HBM once and from L2 afterwards
+            // (crop fastest, then slab: 2.72 GB of DRAM reads at 2 560 crops against 2.23 GB for the per-item kernel).
+            const int pz = t % (P * nslabs), c = t / (P * nslabs);
+            const int z = pz % nslabs, p = pz / nslabs;
             const int ry0 = z * slab, nrows = (ry0 + slab < oh ? ry0 + slab : oh) - ry0;
             s_chan[h] = c;
             Entry *xt = tab + (size_t)h * tab_n;
@@ -870,9 +874,12 @@ int launch_stream(const CropParams &prm, int total, size_t smem, cudaStream_t st
     return prm.ow % (32 * C) == 0 ? launch_stream_full<T, O, C, true>(prm, total, smem, st, mode) : launch_stream_full<T, O, C, false>(prm, total, smem, st, mode);
 }
 
-// Row slabs of the persistent kernel (SPP_CROP_SPLIT overrides), at most kPlanMaxSlabs: 32 output rows for fp32 frames
-// (memory-bound: short items, short drain), 64 for uint8 frames (issue-bound: the per-item work of the consumers counts).
-// Measured at cfg2: fp32 166 / 164 / 156 / 166 us at 3 / 4 / 8 / 16 slabs, uint8 151 / 153 / 163 / 191 us.
+// Row slabs of the persistent kernel (SPP_CROP_SPLIT overrides), at most kPlanMaxSlabs.  Measured at cfg2 with `rows` = 64 / 32 /
+// 16: fp32 frames 156 / 145 / 160 us, uint8 frames 154 / 163 / 191 us; at cfg4 (6 400 crops) fp32 1 029 / 1 116 / 1 327 us.
+std::atomic<int> &crop_policy() {
+    static std::atomic<int> policy{env_int("SPP_CROP_PERSIST", 1, 0, 2)};
+    return policy;
+}
 int stream_split(int out_h, int split_env, int rows) {
     int split = split_env ? split_env : (out_h + rows - 1) / rows;
     if (split > kPlanMaxSlabs) split = kPlanMaxSlabs;
@@ -934,14 +941,14 @@ int launch_crop(const void *frames, int num_frames, int frame_h, int frame_w, co
     }
     // Persistent plan + stream kernels when the caller brings a workspace (spp_crop_affine*_ws).  They need exactly
     // kCropWarps consumer warps and table slices that bulk TMA can copy (16-byte multiples: even sizes for 8-byte entries).
-    // Chosen for launches of up to ~8 waves of per-item CTAs, where the set-up bubbles and the drain at the end are 10 % of the
-    // time; beyond that the one-CTA-per-item kernel's steady state is faster (measured: 157 vs 161 us at 640 crops, 320 vs 308 at
-    // 1 280, 671 vs 599 at 2 560; SPP_CROP_PERSIST=0 / 2 = never / always).
-    static const int persist = env_int("SPP_CROP_PERSIST", 1, 0, 2);
-    const int sms_ = sm_count() > 0 ? sm_count() : 148;
-    const bool few = (long long)p * 3 * 2 <= 8LL * 5 * sms_;
-    if (workspace && (persist == 2 || (persist == 1 && few)) && prm.ncc * prm.rg == kCropWarps) {
-        const int psplit = stream_split(out_h, split_env, sizeof(T) == 1 ? 64 : 32);
+    // Policy (spp_crop_policy: 0 never / 1 automatic / 2 always; SPP_CROP_PERSIST sets the initial value).  Automatic = fp32
+    // frames only: measured 145 / 276 / 538 us against 161 / 308 / 599 for the per-item kernel at 640 / 1 280 / 2 560 crops of ten
+    // per frame, and 1 029 against 1 017 us at 6 400 crops of a hundred per frame; with uint8 frames the kernel is bound by its
+    // instruction stream and the per-item kernel is as fast or faster (151 against 154 us at cfg2, 1 210 against 1 281 at cfg4).
+    const int persist = crop_policy().load(std::memory_order_relaxed);
+    if (workspace && (persist == 2 || (persist == 1 && sizeof(T) == 4)) && prm.ncc * prm.rg == kCropWarps) {
+        // 32-row slabs (short items, short drain) up to 2 048 crops, 64-row slabs beyond and for uint8 frames
+        const int psplit = stream_split(out_h, split_env, (sizeof(T) == 1 || p > 2048) ? 64 : 32);
         const int pslab = (out_h + psplit - 1) / psplit, nslabs = (out_h + pslab - 1) / pslab;
         const bool even = sizeof(AxisEntry<T>) % 16 == 0 || (out_w % 2 == 0 && out_h % 2 == 0 && pslab % 2 == 0);
         if (even && nslabs <= kPlanMaxSlabs) {
@@ -1002,6 +1009,12 @@ extern "C" int spp_crop_affine_ex(const void *frames, int frames_u8, int num_fra
                                                             out, stream, workspace, workspace_bytes, mode)
                     : spp::launch_crop<float, float>(frames, num_frames, frame_h, frame_w, boxes, frame_idx, p, out_h, out_w, mean, std, variant, out,
                                                      stream, workspace, workspace_bytes, mode);
+}
+
+extern "C" int spp_crop_policy(int mode) {
+    if (mode < 0) return spp::crop_policy().load();
+    if (mode > 2) return -1;
+    return spp::crop_policy().exchange(mode);
 }
 
 extern "C" size_t spp_crop_workspace_bytes(int p, int out_h, int out_w, int frames_u8) {

@@ -31,8 +31,10 @@ def crop_path(request, spp):
     one-CTA-per-item kernels (spp_crop_affine / _u8, no workspace)."""
     prev = spp.ops.CROP_USE_WORKSPACE
     spp.ops.CROP_USE_WORKSPACE = request.param == "persistent"
+    prev_policy = spp._lib.lib().spp_crop_policy(2 if request.param == "persistent" else 0)     # also for uint8 frames
     yield request.param
     spp.ops.CROP_USE_WORKSPACE = prev
+    spp._lib.lib().spp_crop_policy(prev_policy)
 
 
 @pytest.fixture(scope="module")
@@ -1219,6 +1221,7 @@ def test_crop_persistent_equals_per_item_and_planned(spp, synth, dev):
             ref = spp.crop_affine(frames, bx, fi, **kw)
         finally:
             spp.ops.CROP_USE_WORKSPACE = True
+        prev_policy = spp._lib.lib().spp_crop_policy(2)          # the persistent kernels for uint8 frames too
         got = spp.crop_affine(frames, bx, fi, **kw)
         assert torch.equal(got, ref)
         ws = spp.ops.alloc_workspace(dev, spp.crop_workspace_bytes(bx.shape[0], 256, 192, frames.dtype == torch.uint8))
@@ -1251,6 +1254,7 @@ def test_crop_persistent_equals_per_item_and_planned(spp, synth, dev):
                                        vp(ws), ws.numel(), st) == 0
             assert fn(*head, vp(o), *tail, st) == 0, spp._lib.lib().spp_last_error()
             assert torch.equal(o, ref), name
+        spp._lib.lib().spp_crop_policy(prev_policy)
 
 
 @pytest.mark.gpu
