@@ -286,8 +286,12 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1)) crop_affine_kernel(cons
     extern __shared__ __align__(128) unsigned char crop_smem[];
     const int ow = prm.ow, oh = prm.oh;
     const int kStageBytes = prm.stage_bytes;
-    const int slab = (oh + (int)gridDim.z - 1) / (int)gridDim.z;
-    const int ry0 = (int)blockIdx.z * slab;
+    // 1-D grid of items in (slab, crop, channel) order, slab fastest: the slabs of a crop and the crops of a frame are
+    // resident together, so the source rows that overlapping boxes share come from L2 (see crop_stream_kernel).
+    const int nsl = prm.split;
+    const int slab = (oh + nsl - 1) / nsl;
+    const int item_z = (int)(blockIdx.x % (unsigned)nsl), item_pc = (int)(blockIdx.x / (unsigned)nsl);
+    const int ry0 = item_z * slab;
     const int ry1 = (ry0 + slab < oh ? ry0 + slab : oh) - 1;                             // inclusive
     if (ry0 > ry1) return;
     Entry *xt = reinterpret_cast<Entry *>(crop_smem + (size_t)prm.stages * kStageBytes); // [ow]
@@ -297,7 +301,7 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1)) crop_affine_kernel(cons
     __shared__ int s_v[4];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
-    const int p = blockIdx.x, c = blockIdx.y;
+    const int p = item_pc % prm.P, c = item_pc / prm.P;
     __shared__ AxisMap s_map;
     int f = __ldg(prm.frame_idx + p);
     if (warp == 0) {          // the fp64 map (about ten fp64 divisions) is built by one warp, not by all seven
@@ -983,7 +987,9 @@ int launch_crop(const void *frames, int num_frames, int frame_h, int frame_w, co
     const int slab = (out_h + split - 1) / split;
     const size_t smem = (size_t)prm.stages * prm.stage_bytes + (size_t)(out_w + slab) * sizeof(AxisEntry<T>) + 16 * (size_t)prm.stages;
     SPP_CHECK_ARG(smem <= 200 * 1024, "crop_affine: output size too large");
-    dim3 grid(p, 3, split);
+    prm.split = split;
+    SPP_CHECK_ARG((long long)p * 3 * split < (1LL << 31), "crop_affine: too many crops");
+    dim3 grid((unsigned)((long long)p * 3 * split));
     return cols == 3 ? launch_staged<T, O, 3>(prm, grid, smem, st) : launch_staged<T, O, 6>(prm, grid, smem, st);
 }
 }  // namespace
