@@ -169,6 +169,24 @@ def roi_bytes(boxes, frame_h, frame_w, out_h=256, out_w=192):
     return float(((x1 - x0 + 1) * (y1 - y0 + 1)).sum()) * 3 * 4
 
 
+def roi_union_bytes(boxes, frame_idx, frame_h, frame_w, out_h=256, out_w=192):
+    """Source bytes that have to cross HBM at least once: the UNION of the crops' source windows per frame (boxes of one
+    frame overlap; `roi_bytes` counts every window), 3 x fp32."""
+    import numpy as np
+    spp = importlib.import_module(PKG)
+    cs = spp.hostmath.hf_center_scale(boxes, out_w, out_h)
+    w, h = cs[:, 2] * 200.0, cs[:, 3] * 200.0
+    x0 = (cs[:, 0] - w / 2).clamp(0, frame_w - 1).floor().long().tolist()
+    x1 = (cs[:, 0] + w / 2).clamp(0, frame_w - 1).ceil().long().tolist()
+    y0 = (cs[:, 1] - h / 2).clamp(0, frame_h - 1).floor().long().tolist()
+    y1 = (cs[:, 1] + h / 2).clamp(0, frame_h - 1).ceil().long().tolist()
+    masks = {}
+    for f, a, b, c, d in zip(frame_idx.tolist(), x0, x1, y0, y1):
+        m = masks.setdefault(int(f), np.zeros((frame_h, frame_w), bool))
+        m[c:d + 1, a:b + 1] = True
+    return float(sum(int(m.sum()) for m in masks.values())) * 3 * 4
+
+
 def shared_config(args, wl, world: int, shard: bool, collective: str) -> dict:
     """The `config` object both arms print (same keys, same values: the driver compares them)."""
     return {
@@ -450,7 +468,15 @@ def main():
     match_flops = 2.0 * M * wl["gallery"] * 512
     kernels = {
         "heatmap_decode": dict(bound="hbm", us=kern_us["heatmap_decode"], bytes=hm_bytes),
-        "crop_affine": dict(bound="hbm", us=kern_us["crop_affine"], bytes=crop_bytes),
+        # `bytes` = SURVEY 8(d)'s algorithmic figure: output + every crop's own source window.  Boxes of one frame overlap, and
+        # the kernel keeps the crops of a frame in flight together so that shared rows come from L2: `frac` can exceed 1.
+        # `min_bytes` = output + the UNION of the windows, what has to cross HBM at least once.
+        "crop_affine": dict(bound="hbm", us=kern_us["crop_affine"], bytes=crop_bytes,
+                            min_bytes=P * 3 * 256 * 192 * 4 + roi_union_bytes(inp.boxes, inp.frame_idx, wl["height"], wl["width"]) *
+                            (0.25 if args.frames == "u8" else 1.0),
+                            note="frac = algorithmic bytes (every crop's own source window) / time / peak: above 1 because overlapping boxes of a "
+                                 "frame share source rows through L2; frac_min = (output + union of the windows) / time / peak; frac_dram = ncu DRAM "
+                                 "bytes (static) / time / peak"),
         # decode+NMS reads the class planes of every anchor and the 64 DFL planes of candidate anchors only: a
         # latency-bound chain of three small launches, not an HBM stream.  `survey_bytes` (every plane of the
         # head, what the reference's Head.forward reads) is given for scale only — no fraction of peak is derived from it.
@@ -467,6 +493,8 @@ def main():
             if tr:
                 d["traffic"] = tr
                 d["frac_dram"] = tr / (d["us"] * 1e-6) / 1e9 / peaks["hbm"]
+            if "min_bytes" in d:
+                d["frac_min"] = d["min_bytes"] / (d["us"] * 1e-6) / 1e9 / peaks["hbm"]
         elif d["bound"] == "tensor":
             d["achieved"] = d["flops"] / (d["us"] * 1e-6) / 1e12
             d["peak"], d["unit"] = peaks["bf16"], "TFLOP/s"
@@ -484,6 +512,7 @@ def main():
                     frac=round(dk["frac"], 4), traffic=dk.get("traffic"), frac_dram=round(dk["frac_dram"], 4) if "frac_dram" in dk else None,
                     traffic_source=traffic_note, peak_source=peaks["source"],
                     launch_us=round(dk["us"], 2), algorithmic=dk.get("bytes", dk.get("flops")),
+                    **({"frac_min": round(dk["frac_min"], 4), "min_bytes": dk["min_bytes"], "note": dk["note"]} if "frac_min" in dk else {}),
                     step_share=round(dk["us"] / sum(v["us"] for v in kernels.values()), 3))
     step_floor = None
     if traffic_all:
