@@ -265,8 +265,7 @@ int spp_crop_affine_u8(const uint8_t *frames, int num_frames, int frame_h, int f
  * Replaces the same reference code as spp_crop_affine (HF image_processing_vitpose.py:68-172, 386-448). */
 size_t spp_crop_workspace_bytes(int p, int out_h, int out_w, int frames_u8);
 /* Which implementation a call WITH a workspace runs: 0 = always one CTA per work item, 1 = automatic (the persistent kernels for
- * fp32 frames, where they are faster at every crop count measured; the per-item kernel for uint8 frames, which is bound by its
- * instruction stream), 2 = always the persistent kernels.  Process-wide; mode < 0 only queries; returns the previous value. */
+ * fp32 frames up to 4 096 crops; the per-item kernel beyond, and for uint8 frames, which are bound by their instruction stream), 2 = always the persistent kernels.  Process-wide; mode < 0 only queries; returns the previous value. */
 int spp_crop_policy(int mode);
 int spp_crop_affine_ws(const float *frames, int num_frames, int frame_h, int frame_w, const float *boxes,
                        const int *frame_idx, int p, int out_h, int out_w, const float *mean, const float *std,

@@ -946,11 +946,13 @@ int launch_crop(const void *frames, int num_frames, int frame_h, int frame_w, co
     // Persistent plan + stream kernels when the caller brings a workspace (spp_crop_affine*_ws).  They need exactly
     // kCropWarps consumer warps and table slices that bulk TMA can copy (16-byte multiples: even sizes for 8-byte entries).
     // Policy (spp_crop_policy: 0 never / 1 automatic / 2 always; SPP_CROP_PERSIST sets the initial value).  Automatic = fp32
-    // frames only: measured 145 / 276 / 538 us against 161 / 308 / 599 for the per-item kernel at 640 / 1 280 / 2 560 crops of ten
-    // per frame, and 1 029 against 1 017 us at 6 400 crops of a hundred per frame; with uint8 frames the kernel is bound by its
-    // instruction stream and the per-item kernel is as fast or faster (151 against 154 us at cfg2, 1 210 against 1 281 at cfg4).
+    // frames, up to 4 096 crops: measured 145 / 276 / 538 us against 152 / 308 / 599 for the per-item kernel at 640 / 1 280 / 2 560
+    // crops of ten per frame, but 1 029-1 037 against 1 013 us at 6 400 crops of a hundred per frame (cfg4: most source rows are
+    // L2 hits either way and the per-item kernel's single 256-row item per crop channel has the least overhead); with uint8 frames
+    // the kernel is bound by its instruction stream and the per-item kernel is faster (149 against 154 us at cfg2, 1 190 against
+    // 1 281 at cfg4).
     const int persist = crop_policy().load(std::memory_order_relaxed);
-    if (workspace && (persist == 2 || (persist == 1 && sizeof(T) == 4)) && prm.ncc * prm.rg == kCropWarps) {
+    if (workspace && (persist == 2 || (persist == 1 && sizeof(T) == 4 && p <= 4096)) && prm.ncc * prm.rg == kCropWarps) {
         // 32-row slabs (short items, short drain) up to 4 096 crops (2 560 crops of ten per frame: 538 us against 579 with 64-row
         // slabs), 64-row slabs beyond (6 400 crops of a hundred per frame: 1 029 against 1 116 us) and for uint8 frames
         const int psplit = stream_split(out_h, split_env, (sizeof(T) == 1 || p > 4096) ? 64 : 32);
