@@ -255,6 +255,9 @@ def main():
     ap.add_argument("--det-max-candidates", type=int, default=-1,
                     help="bound on NMS candidates per image (<= 512 selects the small-footprint NMS kernel); -1 = 512 for cfg1/cfg2, unbounded else")
     ap.add_argument("--match-sms", type=int, default=0, help="SMs reserved for the match GEMM beside the heatmap decode; 0 = no split (measured best)")
+    ap.add_argument("--det-after-heatmap", type=int, default=-1, choices=[-1, 0, 1, 2],
+                    help="detection chains that wait for the heatmap decode and run beside the crop (pipeline default: -1)")
+    ap.add_argument("--crop-free-ctas", type=int, default=-1, help="CTA slots the persistent crop leaves free (pipeline default: -1)")
     ap.add_argument("--crop-first", action="store_true", help="round-1 order: crop then heatmap decode on the main stream")
     ap.add_argument("--copy-streams", type=int, default=2, help="streams the per-step H2D copies of the e2e region are spread over")
     args = ap.parse_args()
@@ -285,6 +288,10 @@ def main():
         args.det_max_candidates = 512 if args.workload in ("cfg1", "cfg2") else 0
     pipe_kw = dict(decode_mode=args.decode_mode, use_graph=not args.no_graph, concurrent=not args.serial,
                    det_max_candidates=args.det_max_candidates, match_sms=args.match_sms, heatmap_first=not args.crop_first)
+    if args.det_after_heatmap >= 0:
+        pipe_kw["det_after_heatmap"] = args.det_after_heatmap
+    if args.crop_free_ctas >= 0:
+        pipe_kw["crop_free_ctas"] = args.crop_free_ctas
 
     if args.impl == "reference":
         run_reference(args, wl, rank, world, pipeline, emit)

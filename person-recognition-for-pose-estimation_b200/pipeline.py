@@ -80,7 +80,7 @@ class SelectivePosePipeline:
                  id_offset: int = 0, concurrent: bool = True, matcher=None, capture_collectives: bool = False,
                  select_on_device: bool = False, gallery_f32: Optional[torch.Tensor] = None, max_row_norm: float = 1.0,
                  det_max_candidates: int = 0, match_sms: int = 0, heatmap_first: bool = True, det_fused: Optional[bool] = None,
-                 det_after_heatmap: int = 0, crop_free_ctas: int = 48):
+                 det_after_heatmap: Optional[int] = None, crop_free_ctas: int = 48):
         self.device = device
         self.threshold, self.conf, self.iou, self.mode = threshold, conf_thres, iou_thres, decode_mode
         self.id_offset = id_offset
@@ -97,7 +97,14 @@ class SelectivePosePipeline:
         self.det_max_candidates, self.match_sms = int(det_max_candidates), int(match_sms)
         self.det_fused = (0 < self.det_max_candidates <= 512) if det_fused is None else bool(det_fused)
         self.heatmap_first = heatmap_first and not select_on_device
-        # experiment knob: number of detection chains (0, 1, 2) that wait for the heatmap decode and run under the crop instead
+        # det_after_heatmap: number of detection chains (0, 1, 2) that wait for the heatmap decode and run beside the crop instead.
+        # Their candidate decode is ~450 k isolated 128-byte line fetches; beside the heatmap decode the two cost each other 40 us
+        # (heatmap decode 100 us instead of 62), beside the persistent crop 27 us: 0.237-0.240 ms per step with 2 against 0.247
+        # with 0 and 0.251 with 1 (measured with the round-2 kernels; with the round-1 crop it was a tie).
+        # Default: 2 with the fused small-footprint detection kernels, 0 otherwise (cfg4: unbounded candidate lists, three launches
+        # with a 112 KB NMS CTA; beside the crop they cost more than under the 3 ms heatmap decode: 4.39 against 4.28 ms per step).
+        if det_after_heatmap is None:
+            det_after_heatmap = 2 if self.det_fused else 0
         self.det_after_heatmap = int(det_after_heatmap) if self.heatmap_first else 0
         # crop_free_ctas: CTA slots the persistent crop kernel leaves free (SPP_LIMIT_CROP_FREE_CTAS) so that the match re-score,
         # which becomes ready while the crop holds the machine, runs beside it instead of after it.

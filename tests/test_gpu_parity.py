@@ -651,7 +651,8 @@ def test_pipeline_graph_vs_eager_and_device_selection(spp, synth, dev):
     # bench.py's configuration: bounded candidate list -> fused small-footprint detection kernels, heatmap decode first,
     # match GEMM on reserved SMs; and the round-1 order.  Same tensors, bit for bit.
     for kw in (dict(det_max_candidates=512), dict(det_max_candidates=512, match_sms=24), dict(det_max_candidates=512, det_fused=False),
-               dict(heatmap_first=False)):
+               dict(heatmap_first=False), dict(det_max_candidates=512, det_after_heatmap=0), dict(det_max_candidates=512, det_after_heatmap=1),
+               dict(det_max_candidates=512, crop_free_ctas=0)):
         v = pipeline.SelectivePosePipeline(inp, gal, dev, use_graph=True, concurrent=True, **kw)
         for _ in range(2):
             v.step()

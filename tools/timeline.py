@@ -32,7 +32,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "u8":
 pipe = pipeline.SelectivePosePipeline(inp, ms.gallery.to(torch.bfloat16), dev, use_graph=os.environ.get("SPP_TL_NOGRAPH", "0") in ("", "0"),
                                       det_max_candidates=int(os.environ.get("SPP_TL_MAXCAND", "512")), match_sms=int(os.environ.get("SPP_TL_MATCH_SMS", "0")),
                                       heatmap_first=os.environ.get("SPP_TL_CROP_FIRST", "0") in ("", "0"),
-                                      det_after_heatmap=int(os.environ.get("SPP_TL_DET_LATE", "0")),
+                                      det_after_heatmap=int(os.environ["SPP_TL_DET_LATE"]) if os.environ.get("SPP_TL_DET_LATE") else None,
                                       crop_free_ctas=int(os.environ.get("SPP_TL_CROP_FREE", "48")))
 for _ in range(5):
     pipe.step()
