@@ -333,6 +333,23 @@ def main():
     gallery_bf16 = ms.gallery.to(torch.bfloat16)
     shard_lo, shard_hi = spp.dist.shard_bounds(wl["gallery"], world, rank)
     matcher, peers = None, None
+    # Pre-flight for the peer exchange (cudaMalloc + CUDA IPC between the ranks of the box): if ANY rank cannot map its peers'
+    # buffers (a box without peer access, a container that forbids IPC handles), every rank falls back to the NCCL exchange
+    # together, and the JSON line says so, instead of the run dying without a line.
+    collective_fallback = None
+    if world > 1 and args.collective == "peer":
+        ok, why, probe = 1, "", None
+        try:
+            probe = spp.dist.PeerGroup(8)
+        except Exception as e:          # noqa: BLE001 - whatever the failure, the decision has to be collective
+            ok, why = 0, f"{type(e).__name__}: {e}"
+        flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+        if probe is not None:
+            probe.close(barrier=int(flag.item()) == 1)     # every rank is here only if every rank succeeded
+        if int(flag.item()) == 0:
+            args.collective = "nccl"
+            collective_fallback = "peer exchange unavailable on this box (" + (why or "another rank failed") + "): NCCL all_gather + all_reduce(MAX) instead"
     # Placement policy: a gallery of <= 100k ids (<= 102 MB bf16) is replicated on every GPU and
     # the step has no collective at all; larger galleries are sharded by rows (cfg3 record below).
     shard = world > 1 and (args.shard_gallery == "yes" or (args.shard_gallery == "auto" and wl["gallery"] > 100_000))
@@ -568,6 +585,7 @@ def main():
                 "det_max_candidates": args.det_max_candidates or "unbounded",
                 "det_overflow": det_overflow,
                 "sm_split": (f"match GEMM on {args.match_sms} SMs beside the heatmap decode on the others" if args.match_sms else "none"),
+                **({"collective_fallback": collective_fallback} if collective_fallback else {}),
                 "host_numa": numa,
             },
             "crops_per_s": round(world * P * args.steps / (dev_ms / 1e3), 1),

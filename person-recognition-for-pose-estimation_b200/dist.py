@@ -169,11 +169,13 @@ class PeerGroup:
             out.append(g)
         return out
 
-    def close(self) -> None:
+    def close(self, barrier: bool = True) -> None:
+        """Unmap the peers' buffers and free this rank's.  ``barrier=False`` only when no rank can still be using them and the
+        ranks may not all be calling (a failed collective set-up)."""
         from . import _lib
         if self._injected or self._own is None:
             return
-        if self.world > 1 and dist.is_initialized():
+        if barrier and self.world > 1 and dist.is_initialized():
             dist.barrier(self.group)
         for p in self._opened:
             _lib.check(_lib.lib().spp_peer_close(p), "spp_peer_close")
