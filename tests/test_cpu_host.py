@@ -45,6 +45,19 @@ def test_no_cpu_fallback(spp):
     assert spp._lib.lib().spp_nms_workspace_bytes(64, 19320, 1, 0) > 64 * 19320 * 8
     assert spp._lib.lib().spp_match_workspace_bytes(640, 10000, 512) > 640 * 512 * 6
     assert spp._lib.lib().spp_match_workspace_bytes(640, 10000, 256) == 0
+    # crop: header + (out_w + out_h) table entries per crop (8 B for fp32 frames, 16 B for uint8) + one 64-byte descriptor per slab
+    L = spp._lib.lib()
+    assert L.spp_crop_workspace_bytes(0, 256, 192, 0) == 0
+    assert L.spp_crop_workspace_bytes(640, 256, 192, 0) == 256 + 640 * (448 * 8 + 32 * 64)
+    assert L.spp_crop_workspace_bytes(640, 256, 192, 1) == 256 + 640 * (448 * 16 + 32 * 64)
+    assert spp.crop_workspace_bytes(640) == L.spp_crop_workspace_bytes(640, 256, 192, 0)
+    # implementation policy and CTA budgets are process-wide host state: set, query, restore
+    prev = L.spp_crop_policy(2)
+    assert L.spp_crop_policy(-1) == 2 and L.spp_crop_policy(7) == -1
+    L.spp_crop_policy(prev)
+    assert L.spp_crop_policy(-1) == prev
+    assert L.spp_set_launch_limit(2, 48) == 0 and L.spp_set_launch_limit(2, -1) == 48 and L.spp_set_launch_limit(2, 0) == 48
+    assert L.spp_set_launch_limit(3, 1) == -1
 
 
 def test_key_packing_round_trip_and_order(spp):
