@@ -166,7 +166,7 @@ struct Best {
 };
 
 template <bool FLIP, int RADIUS, bool HFQ, typename T>
-__global__ void __launch_bounds__(FLIP ? 256 : 512, 1) heatmap_decode_kernel(const DecodeParams prm) {
+__global__ void __launch_bounds__((FLIP && sizeof(T) == 4) ? 256 : 512, 1) heatmap_decode_kernel(const DecodeParams prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int H = prm.H, W = prm.W, K = prm.K;
@@ -543,7 +543,8 @@ int heatmap_decode_impl(const T *hm, const T *hm_flipped, const int *perm, int p
     // 8 warps per SM hide the ALU latency of the scan; whatever shared memory is left deepens each
     // warp's private ring (flip test, 64x48: 8 warps x 1 stage x 24 KB).
     // (without the flip test a map is half the bytes for the same refinement work: 16 warps x 1 stage)
-    const int max_warps = flip ? 8 : 16;
+    // (bf16 maps with the flip test are the same 12 KB per stage as fp32 maps without it: 16 warps as well)
+    const int max_warps = (flip && sizeof(T) == 4) ? 8 : 16;
     int warps = slots < max_warps ? slots : max_warps;
     int stages = slots / warps;
     if (stages > 4) stages = 4;
