@@ -172,6 +172,10 @@ struct GemmParams {
     int m, n;
     int tiles_n, nsplit;   // every M-tile is cut into nsplit chunks of gallery tiles; work item = (M-tile, chunk)
     int items;             // m_tiles * nsplit, distributed round-robin over the persistent CTAs
+    int m_tiles;           // items are numbered probe tile fastest (mt = item % m_tiles, chunk = item / m_tiles): the CTAs of one round
+                           // work on the same few gallery chunks, whose tiles then cross HBM once and come from L2 for the other
+                           // probe tiles (chunk fastest, 640 x 1 M: each chunk was streamed from HBM in both rounds)
+    int chunk_fastest;     // SPP_MATCH_ORDER=chunk: the old numbering (profiling knob)
     const unsigned *step;  // peer exchange: device step counter, parity selects the probe buffer (tmap_a0 / tmap_a1); NULL: tmap_a0
     Cand *part;            // [m_tiles*BM, nsplit, 2]  best two (score, id) of every (probe row, chunk)
     float *dropped;        // [tiles_n, m_tiles*BM]    per (gallery tile, probe row): upper bound of the scores of that tile's
@@ -233,7 +237,7 @@ match_gemm_top2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid
             int stage = 0;
             uint32_t phase = 0, it = 0;
             for (int item = blockIdx.x; item < prm.items; item += gridDim.x, ++it) {
-                const int mt = item / prm.nsplit, sp = item - mt * prm.nsplit;
+                const int mt = prm.chunk_fastest ? item / prm.nsplit : item % prm.m_tiles, sp = prm.chunk_fastest ? item % prm.nsplit : item / prm.m_tiles;
                 int nt0, ntiles;
                 chunk_range(sp, nt0, ntiles);
                 mbar_wait(a_empty, (it & 1) ^ 1);            // previous item's MMAs are done with the probe tile
@@ -259,7 +263,7 @@ match_gemm_top2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid
             int stage = 0;
             uint32_t phase = 0, it = 0, tcount = 0;          // tcount: tiles issued by this CTA (accumulator ring)
             for (int item = blockIdx.x; item < prm.items; item += gridDim.x, ++it) {
-                const int sp = item % prm.nsplit;
+                const int sp = prm.chunk_fastest ? item % prm.nsplit : item / prm.m_tiles;
                 int nt0, ntiles;
                 chunk_range(sp, nt0, ntiles);
                 mbar_wait(a_full, it & 1);
@@ -294,7 +298,7 @@ match_gemm_top2_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid
         const int m_pad = ((prm.m + BM - 1) / BM) * BM;
         uint32_t tcount = 0;
         for (int item = blockIdx.x; item < prm.items; item += gridDim.x) {
-            const int mt = item / prm.nsplit, sp = item - mt * prm.nsplit;
+            const int mt = prm.chunk_fastest ? item / prm.nsplit : item % prm.m_tiles, sp = prm.chunk_fastest ? item % prm.nsplit : item / prm.m_tiles;
             int nt0, ntiles;
             chunk_range(sp, nt0, ntiles);
             uint32_t K1 = 0, K2 = 0;                     // running best two keys of the chunk and the tiles they came from
@@ -926,7 +930,8 @@ int launch_search(const __nv_bfloat16 *qb0, const __nv_bfloat16 *qb1, const unsi
     // per device and per context: set on every launch (about a microsecond; legal during stream capture)
     SPP_CHECK_CUDA(cudaFuncSetAttribute(match_gemm_top2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
     const int items = p.m_tiles * p.nsplit;
-    GemmParams gp{m, n, p.tiles_n, p.nsplit, items, step, part, dropped, match_key_offset(max_row_norm)};
+    static const int chunk_fastest = [] { const char *e = getenv("SPP_MATCH_ORDER"); return (e && e[0] == 'c') ? 1 : 0; }();
+    GemmParams gp{m, n, p.tiles_n, p.nsplit, items, p.m_tiles, chunk_fastest, step, part, dropped, match_key_offset(max_row_norm)};
     match_gemm_top2_kernel<<<items < p.sms ? items : p.sms, kGemmThreads, kGemmSmem, st>>>(ta0, ta1, tb, gp);
     SPP_CHECK_LAUNCH();
     return SPP_OK;
