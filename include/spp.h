@@ -284,7 +284,8 @@ int spp_crop_affine_ex(const void *frames, int frames_u8, int num_frames, int fr
 
 /* The two halves of spp_crop_affine*_ws as separate calls, same arguments and workspace: the plan reads only the boxes, so it
  * can be enqueued early (SelectivePosePipeline runs it beside the heatmap decode); the run must follow ITS plan on the device
- * (every run consumes the ticket counter its plan reset).  frames_u8 selects the table format of the uint8 kernels. */
+ * (every run consumes the ticket counter its plan reset; a run on a workspace without a plan for this crop count traps, and
+ * spp_crop_policy must not change between a plan and its run).  frames_u8 selects the table format of the uint8 kernels. */
 int spp_crop_plan(int frames_u8, int num_frames, int frame_h, int frame_w, const float *boxes, const int *frame_idx, int p,
                   int out_h, int out_w, int variant, void *workspace, size_t workspace_bytes, spp_stream_t stream);
 int spp_crop_affine_run(const float *frames, int num_frames, int frame_h, int frame_w, const float *boxes,

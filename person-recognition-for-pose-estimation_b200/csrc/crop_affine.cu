@@ -500,6 +500,9 @@ static_assert(sizeof(CropItem) == 64, "CropItem is copied by bulk TMA");
 enum { kItemStaged = 0, kItemConstant = 1, kItemMirrored = 2, kItemStop = 3 };
 constexpr int kPlanHeader = 256;              // workspace: [header: ticket counter][tables P x (ow + oh)][items P x nslabs]
 constexpr int kPlanMaxSlabs = 32;
+// header word 1: written by the plan kernel, checked by the stream kernel — a run on a workspace that was never planned for
+// this (crop count, slab count) traps instead of producing crops from stale tables
+__host__ __device__ __forceinline__ unsigned plan_tag(int P, int nslabs) { return 0x53505043u ^ ((unsigned)P * 2654435761u) ^ ((unsigned)nslabs << 24); }
 
 template <typename T>
 __global__ void __launch_bounds__(256) crop_plan_kernel(const CropParams prm) {
@@ -511,7 +514,10 @@ __global__ void __launch_bounds__(256) crop_plan_kernel(const CropParams prm) {
     CropItem *items = reinterpret_cast<CropItem *>(prm.ws + kPlanHeader + (size_t)prm.P * (ow + oh) * sizeof(Entry)) + (size_t)p * nslabs;
     __shared__ AxisMap s_map;
     __shared__ int s_x[2], s_y[kPlanMaxSlabs][2];
-    if (p == 0 && tid == 0) *reinterpret_cast<unsigned int *>(prm.ws) = 0u;          // the stream kernel's ticket counter
+    if (p == 0 && tid == 0) {
+        reinterpret_cast<unsigned int *>(prm.ws)[0] = 0u;                            // the stream kernel's ticket counter
+        reinterpret_cast<unsigned int *>(prm.ws)[1] = plan_tag(prm.P, nslabs);
+    }
     if (tid < 32) {
         const float4 box = __ldg(reinterpret_cast<const float4 *>(prm.boxes) + p);
         const AxisMap mm = crop_axis_map(box, ow, oh, prm.variant);
@@ -647,6 +653,10 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1), 5) crop_stream_kernel(c
             bulk_g2s(xt + ow, gtab + (size_t)p * (ow + oh) + ow + ry0, by, &ready[h]);
             bulk_g2s(&items[h], gitems + (size_t)p * nslabs + z, (uint32_t)sizeof(CropItem), &ready[h]);
         };
+        if (lane == 0 && __ldcg(reinterpret_cast<const unsigned int *>(prm.ws) + 1) != plan_tag(P, nslabs)) {
+            if (blockIdx.x == 0) printf("crop_stream_kernel: the workspace holds no plan for %d crops x %d slabs (spp_crop_plan first)\n", P, nslabs);
+            __trap();
+        }
         fetch((int)blockIdx.x, 0);
         int t_next = 0;                                    // lane 0: ticket of item k + 1, requested one item early
         if (lane == 0) t_next = (int)gridDim.x + (int)atomicAdd(tk, 1u);
