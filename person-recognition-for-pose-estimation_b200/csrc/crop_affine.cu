@@ -653,13 +653,14 @@ __global__ void __launch_bounds__(32 * (kCropWarps + 1), 5) crop_stream_kernel(c
             bulk_g2s(xt + ow, gtab + (size_t)p * (ow + oh) + ow + ry0, by, &ready[h]);
             bulk_g2s(&items[h], gitems + (size_t)p * nslabs + z, (uint32_t)sizeof(CropItem), &ready[h]);
         };
-        if (lane == 0 && __ldcg(reinterpret_cast<const unsigned int *>(prm.ws) + 1) != plan_tag(P, nslabs)) {
-            if (blockIdx.x == 0) printf("crop_stream_kernel: the workspace holds no plan for %d crops x %d slabs (spp_crop_plan first)\n", P, nslabs);
-            __trap();
-        }
+        const unsigned tag = lane == 0 ? __ldcg(reinterpret_cast<const unsigned int *>(prm.ws) + 1) : 0u;   // checked below, off the critical path
         fetch((int)blockIdx.x, 0);
         int t_next = 0;                                    // lane 0: ticket of item k + 1, requested one item early
         if (lane == 0) t_next = (int)gridDim.x + (int)atomicAdd(tk, 1u);
+        if (lane == 0 && tag != plan_tag(P, nslabs)) {
+            if (blockIdx.x == 0) printf("crop_stream_kernel: the workspace holds no plan for %d crops x %d slabs (spp_crop_plan first)\n", P, nslabs);
+            __trap();
+        }
         uint32_t gb = 0;                                   // bands issued so far, over all items
         for (int k = 0;; ++k) {
             mbar_wait(&ready[k & 1], (uint32_t)((k >> 1) & 1));
