@@ -1281,3 +1281,37 @@ def test_crop_output_sizes_vs_oracle(spp, synth, dev, crop_path, out_hw):
         got8 = spp.crop_affine(fr8.to(dev), boxes.to(dev), cs.frame_idx.to(dev), out_hw=out_hw, mean=m.tolist(), std=sd.tolist())
         d8 = np.abs(got8.cpu().numpy() - want8)
         assert float(d8.max()) < 2e-5, (out_hw, fw, float(d8.max()))      # a flipped uint8 rounding would show up as ~0.017
+
+
+@pytest.mark.gpu
+def test_crop_fuzz_both_implementations_agree(spp, dev):
+    """Random and degenerate boxes (NaN, infinities, zero and negative sizes, boxes far outside the frame, sub-pixel and
+    frame-sized boxes, out-of-range frame indices) through the persistent and the per-item kernels: both finish, agree bit for
+    bit, and produce finite pixels — fp32 and uint8 frames, fp32 and bf16 output."""
+    g = torch.Generator().manual_seed(123)
+    fr = torch.rand(5, 3, 96, 160, generator=g)
+    n = 400
+    boxes = torch.empty(n, 4)
+    boxes[:, 0] = torch.empty(n).uniform_(-200, 300, generator=g)
+    boxes[:, 1] = torch.empty(n).uniform_(-150, 200, generator=g)
+    boxes[:, 2] = torch.empty(n).uniform_(-50, 400, generator=g)
+    boxes[:, 3] = torch.empty(n).uniform_(-50, 300, generator=g)
+    special = [float("nan"), float("inf"), -float("inf"), 0.0, 1e-3, 1e6, -1e6, 1e30]
+    for i in range(0, 120):
+        boxes[i, int(torch.randint(0, 4, (1,), generator=g))] = special[i % len(special)]
+    boxes[120] = torch.tensor([0.0, 0.0, 160.0, 96.0])
+    boxes[121] = torch.tensor([10.5, 20.25, 0.5, 0.5])
+    fidx = torch.randint(-2, 8, (n,), generator=g, dtype=torch.int32)          # clamped by the kernels, as the shim documents
+    L = spp._lib.lib()
+    for frames, kw in ((fr.to(dev), {}), ((fr * 255).round().to(torch.uint8).to(dev), {"mean": [120.0, 115.0, 100.0], "std": [58.0, 57.0, 57.0]})):
+        for od in (torch.float32, torch.bfloat16):
+            prev = L.spp_crop_policy(0)
+            try:
+                a = spp.crop_affine(frames, boxes.to(dev), fidx.to(dev), out_dtype=od, **kw)
+                L.spp_crop_policy(2)
+                b = spp.crop_affine(frames, boxes.to(dev), fidx.to(dev), out_dtype=od, **kw)
+            finally:
+                L.spp_crop_policy(prev)
+            torch.cuda.synchronize()
+            assert torch.equal(a, b), (frames.dtype, od)
+            assert bool(torch.isfinite(a.float()).all())
