@@ -1315,3 +1315,53 @@ def test_crop_fuzz_both_implementations_agree(spp, dev):
             torch.cuda.synchronize()
             assert torch.equal(a, b), (frames.dtype, od)
             assert bool(torch.isfinite(a.float()).all())
+
+
+@pytest.mark.gpu
+def test_kernels_survive_nonfinite_inputs(spp, synth, dev):
+    """NaN / +-inf in the backbone outputs (a diverged model) must not hang or fault a kernel: every op completes, counts stay
+    in range, and the finite part of the batch is unaffected where the op is per-item."""
+    g = torch.Generator().manual_seed(7)
+    bad = torch.tensor([float("nan"), float("inf"), -float("inf")])
+    # detection head: poison frame 1 of 3, frames 0 and 2 must decode as before
+    hm = synth.make_head_maps(3, 320, 320, n_obj=4, nc=1, seed=3)
+    clean = spp.decode_nms([l.to(dev) for l in hm.levels])
+    lv = [l.clone() for l in hm.levels]
+    for l in lv:
+        idx = torch.randint(0, l[1].numel(), (l[1].numel() // 7,), generator=g)
+        l[1].view(-1)[idx] = bad[torch.randint(0, 3, (idx.numel(),), generator=g)]
+    for mc in (0, 512):
+        res = spp.decode_nms([l.to(dev) for l in lv], max_candidates=mc)
+        torch.cuda.synchronize()
+        cnt = res.count.cpu()
+        assert int(cnt[0]) == int(clean.count[0]) and int(cnt[2]) == int(clean.count[2])
+        assert torch.equal(res.dets[0], clean.dets[0]) and torch.equal(res.dets[2], clean.dets[2])
+        assert -301 <= int(cnt[1]) <= 300
+    # heatmaps: poison some maps, the others decode as before
+    hs = synth.make_heatmaps(6, 17, seed=21)
+    boxes = torch.tensor([[10.0, 20.0, 100.0, 200.0]]).repeat(6, 1).to(dev)
+    ref = spp.ops.heatmap_decode(hs.heatmaps.to(dev), hs.flipped.to(dev), hs.perm.to(dev), boxes, "dark", 11, 0)
+    h2 = hs.heatmaps.clone()
+    h2[2, 3].view(-1)[::5] = float("nan")
+    h2[4, 0] = float("inf")
+    h2[4, 1] = -float("inf")
+    for mode in ("dark", "softargmax", "quarter"):
+        out = spp.ops.heatmap_decode(h2.to(dev), hs.flipped.to(dev), hs.perm.to(dev), boxes, mode, 11, 0)
+        torch.cuda.synchronize()
+        assert out[0].shape == (6, 17, 2)
+    out = spp.ops.heatmap_decode(h2.to(dev), hs.flipped.to(dev), hs.perm.to(dev), boxes, "dark", 11, 0)
+    for p_ in (0, 1, 3, 5):
+        assert torch.equal(out[0][p_], ref[0][p_]) and torch.equal(out[2][p_], ref[2][p_])
+    # match: zero, NaN and inf probes beside ordinary ones
+    ms = synth.make_match_set(16, 300, seed=9)
+    gal = ms.gallery.to(torch.bfloat16).to(dev)
+    ids0, sims0 = spp.match_top1(ms.embeddings.to(dev), gal, 0.4)
+    emb = ms.embeddings.clone()
+    emb[3] = 0.0
+    emb[5, 7] = float("nan")
+    emb[9, 0] = float("inf")
+    ids, sims = spp.match_top1(emb.to(dev), gal, 0.4)
+    torch.cuda.synchronize()
+    keep = [i for i in range(16) if i not in (3, 5, 9)]
+    assert torch.equal(ids[keep], ids0[keep]) and torch.equal(sims[keep], sims0[keep])
+    assert int(ids[3]) == -1                                   # a zero probe has similarity 0 with every identity: below the gate
