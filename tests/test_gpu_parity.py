@@ -1365,3 +1365,44 @@ def test_kernels_survive_nonfinite_inputs(spp, synth, dev):
     keep = [i for i in range(16) if i not in (3, 5, 9)]
     assert torch.equal(ids[keep], ids0[keep]) and torch.equal(sims[keep], sims0[keep])
     assert int(ids[3]) == -1                                   # a zero probe has similarity 0 with every identity: below the gate
+
+
+@pytest.mark.gpu
+def test_crop_graph_replay_with_new_boxes_and_concurrent_streams(spp, synth, dev):
+    """The persistent crop inside a CUDA graph: the plan kernel is part of the graph, so a replay after the boxes changed in
+    place crops the NEW boxes (tables, band layout and the ticket counter are rebuilt every replay).  And two crops enqueued on
+    two streams at once, each with its own workspace and ticket counter, do not disturb each other."""
+    cs = synth.make_crop_set(12, 240, 320, per_frame=9, seed=31)          # 108 crops x 3 x 8 slabs = 2 592 items > 740 CTAs
+    fr, bx, fi = cs.frames.to(dev), cs.boxes.to(dev).clone(), cs.frame_idx.to(dev)
+    ws = spp.ops.alloc_workspace(dev, spp.crop_workspace_bytes(bx.shape[0]))
+    out = torch.empty(bx.shape[0], 3, 256, 192, device=dev)
+    s = torch.cuda.Stream(dev)
+    with torch.cuda.stream(s):
+        spp.crop_affine(fr, bx, fi, out=out, workspace=ws)                # warm-up outside the capture
+    s.synchronize()
+    gph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gph, stream=s):
+        spp.crop_affine(fr, bx, fi, out=out, workspace=ws)
+    gph.replay()
+    torch.cuda.synchronize()
+    first = out.clone()
+    assert torch.equal(first, spp.crop_affine(fr, bx, fi))
+    other = synth.make_crop_set(12, 240, 320, per_frame=9, seed=77).boxes.to(dev)
+    bx.copy_(other)                                                        # same buffer the graph reads
+    gph.replay()
+    torch.cuda.synchronize()
+    want = spp.crop_affine(fr, other, fi)
+    assert torch.equal(out, want) and not torch.equal(out, first)
+    # two streams at once
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    w1 = spp.ops.alloc_workspace(dev, spp.crop_workspace_bytes(bx.shape[0]))
+    w2 = spp.ops.alloc_workspace(dev, spp.crop_workspace_bytes(bx.shape[0]))
+    o1, o2 = torch.empty_like(out), torch.empty_like(out)
+    torch.cuda.synchronize()
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            spp.crop_affine(fr, other, fi, out=o1, workspace=w1)
+        with torch.cuda.stream(s2):
+            spp.crop_affine(fr, cs.boxes.to(dev), fi, out=o2, workspace=w2)
+    torch.cuda.synchronize()
+    assert torch.equal(o1, want) and torch.equal(o2, first)
