@@ -186,3 +186,20 @@ def test_torch_ops_registered_with_fake_kernels(spp):
         assert pix.shape == (3, 3, 256, 192)
     with pytest.raises((NotImplementedError, RuntimeError)):
         torch.ops.spp.l2_normalize(torch.zeros(2, 512))          # CPU tensors: no kernel registered
+
+
+def test_bench_roi_bytes_union_vs_sum():
+    """bench.py's two source-byte figures for the crop roofline: every crop's own window and the union of the
+    windows per frame (what has to cross HBM at least once)."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    boxes = torch.tensor([[100.0, 100.0, 60.0, 80.0], [100.0, 100.0, 60.0, 80.0], [700.0, 300.0, 60.0, 80.0]])
+    same_frame = torch.tensor([0, 0, 0], dtype=torch.int32)
+    other_frame = torch.tensor([0, 1, 2], dtype=torch.int32)
+    total = bench.roi_bytes(boxes, 720, 1280)
+    u_same = bench.roi_union_bytes(boxes, same_frame, 720, 1280)
+    u_other = bench.roi_union_bytes(boxes, other_frame, 720, 1280)
+    assert u_same < u_other                                   # two identical boxes in one frame are read once
+    assert abs(u_same / u_other - 2.0 / 3.0) < 0.02
+    assert 0.9 < u_other / total < 1.1                        # disjoint windows: union = sum (up to the rounding of the window edges)
